@@ -1,0 +1,186 @@
+"""Generate golden vectors by running the UNMODIFIED reference (Kaeryv/Khepri).
+
+Run in the build container only (the reference tree does not travel to the GPU box):
+
+    PYTHONPATH=/root/reference PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Writes small ``.npz`` fixtures to ``tests/golden/``.  Inputs come from ``tests/cases.py``
+(deterministic, no RNG); pixmaps are rebuilt from the same helpers at test time, and this script
+asserts that those helpers reproduce ``khepri.draw.Drawing`` bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+from khepri.crystal import Crystal  # noqa: E402
+from khepri.draw import Drawing  # noqa: E402
+from khepri.expansion import Expansion  # noqa: E402
+from khepri.layer import Layer  # noqa: E402
+from khepri.tools import convolution_matrix, convolution_matrix_fourier  # noqa: E402
+from khepri.alternative import redheffer_product  # noqa: E402
+from khepri.misc import coords  # noqa: E402
+from khepri.beams import gen_bzi_grid  # noqa: E402
+from khepri.factory import make_woodpile  # noqa: E402
+
+from tests import cases  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def ref_crystal(st, fields=False):
+    cl = Crystal(st["pw"], lattice=st["lattice"], epsi=st["epsi"], epse=st["epse"])
+    for name, spec in st["layers"].items():
+        if spec[0] == "uniform":
+            cl.add_layer_uniform(name, spec[1], spec[2])
+        else:
+            cl.add_layer_pixmap(name, spec[1], spec[2])
+    cl.set_device(st["stack"], [fields] * len(st["stack"]))
+    return cl
+
+
+def sweep(st, srcs, per_order=False):
+    cl = ref_crystal(st)
+    rt, orders = [], []
+    for s in srcs:
+        cl.set_source(**s)
+        cl.solve()
+        rt.append(cl.poynting_flux_end())
+        if per_order:
+            (_, rg), (_, tg) = cl.poynting_flux_end(only_total=False)
+            orders.append(np.stack([rg, tg]))
+    return np.array(rt, dtype=float), (np.array(orders) if per_order else None), cl
+
+
+def check_helpers():
+    d = Drawing((128, 128), 12)
+    d.disc((0, 0), 0.4, 1.0)
+    assert np.array_equal(d.canvas(), cases.disc_pixmap((128, 128), 12, (0, 0), 0.4, 1.0))
+    d = Drawing((128, 128), 1)
+    d.rectangle((0, 0), (0.5, 1), 4)
+    assert np.array_equal(d.canvas(), cases.rect_pixmap((128, 128), 1, (0, 0), (0.5, 1), 4))
+    wp = make_woodpile(0.28, 3.6 ** 2, 0.5, 1.414 / 4, (3, 3), (256, 256))
+    st = cases.woodpile_structure((3, 3))
+    for k in "ABCD":
+        assert np.array_equal(wp.layers[k].epsilon, st["layers"][k][1]), k
+    assert np.array_equal(gen_bzi_grid((64, 64)), cases.bzi_kgrid((64, 64)))
+    print("helpers reproduce Drawing / make_woodpile / gen_bzi_grid exactly")
+
+
+def main():
+    check_helpers()
+
+    # --- convolution matrix: bit-exact gather on an index-coded array + FFT coefficients
+    P, Q = 5, 3
+    Nx, Ny = 16, 12
+    coded = (np.arange(Nx)[:, None] * 1000 + np.arange(Ny)[None, :]).astype(complex) + 0.5j
+    np.savez(os.path.join(OUT, "toeplitz.npz"), coded=coded, pw=np.array([P, Q]),
+             C=convolution_matrix_fourier(coded, (P, Q)))
+    pm = cases.disc_pixmap((96, 64), 2.25, (0.05, -0.1), 0.3, 6.0)
+    np.savez(os.path.join(OUT, "convmat.npz"), pw=np.array([5, 3]), C=convolution_matrix(pm, (5, 3)),
+             C77=convolution_matrix(cases.disc_pixmap((128, 128), 12, (0, 0), 0.4, 1.0), (7, 7)))
+    print("convmat done")
+
+    # --- C1: README suh03, full 151-frequency spectrum; plus Stot at three frequencies
+    st, srcs = cases.case_suh03()
+    rt, orders, cl = sweep(st, srcs, per_order=True)
+    S_samples = []
+    for i in (0, 75, 150):
+        cl.set_source(**srcs[i])
+        cl.solve()
+        S_samples.append(np.asarray(cl.Stot))
+    np.savez(os.path.join(OUT, "suh03.npz"), RT=rt, orders=orders, Stot=np.array(S_samples), Sidx=np.array([0, 75, 150]))
+    print("suh03 done", rt[:2])
+
+    # --- C2: BZI 7x7, sub-sampled k-grid x wavelengths
+    st, srcs = cases.case_bzi((7, 7), nk=3, nwl=3)
+    rt, _, _ = sweep(st, srcs)
+    np.savez(os.path.join(OUT, "bzi77.npz"), RT=rt)
+    st, srcs = cases.case_bzi((3, 3), nk=4, nwl=5)
+    rt, _, _ = sweep(st, srcs)
+    np.savez(os.path.join(OUT, "bzi33.npz"), RT=rt)
+    print("bzi done")
+
+    # --- C3: woodpile 11x11 (4 solves) and 5x5 (9 solves), incl. the Stot (x) Stot doubling (woodpile.py:85)
+    for pw, nk, nf, tag in (((11, 11), 2, 2, "woodpile1111"), ((5, 5), 3, 3, "woodpile55")):
+        st, srcs = cases.case_woodpile(pw, nk, nf)
+        cl = ref_crystal(st)
+        rt, rt2 = [], []
+        for s in srcs:
+            cl.set_source(**s)
+            cl.solve()
+            rt.append(cl.poynting_flux_end())
+            cl.Stot = redheffer_product(cl.Stot, cl.Stot)
+            rt2.append(cl.poynting_flux_end())
+        np.savez(os.path.join(OUT, tag + ".npz"), RT=np.array(rt), RT_doubled=np.array(rt2))
+    print("woodpile done")
+
+    # --- oblique / hexagonal / lossy / epsi, epse != 1
+    st, srcs = cases.case_oblique()
+    rt, orders, _ = sweep(st, srcs, per_order=True)
+    np.savez(os.path.join(OUT, "oblique.npz"), RT=rt, orders=orders)
+    print("oblique done")
+
+    # --- Fresnel (the reference's own asserted test)
+    fcases, rfres = cases.case_fresnel()
+    rt = []
+    for st, src in fcases:
+        cl = ref_crystal(st)
+        cl.set_source(**src)
+        cl.solve()
+        rt.append(cl.poynting_flux_end())
+    rt = np.array(rt)
+    np.testing.assert_allclose(rfres, rt[:, 0])
+    np.savez(os.path.join(OUT, "fresnel.npz"), RT=rt, R_fresnel=rfres)
+    print("fresnel done")
+
+    # --- C5: field maps on sliced holey pair (5x5 and 7x7), small xyz grid
+    for pp, tag in ((5, "fields55"), (7, "fields77")):
+        st, src, (X, Y, z) = cases.case_fields(pp)
+        cl = ref_crystal(st, fields=True)
+        cl.set_source(**src)
+        cl.solve()
+        E, H = cl.fields_volume(X, Y, z)
+        np.savez(os.path.join(OUT, tag + ".npz"), E=E, H=H, RT=np.array(cl.poynting_flux_end()))
+    x, y, z = coords(0, 1, 0, 1, 0.0001, 2.2, (12, 10, 9))
+    st, src, (X, Y, Z) = cases.case_fields(5)
+    assert np.array_equal(x, X) and np.array_equal(y, Y) and np.allclose(z, Z)
+    print("fields done")
+
+    # --- C4: twisted bilayer, extended RCWA (3,3)+(3,3)
+    tw = cases.twisted_case()
+    canvas = tw["pixmap"]
+    d = Drawing((128, 128), 4)
+    d.disc((0, 0), 0.25, 1)
+    assert np.array_equal(d.canvas(), canvas)
+    rt = []
+    S_first = None
+    for f in tw["freqs"]:
+        for ta in tw["twists"]:
+            e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
+            e1.rotate(ta / 2)
+            e2.rotate(-ta / 2)
+            cl = Crystal.from_expansion(e1 + e2)
+            cl.add_layer("upper_layer", Layer.pixmap(e1, canvas, tw["depths"][0]), extended=True)
+            cl.add_layer("lower_layer", Layer.pixmap(e2, canvas, tw["depths"][2]), extended=True)
+            cl.add_layer("interlayer", Layer.uniform(e1, 1, tw["depths"][1]), extended=True)
+            cl.set_device(["upper_layer", "interlayer", "lower_layer"])
+            cl.set_source(wavelength=1 / f, te=1, tm=0)
+            cl.solve()
+            rt.append(cl.poynting_flux_end())
+            if S_first is None:
+                S_first = np.asarray(cl.layers["upper_layer"].S)[0, 0]
+    np.savez(os.path.join(OUT, "twisted33.npz"), RT=np.array(rt).reshape(len(tw["freqs"]), len(tw["twists"]), 2),
+             S11_upper_first=S_first)
+    print("twisted done")
+
+
+if __name__ == "__main__":
+    main()

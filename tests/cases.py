@@ -1,0 +1,144 @@
+"""Deterministic synthetic cases shared by the golden generator, the oracle tests and the GPU
+parity tests.  Geometry follows SURVEY.md §8(d); sweeps are sub-sampled so the oracle finishes
+in seconds.  A *case* = (structure dict as in oracle/rcwa_oracle.py, list of sources), each source
+being a dict of ``set_source`` keyword arguments (khepri/crystal.py:345-360).
+"""
+import numpy as np
+
+
+def disc_pixmap(shape, eps_bg, center, radius, eps):
+    xs = np.linspace(-0.5, 0.5, shape[0])[:, None]
+    ys = np.linspace(-0.5, 0.5, shape[1])[None, :]
+    pm = np.full(shape, float(eps_bg))
+    pm[np.sqrt((xs - center[0]) ** 2 + (ys - center[1]) ** 2) < radius] = eps
+    return pm
+
+
+def rect_pixmap(shape, eps_bg, center, wh, eps, base=None):
+    xs = np.linspace(-0.5, 0.5, shape[0])[:, None]
+    ys = np.linspace(-0.5, 0.5, shape[1])[None, :]
+    pm = np.full(shape, float(eps_bg)) if base is None else base
+    x0, y0 = center[0] - wh[0] / 2, center[1] - wh[1] / 2
+    m = (xs >= x0) & (xs <= x0 + wh[0]) & (ys >= y0) & (ys <= y0 + wh[1])
+    pm[m] = eps
+    return pm
+
+
+def _st(pw, layers, stack, lattice=None, epsi=1, epse=1):
+    lattice = np.eye(2) if lattice is None else np.asarray(lattice, dtype=float)
+    return {"pw": tuple(pw), "lattice": lattice, "epsi": epsi, "epse": epse,
+            "layers": dict(layers), "stack": list(stack)}
+
+
+def holey_pair(pp=5, res=128, slices=1):
+    """README suh03 / examples/crystal_api/test_crystal.py:23-32 (C1, C5)."""
+    pm = disc_pixmap((res, res), 12, (0.0, 0.0), 0.4, 1.0)
+    layers = {"S1": ("uniform", 1, 1.1 / slices), "Scyl": ("pixmap", pm, 0.55 / slices)}
+    stack = ["Scyl"] * slices + ["S1"] * slices + ["Scyl"] * slices
+    return _st((pp, pp), layers, stack)
+
+
+def case_suh03(nf=151):
+    st = holey_pair(5, 128)
+    freqs = np.linspace(0.49, 0.6, 151)
+    if nf < 151:
+        freqs = freqs[:: max(1, 151 // nf)][:nf]
+    return st, [dict(wavelength=1 / f, te=1.0, tm=0.0, theta=0.0, phi=0.0) for f in freqs]
+
+
+def bzi_structure(pw=(7, 7)):
+    """examples/bzi/bzi_animation.py:55-68 (C2)."""
+    pm = rect_pixmap((128, 128), 1, (0, 0), (0.5, 1), 4)
+    layers = {"S1": ("uniform", 1, 0.99), "S2": ("uniform", 4, 16.99), "S3": ("pixmap", pm, 0.4)}
+    return _st(pw, layers, ["S1"] * 14 + ["S3", "S2"], epsi=1, epse=4)
+
+
+def bzi_kgrid(shape):
+    """khepri/beams.py:193-207 (square lattice, a=1)."""
+    si, sj = 1 / shape[0], 1 / shape[1]
+    i, j = np.meshgrid(np.arange(-0.5 + si / 2, 0.5, si), np.arange(-0.5 + sj / 2, 0.5, sj), indexing="ij")
+    return np.stack([2 * np.pi * i, 2 * np.pi * j])
+
+
+def case_bzi(pw=(7, 7), nk=2, nwl=3):
+    st = bzi_structure(pw)
+    kg = bzi_kgrid((64, 64))
+    wls = 1 / np.linspace(0.8, 1.0, 101)
+    srcs = []
+    for a in np.linspace(3, 60, nk).astype(int):
+        for w in wls[:: max(1, 101 // nwl)][:nwl]:
+            srcs.append(dict(wavelength=float(w), te=1.0, tm=1.0, kp=(float(kg[0, a, (a * 7) % 64]), float(kg[1, a, (a * 7) % 64]))))
+    return st, srcs
+
+
+def woodpile_structure(pw=(11, 11), res=(256, 256)):
+    """khepri/factory.py:3-24 with examples/crystal_api/woodpile.py:36-39 parameters (C3)."""
+    w, eps, shift, h = 0.28, 3.6 ** 2, 0.5, 1.414 / 4
+    p1 = rect_pixmap(res, 1, (0, 0), (1, w), eps)
+    p2 = rect_pixmap(res, 1, (0, shift), (1, w), eps)
+    p2 = rect_pixmap(res, 1, (0, -shift), (1, w), eps, base=p2)
+    layers = {"A": ("pixmap", p1, h), "B": ("pixmap", p1.T.copy(), h),
+              "C": ("pixmap", p2, h), "D": ("pixmap", p2.T.copy(), h)}
+    return _st(pw, layers, ["A", "B", "C", "D"])
+
+
+def case_woodpile(pw=(11, 11), nk=2, nf=2):
+    st = woodpile_structure(pw)
+    freqs = np.linspace(0.4 / 1.414, 0.65 / 1.414, 200)
+    kxs = np.linspace(0, 0.99 * np.pi, 200)
+    srcs = []
+    for ik in np.linspace(5, 190, nk).astype(int):
+        for jf in np.linspace(10, 180, nf).astype(int):
+            srcs.append(dict(wavelength=float(1 / freqs[jf]), te=1.0, tm=1.0, kp=(float(kxs[ik]), 0.0)))
+    return st, srcs
+
+
+def case_oblique():
+    """Hexagonal lattice, lossy uniform layer, epsi/epse != 1, oblique incidence, both polarisations."""
+    lat = 0.9 * np.array([[np.sqrt(3) / 2, 0.5], [np.sqrt(3) / 2, -0.5]])
+    pm = disc_pixmap((96, 64), 2.25, (0.05, -0.1), 0.3, 6.0)
+    layers = {"U": ("uniform", 2.1 - 0.3j, 0.37), "G": ("pixmap", pm, 0.21), "V": ("uniform", 1.7, 0.15)}
+    st = _st((5, 3), layers, ["U", "G", "V", "G"], lattice=lat, epsi=1.44, epse=2.25)
+    srcs = [dict(wavelength=wl, te=te, tm=tm, theta=th, phi=ph)
+            for wl, te, tm, th, ph in [(1.31, 1.0, 0.0, 12.0, 0.0), (1.31, 0.0, 1.0, 12.0, 30.0),
+                                       (0.93, 0.7, 0.4, 35.0, 75.0), (1.77, 1.0, 1.0, 5.0, -20.0),
+                                       (0.81, 0.3, 1.0, 50.0, 10.0)]]
+    return st, srcs
+
+
+def case_fresnel():
+    """test/integration/test_complex_eps.py:14-42 (pw=(1,1) lossy slab; closed-form Fresnel check)."""
+    covera = 299792458 / 1e-6
+    e0, sigma, h = 8.85418782e-12, 0.01e6, 1.2
+    wls = np.linspace(0.7, 2.0)
+    cases = []
+    for wl in wls:
+        omega = 2 * np.pi * covera / wl
+        eps = 1.6 ** 2 - 1j * sigma / omega / e0
+        cases.append((_st((1, 1), {"1": ("uniform", eps, h)}, ["1"]), dict(wavelength=float(wl), te=1, tm=1)))
+    omega = 2 * np.pi * covera / wls
+    eps = 1.6 ** 2 + 1j * sigma / omega / e0
+    n2 = np.conj(np.sqrt(eps))
+    r12, r23 = (1 - n2) / (1 + n2), (n2 - 1) / (n2 + 1)
+    ph = np.exp(-2j * 2 * np.pi / wls * n2 * h)
+    return cases, np.abs((r12 + r23 * ph) / (1 + r12 * r23 * ph)) ** 2
+
+
+def case_fields(pp=5, slices=4, res=128, grid=(12, 10, 9)):
+    """C5 geometry (holey pair, sliced for conditioning -- SURVEY.md §7.5) on a small xyz grid."""
+    st = holey_pair(pp, res, slices)
+    x = np.linspace(0, 1, grid[0])
+    y = np.linspace(0, 1, grid[1])
+    depth = 0.55 * 2 + 1.1
+    z = np.linspace(0.0001, depth, grid[2])
+    X, Y = np.meshgrid(x, y, indexing="xy")
+    src = dict(wavelength=1 / 0.53, te=1.0, tm=0.0, theta=0.0, phi=0.0)
+    return st, src, (X, Y, z)
+
+
+def twisted_case(pw=(3, 3), nf=3, nt=3):
+    """notebooks/PRL_2021_BL.ipynb cells 2-8 (C4 parity set), sub-sampled."""
+    pm = disc_pixmap((128, 128), 4, (0, 0), 0.25, 1.0)
+    freqs = np.linspace(0.7, 0.83, 50)[:: 50 // nf][:nf]
+    twists = np.deg2rad(np.linspace(0, 45, 50))[3:: 50 // nt][:nt]
+    return {"pw": pw, "pixmap": pm, "depths": (0.2, 0.3, 0.2), "freqs": freqs, "twists": twists}

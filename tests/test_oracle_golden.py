@@ -1,0 +1,130 @@
+"""CPU: pin the oracle (oracle/rcwa_oracle.py) against golden vectors produced by the unmodified
+reference (oracle/gen_golden.py) and against the reference's own known-answer test."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rcwa_oracle as orc
+from tests import cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def src_kp(st, s):
+    if s.get("kp") is not None:
+        return tuple(s["kp"])
+    return tuple(orc.kplanar(st["epsi"], s["wavelength"], s.get("theta", 0.0), s.get("phi", 0.0)))
+
+
+def oracle_sweep(st, srcs):
+    out = []
+    for s in srcs:
+        sol = orc.solve_structure(st, s["wavelength"], src_kp(st, s), want_reverse=False)
+        out.append(orc.flux_end(st, sol, s.get("te", 1.0), s.get("tm", 1.0)))
+    return np.array(out)
+
+
+def test_toeplitz_gather_bit_exact():
+    g = gold("toeplitz")
+    C = orc.toeplitz_gather(g["coded"], tuple(g["pw"]))
+    assert np.array_equal(C, g["C"])
+
+
+def test_convolution_matrix():
+    g = gold("convmat")
+    pm = cases.disc_pixmap((96, 64), 2.25, (0.05, -0.1), 0.3, 6.0)
+    assert np.array_equal(orc.convolution_matrix(pm, (5, 3)), g["C"])
+    pm = cases.disc_pixmap((128, 128), 12, (0, 0), 0.4, 1.0)
+    assert np.array_equal(orc.convolution_matrix(pm, (7, 7)), g["C77"])
+
+
+def test_suh03_spectrum():
+    g = gold("suh03")
+    st, srcs = cases.case_suh03()
+    idx = list(range(0, 151, 6)) + [150]
+    rt = oracle_sweep(st, [srcs[i] for i in idx])
+    np.testing.assert_allclose(rt, g["RT"][idx], rtol=1e-10, atol=1e-12)
+    for k, i in enumerate(g["Sidx"]):
+        sol = orc.solve_structure(st, srcs[i]["wavelength"], src_kp(st, srcs[i]), want_reverse=False)
+        np.testing.assert_allclose(sol["Stot"], g["Stot"][k], rtol=0, atol=1e-10)
+        (_, rg), (_, tg) = orc.flux_end(st, sol, srcs[i]["te"], srcs[i]["tm"], only_total=False)
+        np.testing.assert_allclose(np.stack([rg, tg]), g["orders"][i], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("pw,nk,nwl,tag", [((7, 7), 3, 3, "bzi77"), ((3, 3), 4, 5, "bzi33")])
+def test_bzi(pw, nk, nwl, tag):
+    st, srcs = cases.case_bzi(pw, nk, nwl)
+    np.testing.assert_allclose(oracle_sweep(st, srcs), gold(tag)["RT"], rtol=1e-9, atol=1e-12)
+
+
+def test_woodpile55_with_doubling():
+    g = gold("woodpile55")
+    st, srcs = cases.case_woodpile((5, 5), 3, 3)
+    rt, rt2 = [], []
+    for s in srcs:
+        sol = orc.solve_structure(st, s["wavelength"], src_kp(st, s), want_reverse=False)
+        rt.append(orc.flux_end(st, sol, s["te"], s["tm"]))
+        sol["Stot"] = orc.star(sol["Stot"], sol["Stot"])
+        rt2.append(orc.flux_end(st, sol, s["te"], s["tm"]))
+    np.testing.assert_allclose(np.array(rt), g["RT"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.array(rt2), g["RT_doubled"], rtol=1e-9, atol=1e-12)
+
+
+def test_woodpile1111_one_solve():
+    g = gold("woodpile1111")
+    st, srcs = cases.case_woodpile((11, 11), 2, 2)
+    np.testing.assert_allclose(oracle_sweep(st, srcs[:1]), g["RT"][:1], rtol=1e-9, atol=1e-12)
+
+
+def test_oblique_hexagonal_lossy():
+    g = gold("oblique")
+    st, srcs = cases.case_oblique()
+    np.testing.assert_allclose(oracle_sweep(st, srcs), g["RT"], rtol=1e-10, atol=1e-12)
+
+
+def test_fresnel_known_answer():
+    g = gold("fresnel")
+    fcases, rfres = cases.case_fresnel()
+    rt = np.array([oracle_sweep(st, [src])[0] for st, src in fcases])
+    np.testing.assert_allclose(rt, g["RT"], rtol=1e-12)
+    np.testing.assert_allclose(rfres, rt[:, 0], rtol=1e-7)     # test_complex_eps.py:42
+
+
+@pytest.mark.parametrize("pp,tag,tol", [(5, "fields55", 1e-9), (7, "fields77", 1e-8)])
+def test_fields_volume(pp, tag, tol):
+    g = gold(tag)
+    st, src, (X, Y, z) = cases.case_fields(pp)
+    sol = orc.solve_structure(st, src["wavelength"], src_kp(st, src))
+    E, H = orc.fields_volume(st, sol, X, Y, z, src["te"], src["tm"])
+    scale = np.abs(g["E"]).max()
+    assert np.abs(E - g["E"]).max() <= tol * scale
+    assert np.abs(H - g["H"]).max() <= tol * np.abs(g["H"]).max()
+    np.testing.assert_allclose(orc.flux_end(st, sol, src["te"], src["tm"]), g["RT"], rtol=1e-10)
+
+
+def test_twisted_bilayer_extended():
+    g = gold("twisted33")
+    tw = cases.twisted_case()
+    g0 = orc.g_vectors(tw["pw"], np.eye(2))
+    rt = np.empty((len(tw["freqs"]), len(tw["twists"]), 2))
+    first = True
+    for i, f in enumerate(tw["freqs"]):
+        for j, ta in enumerate(tw["twists"]):
+            desc = {"pw": tw["pw"], "g1": orc.rotation(ta / 2) @ g0, "g2": orc.rotation(-ta / 2) @ g0,
+                    "epsi": 1, "epse": 1, "stack": ["upper", "inter", "lower"],
+                    "layers": {"upper": (("pixmap", tw["pixmap"], tw["depths"][0]), 1),
+                               "lower": (("pixmap", tw["pixmap"], tw["depths"][2]), 2),
+                               "inter": (("uniform", 1, tw["depths"][1]), 1)}}
+            sol = orc.solve_twisted(desc, 1 / f, (0j, 0j))
+            if first:
+                np.testing.assert_allclose(sol["layers"]["upper"]["S"][0, 0], g["S11_upper_first"], atol=1e-10)
+                first = False
+            st = {"pw": (tw["pw"][0] ** 2, tw["pw"][1] ** 2), "epsi": 1, "epse": 1}
+            sol["layers"]["Sref"]["W"] = sol["layers"]["Strans"]["W"] = np.identity(sol["Stot"].shape[-1])
+            rt[i, j] = orc.flux_end(st, sol, 1.0, 0.0)
+    np.testing.assert_allclose(rt, g["RT"], rtol=1e-9, atol=1e-12)
