@@ -1,0 +1,496 @@
+// khepri_b200 C-ABI: host-side orchestration of the batched RCWA solve (see include/khepri_b200.h).
+//
+// One (wavelength, k-point) solve = Crystal.solve() + poynting_flux_end() of the reference
+// (khepri/crystal.py:180-206, 363-396).  A batch is processed in chunks sized to the caller's
+// workspace; inside a chunk every step is one batched kernel launch over all solves of the chunk.
+#include "../../include/khepri_b200.h"
+#include "kh_common.cuh"
+#include "kh_zgemm.cuh"
+#include "kh_zinv.cuh"
+#include "kh_zgeev.cuh"
+#include "kh_rcwa.cuh"
+#include "kh_convmat.cuh"
+#include "kh_fields.cuh"
+
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define KH_TRY(expr)                                                                  \
+    do {                                                                              \
+        int _e = (expr);                                                              \
+        if (_e != 0) return fail(_e, std::string(#expr) + " failed at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+extern "C" int kh_abi_version(void) { return KH_ABI_VERSION; }
+extern "C" const char* kh_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------- small utilities
+struct Bump {                       // bump allocator over the caller's workspace (dry run when base == null)
+    char* base; size_t cap, off;
+    template <class T> T* get(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : (T*)0;
+        off += count * sizeof(T);
+        return p;
+    }
+    bool ok() const { return base == nullptr || off <= cap; }
+};
+
+struct copy4_args { int n2; MatRef src[4]; cd* dst; long long dst_stride; };   // dst[b][blk] = src[blk](b)
+KH_DEV void copy4_body(const Cta& c, const copy4_args& a) {
+    const cd* s = mat_ptr(a.src[c.by], c.bx);
+    cd* d = a.dst + (long long)c.bx * a.dst_stride + (long long)c.by * a.n2;
+    for (int e = c.tid; e < a.n2; e += c.nthr) d[e] = s[e];
+}
+struct copyv_args { long long count; const cd* src; long long sstride; cd* dst; long long dstride; };   // strided vector copy
+KH_DEV void copyv_body(const Cta& c, const copyv_args& a) {
+    const cd* s = a.src + (long long)c.bx * a.sstride;
+    cd* d = a.dst + (long long)c.bx * a.dstride;
+    for (long long e = c.tid; e < a.count; e += c.nthr) d[e] = s[e];
+}
+struct info_args { int B; const int* e1; const int* e2; int* out; };
+KH_DEV void info_body(const Cta& c, const info_args& a) {
+    int b = c.bx * c.nthr + c.tid;
+    if (b < a.B) { int v = 0; if (a.e1 && a.e1[b]) v |= 1; if (a.e2 && a.e2[b]) v |= 2; if (v) KH_ATOMIC_OR(&a.out[b], v); }
+}
+struct zero_int_args { int B; int* p; };
+KH_DEV void zero_int_body(const Cta& c, const zero_int_args& a) {
+    int b = c.bx * c.nthr + c.tid;
+    if (b < a.B) a.p[b] = 0;
+}
+
+// a full S-matrix as four block references (or a compact BD table)
+struct SRef {
+    bool bd;
+    cd* bdp;            // BD: [Bc][4][4][N]
+    MatRef blk[4];      // dense: per-block batch references
+};
+static SRef sref_dense(cd* base, int n) {     // [Bc][4][n][n]
+    SRef s; s.bd = false; s.bdp = nullptr;
+    for (int i = 0; i < 4; ++i) s.blk[i] = mref(base + (long long)i * n * n, 4LL * n * n, n);
+    return s;
+}
+static SRef sref_sym(cd* base, int n) {       // [Bc][2][n][n] = (S11, S12); S21 = S12, S22 = S11
+    SRef s; s.bd = false; s.bdp = nullptr;
+    const int map[4] = {0, 1, 1, 0};
+    for (int i = 0; i < 4; ++i) s.blk[i] = mref(base + (long long)map[i] * n * n, 2LL * n * n, n);
+    return s;
+}
+static SRef sref_bd(cd* p) { SRef s; s.bd = true; s.bdp = p; for (int i = 0; i < 4; ++i) s.blk[i] = mref(nullptr, 0, 0); return s; }
+
+static int gemm(kh_stream_t st, int batch, int n, MatRef A, MatRef B, MatRef C, double alpha = 1.0,
+                const MatRef* Cin = nullptr, double beta = 0.0, double diag = 0.0) {
+    zgemm_args g = zgemm_make(n, n, n, A, B, C, alpha);
+    if (Cin) { g.Cin = *Cin; g.beta = beta; }
+    g.diag = diag;
+    return zgemm_launch(st, batch, g);
+}
+
+// dense Redheffer star product (alternative.py:19-30) with the push-through identity
+// D^-1 B11 = B11 F^-1, F = I - A22 B11:  one inverse + ten GEMMs.  tmp: 7 slabs of [Bc][n][n].
+static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info) {
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
+    MatRef U = mref(tmp + 4 * slab, n2, n), Z = mref(tmp + 5 * slab, n2, n), Vt = mref(tmp + 6 * slab, n2, n);
+    SRef O = sref_dense(out, n);
+    int e;
+    if ((e = gemm(st, Bc, n, A.blk[3], B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;     // F = I - A22 B11
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                    // X = F^-1 A21
+    if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                    // Y = F^-1 A22
+    if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                              // S21 = B21 X
+    if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                     // U = B11 X
+    if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;         // S11 = A11 + A12 U
+    if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                     // Z = Y B12
+    if ((e = gemm(st, Bc, n, B.blk[2], Z, O.blk[3], 1.0, &B.blk[3], 1.0))) return e;         // S22 = B22 + B21 Z
+    if ((e = gemm(st, Bc, n, B.blk[0], Z, Vt, 1.0, &B.blk[1], 1.0))) return e;               // Vt = B12 + B11 Z
+    if ((e = gemm(st, Bc, n, A.blk[1], Vt, O.blk[1]))) return e;                             // S12 = A12 Vt
+    return 0;
+}
+#define STAR_TMP_SLABS 7
+
+// ---------------------------------------------------------------------------- plan
+struct kh_plan {
+    int P, Q, N, n;
+    const double* g_dev;
+    cd epsi, epse;
+    std::vector<kh_layer_desc> layers;
+    std::vector<int> stack;
+    int Nb; const double* glhs_dev; const double* grhs_dev;
+    bool has_ext;
+};
+
+extern "C" int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev, double epsi_re, double epsi_im,
+                              double epse_re, double epse_im, int n_layers, const kh_layer_desc* layers, int n_stack,
+                              const int* stack, int Nb, const double* glhs_dev, const double* grhs_dev) {
+    if (!plan || P < 1 || Q < 1 || !g_dev || n_layers < 1 || !layers || n_stack < 1 || !stack)
+        return fail(KH_EINVAL, "kh_plan_create: bad arguments");
+    kh_plan* p = new kh_plan();
+    p->P = P; p->Q = Q; p->N = P * Q; p->n = 2 * P * Q; p->g_dev = g_dev;
+    p->epsi = mk(epsi_re, epsi_im); p->epse = mk(epse_re, epse_im);
+    p->layers.assign(layers, layers + n_layers);
+    p->stack.assign(stack, stack + n_stack);
+    p->Nb = Nb; p->glhs_dev = glhs_dev; p->grhs_dev = grhs_dev; p->has_ext = false;
+    for (int i = 0; i < n_layers; ++i) {
+        const kh_layer_desc& L = layers[i];
+        bool ok = L.kind == KH_LAYER_UNIFORM || L.kind == KH_LAYER_HALF_INC || L.kind == KH_LAYER_HALF_TRN ||
+                  (L.kind == KH_LAYER_PIXMAP && L.C_dev && L.IC_dev) ||
+                  (L.kind == KH_LAYER_EXTENDED && L.ext_base >= 0 && L.ext_base < n_layers && L.ext_base != i &&
+                   layers[L.ext_base].kind != KH_LAYER_EXTENDED && Nb > 0 && Nb * Nb == p->N && glhs_dev && grhs_dev);
+        if (!ok) { delete p; return fail(KH_EINVAL, "kh_plan_create: bad layer " + std::to_string(i)); }
+        if (L.kind == KH_LAYER_EXTENDED) p->has_ext = true;
+    }
+    for (int i = 0; i < n_stack; ++i)
+        if (stack[i] < 0 || stack[i] >= n_layers) { delete p; return fail(KH_EINVAL, "kh_plan_create: bad stack index"); }
+    *plan = p;
+    return 0;
+}
+extern "C" void kh_plan_destroy(kh_plan* plan) { delete plan; }
+
+// ---------------------------------------------------------------------------- patterned-layer solve
+#define LAYER_TMP_SLABS 17
+struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; int* info_eig; int* info_inv; };
+
+// Solves one patterned layer for Bc solves of dimension n = 2N (alternative.py:158-195):
+// P, Q -> Omega^2 -> eig -> W, lambda, V -> A, B, X -> S11, S12 (written to Sout [Bc][2][n][n]).
+static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd* IC, double depth,
+                           const cd* Kx, const cd* Ky, const double* k0, cd* pool, const LayerVec& v, cd* Sout,
+                           cd* Wkeep, cd* Vkeep, cd* Lkeep, long long keep_stride, long long lkeep_stride) {
+    const int n = 2 * N;
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    auto S = [&](int s) { return pool + (long long)s * slab; };
+    auto M = [&](int s) { return mref(S(s), n2, n); };
+    {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};
+        KH_TRY((kh_launch<pq_args, pq_body>(dim3(Bc), 256, 0, st, a))); }
+    KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q
+    {   zgeev_args a;
+        a.n = n; a.A = M(2); a.Hw = M(2); a.Zt = M(3); a.X = M(4);
+        a.w = v.w; a.w_stride = n; a.scale = v.scale; a.scale_stride = n; a.info = v.info_eig;
+        KH_TRY(zgeev_launch(st, Bc, a)); }
+    {   zgemm_args g = zgemm_make(n, n, n, M(3), M(4), M(5));                    // W = diag(scale) Z X
+        g.transA = 1; g.rowscale = v.scale; g.rs_stride = n; g.rs_group = 1;
+        KH_TRY(zgemm_launch(st, Bc, g)); }
+    {   lam_args a{Bc, n, depth, v.w, k0, v.lam, v.xexp};
+        KH_TRY((kh_launch<lam_args, lam_body>(dim3(Bc), 128, 0, st, a))); }
+    {   zgemm_args g = zgemm_make(n, n, n, M(1), M(5), M(6));                    // V = Q W / lambda
+        g.colscale = v.lam; g.cs_stride = n; g.cs_group = 1; g.cs_divide = 1;
+        KH_TRY(zgemm_launch(st, Bc, g)); }
+    if (Wkeep) {
+        copyv_args cw{n2, S(5), n2, Wkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cw)));
+        copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
+        copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
+    }
+    // W^-1 and V^-1 in one launch over 2*Bc matrices (slabs 5,6 -> 7,8)
+    KH_TRY(zinv_launch(st, 2 * Bc, n, mref(S(5), slab, n, Bc, n2), mref(S(7), slab, n, Bc, n2), v.info_inv));
+    {   ab_args a{Bc, N, S(7), S(8), Kx, Ky, v.xexp, S(0), S(11), S(9), S(10)};  // A->0, B->11, XB->9, XA->10
+        KH_TRY((kh_launch<ab_args, ab_body>(dim3(Bc), 256, 0, st, a))); }
+    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv));                     // A^-1 -> 1
+    // [M1|M2|M3] = A^-1 [XB|XA|B]   (slabs 9..11 -> 12..14)
+    KH_TRY(gemm(st, 3 * Bc, n, mref(S(1), 0, n, Bc, n2), mref(S(9), slab, n, Bc, n2), mref(S(12), slab, n, Bc, n2)));
+    {   MatRef A = M(0), Bm = M(11);
+        KH_TRY(gemm(st, Bc, n, M(9), M(12), M(2), -1.0, &A, 1.0));               // T  = A - XB M1
+        KH_TRY(gemm(st, Bc, n, M(9), M(13), M(15), 1.0, &Bm, -1.0));             // R1 = XB M2 - B
+        zgemm_args g = zgemm_make(n, n, n, M(11), M(14), M(16), -1.0);           // R2 = X (A - B M3)
+        g.Cin = A; g.beta = 1.0; g.rowscale = v.xexp; g.rs_stride = n; g.rs_group = 1;
+        KH_TRY(zgemm_launch(st, Bc, g)); }
+    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv));                     // T^-1 -> 3
+    // [S11|S12] = T^-1 [R1|R2]
+    KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- chunk layout
+struct ChunkBufs {
+    cd *Kx, *Ky; double* k0;
+    std::vector<cd*> layerS;        // per layer: BD table [Bc][16N] or dense sym [Bc][2][n][n] or dense full [Bc][4][n][n] (extended)
+    std::vector<cd*> layerV;        // per BD layer (retain): [Bc][4][N]
+    std::vector<cd*> layerL;        // per BD layer (retain): [Bc][N]
+    cd* pool;                       // LAYER_TMP_SLABS x [Bc][n][n]
+    LayerVec vec;
+    cd* accD[2]; cd* accB[2]; cd* expA; cd* expB; cd* accR[2];
+    int* info;
+    // extended-layer scratch (small base problems at Nb harmonics, Bc*Nb sub-solves)
+    cd *eKx, *eKy; double* ek0; cd* epool; LayerVec evec; cd* eS; cd* ebd; double* ewl; cd* ekp;
+};
+
+static bool layer_is_bd(const kh_plan* p, int i) {
+    int k = p->layers[i].kind;
+    return k == KH_LAYER_UNIFORM || k == KH_LAYER_HALF_INC || k == KH_LAYER_HALF_TRN;
+}
+
+static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs& cb) {
+    const int N = p->N, n = p->n;
+    const size_t n2 = (size_t)n * n;
+    cb.Kx = b.get<cd>((size_t)Bc * N); cb.Ky = b.get<cd>((size_t)Bc * N); cb.k0 = b.get<double>(Bc);
+    cb.layerS.assign(p->layers.size(), nullptr);
+    cb.layerV.assign(p->layers.size(), nullptr);
+    cb.layerL.assign(p->layers.size(), nullptr);
+    bool any_dense = false;
+    for (size_t i = 0; i < p->layers.size(); ++i) {
+        const kh_layer_desc& L = p->layers[i];
+        if (layer_is_bd(p, (int)i)) {
+            cb.layerS[i] = b.get<cd>((size_t)Bc * 16 * N);
+            if (flags & KH_WANT_FIELDS) { cb.layerV[i] = b.get<cd>((size_t)Bc * 4 * N); cb.layerL[i] = b.get<cd>((size_t)Bc * N); }
+        } else if (L.kind == KH_LAYER_PIXMAP) { cb.layerS[i] = b.get<cd>((size_t)Bc * 2 * n2); any_dense = true; }
+        else { cb.layerS[i] = b.get<cd>((size_t)Bc * 4 * n2); any_dense = true; }
+    }
+    (void)any_dense;
+    cb.pool = b.get<cd>((size_t)LAYER_TMP_SLABS * Bc * n2);
+    cb.vec.w = b.get<cd>((size_t)Bc * n); cb.vec.lam = b.get<cd>((size_t)Bc * n);
+    cb.vec.xexp = b.get<cd>((size_t)Bc * n); cb.vec.scale = b.get<cd>((size_t)Bc * n);
+    cb.vec.info_eig = b.get<int>(Bc); cb.vec.info_inv = b.get<int>((size_t)3 * Bc);
+    for (int i = 0; i < 2; ++i) { cb.accD[i] = b.get<cd>((size_t)Bc * 4 * n2); cb.accB[i] = b.get<cd>((size_t)Bc * 16 * N); }
+    cb.expA = b.get<cd>((size_t)Bc * 4 * n2); cb.expB = b.get<cd>((size_t)Bc * 4 * n2);
+    cb.accR[0] = cb.accR[1] = nullptr;
+    if (flags & KH_WANT_FIELDS) { cb.accR[0] = b.get<cd>((size_t)Bc * 4 * n2); cb.accR[1] = b.get<cd>((size_t)Bc * 4 * n2); }
+    cb.info = b.get<int>(Bc);
+    cb.eKx = cb.eKy = nullptr; cb.ek0 = nullptr; cb.epool = nullptr; cb.eS = nullptr; cb.ebd = nullptr; cb.ewl = nullptr; cb.ekp = nullptr;
+    if (p->has_ext) {
+        const int Nb = p->Nb, nb = 2 * Nb;
+        const size_t Be = (size_t)Bc * Nb, nb2 = (size_t)nb * nb;
+        cb.eKx = b.get<cd>(Be * Nb); cb.eKy = b.get<cd>(Be * Nb); cb.ek0 = b.get<double>(Be);
+        cb.epool = b.get<cd>((size_t)LAYER_TMP_SLABS * Be * nb2);
+        cb.evec.w = b.get<cd>(Be * nb); cb.evec.lam = b.get<cd>(Be * nb); cb.evec.xexp = b.get<cd>(Be * nb); cb.evec.scale = b.get<cd>(Be * nb);
+        cb.evec.info_eig = b.get<int>(Be); cb.evec.info_inv = b.get<int>(3 * Be);
+        cb.eS = b.get<cd>(Be * 2 * nb2); cb.ebd = b.get<cd>(Be * 16 * Nb);
+        cb.ewl = b.get<double>(Be); cb.ekp = b.get<cd>(Be * 2);
+    }
+}
+
+extern "C" size_t kh_solve_workspace_bytes(const kh_plan* plan, int chunk, int flags) {
+    if (!plan || chunk < 1) return 0;
+    Bump b{nullptr, 0, 0};
+    ChunkBufs cb;
+    layout_chunk(plan, chunk, flags, b, cb);
+    return b.off + 256;
+}
+
+// materialise an S reference as a dense [Bc][4][n][n] stack at dst (per-solve stride dst_stride)
+static int materialise(kh_stream_t st, int Bc, int N, const SRef& s, cd* dst, long long dst_stride, cd* scratch4) {
+    const int n = 2 * N;
+    SRef d = s;
+    if (s.bd) {
+        if (dst_stride == 4LL * n * n) { bd_expand_args a{Bc, N, s.bdp, dst}; return kh_launch<bd_expand_args, bd_expand_body>(dim3(Bc, 4), 256, 0, st, a); }
+        bd_expand_args a{Bc, N, s.bdp, scratch4};
+        int e = kh_launch<bd_expand_args, bd_expand_body>(dim3(Bc, 4), 256, 0, st, a);
+        if (e) return e;
+        d = sref_dense(scratch4, n);
+    }
+    copy4_args c; c.n2 = n * n; for (int i = 0; i < 4; ++i) c.src[i] = d.blk[i]; c.dst = dst; c.dst_stride = dst_stride;
+    return kh_launch<copy4_args, copy4_body>(dim3(Bc, 4), 256, 0, st, c);
+}
+
+#include "kh_extended.cuh"
+
+// ---------------------------------------------------------------------------- the batched solve
+extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* pol_dev,
+                              const kh_outputs* out, void* ws_dev, size_t ws_bytes, void* stream) {
+    if (!plan || B < 0 || !wl_dev || !kp_dev || !out || !ws_dev) return fail(KH_EINVAL, "kh_solve_batch: bad arguments");
+    if (B == 0) return 0;
+    kh_stream_t st = (kh_stream_t)stream;
+    const kh_plan* p = plan;
+    const int N = p->N, n = p->n, Ls = (int)p->stack.size();
+    const long long n2 = (long long)n * n;
+    int flags = 0;
+    if (out->Stot_dev) flags |= KH_WANT_STOT;
+    if (out->RT_dev || out->orders_dev) flags |= KH_WANT_FLUX;
+    const bool want_fields = out->prefix_dev || out->suffix_dev || out->W_dev || out->V_dev || out->L_dev;
+    if (want_fields) {
+        if (!(out->prefix_dev && out->suffix_dev && out->W_dev && out->V_dev && out->L_dev))
+            return fail(KH_EINVAL, "kh_solve_batch: field outputs must be given together");
+        flags |= KH_WANT_FIELDS;
+    }
+    if ((flags & KH_WANT_FLUX) && (!out->RT_dev || !pol_dev)) return fail(KH_EINVAL, "kh_solve_batch: flux needs RT_dev and pol_dev");
+    // chunk size: largest that fits the workspace
+    size_t per1 = kh_solve_workspace_bytes(p, 1, flags), per2 = kh_solve_workspace_bytes(p, 2, flags);
+    size_t slope = per2 > per1 ? per2 - per1 : 1;
+    if (ws_bytes < per1) return fail(KH_ENOMEM, "kh_solve_batch: workspace smaller than one solve (" + std::to_string(per1) + " bytes)");
+    long long chunk = 1 + (long long)((ws_bytes - per1) / (slope + 1024));
+    if (chunk > B) chunk = B;
+    while (chunk > 1 && kh_solve_workspace_bytes(p, (int)chunk, flags) > ws_bytes) --chunk;
+
+    if (out->info_dev) { zero_int_args z{B, out->info_dev}; KH_TRY((kh_launch<zero_int_args, zero_int_body>(dim3((B + 255) / 256), 256, 0, st, z))); }
+
+    for (int b0 = 0; b0 < B; b0 += (int)chunk) {
+        const int Bc = (int)((B - b0 < chunk) ? B - b0 : chunk);
+        Bump bump{(char*)ws_dev, ws_bytes, 0};
+        ChunkBufs cb;
+        layout_chunk(p, Bc, flags, bump, cb);
+        if (!bump.ok()) return fail(KH_ENOMEM, "kh_solve_batch: internal workspace overflow");
+        const double* wl = wl_dev + b0;
+        const cd* kp = (const cd*)kp_dev + 2LL * b0;
+        const cd* pol = pol_dev ? (const cd*)pol_dev + 2LL * b0 : nullptr;
+        int* info_out = out->info_dev ? out->info_dev + b0 : nullptr;
+
+        {   kvec_args a{Bc, N, wl, kp, p->g_dev, cb.Kx, cb.Ky, cb.k0};
+            KH_TRY((kh_launch<kvec_args, kvec_body>(dim3(Bc), 128, 0, st, a))); }
+
+        // ---- distinct layers (crystal.py:183-186 solves each required layer once)
+        std::vector<SRef> S(p->layers.size());
+        std::vector<char> used(p->layers.size(), 0);
+        for (int i : p->stack) used[i] = 1;
+        for (size_t i = 0; i < p->layers.size(); ++i) {
+            if (!used[i]) continue;
+            const kh_layer_desc& L = p->layers[i];
+            if (layer_is_bd(p, (int)i)) {
+                bd_layer_args a{Bc, N, L.kind, mk(L.eps_re, L.eps_im), L.depth, cb.Kx, cb.Ky, cb.k0, cb.layerS[i], cb.layerV[i], cb.layerL[i]};
+                KH_TRY((kh_launch<bd_layer_args, bd_layer_body>(dim3(Bc), 128, 0, st, a)));
+                S[i] = sref_bd(cb.layerS[i]);
+            } else if (L.kind == KH_LAYER_PIXMAP) {
+                const int nL = (int)p->layers.size();
+                cd* Wk = want_fields ? (cd*)out->W_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
+                cd* Vk = want_fields ? (cd*)out->V_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
+                cd* Lk = want_fields ? (cd*)out->L_dev + ((long long)b0 * nL + (long long)i) * n : nullptr;
+                KH_TRY(solve_patterned(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, cb.Kx, cb.Ky, cb.k0, cb.pool,
+                                       cb.vec, cb.layerS[i], Wk, Vk, Lk, (long long)nL * n2, (long long)nL * n));
+                if (info_out) { info_args ia{Bc, cb.vec.info_eig, cb.vec.info_inv, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                S[i] = sref_sym(cb.layerS[i], n);
+            } else {
+                if (want_fields) return fail(KH_EINVAL, "kh_solve_batch: field outputs are not available for extended layers");
+                KH_TRY(solve_extended(st, p, Bc, (int)i, wl, kp, cb, info_out));
+                S[i] = sref_dense(cb.layerS[i], n);
+            }
+        }
+        if (want_fields) KH_TRY(keep_eigenspace_bd(st, p, Bc, cb, out, b0));
+
+        // ---- forward chain (layer.py:41-47).  The reference starts from the identity S-matrix,
+        // and identity (*) S0 == S0 exactly, so the chain starts at the first layer.
+        SRef acc = S[p->stack[0]];
+        cd* acc_full = nullptr;                 // set when acc is a contiguous dense [Bc][4][n][n] stack
+        int pd = 0, pb = 0;
+        if (want_fields) KH_TRY(materialise(st, Bc, N, acc, (cd*)out->prefix_dev + ((long long)b0 * Ls + 0) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
+        for (int i = 1; i < Ls; ++i) {
+            const SRef& R = S[p->stack[i]];
+            if (acc.bd && R.bd) {
+                bd_star_args a{Bc, N, acc.bdp, R.bdp, cb.accB[pb]};
+                KH_TRY((kh_launch<bd_star_args, bd_star_body>(dim3(Bc), 128, 0, st, a)));
+                acc = sref_bd(cb.accB[pb]); pb ^= 1;
+            } else {
+                SRef Ad = acc, Rd = R;
+                if (acc.bd) { KH_TRY(materialise(st, Bc, N, acc, cb.expA, 4 * n2, nullptr)); Ad = sref_dense(cb.expA, n); }
+                if (R.bd) { KH_TRY(materialise(st, Bc, N, R, cb.expB, 4 * n2, nullptr)); Rd = sref_dense(cb.expB, n); }
+                KH_TRY(dense_star(st, Bc, n, Ad, Rd, cb.accD[pd], cb.pool, cb.vec.info_inv + 2 * Bc));
+                if (info_out) { info_args ia{Bc, nullptr, cb.vec.info_inv + 2 * Bc, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                acc = sref_dense(cb.accD[pd], n); acc_full = cb.accD[pd]; pd ^= 1;
+            }
+            if (want_fields) KH_TRY(materialise(st, Bc, N, acc, (cd*)out->prefix_dev + ((long long)b0 * Ls + i) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
+        }
+        if (acc.bd || !acc_full) { KH_TRY(materialise(st, Bc, N, acc, cb.accD[pd], 4 * n2, nullptr)); acc_full = cb.accD[pd]; }
+        cd* final_dst = acc_full;
+        if (out->Stot_dev) {
+            copyv_args cs{4 * n2, acc_full, 4 * n2, (cd*)out->Stot_dev + (long long)b0 * 4 * n2, 4 * n2};
+            KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cs)));
+        }
+
+        // ---- reverse chain (layer.py:49-59), only when fields are wanted
+        if (want_fields) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0));
+
+        if (flags & KH_WANT_FLUX) {
+            flux_args a{Bc, N, final_dst, wl, kp, pol, p->g_dev, p->epsi, p->epse,
+                        out->RT_dev + 2LL * b0, out->orders_dev ? out->orders_dev + 2LL * b0 * N : nullptr};
+            KH_TRY((kh_launch<flux_args, flux_body>(dim3(Bc), 64, 256 * sizeof(double), st, a)));
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- stand-alone star / flux
+extern "C" size_t kh_star_workspace_bytes(int B, int n) {
+    return (size_t)STAR_TMP_SLABS * B * n * n * sizeof(cd) + (size_t)B * sizeof(int) + 1024;
+}
+extern "C" int kh_star_batch(int B, int n, const void* SA_dev, const void* SB_dev, void* SO_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+    if (B < 0 || n < 1 || !SA_dev || !SB_dev || !SO_dev || !ws_dev) return fail(KH_EINVAL, "kh_star_batch: bad arguments");
+    if (SO_dev == SA_dev || SO_dev == SB_dev) return fail(KH_EINVAL, "kh_star_batch: output must not alias an input");
+    if (ws_bytes < kh_star_workspace_bytes(B, n)) return fail(KH_ENOMEM, "kh_star_batch: workspace too small");
+    if (B == 0) return 0;
+    Bump b{(char*)ws_dev, ws_bytes, 0};
+    cd* tmp = b.get<cd>((size_t)STAR_TMP_SLABS * B * n * n);
+    int* info = b.get<int>(B);
+    KH_TRY(dense_star((kh_stream_t)stream, B, n, sref_dense((cd*)SA_dev, n), sref_dense((cd*)SB_dev, n), (cd*)SO_dev, tmp, info));
+    return 0;
+}
+extern "C" int kh_flux_batch(const kh_plan* plan, int B, const void* Stot_dev, const double* wl_dev, const void* kp_dev,
+                             const void* pol_dev, double* RT_dev, double* orders_dev, void* stream) {
+    if (!plan || B < 0 || !Stot_dev || !wl_dev || !kp_dev || !pol_dev || !RT_dev) return fail(KH_EINVAL, "kh_flux_batch: bad arguments");
+    if (B == 0) return 0;
+    flux_args a{B, plan->N, (const cd*)Stot_dev, wl_dev, (const cd*)kp_dev, (const cd*)pol_dev, plan->g_dev, plan->epsi, plan->epse, RT_dev, orders_dev};
+    KH_TRY((kh_launch<flux_args, flux_body>(dim3(B), 64, 256 * sizeof(double), (kh_stream_t)stream, a)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- primitives
+extern "C" int kh_zgemm_batched(int batch, int M, int N, int K, int transA, const void* A, int lda, long long sA,
+                                const void* B, int ldb, long long sB, void* C, int ldc, long long sC, double alpha, void* stream) {
+    if (batch < 0 || M < 0 || N < 0 || K < 1 || !A || !B || !C) return fail(KH_EINVAL, "kh_zgemm_batched: bad arguments");
+    zgemm_args g = zgemm_make(M, N, K, mref(A, sA, lda), mref(B, sB, ldb), mref(C, sC, ldc), alpha);
+    g.transA = transA;
+    KH_TRY(zgemm_launch((kh_stream_t)stream, batch, g));
+    return 0;
+}
+extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int* info, void* stream) {
+    if (batch < 0 || n < 1 || !A || !Ainv) return fail(KH_EINVAL, "kh_zinv_batched: bad arguments");
+    KH_TRY(zinv_launch((kh_stream_t)stream, batch, n, mref(A, (long long)n * n, n), mref(Ainv, (long long)n * n, n), info));
+    return 0;
+}
+extern "C" size_t kh_zgeev_work_bytes(int batch, int n) {
+    return (size_t)batch * ((size_t)3 * n * n + n) * sizeof(cd) + 4096;
+}
+extern "C" int kh_zgeev_batched(int batch, int n, const void* A, void* w, void* W, void* work, size_t work_bytes, int* info, void* stream) {
+    if (batch < 0 || n < 1 || !A || !w || !W || !work) return fail(KH_EINVAL, "kh_zgeev_batched: bad arguments");
+    if (work_bytes < kh_zgeev_work_bytes(batch, n)) return fail(KH_ENOMEM, "kh_zgeev_batched: workspace too small");
+    if (batch == 0) return 0;
+    Bump b{(char*)work, work_bytes, 0};
+    const size_t n2 = (size_t)n * n;
+    cd* H = b.get<cd>(batch * n2); cd* Zt = b.get<cd>(batch * n2); cd* X = b.get<cd>(batch * n2); cd* sc = b.get<cd>((size_t)batch * n);
+    kh_stream_t st = (kh_stream_t)stream;
+    zgeev_args a;
+    a.n = n; a.A = mref(A, n2, n); a.Hw = mref(H, n2, n); a.Zt = mref(Zt, n2, n); a.X = mref(X, n2, n);
+    a.w = (cd*)w; a.w_stride = n; a.scale = sc; a.scale_stride = n; a.info = info;
+    KH_TRY(zgeev_launch(st, batch, a));
+    zgemm_args g = zgemm_make(n, n, n, a.Zt, a.X, mref(W, n2, n));
+    g.transA = 1; g.rowscale = sc; g.rs_stride = n; g.rs_group = 1;
+    KH_TRY(zgemm_launch(st, batch, g));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- convolution matrix
+extern "C" size_t kh_convmat_work_bytes(int L, int Nx, int Ny, int P, int Q) {
+    (void)Ny;
+    return ((size_t)L * Nx * (2 * Q - 1) + (size_t)L * (2 * P - 1) * (2 * Q - 1)) * sizeof(cd) + 1024;
+}
+extern "C" int kh_convmat(int L, int Nx, int Ny, int is_complex, const void* pix, int P, int Q, void* C, void* F,
+                          void* work, size_t work_bytes, void* stream) {
+    if (L < 1 || Nx < 1 || Ny < 1 || P < 1 || Q < 1 || !pix || !C || !work) return fail(KH_EINVAL, "kh_convmat: bad arguments");
+    if (Nx / 2 + (P - 1) >= Nx + (Nx == 1 && P == 1) || Ny / 2 + (Q - 1) >= Ny + (Ny == 1 && Q == 1))
+        if (!((P == 1 || Nx / 2 + P - 1 < Nx) && (Q == 1 || Ny / 2 + Q - 1 < Ny)))
+            return fail(KH_EINVAL, "kh_convmat: harmonic differences exceed the Fourier grid (IndexError in the reference)");
+    if (work_bytes < kh_convmat_work_bytes(L, Nx, Ny, P, Q)) return fail(KH_ENOMEM, "kh_convmat: workspace too small");
+    kh_stream_t st = (kh_stream_t)stream;
+    Bump b{(char*)work, work_bytes, 0};
+    cd* G = b.get<cd>((size_t)L * Nx * (2 * Q - 1));
+    cd* Ft = F ? (cd*)F : b.get<cd>((size_t)L * (2 * P - 1) * (2 * Q - 1));
+    dft1_args a1{Nx, Ny, Q, is_complex, pix, G};
+    KH_TRY((kh_launch<dft1_args, dft1_body>(dim3(Nx, L), 256, (size_t)2 * Ny * sizeof(cd), st, a1)));
+    dft2_args a2{Nx, Ny, P, Q, G, Ft};
+    KH_TRY((kh_launch<dft2_args, dft2_body>(dim3((2 * P - 1) * (2 * Q - 1), L), 128, 256 * sizeof(double), st, a2)));
+    gather_args a3{P, Q, Ft, (cd*)C};
+    KH_TRY((kh_launch<gather_args, gather_body>(dim3(64, L), 256, 0, st, a3)));
+    return 0;
+}
+extern "C" int kh_toeplitz_gather(const void* F, int Nx, int Ny, int P, int Q, void* C, int* err, void* stream) {
+    if (!F || !C || !err || Nx < 1 || Ny < 1 || P < 1 || Q < 1) return fail(KH_EINVAL, "kh_toeplitz_gather: bad arguments");
+    gather_full_args a{P, Q, Nx, Ny, (const cd*)F, (cd*)C, err};
+    KH_TRY((kh_launch<gather_full_args, gather_full_body>(dim3(64), 256, 0, (kh_stream_t)stream, a)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- fields (implemented in kh_fields.cuh)
+#ifndef KH_FIELDS_IMPL
+extern "C" size_t kh_fields_workspace_bytes(const kh_plan*, int, int, int, int) { return 0; }
+extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, int,
+                               const double*, int, const double*, int, void*, void*, void*, size_t, void*) {
+    return fail(KH_ESTATE, "kh_fields_batch: not built");
+}
+#endif

@@ -1,0 +1,204 @@
+// khepri_b200 -- common definitions for the sm_100a RCWA kernels.
+//
+// All kernels are written against a tiny "CTA context" (struct Cta) instead of raw threadIdx /
+// __syncthreads so that the very same source also compiles as plain host C++ with
+// -DKH_HOST_EMU (one virtual thread per CTA, barriers are no-ops).  The host-emulation build is
+// TEST INFRASTRUCTURE (tests/hostemu): it lets the algorithm logic (eigensolver, Gauss-Jordan,
+// star-product orchestration) be checked on a machine without a GPU.  The product library is
+// only ever built by nvcc for sm_100a and has no CPU fallback.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#ifdef KH_HOST_EMU
+#define KH_HD inline
+#define KH_DEV inline
+#include <algorithm>
+typedef void* kh_stream_t;
+#else
+#include <cuda_runtime.h>
+#define KH_HD __host__ __device__ __forceinline__
+#define KH_DEV __device__ __forceinline__
+typedef cudaStream_t kh_stream_t;
+#endif
+
+// ------------------------------------------------------------------ complex128
+struct alignas(16) cd {
+    double x, y;
+};
+KH_HD cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
+KH_HD cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
+KH_HD cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+KH_HD cd operator-(cd a) { return mk(-a.x, -a.y); }
+KH_HD cd operator*(cd a, cd b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+KH_HD cd operator*(double s, cd a) { return mk(s * a.x, s * a.y); }
+KH_HD cd operator*(cd a, double s) { return mk(s * a.x, s * a.y); }
+KH_HD cd cconj(cd a) { return mk(a.x, -a.y); }
+KH_HD double cabs1(cd a) { return fabs(a.x) + fabs(a.y); }
+KH_HD double cabs2(cd a) { return a.x * a.x + a.y * a.y; }
+KH_HD double cabsd(cd a) { return hypot(a.x, a.y); }
+// c += a*b
+KH_HD void cfma(cd& c, cd a, cd b) {
+    c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+}
+// c -= a*b
+KH_HD void cfms(cd& c, cd a, cd b) {
+    c.x = fma(-a.x, b.x, c.x); c.x = fma(a.y, b.y, c.x);
+    c.y = fma(-a.x, b.y, c.y); c.y = fma(-a.y, b.x, c.y);
+}
+// Smith's algorithm (what numpy uses for complex division)
+KH_HD cd operator/(cd a, cd b) {
+    if (fabs(b.x) >= fabs(b.y)) {
+        double r = b.y / b.x, d = b.x + b.y * r;
+        return mk((a.x + a.y * r) / d, (a.y - a.x * r) / d);
+    } else {
+        double r = b.x / b.y, d = b.x * r + b.y;
+        return mk((a.x * r + a.y) / d, (a.y * r - a.x) / d);
+    }
+}
+KH_HD cd crecip(cd b) { return mk(1.0, 0.0) / b; }
+// principal square root with C99 signed-zero semantics (matches numpy.sqrt on complex input)
+KH_HD cd csqrt_(cd z) {
+    if (z.x == 0.0 && z.y == 0.0) return mk(0.0, z.y);
+    double t = sqrt(0.5 * (fabs(z.x) + hypot(z.x, z.y)));
+    if (z.x >= 0.0) return mk(t, z.y / (2.0 * t));
+    return mk(fabs(z.y) / (2.0 * t), copysign(t, z.y));
+}
+KH_HD cd cexp_(cd z) {
+    double e = exp(z.x), s, c;
+#ifdef __CUDA_ARCH__
+    sincos(z.y, &s, &c);
+#else
+    s = sin(z.y); c = cos(z.y);
+#endif
+    return mk(e * c, e * s);
+}
+
+// ------------------------------------------------------------------ CTA context
+struct Cta {
+    int tid, nthr;           // thread index / threads per CTA
+    int bx, by;              // block indices
+    unsigned char* smem;     // dynamic shared memory
+#ifdef KH_HOST_EMU
+    inline void sync() const {}
+#else
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+#endif
+};
+
+#ifdef KH_HOST_EMU
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+template <class Args, void (*Body)(const Cta&, const Args&)>
+static inline int kh_launch(dim3 grid, int /*block*/, size_t smem, kh_stream_t, const Args& a) {
+    unsigned char* buf = (unsigned char*)malloc(smem + 64);
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            memset(buf, 0xFF, smem + 64);   // NaN pattern: catches reads of uninitialised shared memory
+            Cta c{0, 1, (int)bx, (int)by, buf};
+            Body(c, a);
+        }
+    free(buf);
+    return 0;
+}
+#define KH_ATOMIC_MAX(ptr, v) (*(ptr) = std::max(*(ptr), (v)))
+#define KH_ATOMIC_OR(ptr, v) (*(ptr) |= (v))
+#else
+template <class Args, void (*Body)(const Cta&, const Args&)>
+__global__ void kh_entry(const __grid_constant__ Args a) {
+    extern __shared__ __align__(16) unsigned char kh_smem[];
+    Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
+    Body(c, a);
+}
+template <class Args, void (*Body)(const Cta&, const Args&)>
+static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, const Args& a) {
+    if (grid.x == 0 || grid.y == 0) return 0;
+    static size_t configured = 0;            // per-instantiation opt-in to > 48 KB dynamic smem
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kh_entry<Args, Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+#define KH_ATOMIC_MAX(ptr, v) atomicMax((ptr), (v))
+#define KH_ATOMIC_OR(ptr, v) atomicOr((ptr), (v))
+#endif
+
+// Largest dynamic shared memory a CTA may opt in to on sm_100 (227 KB).
+#define KH_SMEM_MAX (227 * 1024)
+
+// ------------------------------------------------------------------ CTA-wide reductions
+// scratch: at least 64 doubles of shared memory.  All threads get the result.
+KH_DEV double cta_sum(const Cta& c, double v, double* scratch) {
+#ifdef KH_HOST_EMU
+    (void)c; (void)scratch;
+    return v;
+#else
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+    c.sync();
+    if ((c.tid & 31) == 0) scratch[w] = v;
+    c.sync();
+    double r = 0.0;
+    for (int i = 0; i < nw; ++i) r += scratch[i];
+    return r;
+#endif
+}
+KH_DEV double cta_max(const Cta& c, double v, double* scratch) {
+#ifdef KH_HOST_EMU
+    (void)c; (void)scratch;
+    return v;
+#else
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int w = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+    c.sync();
+    if ((c.tid & 31) == 0) scratch[w] = v;
+    c.sync();
+    double r = scratch[0];
+    for (int i = 1; i < nw; ++i) r = fmax(r, scratch[i]);
+    return r;
+#endif
+}
+// argmax of (value, index); ties -> smallest index.  scratch: 64 doubles + 64 ints.
+KH_DEV int cta_argmax(const Cta& c, double v, int idx, double* scratch) {
+#ifdef KH_HOST_EMU
+    (void)c; (void)scratch; (void)v;
+    return idx;
+#else
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    int w = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+    int* iscr = (int*)(scratch + 64);
+    c.sync();
+    if ((c.tid & 31) == 0) { scratch[w] = v; iscr[w] = idx; }
+    c.sync();
+    double bv = scratch[0]; int bi = iscr[0];
+    for (int i = 1; i < nw; ++i)
+        if (scratch[i] > bv || (scratch[i] == bv && iscr[i] < bi)) { bv = scratch[i]; bi = iscr[i]; }
+    return bi;
+#endif
+}
+
+// batch addressing with two levels: matrix b lives at base + (b / inner) * so + (b % inner) * si
+struct MatRef {
+    cd* p;
+    long long so, si;
+    int inner, ld;
+};
+KH_HD MatRef mref(const void* p, long long so, int ld, int inner = 1, long long si = 0) {
+    MatRef m; m.p = (cd*)p; m.so = so; m.si = si; m.inner = inner < 1 ? 1 : inner; m.ld = ld; return m;
+}
+KH_HD cd* mat_ptr(const MatRef& m, int b) {
+    return m.p ? m.p + (long long)(b / m.inner) * m.so + (long long)(b % m.inner) * m.si : (cd*)0;
+}

@@ -1,0 +1,335 @@
+// RCWA-specific kernels around the dense primitives (all complex128, one batch element = one
+// (wavelength, k-point) solve).  Notation follows SURVEY.md §8: N harmonics, n = 2N.
+//
+// "BD" = a 2N x 2N matrix made of 2x2 blocks of N-diagonals (what uniform layers and half spaces
+// produce).  It is stored compactly as four N-vectors (a, b; c, d) = one 2x2 complex matrix per
+// harmonic, so BD (*) BD star products are O(N) instead of O(n^3).
+#pragma once
+#include "kh_common.cuh"
+
+#define KH_TWO_PI 6.283185307179586476925286766559
+
+struct m22 { cd a, b, c, d; };
+KH_HD m22 m22_mul(const m22& p, const m22& q) {
+    m22 r;
+    r.a = p.a * q.a + p.b * q.c; r.b = p.a * q.b + p.b * q.d;
+    r.c = p.c * q.a + p.d * q.c; r.d = p.c * q.b + p.d * q.d;
+    return r;
+}
+KH_HD m22 m22_add(const m22& p, const m22& q) { m22 r; r.a = p.a + q.a; r.b = p.b + q.b; r.c = p.c + q.c; r.d = p.d + q.d; return r; }
+KH_HD m22 m22_sub(const m22& p, const m22& q) { m22 r; r.a = p.a - q.a; r.b = p.b - q.b; r.c = p.c - q.c; r.d = p.d - q.d; return r; }
+KH_HD m22 m22_scale(cd s, const m22& p) { m22 r; r.a = s * p.a; r.b = s * p.b; r.c = s * p.c; r.d = s * p.d; return r; }
+KH_HD m22 m22_eye() { m22 r; r.a = mk(1, 0); r.b = mk(0, 0); r.c = mk(0, 0); r.d = mk(1, 0); return r; }
+KH_HD m22 m22_inv(const m22& p) {
+    // Gaussian elimination with row pivoting (what LAPACK does on each decoupled 2x2 block)
+    m22 r;
+    if (cabs1(p.a) >= cabs1(p.c)) {
+        cd l = p.c / p.a;                 // eliminate c
+        cd u22 = p.d - l * p.b;
+        cd i22 = crecip(u22), i11 = crecip(p.a);
+        // inverse of [[a, b], [0, u22]] times [[1, 0], [-l, 1]]
+        cd t = -(p.b * i22) * i11;        // upper-right of U^-1
+        r.a = i11 - t * l; r.b = t;
+        r.c = -(i22 * l); r.d = i22;
+    } else {
+        cd l = p.a / p.c;                 // rows swapped: [[c, d], [a, b]]
+        cd u22 = p.b - l * p.d;
+        cd i22 = crecip(u22), i11 = crecip(p.c);
+        cd t = -(p.d * i22) * i11;
+        // (P A)^-1 = [[i11 - t*l, t], [-i22*l, i22]] ; A^-1 = (P A)^-1 P  -> swap columns
+        r.b = i11 - t * l; r.a = t;
+        r.d = -(i22 * l); r.c = i22;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ k-vectors (expansion.py:43-50)
+struct kvec_args {
+    int B, N;
+    const double* wl;        // [B]
+    const cd* kp;            // [B][2]
+    const double* g;         // [2][N]
+    cd* Kx; cd* Ky;          // [B][N]
+    double* k0;              // [B]
+};
+KH_DEV void kvec_body(const Cta& c, const kvec_args& a) {
+    const int b = c.bx;
+    const double k0 = KH_TWO_PI / a.wl[b];
+    if (c.tid == 0) a.k0[b] = k0;
+    const cd kpx = a.kp[2 * b], kpy = a.kp[2 * b + 1];
+    for (int g = c.tid; g < a.N; g += c.nthr) {
+        a.Kx[(long long)b * a.N + g] = mk((kpx.x + a.g[g]) / k0, kpx.y / k0);
+        a.Ky[(long long)b * a.N + g] = mk((kpy.x + a.g[a.N + g]) / k0, kpy.y / k0);
+    }
+}
+
+// free-space branch of kz (alternative.py:92-96, 146-149): sign of Re(kz^2) picks the root
+KH_HD cd kz_branch(cd arg) {
+    if (arg.x < 0.0) { cd s = csqrt_(-arg); return mk(s.y, -s.x); }     // -i * sqrt(-arg)
+    return csqrt_(arg);
+}
+KH_HD cd times_i(cd z) { return mk(-z.y, z.x); }
+
+// V-type 2x2 block  Q(eps)/lambda  for one harmonic:  [[KxKy, eps-Kx^2],[Ky^2-eps, -KyKx]] / lam
+KH_HD m22 q_over_lam(cd kx, cd ky, cd eps, cd lam) {
+    m22 q;
+    q.a = (kx * ky) / lam; q.b = (eps - kx * kx) / lam;
+    q.c = (ky * ky - eps) / lam; q.d = (-(ky * kx)) / lam;
+    return q;
+}
+KH_HD m22 v0_block(cd kx, cd ky) {                                      // alternative.py:84-99
+    cd one = mk(1, 0);
+    cd lam0 = times_i(kz_branch(one - kx * kx - ky * ky));
+    return q_over_lam(kx, ky, one, lam0);
+}
+
+// ------------------------------------------------------------------ analytic BD layers
+// kinds follow khepri/layer.py:19-24 (Formulation): 0 uniform, 3 half-space incidence, 4 half-space emergence
+struct bd_layer_args {
+    int B, N;
+    int kind;
+    cd eps; double depth;
+    const cd* Kx; const cd* Ky; const double* k0;
+    cd* S;            // [B][4 blocks][4 entries a,b,c,d][N]
+    cd* V;            // optional [B][4][N]: the layer's V block (fields); null otherwise
+    cd* lam;          // optional [B][N]
+};
+KH_DEV void bd_store(cd* S, long long base, int N, int blk, int g, const m22& m) {
+    cd* p = S + base + (long long)blk * 4 * N + g;
+    p[0] = m.a; p[N] = m.b; p[2 * N] = m.c; p[3 * N] = m.d;
+}
+KH_DEV m22 bd_load(const cd* S, long long base, int N, int blk, int g) {
+    const cd* p = S + base + (long long)blk * 4 * N + g;
+    m22 m; m.a = p[0]; m.b = p[N]; m.c = p[2 * N]; m.d = p[3 * N];
+    return m;
+}
+KH_DEV void bd_layer_body(const Cta& c, const bd_layer_args& a) {
+    const int b = c.bx, N = a.N;
+    const long long base = (long long)b * 16 * N;
+    const cd one = mk(1, 0);
+    for (int g = c.tid; g < N; g += c.nthr) {
+        cd kx = a.Kx[(long long)b * N + g], ky = a.Ky[(long long)b * N + g];
+        m22 V0 = v0_block(kx, ky);
+        m22 S11, S12, S21, S22, V;
+        cd lam;
+        if (a.kind == 0) {
+            // solve_uniform_layer + build_scatmat (alternative.py:130-156, 181-195), W = I
+            lam = times_i(kz_branch(a.eps - kx * kx - ky * ky));
+            m22 q;
+            cd ie = crecip(a.eps);
+            q.a = a.eps * (ie * (kx * ky)); q.b = a.eps * (ie * (a.eps - kx * kx));
+            q.c = a.eps * (ie * (ky * ky - a.eps)); q.d = a.eps * (ie * (-(ky * kx)));
+            V.a = q.a / lam; V.b = q.b / lam; V.c = q.c / lam; V.d = q.d / lam;
+            m22 t2 = m22_mul(m22_inv(V), V0);
+            m22 A = m22_add(m22_eye(), t2), Bm = m22_sub(m22_eye(), t2);
+            cd X = cexp_((-a.depth * a.k0[b]) * lam);
+            m22 Ai = m22_inv(A);
+            m22 XB = m22_scale(X, Bm);
+            m22 XBAiX = m22_scale(X, m22_mul(XB, Ai));            // X B A^-1 X
+            m22 T = m22_sub(A, m22_mul(XBAiX, Bm));
+            m22 Ti = m22_inv(T);
+            S11 = m22_mul(Ti, m22_sub(m22_mul(XBAiX, A), Bm));
+            S12 = m22_mul(Ti, m22_scale(X, m22_sub(A, m22_mul(Bm, m22_mul(Ai, Bm)))));
+            S21 = S12; S22 = S11;
+        } else {
+            // scattering_reflection / scattering_transmission (alternative.py:32-82), W = I
+            cd kz = cconj(csqrt_(a.eps - kx * kx - ky * ky));
+            lam = times_i(kz);
+            V = q_over_lam(kx, ky, a.eps, lam);
+            m22 t2 = m22_mul(m22_inv(V0), V);
+            m22 A = m22_add(m22_eye(), t2), Bm = m22_sub(m22_eye(), t2);
+            m22 Ai = m22_inv(A);
+            m22 AiB = m22_mul(Ai, Bm);
+            m22 mAiB = m22_scale(mk(-1, 0), AiB);
+            m22 twoAi = m22_scale(mk(2, 0), Ai);
+            m22 half = m22_scale(mk(0.5, 0), m22_sub(A, m22_mul(Bm, AiB)));
+            m22 BAi = m22_mul(Bm, Ai);
+            if (a.kind == 3) { S11 = mAiB; S12 = twoAi; S21 = half; S22 = BAi; }
+            else { S11 = BAi; S12 = half; S21 = twoAi; S22 = mAiB; }
+        }
+        (void)one;
+        bd_store(a.S, base, N, 0, g, S11); bd_store(a.S, base, N, 1, g, S12);
+        bd_store(a.S, base, N, 2, g, S21); bd_store(a.S, base, N, 3, g, S22);
+        if (a.V) { cd* p = a.V + (long long)b * 4 * N + g; p[0] = V.a; p[N] = V.b; p[2 * N] = V.c; p[3 * N] = V.d; }
+        if (a.lam) a.lam[(long long)b * N + g] = lam;
+    }
+}
+
+// identity S-matrix in BD form (alternative.py:220-232)
+struct bd_identity_args { int B, N; cd* S; };
+KH_DEV void bd_identity_body(const Cta& c, const bd_identity_args& a) {
+    const long long base = (long long)c.bx * 16 * a.N;
+    m22 z; z.a = z.b = z.c = z.d = mk(0, 0);
+    for (int g = c.tid; g < a.N; g += c.nthr) {
+        bd_store(a.S, base, a.N, 0, g, z); bd_store(a.S, base, a.N, 1, g, m22_eye());
+        bd_store(a.S, base, a.N, 2, g, m22_eye()); bd_store(a.S, base, a.N, 3, g, z);
+    }
+}
+
+// BD (*) BD Redheffer star product (alternative.py:19-30), per harmonic
+struct bd_star_args { int B, N; const cd* SA; const cd* SB; cd* SO; };
+KH_DEV void bd_star_body(const Cta& c, const bd_star_args& a) {
+    const int N = a.N;
+    const long long base = (long long)c.bx * 16 * N;
+    for (int g = c.tid; g < N; g += c.nthr) {
+        m22 A11 = bd_load(a.SA, base, N, 0, g), A12 = bd_load(a.SA, base, N, 1, g);
+        m22 A21 = bd_load(a.SA, base, N, 2, g), A22 = bd_load(a.SA, base, N, 3, g);
+        m22 B11 = bd_load(a.SB, base, N, 0, g), B12 = bd_load(a.SB, base, N, 1, g);
+        m22 B21 = bd_load(a.SB, base, N, 2, g), B22 = bd_load(a.SB, base, N, 3, g);
+        m22 Di = m22_inv(m22_sub(m22_eye(), m22_mul(B11, A22)));
+        m22 Fi = m22_inv(m22_sub(m22_eye(), m22_mul(A22, B11)));
+        m22 S11 = m22_add(A11, m22_mul(m22_mul(A12, m22_mul(Di, B11)), A21));
+        m22 S12 = m22_mul(A12, m22_mul(Di, B12));
+        m22 S21 = m22_mul(B21, m22_mul(Fi, A21));
+        m22 S22 = m22_add(B22, m22_mul(m22_mul(B21, m22_mul(Fi, A22)), B12));
+        bd_store(a.SO, base, N, 0, g, S11); bd_store(a.SO, base, N, 1, g, S12);
+        bd_store(a.SO, base, N, 2, g, S21); bd_store(a.SO, base, N, 3, g, S22);
+    }
+}
+
+// BD -> dense [B][4][n][n]
+struct bd_expand_args { int B, N; const cd* S; cd* D; };
+KH_DEV void bd_expand_body(const Cta& c, const bd_expand_args& a) {
+    const int N = a.N, n = 2 * N, blk = c.by;
+    const cd* s = a.S + (long long)c.bx * 16 * N + (long long)blk * 4 * N;
+    cd* d = a.D + ((long long)c.bx * 4 + blk) * n * n;
+    for (int e = c.tid; e < n * n; e += c.nthr) {
+        int i = e / n, j = e - i * n;
+        int gi = i < N ? i : i - N, gj = j < N ? j : j - N;
+        cd v = mk(0, 0);
+        if (gi == gj) v = s[((i >= N) * 2 + (j >= N)) * N + gi];
+        d[e] = v;
+    }
+}
+
+// ------------------------------------------------------------------ patterned layer: P, Q (alternative.py:158-171)
+struct pq_args {
+    int B, N;
+    const cd* C; const cd* IC;          // [N][N], shared by the batch
+    const cd* Kx; const cd* Ky;         // [B][N]
+    cd* P; cd* Q;                       // [B][n][n]
+};
+KH_DEV void pq_body(const Cta& c, const pq_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const cd* kx = a.Kx + (long long)b * N;
+    const cd* ky = a.Ky + (long long)b * N;
+    cd* P = a.P + (long long)b * n * n;
+    cd* Q = a.Q + (long long)b * n * n;
+    for (int e = c.tid; e < N * N; e += c.nthr) {
+        int r = e / N, q = e - r * N;
+        cd ic = a.IC[e], cc = a.C[e];
+        double dl = (r == q) ? 1.0 : 0.0;
+        cd icky = ic * ky[q], ickx = ic * kx[q];
+        cd p11 = kx[r] * icky, p12 = mk(dl, 0) - kx[r] * ickx;
+        cd p21 = ky[r] * icky - mk(dl, 0), p22 = -(ky[r] * ickx);
+        P[(long long)r * n + q] = p11; P[(long long)r * n + N + q] = p12;
+        P[(long long)(N + r) * n + q] = p21; P[(long long)(N + r) * n + N + q] = p22;
+        cd z = mk(0, 0);
+        cd q11 = z, q12 = cc, q21 = -cc, q22 = z;
+        if (r == q) {
+            q11 = kx[r] * ky[r]; q12 = cc - kx[r] * kx[r];
+            q21 = ky[r] * ky[r] - cc; q22 = -(ky[r] * kx[r]);
+        }
+        Q[(long long)r * n + q] = q11; Q[(long long)r * n + N + q] = q12;
+        Q[(long long)(N + r) * n + q] = q21; Q[(long long)(N + r) * n + N + q] = q22;
+    }
+}
+
+// lambda = sqrt(lambda^2 + 0j), X = exp(-lambda d k0)   (alternative.py:173, 186)
+struct lam_args { int B, n; double depth; const cd* w; const double* k0; cd* lam; cd* xexp; };
+KH_DEV void lam_body(const Cta& c, const lam_args& a) {
+    const int b = c.bx;
+    for (int i = c.tid; i < a.n; i += c.nthr) {
+        cd w = a.w[(long long)b * a.n + i];
+        cd l = csqrt_(mk(w.x + 0.0, w.y + 0.0));
+        a.lam[(long long)b * a.n + i] = l;
+        a.xexp[(long long)b * a.n + i] = cexp_((-a.depth * a.k0[b]) * l);
+    }
+}
+
+// A = W^-1 + V^-1 V0 ; B = W^-1 - V^-1 V0 ; XB = X B ; XA = X A     (alternative.py:182-186; W0 = I)
+struct ab_args {
+    int B, N;
+    const cd* Winv; const cd* Vinv;      // [B][n][n]
+    const cd* Kx; const cd* Ky; const cd* xexp;
+    cd* A; cd* Bm; cd* XB; cd* XA;       // [B][n][n] each
+};
+KH_DEV void ab_body(const Cta& c, const ab_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const long long off = (long long)b * n * n;
+    const cd* kx = a.Kx + (long long)b * N;
+    const cd* ky = a.Ky + (long long)b * N;
+    const cd* x = a.xexp + (long long)b * n;
+    for (int e = c.tid; e < n * N; e += c.nthr) {
+        int i = e / N, g = e - i * N;
+        m22 V0 = v0_block(kx[g], ky[g]);
+        cd v1 = a.Vinv[off + (long long)i * n + g], v2 = a.Vinv[off + (long long)i * n + N + g];
+        cd t1 = v1 * V0.a + v2 * V0.c, t2 = v1 * V0.b + v2 * V0.d;
+        cd w1 = a.Winv[off + (long long)i * n + g], w2 = a.Winv[off + (long long)i * n + N + g];
+        cd a1 = w1 + t1, a2 = w2 + t2, b1 = w1 - t1, b2 = w2 - t2;
+        long long o1 = off + (long long)i * n + g, o2 = o1 + N;
+        a.A[o1] = a1; a.A[o2] = a2; a.Bm[o1] = b1; a.Bm[o2] = b2;
+        a.XB[o1] = x[i] * b1; a.XB[o2] = x[i] * b2;
+        a.XA[o1] = x[i] * a1; a.XA[o2] = x[i] * a2;
+    }
+}
+
+// ------------------------------------------------------------------ flux (crystal.py:363-396, alternative.py:101-128, 235-245)
+struct flux_args {
+    int B, N;
+    const cd* Stot;            // [B][4][n][n]
+    const double* wl; const cd* kp; const cd* pol;   // pol [B][2] = (te, tm)
+    const double* g;
+    cd epsi, epse;
+    double* RT;                // [B][2]
+    double* orders;            // optional [B][2][N]
+};
+KH_DEV double cnorm3(cd a, cd b, cd c3) { return sqrt(cabs2(a) + cabs2(b) + cabs2(c3)); }
+KH_DEV void flux_body(const Cta& c, const flux_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    double* scratch = (double*)c.smem;
+    const double k0 = KH_TWO_PI / a.wl[b];
+    const cd kpx = a.kp[2 * b], kpy = a.kp[2 * b + 1];
+    // incident(): polarisation vector
+    cd te = a.pol[2 * b], tm = a.pol[2 * b + 1];
+    double pn = hypot(cabsd(te), cabsd(tm));
+    te = (1.0 / pn) * te; tm = (1.0 / pn) * tm;
+    cd kzi = cconj(csqrt_(mk(k0 * k0, 0) * a.epsi - kpx * kpx - kpy * kpy));
+    double kn = cnorm3(kpx, kpy, kzi);
+    cd kbx = (1.0 / kn) * kpx, kby = (1.0 / kn) * kpy, kbz = (1.0 / kn) * kzi;
+    cd px, py;
+    if (sqrt(cabs2(kpx) + cabs2(kpy)) < 1e-8) { px = te; py = tm; }
+    else {
+        cd ex = -kby, ey = kbx;                                  // -cross((0,0,-1), kbar)
+        double en = sqrt(cabs2(ex) + cabs2(ey));
+        ex = (1.0 / en) * ex; ey = (1.0 / en) * ey;
+        cd mx = ey * kbz, my = -(ex * kbz), mz = ex * kby - ey * kbx;   // cross(aTE, kbar)
+        double mn = cnorm3(mx, my, mz);
+        mx = (1.0 / mn) * mx; my = (1.0 / mn) * my;
+        px = te * ex + tm * mx; py = te * ey + tm * my;
+    }
+    const int g0 = (N - 1) / 2;
+    const cd kzin = (1.0 / k0) * kzi;                            // poynting_fluxes: kzi / k0
+    const cd* S11 = a.Stot + (long long)b * 4 * n * n;
+    const cd* S21 = S11 + 2LL * n * n;
+    double accR = 0.0, accT = 0.0;
+    for (int g = c.tid; g < N; g += c.nthr) {
+        cd kxg = mk(kpx.x + a.g[g], kpx.y), kyg = mk(kpy.x + a.g[N + g], kpy.y);
+        cd kx = mk(kxg.x / k0, kxg.y / k0), ky = mk(kyg.x / k0, kyg.y / k0);
+        for (int side = 0; side < 2; ++side) {
+            const cd* S = side ? S21 : S11;
+            cd eps = side ? a.epse : a.epsi;
+            cd sx = S[(long long)g * n + g0] * px + S[(long long)g * n + N + g0] * py;
+            cd sy = S[(long long)(N + g) * n + g0] * px + S[(long long)(N + g) * n + N + g0] * py;
+            cd kzf = cconj(csqrt_(mk(k0 * k0, 0) * cconj(eps) - kxg * kxg - kyg * kyg));
+            cd kz = mk(kzf.x / k0, kzf.y / k0);
+            cd sz = (-(kx * sx + ky * sy)) / kz;
+            double t = kz.x / kzin.x * (cabs2(sx) + cabs2(sy) + cabs2(sz));
+            if (a.orders) a.orders[((long long)b * 2 + side) * N + g] = t;
+            if (side) accT += t; else accR += t;
+        }
+    }
+    accR = cta_sum(c, accR, scratch);
+    accT = cta_sum(c, accT, scratch);
+    if (c.tid == 0) { a.RT[2 * b] = accR; a.RT[2 * b + 1] = accT; }
+}

@@ -1,0 +1,312 @@
+"""Host-side plumbing between torch tensors and the C ABI (include/khepri_b200.h).
+
+PyTorch is used only for device memory, streams and (in bench.py) torch.distributed; all compute
+happens in the hand-written sm_100a kernels of ``khepri_b200/lib/libkhepri_b200.so``.
+
+There is no CPU fallback.  ``Engine()`` raises when the CUDA library or a CUDA device is missing.
+(The ``device="cpu"`` + ``lib_path=`` combination exists solely so that tests/hostemu can drive a
+host-emulation build of the very same kernel sources through this code; the package never selects
+it by itself.)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KhepriError, LayerDesc, Outputs, check
+
+_c128 = torch.complex128
+_f64 = torch.float64
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class Plan:
+    """Device-side description of a Crystal's geometry (crystal.py:42-164)."""
+
+    def __init__(self, engine, pw, g, epsi, epse, layers, stack, Nb=0, glhs=None, grhs=None):
+        self.engine = engine
+        self.pw = (int(pw[0]), int(pw[1]))
+        self.N = self.pw[0] * self.pw[1]
+        self.n = 2 * self.N
+        self.layers = layers
+        self.stack = [int(s) for s in stack]
+        self.Ls = len(self.stack)
+        self.nL = len(layers)
+        dev = engine.device
+        self.g = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64), device=dev)
+        assert self.g.shape == (2, self.N), "g-vectors must have shape (2, N)"
+        self.glhs = torch.as_tensor(np.ascontiguousarray(glhs, dtype=np.float64), device=dev) if glhs is not None else None
+        self.grhs = torch.as_tensor(np.ascontiguousarray(grhs, dtype=np.float64), device=dev) if grhs is not None else None
+        self._keep = []
+        descs = (LayerDesc * len(layers))()
+        for i, L in enumerate(layers):
+            d = descs[i]
+            d.kind = int(L["kind"])
+            eps = complex(L.get("eps", 1.0))
+            d.eps_re, d.eps_im = eps.real, eps.imag
+            d.depth = float(L.get("depth", 0.0))
+            d.retain = int(bool(L.get("retain", False)))
+            d.ext_base = int(L.get("ext_base", -1))
+            d.ext_mode = int(L.get("ext_mode", 0))
+            d.C_dev = d.IC_dev = None
+            if d.kind == _lib.LAYER_PIXMAP:
+                Cm = L["C"].to(device=dev, dtype=_c128).contiguous()
+                ICm = L["IC"].to(device=dev, dtype=_c128).contiguous()
+                self._keep += [Cm, ICm]
+                d.C_dev, d.IC_dev = Cm.data_ptr(), ICm.data_ptr()
+        stack_arr = (C.c_int * self.Ls)(*self.stack)
+        handle = C.c_void_p()
+        lib = engine.lib
+        check(lib, lib.kh_plan_create(C.byref(handle), self.pw[0], self.pw[1], _ptr(self.g),
+                                      complex(epsi).real, complex(epsi).imag, complex(epse).real, complex(epse).imag,
+                                      len(layers), descs, self.Ls, stack_arr, int(Nb), _ptr(self.glhs), _ptr(self.grhs)),
+              "kh_plan_create")
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.engine.lib.kh_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    _default = None
+
+    def __init__(self, device=None, lib_path=None, workspace_cap_bytes=None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise KhepriError("khepri_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and lib_path is None:
+            raise KhepriError("khepri_b200 only runs on CUDA devices; there is no CPU fallback.")
+        self.lib = _lib.bind(lib_path)
+        self._ws = None
+        self.workspace_cap_bytes = workspace_cap_bytes
+        self.launch_count = 0
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = cls()
+        return cls._default
+
+    # ------------------------------------------------------------------ helpers
+    def stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(None)
+
+    def _cap(self):
+        if self.workspace_cap_bytes is not None:
+            return int(self.workspace_cap_bytes)
+        if self.device.type == "cuda":
+            free, _total = torch.cuda.mem_get_info(self.device)
+            held = self._ws.numel() if self._ws is not None else 0
+            return int(min(48 << 30, 0.6 * (free + held)))
+        return 1 << 30
+
+    def workspace(self, nbytes):
+        nbytes = int(nbytes)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def to_dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        arr = np.ascontiguousarray(a)
+        t = torch.from_numpy(arr)
+        if self.device.type == "cuda":
+            t = t.pin_memory().to(self.device, non_blocking=True)
+        return t.to(dtype).contiguous()
+
+    # ------------------------------------------------------------------ convolution matrix
+    def convmat(self, pixmaps, pw, return_coefficients=False):
+        """tools.convolution_matrix for a stack of pixmaps [L, Nx, Ny] (real or complex)."""
+        pix = pixmaps if isinstance(pixmaps, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pixmaps))
+        if pix.dim() == 2:
+            pix = pix[None]
+        is_complex = pix.is_complex()
+        pix = pix.to(device=self.device, dtype=_c128 if is_complex else _f64).contiguous()
+        L, Nx, Ny = pix.shape
+        P, Q = int(pw[0]), int(pw[1])
+        if (P > 1 and Nx // 2 + P - 1 >= Nx) or (Q > 1 and Ny // 2 + Q - 1 >= Ny):
+            raise IndexError("harmonic differences exceed the Fourier grid")      # as the reference's gather would
+        N = P * Q
+        Cm = torch.empty((L, N, N), dtype=_c128, device=self.device)
+        F = torch.empty((L, 2 * P - 1, 2 * Q - 1), dtype=_c128, device=self.device)
+        wb = self.lib.kh_convmat_work_bytes(L, Nx, Ny, P, Q)
+        ws = self.workspace(wb)
+        check(self.lib, self.lib.kh_convmat(L, Nx, Ny, int(is_complex), _ptr(pix), P, Q, _ptr(Cm), _ptr(F), _ptr(ws), ws.numel(), self.stream()), "kh_convmat")
+        return (Cm, F) if return_coefficients else Cm
+
+    def toeplitz_gather(self, F, pw):
+        """tools.convolution_matrix_fourier (bit-exact index gather)."""
+        Ft = self.to_dev(F, _c128)
+        Nx, Ny = Ft.shape
+        P, Q = int(pw[0]), int(pw[1])
+        Cm = torch.empty((P * Q, P * Q), dtype=_c128, device=self.device)
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self.lib, self.lib.kh_toeplitz_gather(_ptr(Ft), Nx, Ny, P, Q, _ptr(Cm), _ptr(err), self.stream()), "kh_toeplitz_gather")
+        if int(err.item()):
+            raise IndexError("harmonic differences exceed the Fourier grid")
+        return Cm
+
+    # ------------------------------------------------------------------ dense primitives
+    def zgemm(self, A, B, transA=False, alpha=1.0):
+        A = self.to_dev(A, _c128)
+        B = self.to_dev(B, _c128)
+        if A.dim() == 2:
+            A = A[None]
+        if B.dim() == 2:
+            B = B[None]
+        batch = max(A.shape[0], B.shape[0])
+        M, K = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
+        N = B.shape[2]
+        assert B.shape[1] == K
+        out = torch.empty((batch, M, N), dtype=_c128, device=self.device)
+        sA = 0 if A.shape[0] == 1 and batch > 1 else A.shape[1] * A.shape[2]
+        sB = 0 if B.shape[0] == 1 and batch > 1 else B.shape[1] * B.shape[2]
+        check(self.lib, self.lib.kh_zgemm_batched(batch, M, N, K, int(transA), _ptr(A), A.shape[2], sA, _ptr(B), B.shape[2], sB,
+                                                  _ptr(out), N, M * N, float(alpha), self.stream()), "kh_zgemm_batched")
+        return out
+
+    def zinv(self, A, return_info=False):
+        A = self.to_dev(A, _c128)
+        squeeze = A.dim() == 2
+        if squeeze:
+            A = A[None]
+        batch, n, _ = A.shape
+        out = torch.empty_like(A)
+        info = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        check(self.lib, self.lib.kh_zinv_batched(batch, n, _ptr(A), _ptr(out), _ptr(info), self.stream()), "kh_zinv_batched")
+        out = out[0] if squeeze else out
+        return (out, info) if return_info else out
+
+    def zgeev(self, A):
+        A = self.to_dev(A, _c128)
+        if A.dim() == 2:
+            A = A[None]
+        batch, n, _ = A.shape
+        w = torch.empty((batch, n), dtype=_c128, device=self.device)
+        W = torch.empty((batch, n, n), dtype=_c128, device=self.device)
+        info = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        wb = self.lib.kh_zgeev_work_bytes(batch, n)
+        ws = self.workspace(wb)
+        check(self.lib, self.lib.kh_zgeev_batched(batch, n, _ptr(A), _ptr(w), _ptr(W), _ptr(ws), ws.numel(), _ptr(info), self.stream()), "kh_zgeev_batched")
+        return w, W, info
+
+    # ------------------------------------------------------------------ the batched solve
+    def solve_batch(self, plan, wl, kp, pol=None, want_S=False, want_flux=True, want_orders=False, want_fields=False, chunk=None):
+        """Crystal.solve (+ poynting_flux_end) for B sources.  wl [B], kp [B,2] complex, pol [B,2] = (te, tm).
+
+        Returns a dict of DEVICE tensors: RT [B,2], orders [B,2,N], Stot [B,2,2,n,n], info [B] and, with
+        want_fields, prefix/suffix [B,Ls,2,2,n,n], W/V [B,nL,n,n], L [B,nL,n].
+        """
+        wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(-1) if not isinstance(wl, torch.Tensor) else wl.reshape(-1), _f64)
+        B = wl_d.numel()
+        kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2) if not isinstance(kp, torch.Tensor) else kp.reshape(B, 2), _c128)
+        pol_d = None
+        if want_flux:
+            assert pol is not None, "flux needs the (te, tm) polarisation"
+            pol_d = self.to_dev(np.asarray(pol, dtype=np.complex128).reshape(B, 2) if not isinstance(pol, torch.Tensor) else pol.reshape(B, 2), _c128)
+        n, N, Ls, nL = plan.n, plan.N, plan.Ls, plan.nL
+        dev = self.device
+        res = {"info": torch.zeros(B, dtype=torch.int32, device=dev)}
+        out = Outputs()
+        out.info_dev = res["info"].data_ptr()
+        flags = 0
+        if want_S:
+            res["Stot"] = torch.empty((B, 2, 2, n, n), dtype=_c128, device=dev)
+            out.Stot_dev = res["Stot"].data_ptr()
+            flags |= _lib.WANT_STOT
+        if want_flux:
+            res["RT"] = torch.empty((B, 2), dtype=_f64, device=dev)
+            out.RT_dev = res["RT"].data_ptr()
+            flags |= _lib.WANT_FLUX
+            if want_orders:
+                res["orders"] = torch.empty((B, 2, N), dtype=_f64, device=dev)
+                out.orders_dev = res["orders"].data_ptr()
+        if want_fields:
+            res["prefix"] = torch.empty((B, Ls, 2, 2, n, n), dtype=_c128, device=dev)
+            res["suffix"] = torch.empty((B, Ls, 2, 2, n, n), dtype=_c128, device=dev)
+            res["W"] = torch.zeros((B, nL, n, n), dtype=_c128, device=dev)
+            res["V"] = torch.zeros((B, nL, n, n), dtype=_c128, device=dev)
+            res["L"] = torch.zeros((B, nL, n), dtype=_c128, device=dev)
+            out.prefix_dev, out.suffix_dev = res["prefix"].data_ptr(), res["suffix"].data_ptr()
+            out.W_dev, out.V_dev, out.L_dev = res["W"].data_ptr(), res["V"].data_ptr(), res["L"].data_ptr()
+            flags |= _lib.WANT_FIELDS
+        if B == 0:
+            return res
+        lib = self.lib
+        want = int(chunk) if chunk else B
+        need = lib.kh_solve_workspace_bytes(plan.handle, want, flags)
+        cap = self._cap()
+        one = lib.kh_solve_workspace_bytes(plan.handle, 1, flags)
+        if one > cap:
+            raise KhepriError(f"one solve needs {one} bytes of workspace, cap is {cap}")
+        ws = self.workspace(min(need, cap) if not chunk else need)
+        ws_bytes = min(ws.numel(), need) if chunk else ws.numel()
+        check(lib, lib.kh_solve_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(pol_d), C.byref(out), _ptr(ws), ws_bytes, self.stream()),
+              "kh_solve_batch")
+        return res
+
+    def star(self, SA, SB):
+        """alternative.redheffer_product on stacks [B,2,2,n,n]."""
+        SA = self.to_dev(SA, _c128)
+        SB = self.to_dev(SB, _c128)
+        squeeze = SA.dim() == 4
+        if squeeze:
+            SA, SB = SA[None], SB[None]
+        B, n = SA.shape[0], SA.shape[-1]
+        SO = torch.empty_like(SA)
+        wb = self.lib.kh_star_workspace_bytes(B, n)
+        ws = self.workspace(wb)
+        check(self.lib, self.lib.kh_star_batch(B, n, _ptr(SA), _ptr(SB), _ptr(SO), _ptr(ws), ws.numel(), self.stream()), "kh_star_batch")
+        return SO[0] if squeeze else SO
+
+    def flux(self, plan, Stot, wl, kp, pol, want_orders=False):
+        Stot = self.to_dev(Stot, _c128)
+        if Stot.dim() == 4:
+            Stot = Stot[None]
+        B = Stot.shape[0]
+        wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
+        kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
+        pol_d = self.to_dev(np.asarray(pol, dtype=np.complex128).reshape(B, 2), _c128)
+        RT = torch.empty((B, 2), dtype=_f64, device=self.device)
+        orders = torch.empty((B, 2, plan.N), dtype=_f64, device=self.device) if want_orders else None
+        check(self.lib, self.lib.kh_flux_batch(plan.handle, B, _ptr(Stot), _ptr(wl_d), _ptr(kp_d), _ptr(pol_d), _ptr(RT), _ptr(orders), self.stream()),
+              "kh_flux_batch")
+        return (RT, orders) if want_orders else RT
+
+    def fields(self, plan, solved, wl, kp, inc, x, y, z):
+        """E, H [B, nz, 3, ny, nx] from a want_fields solve.  inc [B, 2, n] = incident (E, H) Fourier vectors."""
+        B = solved["prefix"].shape[0]
+        wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
+        kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
+        inc_d = self.to_dev(np.asarray(inc, dtype=np.complex128).reshape(B, 2, plan.n), _c128)
+        x_d = self.to_dev(np.asarray(x, dtype=np.float64).reshape(-1), _f64)
+        y_d = self.to_dev(np.asarray(y, dtype=np.float64).reshape(-1), _f64)
+        z_h = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(-1))
+        nx, ny, nz = x_d.numel(), y_d.numel(), z_h.size
+        E = torch.empty((B, nz, 3, ny, nx), dtype=_c128, device=self.device)
+        H = torch.empty((B, nz, 3, ny, nx), dtype=_c128, device=self.device)
+        out = Outputs()
+        out.Stot_dev = solved["Stot"].data_ptr()
+        out.prefix_dev, out.suffix_dev = solved["prefix"].data_ptr(), solved["suffix"].data_ptr()
+        out.W_dev, out.V_dev, out.L_dev = solved["W"].data_ptr(), solved["V"].data_ptr(), solved["L"].data_ptr()
+        wb = self.lib.kh_fields_workspace_bytes(plan.handle, B, nx, ny, nz)
+        ws = self.workspace(wb)
+        check(self.lib, self.lib.kh_fields_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out), _ptr(x_d), nx, _ptr(y_d), ny,
+                                                 z_h.ctypes.data_as(C.POINTER(C.c_double)), nz, _ptr(E), _ptr(H), _ptr(ws), ws.numel(), self.stream()),
+              "kh_fields_batch")
+        return E, H

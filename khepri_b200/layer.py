@@ -1,0 +1,91 @@
+"""Layer descriptors (host side).  Same constructors and attributes as khepri/layer.py:63-143; the
+arithmetic of Layer.solve (layer.py:145-194) runs batched on the GPU through the Crystal."""
+from enum import IntEnum
+
+import numpy as np
+
+
+class Formulation(IntEnum):          # layer.py:19-24
+    UNIFORM = 0
+    FFT = 1
+    ANALYTICAL = 2
+    HALF_SPACE_INC = 3
+    HALF_SPACE_TRN = 4
+
+
+class Field(IntEnum):                # layer.py:27-32
+    X = 0
+    Y = 1
+    Z = 2
+    NORM = 3
+    POYNTING = 4
+
+
+class Layer:
+    def __init__(self):
+        self.formulation = None
+        self.expansion = None
+        self.W = None
+        self.V = None
+        self.L = None
+        self.S = None
+        self.IC = None
+        self.fields = False
+        self._cache = None           # device copies of (C, C^-1), keyed on the identity of the pixmap array
+
+    @classmethod
+    def pixmap_or_uniform(cls, expansion, pixmap, depth):
+        eps0 = pixmap.flatten()[0]
+        if np.all(pixmap == eps0):
+            return cls.uniform(expansion, eps0, depth)
+        return cls.pixmap(expansion, pixmap, depth)
+
+    @classmethod
+    def pixmap(cls, expansion, pixmap, depth):
+        layer = cls()
+        layer.expansion = expansion
+        layer.formulation = Formulation.FFT
+        layer.epsilon = pixmap
+        layer.depth = depth
+        return layer
+
+    @classmethod
+    def uniform(cls, expansion, epsilon, depth):
+        layer = cls()
+        layer.expansion = expansion
+        layer.formulation = Formulation.UNIFORM
+        layer.epsilon = epsilon
+        layer.depth = depth
+        return layer
+
+    @classmethod
+    def analytical(cls, expansion, islands_description, eps_host, depth):
+        raise NotImplementedError(
+            "add_layer_analytical / Layer.analytical is the next row of the hot-path scope (SURVEY.md 8f.1); "
+            "rasterise the islands to a pixmap and use Layer.pixmap for now.")
+
+    @classmethod
+    def half_infinite(cls, expansion, type, epsilon):
+        layer = cls()
+        if type == "reflexion":
+            layer.formulation = Formulation.HALF_SPACE_INC
+        elif type == "transmission":
+            layer.formulation = Formulation.HALF_SPACE_TRN
+        else:
+            raise ValueError("half_infinite type must be 'reflexion' or 'transmission'")
+        layer.expansion = expansion
+        layer.depth = 0
+        layer.epsilon = epsilon
+        return layer
+
+    # -- device-side convolution matrix (tools.convolution_matrix + np.linalg.inv, layer.py:157-158),
+    #    computed once per pixmap instead of once per solve
+    def convmat_device(self, engine):
+        key = (id(self.epsilon), tuple(self.expansion.pw), id(engine))
+        if self._cache is None or self._cache[0] != key:
+            Cm = engine.convmat(np.asarray(self.epsilon), self.expansion.pw)[0]
+            ICm, info = engine.zinv(Cm, return_info=True)
+            if int(info.max().item()) != 0:
+                raise np.linalg.LinAlgError("Singular matrix")     # what np.linalg.inv raises in the reference
+            self._cache = (key, Cm, ICm)
+        return self._cache[1], self._cache[2]

@@ -87,7 +87,7 @@ def case_woodpile(pw=(11, 11), nk=2, nf=2):
     freqs = np.linspace(0.4 / 1.414, 0.65 / 1.414, 200)
     kxs = np.linspace(0, 0.99 * np.pi, 200)
     srcs = []
-    for ik in np.linspace(5, 190, nk).astype(int):
+    for ik in np.linspace(5, 100, nk).astype(int):        # below the light line (flux defined)
         for jf in np.linspace(10, 180, nf).astype(int):
             srcs.append(dict(wavelength=float(1 / freqs[jf]), te=1.0, tm=1.0, kp=(float(kxs[ik]), 0.0)))
     return st, srcs
