@@ -120,13 +120,28 @@ int kh_flux_batch(const kh_plan* plan, int B, const void* Stot_dev, const double
                   const void* pol_dev, double* RT_dev, double* orders_dev, void* stream);
 
 /* ---- field reconstruction (crystal.py:234-343, fields.py, fourier.py:136-142) ---------------- */
-/* E,H on a rectilinear grid x[nx], y[ny] (meshgrid 'xy') and depths z[nz] for every solve of the
- * batch, from the KH_WANT_FIELDS outputs of kh_solve_batch.  E_dev/H_dev: [B][nz][3][ny][nx] c128. */
-size_t kh_fields_workspace_bytes(const kh_plan* plan, int B, int nx, int ny, int nz);
-int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* pol_dev,
-                    const kh_outputs* solved, const double* x_dev, int nx, const double* y_dev, int ny,
-                    const double* z_host, int nz, void* E_dev, void* H_dev,
+/* E,H at arbitrary in-plane points (x[p], y[p]), p < npts, and depths z[nz] for every solve of the
+ * batch, from the KH_WANT_FIELDS outputs of kh_solve_batch (+ Stot).  inc_dev [B][2][n] c128 are the
+ * incident (E, H) Fourier vectors (Crystal.get_source_as_field_vectors).  z_host / zpos_host are HOST
+ * arrays: depths, and the Ls+1 interface positions (Crystal.stack_positions, +-inf at the ends).
+ * F_dev: [B][nz][6][npts] c128 = (Ex,Ey,Ez,Hx,Hy,Hz). */
+size_t kh_fields_workspace_bytes(const kh_plan* plan, int B, int npts, int nz);
+int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                    const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts,
+                    const double* z_host, int nz, const double* zpos_host, void* F_dev,
                     void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- measurement helper --------------------------------------------------------------------- */
+/* FP64 peak probe on the current device (registers only): mode 0 = DFMA stream, 1 = DMMA m8n8k4
+ * stream.  Synchronous; returns TFLOP/s.  Used by bench.py for the roofline denominator that
+ * MEASURED_PEAKS.json does not carry. */
+int kh_fp64_peak(int mode, int iters, int blocks, double* scratch_dev, double* tflops_out);
+/* number of kernels this library has launched so far in this process */
+long long kh_launch_count(void);
+/* per-kernel CUDA-event timing: begin() arms it, end() synchronises and writes one line per kernel
+ * class into buf: "name count total_ms total_algorithmic_flops". */
+int kh_profile_begin(void);
+int kh_profile_end(char* buf, size_t len);
 
 #ifdef __cplusplus
 }

@@ -47,9 +47,13 @@ SIGNATURES = {
     "kh_star_workspace_bytes": (sz, [i32, i32]),
     "kh_star_batch": (i32, [i32, i32, vp, vp, vp, vp, sz, vp]),
     "kh_flux_batch": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
-    "kh_fields_workspace_bytes": (sz, [vp, i32, i32, i32, i32]),
-    "kh_fields_batch": (i32, [vp, i32, vp, vp, vp, C.POINTER(Outputs), vp, i32, vp, i32, C.POINTER(f64), i32,
-                              vp, vp, vp, sz, vp]),
+    "kh_fields_workspace_bytes": (sz, [vp, i32, i32, i32]),
+    "kh_fields_batch": (i32, [vp, i32, vp, vp, vp, C.POINTER(Outputs), vp, vp, i32, C.POINTER(f64), i32, C.POINTER(f64),
+                              vp, vp, sz, vp]),
+    "kh_fp64_peak": (i32, [i32, i32, i32, vp, C.POINTER(f64)]),
+    "kh_launch_count": (i64, []),
+    "kh_profile_begin": (i32, []),
+    "kh_profile_end": (i32, [C.c_char_p, sz]),
 }
 
 

@@ -11,6 +11,7 @@
 #include "kh_rcwa.cuh"
 #include "kh_convmat.cuh"
 #include "kh_fields.cuh"
+#include "kh_peak.cuh"
 
 #include <string>
 #include <vector>
@@ -488,9 +489,74 @@ extern "C" int kh_toeplitz_gather(const void* F, int Nx, int Ny, int P, int Q, v
 
 // ---------------------------------------------------------------------------- fields (implemented in kh_fields.cuh)
 #ifndef KH_FIELDS_IMPL
-extern "C" size_t kh_fields_workspace_bytes(const kh_plan*, int, int, int, int) { return 0; }
-extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, int,
-                               const double*, int, const double*, int, void*, void*, void*, size_t, void*) {
+extern "C" size_t kh_fields_workspace_bytes(const kh_plan*, int, int, int) { return 0; }
+extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, const double*, int,
+                               const double*, int, const double*, void*, void*, size_t, void*) {
     return fail(KH_ESTATE, "kh_fields_batch: not built");
 }
 #endif
+
+// ---------------------------------------------------------------------------- FP64 peak probe
+extern "C" int kh_fp64_peak(int mode, int iters, int blocks, double* scratch_dev, double* tflops_out) {
+#ifdef KH_HOST_EMU
+    (void)mode; (void)iters; (void)blocks; (void)scratch_dev; (void)tflops_out;
+    return fail(KH_ESTATE, "kh_fp64_peak: needs a GPU");
+#else
+    if (!scratch_dev || !tflops_out || iters < 1 || blocks < 1) return fail(KH_EINVAL, "kh_fp64_peak: bad arguments");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) {          // first pass warms up
+        cudaEventRecord(e0);
+        if (mode == 0) kh_peak_dfma<<<blocks, 256>>>(scratch_dev, iters, 1.0);
+        else kh_peak_dmma<<<blocks, 256>>>(scratch_dev, iters, 1.0);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail((int)err, "kh_fp64_peak: launch failed");
+    double flops = mode == 0 ? 2.0 * 16 * 256.0 * blocks * (double)iters            // 16 FMA / thread / iter
+                             : 2.0 * 8 * 256.0 * (256.0 / 32.0) * blocks * (double)iters;   // 8 DMMA (8x8x4) / warp / iter
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    return 0;
+#endif
+}
+
+// ---------------------------------------------------------------------------- launch counter / profiler
+extern "C" long long kh_launch_count(void) { return g_prof.launches; }
+extern "C" int kh_profile_begin(void) {
+#ifndef KH_HOST_EMU
+    g_prof.on = true;
+#endif
+    return 0;
+}
+// Synchronises the device, aggregates per kernel name and writes lines "name count total_ms total_work\n".
+extern "C" int kh_profile_end(char* buf, size_t len) {
+    if (!buf || len < 2) return fail(KH_EINVAL, "kh_profile_end: bad buffer");
+    buf[0] = 0;
+#ifndef KH_HOST_EMU
+    g_prof.on = false;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail((int)e, "kh_profile_end: sync failed");
+    struct Agg { std::string name; long long count; double ms, work; };
+    std::vector<Agg> agg;
+    for (auto& r : g_prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        std::string nm = (r.name && r.name[0]) ? r.name : "other";
+        size_t k = 0;
+        for (; k < agg.size(); ++k) if (agg[k].name == nm) break;
+        if (k == agg.size()) agg.push_back({nm, 0, 0.0, 0.0});
+        agg[k].count++; agg[k].ms += ms; agg[k].work += r.work;
+        g_prof.pool.push_back(r.e0); g_prof.pool.push_back(r.e1);
+    }
+    g_prof.recs.clear();
+    std::string out;
+    for (auto& a : agg) out += a.name + " " + std::to_string(a.count) + " " + std::to_string(a.ms) + " " + std::to_string(a.work) + "\n";
+    if (out.size() + 1 > len) return fail(KH_ENOMEM, "kh_profile_end: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+#endif
+    return 0;
+}

@@ -95,8 +95,11 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
+struct KhProf { long long launches; };
+static KhProf g_prof = {0};
 template <class Args, void (*Body)(const Cta&, const Args&)>
-static inline int kh_launch(dim3 grid, int /*block*/, size_t smem, kh_stream_t, const Args& a) {
+static inline int kh_launch(dim3 grid, int /*block*/, size_t smem, kh_stream_t, const Args& a, const char* = "", double = 0.0) {
+    g_prof.launches++;
     unsigned char* buf = (unsigned char*)malloc(smem + 64);
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -116,8 +119,22 @@ __global__ void kh_entry(const __grid_constant__ Args a) {
     Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
     Body(c, a);
 }
+// launch counter + optional per-kernel CUDA-event profiler (kh_profile_begin / kh_profile_end)
+#include <vector>
+struct KhProfRec { const char* name; double work; cudaEvent_t e0, e1; };
+struct KhProf {
+    long long launches;
+    bool on;
+    std::vector<KhProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+};
+static KhProf g_prof = {0, false, {}, {}};
+static inline cudaEvent_t kh_prof_event() {
+    if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
 template <class Args, void (*Body)(const Cta&, const Args&)>
-static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, const Args& a) {
+static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, const Args& a, const char* name = "", double work = 0.0) {
     if (grid.x == 0 || grid.y == 0) return 0;
     static size_t configured = 0;            // per-instantiation opt-in to > 48 KB dynamic smem
     if (smem > 48 * 1024 && smem > configured) {
@@ -125,7 +142,16 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
-    kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+    g_prof.launches++;
+    if (g_prof.on) {
+        KhProfRec r{name, work, kh_prof_event(), kh_prof_event()};
+        cudaEventRecord(r.e0, st);
+        kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+        cudaEventRecord(r.e1, st);
+        g_prof.recs.push_back(r);
+    } else {
+        kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 #define KH_ATOMIC_MAX(ptr, v) atomicMax((ptr), (v))

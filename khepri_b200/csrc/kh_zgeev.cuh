@@ -291,5 +291,5 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     a.ld_s = a.n | 1;
     a.use_smem = zgeev_smem_bytes(a.n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
     int threads = a.n <= 64 ? 128 : 256;
-    return kh_launch<zgeev_args, zgeev_body>(dim3(batch), threads, zgeev_smem_bytes(a.n, a.ld_s, a.use_smem), st, a);
+    return kh_launch<zgeev_args, zgeev_body>(dim3(batch), threads, zgeev_smem_bytes(a.n, a.ld_s, a.use_smem), st, a, "zgeev", 100.0 * a.n * a.n * a.n * batch);
 }

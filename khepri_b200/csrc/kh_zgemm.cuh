@@ -163,7 +163,7 @@ KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     int tiles = ((a.M + ZG_BM - 1) / ZG_BM) * ((a.N + ZG_BN - 1) / ZG_BN);
-    return kh_launch<zgemm_args, zgemm_body>(dim3(batch, tiles), ZG_THREADS, ZG_SMEM, st, a);
+    return kh_launch<zgemm_args, zgemm_body>(dim3(batch, tiles), ZG_THREADS, ZG_SMEM, st, a, "zgemm", 8.0 * a.M * a.N * a.K * batch);
 }
 
 // convenience builder: plain C = alpha*A*B (+ beta*Cin) on [batch, n, n] row-major stacks

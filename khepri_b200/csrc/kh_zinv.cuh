@@ -114,5 +114,5 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
     a.ld_s = n | 1;
     a.use_smem = zinv_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
     int threads = n <= 64 ? 256 : 512;
-    return kh_launch<zinv_args, zinv_body>(dim3(batch), threads, zinv_smem_bytes(n, a.ld_s, a.use_smem), st, a);
+    return kh_launch<zinv_args, zinv_body>(dim3(batch), threads, zinv_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zinv", 8.0 * n * n * n * batch);
 }

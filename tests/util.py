@@ -1,0 +1,61 @@
+"""Shared helpers for the parity tests."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+EMU_LIB = os.path.join(ROOT, "tests", "hostemu", "libkh_hostemu.so")
+
+# Every parity test runs against two builds of the SAME kernel sources through the SAME C ABI:
+#   "cuda": the product library on a B200 (marked gpu)
+#   "emu":  tests/hostemu -- the sources compiled as host C++ with one virtual thread per CTA.  Test
+#           infrastructure only: it checks the kernel logic on machines without a GPU.
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+_engines = {}
+
+
+def engine(kind):
+    if kind in _engines:
+        return _engines[kind]
+    from khepri_b200 import Engine
+    if kind == "cuda":
+        import torch
+        assert torch.cuda.is_available(), "gpu test without a CUDA device"
+        eng = Engine()
+    else:
+        srcs = [os.path.join(ROOT, "khepri_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "khepri_b200", "csrc"))]
+        if not os.path.exists(EMU_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs):
+            subprocess.run(["sh", os.path.join(ROOT, "tests", "hostemu", "build.sh")], check=True)
+        eng = Engine(device="cpu", lib_path=EMU_LIB)
+    _engines[kind] = eng
+    return eng
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def build_crystal(st, eng, fields=False):
+    from khepri_b200 import Crystal
+    cl = Crystal(st["pw"], lattice=st["lattice"], epsi=st["epsi"], epse=st["epse"], engine=eng)
+    for name, spec in st["layers"].items():
+        if spec[0] == "uniform":
+            cl.add_layer_uniform(name, spec[1], spec[2])
+        else:
+            cl.add_layer_pixmap(name, spec[1], spec[2])
+    cl.set_device(st["stack"], [fields] * len(st["stack"]))
+    return cl
+
+
+def sweep_sources(cl, srcs, **kw):
+    """Batched sweep from a list of set_source kwargs."""
+    wl = [s["wavelength"] for s in srcs]
+    te = [s.get("te", 1.0) for s in srcs]
+    tm = [s.get("tm", 1.0) for s in srcs]
+    if srcs[0].get("kp") is not None:
+        return cl.solve_batch(wl, kps=[s["kp"] for s in srcs], te=te, tm=tm, **kw)
+    return cl.solve_batch(wl, te=te, tm=tm, theta=[s.get("theta", 0.0) for s in srcs], phi=[s.get("phi", 0.0) for s in srcs], **kw)
