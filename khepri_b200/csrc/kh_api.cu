@@ -10,7 +10,6 @@
 #include "kh_zgeev.cuh"
 #include "kh_rcwa.cuh"
 #include "kh_convmat.cuh"
-#include "kh_fields.cuh"
 #include "kh_peak.cuh"
 
 #include <string>
@@ -488,6 +487,7 @@ extern "C" int kh_toeplitz_gather(const void* F, int Nx, int Ny, int P, int Q, v
 }
 
 // ---------------------------------------------------------------------------- fields (implemented in kh_fields.cuh)
+#include "kh_fields.cuh"
 #ifndef KH_FIELDS_IMPL
 extern "C" size_t kh_fields_workspace_bytes(const kh_plan*, int, int, int) { return 0; }
 extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, const double*, int,

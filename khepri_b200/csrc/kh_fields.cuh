@@ -1,3 +1,278 @@
-// Field reconstruction kernels (crystal.py:234-343, fields.py, fourier.py:136-142) -- see kh_fields_impl below.
+// Field reconstruction (khepri/crystal.py:234-343, khepri/fields.py, khepri/fourier.py:136-142).
+//
+// The reference redoes, for every z-slice, a 4N x 4N LU of the layer eigenbasis R = [[W, W], [-V, V]],
+// the mode-amplitude translation and a dense N x (nx*ny) phase matrix.  Everything that does not
+// depend on z is hoisted here:
+//   per (solve, stack position i):  c+ = (I - Sl22 Sr11)^-1 Sl21 c1p ; c- = Sr11 c+          (fields.py:18-27)
+//                                   m  = R_i^-1 R_0 [c+; c-]  using the block inverse
+//                                        R^-1 = 1/2 [[W^-1, -V^-1], [W^-1, V^-1]]
+//   per (solve, z):                 t = exp(+-lambda k0 (d - zr)) (.) m   (clipped at 1e14)      (fields.py:29-31,53-62)
+//                                   (sx,sy) = W (t1 + t2) ; (ux,uy) = V (t2 - t1) ; sz, uz      (fields.py:68-76)
+//   per solve:                      one DMMA GEMM  [6 nz x N] . [N x npts]  with the phase matrix
+//                                   exp(i (kx_g x_p + ky_g y_p))                                 (fourier.py:136-142)
+// Included at the end of kh_api.cu (needs kh_plan and the launch helpers).
 #pragma once
-#include "kh_common.cuh"
+#define KH_FIELDS_IMPL 1
+
+// y[i] = sum_j M[i][j] x[j]  (all threads of the CTA take part; caller synchronises afterwards)
+KH_DEV void cta_matvec(const Cta& c, const cd* M, long long ld, const cd* x, cd* y, int rows, int cols) {
+#ifdef KH_HOST_EMU
+    (void)c;
+    for (int i = 0; i < rows; ++i) {
+        cd acc = mk(0, 0);
+        for (int j = 0; j < cols; ++j) cfma(acc, M[i * ld + j], x[j]);
+        y[i] = acc;
+    }
+#else
+    const int warp = c.tid >> 5, lane = c.tid & 31, nw = c.nthr >> 5;
+    for (int i = warp; i < rows; i += nw) {
+        cd acc = mk(0, 0);
+        for (int j = lane; j < cols; j += 32) cfma(acc, M[i * ld + j], x[j]);
+        for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+        if (lane == 0) y[i] = acc;
+    }
+#endif
+}
+
+// c1p = first half of R_ref^-1 [e; h] = 1/2 (e - V_ref^-1 h)          (crystal.py:259-262, W_ref = I)
+struct fld_c1p_args { int B, N; cd eps; const cd* Kx; const cd* Ky; const cd* inc; cd* c1p; };
+KH_DEV void fld_c1p_body(const Cta& c, const fld_c1p_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const cd* e = a.inc + (long long)b * 2 * n;
+    const cd* h = e + n;
+    for (int g = c.tid; g < N; g += c.nthr) {
+        cd kx = a.Kx[(long long)b * N + g], ky = a.Ky[(long long)b * N + g];
+        cd lam = times_i(cconj(csqrt_(a.eps - kx * kx - ky * ky)));
+        m22 Vi = m22_inv(q_over_lam(kx, ky, a.eps, lam));
+        cd v1 = Vi.a * h[g] + Vi.b * h[N + g], v2 = Vi.c * h[g] + Vi.d * h[N + g];
+        a.c1p[(long long)b * n + g] = 0.5 * (e[g] - v1);
+        a.c1p[(long long)b * n + N + g] = 0.5 * (e[N + g] - v2);
+    }
+}
+
+// amplitudes in the gap right of stack position i and their free-space field vector y = R0 [c+; c-]
+struct fld_amp_args {
+    int B, N;
+    MatRef Finv, Sl21, Sr11;
+    const cd* c1p; const cd* Kx; const cd* Ky;
+    cd* y12;                       // [B][2][n]
+};
+KH_DEV void fld_amp_body(const Cta& c, const fld_amp_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    cd* t0 = (cd*)c.smem; cd* cp = t0 + n; cd* cm = cp + n;
+    cta_matvec(c, mat_ptr(a.Sl21, b), a.Sl21.ld, a.c1p + (long long)b * n, t0, n, n);
+    c.sync();
+    cta_matvec(c, mat_ptr(a.Finv, b), a.Finv.ld, t0, cp, n, n);
+    c.sync();
+    cta_matvec(c, mat_ptr(a.Sr11, b), a.Sr11.ld, cp, cm, n, n);
+    c.sync();
+    cd* y1 = a.y12 + (long long)b * 2 * n; cd* y2 = y1 + n;
+    for (int g = c.tid; g < N; g += c.nthr) {
+        m22 V0 = v0_block(a.Kx[(long long)b * N + g], a.Ky[(long long)b * N + g]);
+        cd d1 = cm[g] - cp[g], d2 = cm[N + g] - cp[N + g];
+        y1[g] = cp[g] + cm[g]; y1[N + g] = cp[N + g] + cm[N + g];
+        y2[g] = V0.a * d1 + V0.b * d2; y2[N + g] = V0.c * d1 + V0.d * d2;
+    }
+}
+
+// m = R_i^-1 y :  m1 = 1/2 (W^-1 y1 - V^-1 y2),  m2 = 1/2 (W^-1 y1 + V^-1 y2)
+struct fld_modes_args { int B, n; MatRef Winv, Vinv; const cd* y12; cd* m12; long long m_stride; };
+KH_DEV void fld_modes_body(const Cta& c, const fld_modes_args& a) {
+    const int n = a.n, b = c.bx;
+    cd* p = (cd*)c.smem; cd* q = p + n;
+    const cd* y1 = a.y12 + (long long)b * 2 * n;
+    cta_matvec(c, mat_ptr(a.Winv, b), a.Winv.ld, y1, p, n, n);
+    cta_matvec(c, mat_ptr(a.Vinv, b), a.Vinv.ld, y1 + n, q, n, n);
+    c.sync();
+    cd* m1 = a.m12 + (long long)b * a.m_stride; cd* m2 = m1 + n;
+    for (int i = c.tid; i < n; i += c.nthr) { m1[i] = 0.5 * (p[i] - q[i]); m2[i] = 0.5 * (p[i] + q[i]); }
+}
+
+// Fourier field vectors at one depth: out[b][z][6][N] = (sx, sy, sz, ux, uy, uz)
+struct fld_z_args {
+    int B, N, nz;
+    const int* zpos;               // [nz] stack position of each depth
+    const int* zlayer;             // [nz] layer-table index of each depth
+    const double* zdist;           // [nz] d_layer - z_relative
+    const cd* m12; long long m_bstride, m_pstride;     // [B][Ls][2][n]
+    const cd* W; const cd* V; const cd* L; long long wv_bstride; int nL;   // [B][nL][n][n], [B][nL][n]
+    const cd* const* IC;           // [nL] device pointers to N x N inverse convolution matrices (null: scalar)
+    const cd* ICs;                 // [nL] scalar 1/eps for the layers without a matrix
+    const cd* Kx; const cd* Ky; const double* k0;
+    cd* out;
+};
+KH_DEV void fld_z_body(const Cta& c, const fld_z_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx, iz = c.by;
+    const int li = a.zlayer[iz];
+    cd* ts = (cd*)c.smem; cd* td = ts + n; cd* sxy = td + n; cd* uxy = sxy + n; cd* rhs = uxy + n;
+    const cd* m1 = a.m12 + (long long)b * a.m_bstride + (long long)a.zpos[iz] * a.m_pstride;
+    const cd* m2 = m1 + n;
+    const cd* lam = a.L + ((long long)b * a.nL + li) * n;
+    const double zb = a.k0[b] * a.zdist[iz];
+    for (int i = c.tid; i < n; i += c.nthr) {
+        cd e1 = cexp_(zb * lam[i]), e2 = cexp_((-zb) * lam[i]);
+        double a1 = cabsd(e1), a2 = cabsd(e2);
+        if (a1 > 1e14) e1 = (1.0 / (a1 / 1e14)) * e1;            // fields.py:58-60
+        if (a2 > 1e14) e2 = (1.0 / (a2 / 1e14)) * e2;
+        cd t1 = e1 * m1[i], t2 = e2 * m2[i];
+        ts[i] = t1 + t2; td[i] = t2 - t1;
+    }
+    c.sync();
+    const cd* W = a.W + ((long long)b * a.nL + li) * n * n;
+    const cd* V = a.V + ((long long)b * a.nL + li) * n * n;
+    cta_matvec(c, W, n, ts, sxy, n, n);
+    cta_matvec(c, V, n, td, uxy, n, n);
+    c.sync();
+    const cd* kx = a.Kx + (long long)b * N; const cd* ky = a.Ky + (long long)b * N;
+    cd* o = a.out + ((long long)b * a.nz + iz) * 6 * N;
+    for (int g = c.tid; g < N; g += c.nthr) {
+        cd sx = sxy[g], sy = sxy[N + g], ux = uxy[g], uy = uxy[N + g];
+        o[g] = sx; o[N + g] = sy; o[3 * N + g] = ux; o[4 * N + g] = uy;
+        cd w = kx[g] * sy - ky[g] * sx;
+        o[5 * N + g] = mk(w.y, -w.x);                            // uz = -i (kx sy - ky sx)
+        rhs[g] = kx[g] * uy - ky[g] * ux;
+    }
+    c.sync();
+    const cd* ICm = a.IC[li];
+    if (ICm) {
+        cta_matvec(c, ICm, N, rhs, ts, N, N);
+        c.sync();
+        for (int g = c.tid; g < N; g += c.nthr) o[2 * N + g] = mk(ts[g].y, -ts[g].x);   // sz = -i IC rhs
+    } else {
+        cd s = a.ICs[li];
+        for (int g = c.tid; g < N; g += c.nthr) { cd w = s * rhs[g]; o[2 * N + g] = mk(w.y, -w.x); }   // -1j * IC * rhs
+    }
+}
+
+// phase matrix Ph[b][g][p] = exp(i (kx_g x_p + ky_g y_p)),  kx_g = kp_x + g_x (not normalised)
+struct fld_phase_args { int B, N, npts; const cd* kp; const double* g; const double* x; const double* y; cd* Ph; };
+KH_DEV void fld_phase_body(const Cta& c, const fld_phase_args& a) {
+    const int b = c.bx, g = c.by;
+    cd kx = mk(a.kp[2 * b].x + a.g[g], a.kp[2 * b].y), ky = mk(a.kp[2 * b + 1].x + a.g[a.N + g], a.kp[2 * b + 1].y);
+    cd* o = a.Ph + ((long long)b * a.N + g) * a.npts;
+    for (int p = c.tid; p < a.npts; p += c.nthr) {
+        cd arg = a.x[p] * kx + a.y[p] * ky;
+        o[p] = cexp_(mk(-arg.y, arg.x));
+    }
+}
+
+struct FieldBufs {
+    cd *Kx, *Ky; double* k0; cd* c1p; cd* Fm; cd* Finv; cd* y12; cd* m12; cd* Winv; cd* Vinv; cd* Sall; cd* Ph;
+    int* zpos; int* zlayer; double* zdist; const cd** ICp; cd* ICs; int* info;
+};
+static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, FieldBufs& f) {
+    const size_t N = p->N, n = p->n, n2 = n * n, nL = p->layers.size(), Ls = p->stack.size();
+    f.Kx = b.get<cd>(B * N); f.Ky = b.get<cd>(B * N); f.k0 = b.get<double>(B);
+    f.c1p = b.get<cd>(B * n); f.Fm = b.get<cd>(B * n2); f.Finv = b.get<cd>(B * n2);
+    f.y12 = b.get<cd>(B * 2 * n); f.m12 = b.get<cd>(B * Ls * 2 * n);
+    f.Winv = b.get<cd>(nL * B * n2); f.Vinv = b.get<cd>(nL * B * n2);
+    f.Sall = b.get<cd>((size_t)B * nz * 6 * N); f.Ph = b.get<cd>((size_t)B * N * npts);
+    f.zpos = b.get<int>(nz); f.zlayer = b.get<int>(nz); f.zdist = b.get<double>(nz);
+    f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * B);
+}
+
+extern "C" size_t kh_fields_workspace_bytes(const kh_plan* plan, int B, int npts, int nz) {
+    if (!plan || B < 1 || npts < 1 || nz < 1) return 0;
+    Bump b{nullptr, 0, 0};
+    FieldBufs f;
+    layout_fields(plan, B, npts, nz, b, f);
+    return b.off + 256;
+}
+
+static int kh_h2d(void* dst, const void* src, size_t bytes, kh_stream_t st) {
+#ifdef KH_HOST_EMU
+    (void)st; memcpy(dst, src, bytes); return 0;
+#else
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the host arrays are small temporaries
+    return (int)e;
+#endif
+}
+
+extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                               const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts,
+                               const double* z_host, int nz, const double* zpos_host, void* F_dev,
+                               void* ws_dev, size_t ws_bytes, void* stream) {
+    if (!plan || B < 0 || !wl_dev || !kp_dev || !inc_dev || !solved || !x_dev || !y_dev || npts < 1 || !z_host || nz < 1 || !zpos_host || !F_dev || !ws_dev)
+        return fail(KH_EINVAL, "kh_fields_batch: bad arguments");
+    if (!(solved->prefix_dev && solved->suffix_dev && solved->W_dev && solved->V_dev && solved->L_dev))
+        return fail(KH_EINVAL, "kh_fields_batch: needs the KH_WANT_FIELDS outputs of kh_solve_batch");
+    if (B == 0) return 0;
+    const kh_plan* p = plan;
+    if (p->has_ext) return fail(KH_EINVAL, "kh_fields_batch: extended layers are not supported");
+    if (p->layers[p->stack[0]].kind != KH_LAYER_HALF_INC) return fail(KH_EINVAL, "kh_fields_batch: the stack must start with the incidence half space");
+    if (ws_bytes < kh_fields_workspace_bytes(p, B, npts, nz)) return fail(KH_ENOMEM, "kh_fields_batch: workspace too small");
+    kh_stream_t st = (kh_stream_t)stream;
+    const int N = p->N, n = p->n, Ls = (int)p->stack.size(), nL = (int)p->layers.size();
+    const long long n2 = (long long)n * n;
+    Bump bump{(char*)ws_dev, ws_bytes, 0};
+    FieldBufs f;
+    layout_fields(p, B, npts, nz, bump, f);
+
+    // host: locate every depth (crystal.py:208-232) -> stack position, layer, distance to the right face
+    std::vector<int> zpos(nz), zlay(nz);
+    std::vector<double> zdist(nz);
+    std::vector<char> pos_active(Ls, 0), lay_active(nL, 0);
+    for (int k = 0; k < nz; ++k) {
+        const double z = z_host[k];
+        int idx = 0;
+        while (idx < Ls + 1 && zpos_host[idx] < z) ++idx;        // numpy.searchsorted(side='left')
+        idx -= 1;
+        if (idx < 0) idx = 0;
+        if (idx > Ls - 1) idx = Ls - 1;
+        const double zr = (z <= 0.0) ? z : z - zpos_host[idx];
+        zpos[k] = idx; zlay[k] = p->stack[idx];
+        zdist[k] = p->layers[zlay[k]].depth - zr;
+        pos_active[idx] = 1; lay_active[zlay[k]] = 1;
+    }
+    std::vector<const cd*> icp(nL, nullptr);
+    std::vector<cd> ics(nL, mk(1, 0));
+    for (int i = 0; i < nL; ++i) {
+        const kh_layer_desc& L = p->layers[i];
+        if (L.kind == KH_LAYER_PIXMAP) icp[i] = (const cd*)L.IC_dev;
+        else ics[i] = crecip(mk(L.eps_re, L.eps_im));
+    }
+    KH_TRY(kh_h2d(f.zpos, zpos.data(), nz * sizeof(int), st));
+    KH_TRY(kh_h2d(f.zlayer, zlay.data(), nz * sizeof(int), st));
+    KH_TRY(kh_h2d(f.zdist, zdist.data(), nz * sizeof(double), st));
+    KH_TRY(kh_h2d(f.ICp, icp.data(), nL * sizeof(cd*), st));
+    KH_TRY(kh_h2d(f.ICs, ics.data(), nL * sizeof(cd), st));
+
+    {   kvec_args a{B, N, wl_dev, (const cd*)kp_dev, p->g_dev, f.Kx, f.Ky, f.k0};
+        KH_TRY((kh_launch<kvec_args, kvec_body>(dim3(B), 128, 0, st, a))); }
+    {   const kh_layer_desc& R = p->layers[p->stack[0]];
+        fld_c1p_args a{B, N, mk(R.eps_re, R.eps_im), f.Kx, f.Ky, (const cd*)inc_dev, f.c1p};
+        KH_TRY((kh_launch<fld_c1p_args, fld_c1p_body>(dim3(B), 128, 0, st, a))); }
+
+    cd* Wd = (cd*)solved->W_dev; cd* Vd = (cd*)solved->V_dev;
+    for (int li = 0; li < nL; ++li) {
+        if (!lay_active[li]) continue;
+        KH_TRY(zinv_launch(st, B, n, mref(Wd + (long long)li * n2, (long long)nL * n2, n), mref(f.Winv + (long long)li * B * n2, n2, n), f.info));
+        KH_TRY(zinv_launch(st, B, n, mref(Vd + (long long)li * n2, (long long)nL * n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.info + B));
+    }
+    cd* pre = (cd*)solved->prefix_dev; cd* suf = (cd*)solved->suffix_dev;
+    const long long sstride = (long long)Ls * 4 * n2;
+    for (int i = 0; i < Ls; ++i) {
+        if (!pos_active[i]) continue;
+        MatRef Sl22 = mref(pre + ((long long)i * 4 + 3) * n2, sstride, n), Sl21 = mref(pre + ((long long)i * 4 + 2) * n2, sstride, n);
+        MatRef Sr11 = mref(suf + ((long long)i * 4 + 0) * n2, sstride, n);
+        MatRef Fm = mref(f.Fm, n2, n), Fi = mref(f.Finv, n2, n);
+        KH_TRY(gemm(st, B, n, Sl22, Sr11, Fm, -1.0, nullptr, 0.0, 1.0));
+        KH_TRY(zinv_launch(st, B, n, Fm, Fi, f.info));
+        {   fld_amp_args a{B, N, Fi, Sl21, Sr11, f.c1p, f.Kx, f.Ky, f.y12};
+            KH_TRY((kh_launch<fld_amp_args, fld_amp_body>(dim3(B), 256, (size_t)3 * n * sizeof(cd), st, a))); }
+        const int li = p->stack[i];
+        {   fld_modes_args a{B, n, mref(f.Winv + (long long)li * B * n2, n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.y12,
+                             f.m12 + (long long)i * 2 * n, (long long)Ls * 2 * n};
+            KH_TRY((kh_launch<fld_modes_args, fld_modes_body>(dim3(B), 256, (size_t)2 * n * sizeof(cd), st, a))); }
+    }
+    {   fld_z_args a{B, N, nz, f.zpos, f.zlayer, f.zdist, f.m12, (long long)Ls * 2 * n, 2LL * n,
+                     Wd, Vd, (const cd*)solved->L_dev, (long long)nL * n2, nL, f.ICp, f.ICs, f.Kx, f.Ky, f.k0, f.Sall};
+        KH_TRY((kh_launch<fld_z_args, fld_z_body>(dim3(B, nz), 256, (size_t)5 * n * sizeof(cd), st, a))); }
+    {   fld_phase_args a{B, N, npts, (const cd*)kp_dev, p->g_dev, x_dev, y_dev, f.Ph};
+        KH_TRY((kh_launch<fld_phase_args, fld_phase_body>(dim3(B, N), 256, 0, st, a))); }
+    {   zgemm_args g = zgemm_make(6 * nz, npts, N, mref(f.Sall, (long long)nz * 6 * N, N), mref(f.Ph, (long long)N * npts, npts),
+                                  mref(F_dev, (long long)nz * 6 * npts, npts));
+        KH_TRY(zgemm_launch(st, B, g)); }
+    return 0;
+}

@@ -288,8 +288,9 @@ class Engine:
               "kh_flux_batch")
         return (RT, orders) if want_orders else RT
 
-    def fields(self, plan, solved, wl, kp, inc, x, y, z):
-        """E, H [B, nz, 3, ny, nx] from a want_fields solve.  inc [B, 2, n] = incident (E, H) Fourier vectors."""
+    def fields(self, plan, solved, wl, kp, inc, x, y, z, stack_positions):
+        """(Ex,Ey,Ez,Hx,Hy,Hz) at points (x[p], y[p]) and depths z for every solve of a want_fields
+        solve -> DEVICE tensor [B, nz, 6, npts].  inc [B, 2, n] = incident (E, H) Fourier vectors."""
         B = solved["prefix"].shape[0]
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
         kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
@@ -297,16 +298,18 @@ class Engine:
         x_d = self.to_dev(np.asarray(x, dtype=np.float64).reshape(-1), _f64)
         y_d = self.to_dev(np.asarray(y, dtype=np.float64).reshape(-1), _f64)
         z_h = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(-1))
-        nx, ny, nz = x_d.numel(), y_d.numel(), z_h.size
-        E = torch.empty((B, nz, 3, ny, nx), dtype=_c128, device=self.device)
-        H = torch.empty((B, nz, 3, ny, nx), dtype=_c128, device=self.device)
+        zp_h = np.ascontiguousarray(np.asarray(stack_positions, dtype=np.float64).reshape(-1))
+        assert zp_h.size == plan.Ls + 1, "stack_positions must hold Ls+1 interface positions"
+        npts, nz = x_d.numel(), z_h.size
+        assert y_d.numel() == npts
+        F = torch.empty((B, nz, 6, npts), dtype=_c128, device=self.device)
         out = Outputs()
-        out.Stot_dev = solved["Stot"].data_ptr()
         out.prefix_dev, out.suffix_dev = solved["prefix"].data_ptr(), solved["suffix"].data_ptr()
         out.W_dev, out.V_dev, out.L_dev = solved["W"].data_ptr(), solved["V"].data_ptr(), solved["L"].data_ptr()
-        wb = self.lib.kh_fields_workspace_bytes(plan.handle, B, nx, ny, nz)
+        wb = self.lib.kh_fields_workspace_bytes(plan.handle, B, npts, nz)
         ws = self.workspace(wb)
-        check(self.lib, self.lib.kh_fields_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out), _ptr(x_d), nx, _ptr(y_d), ny,
-                                                 z_h.ctypes.data_as(C.POINTER(C.c_double)), nz, _ptr(E), _ptr(H), _ptr(ws), ws.numel(), self.stream()),
+        dp = C.POINTER(C.c_double)
+        check(self.lib, self.lib.kh_fields_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out), _ptr(x_d), _ptr(y_d), npts,
+                                                 z_h.ctypes.data_as(dp), nz, zp_h.ctypes.data_as(dp), _ptr(F), _ptr(ws), ws.numel(), self.stream()),
               "kh_fields_batch")
-        return E, H
+        return F
