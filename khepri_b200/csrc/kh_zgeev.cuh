@@ -1,24 +1,30 @@
 // Batched non-Hermitian complex128 eigensolver, one CTA per matrix (replaces numpy.linalg.eig /
 // LAPACK zgeev at khepri/alternative.py:172 for the Omega^2 = P Q problem of every patterned layer).
 //
-// Pipeline (all inside one kernel, matrix resident in shared memory when n <= ~118):
-//   1. diagonal balancing with powers of two (exact similarity, as zgebal 'S')
-//   2. Householder reduction to upper Hessenberg form, Schur vectors accumulated (Zt = Z^T in HBM,
-//      so that every column operation on Z is a coalesced row operation on Zt)
-//   3. single-shift QR iteration with Wilkinson / exceptional shifts and LAPACK's (zlahqr)
-//      deflation test, Givens rotations applied to full rows/columns (Schur form T is needed)
-//   4. eigenvectors of T by back substitution (as ztrevc), one thread per eigenvector
+// Three kernels per batch (each phase gets its own launch shape and shows up separately in ncu):
+//   zhess : diagonal balancing with powers of two (exact similarity, as zgebal 'S') and Householder
+//           reduction to upper Hessenberg form with the Schur vectors accumulated.  Z is kept
+//           TRANSPOSED in HBM/L2 (Zt) so every column operation on Z is a coalesced row operation.
+//   zqr   : single-shift QR iteration (Wilkinson / exceptional shifts, LAPACK zlahqr deflation test).
+//           The Hessenberg matrix lives in shared memory in PACKED form (row i holds columns >= i-1),
+//           79 KB at n = 98, so two CTAs share an SM.  Inside a sweep only the active window is
+//           touched, with ONE barrier per Givens rotation: the column step of rotation k and the row
+//           step of rotation k+1 touch disjoint entries except for a 2x2 corner that every thread
+//           carries in registers.  The rotations of a sweep are stored and then applied in one pass
+//           to the rows above / columns right of the window and to Z (coalesced, no barriers).
+//   ztrevc: eigenvectors of the triangular factor by back substitution (as ztrevc), one thread per
+//           eigenvector, lock-step so T is broadcast and X is accessed coalesced.
 // The caller finishes with one DMMA GEMM:  W = diag(scale) * Z * X.
-// Eigenvalue order / eigenvector scaling are free (SURVEY.md §8c): parity is on physical outputs.
+// Eigenvalue order / eigenvector scaling are free (SURVEY.md 8c): parity is on physical outputs.
 #pragma once
 #include "kh_common.cuh"
 
 struct zgeev_args {
     int n;
-    MatRef A;          // input (not modified unless it aliases Hw)
-    MatRef Hw;         // n x n work matrix in global memory (used when the matrix does not fit in smem)
+    MatRef A;          // input (only read by zhess; may alias Hw)
+    MatRef Hw;         // n x n work matrix in global memory: Hessenberg form, then the triangular factor T
     MatRef Zt;         // out: transposed Schur vectors
-    MatRef X;          // out: eigenvectors of the triangular factor (upper triangular, unit diagonal before normalisation)
+    MatRef X;          // out: eigenvectors of T (upper triangular)
     cd* w; long long w_stride;          // out: eigenvalues
     cd* scale; long long scale_stride;  // out: balancing factors as complex (imag 0)
     int* info;         // out: 0 ok, >0 = QR iteration failed to converge at that index+1
@@ -47,35 +53,31 @@ KH_DEV kh_givens make_givens(cd f, cd g) {
     return G;
 }
 
-KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
+// ============================================================================ 1. balance + Hessenberg
+KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     const int n = a.n, b = c.bx;
     const cd* A = mat_ptr(a.A, b);
+    cd* Hg = mat_ptr(a.Hw, b);
     cd* Zt = mat_ptr(a.Zt, b);
-    cd* X = mat_ptr(a.X, b);
-    const int ldz = a.Zt.ld, ldx = a.X.ld;
-    cd* wout = a.w + (long long)b * a.w_stride;
+    const int ldz = a.Zt.ld;
     cd* scout = a.scale + (long long)b * a.scale_stride;
-
-    // shared: [vv n][uu n][scratch 128 dbl (+64 int)][dsc n dbl][ctl 8 int][H]
+    // shared: [vv n][uu n][scratch 192 dbl][dsc n dbl][H]
     cd* vv = (cd*)c.smem;
     cd* uu = vv + n;
     double* scratch = (double*)(uu + n);
-    double* dsc = scratch + 128;
-    int* ctl = (int*)(dsc + n);
+    double* dsc = scratch + 192;
     cd* H; int ld;
-    if (a.use_smem) { H = (cd*)(((uintptr_t)(ctl + 8) + 15) & ~(uintptr_t)15); ld = a.ld_s; }
-    else { H = mat_ptr(a.Hw, b); ld = a.Hw.ld; }
+    if (a.use_smem) { H = (cd*)(((uintptr_t)(dsc + n) + 15) & ~(uintptr_t)15); ld = a.ld_s; }
+    else { H = Hg; ld = a.Hw.ld; }
 #define HH(i, j) H[(long long)(i) * ld + (j)]
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
-#define XX(i, j) X[(long long)(i) * ldx + (j)]
-
     if (a.use_smem || H != A)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; HH(i, j) = A[(long long)i * a.A.ld + j]; }
     for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; ZT(i, j) = mk(i == j ? 1.0 : 0.0, 0.0); }
     for (int i = c.tid; i < n; i += c.nthr) dsc[i] = 1.0;
     c.sync();
 
-    // ---------------------------------------------------------------- 1. balancing
+    // ---- balancing (Jacobi-style sweeps of the EISPACK balanc criterion; powers of two, so exact)
     for (int sweep = 0; sweep < 12; ++sweep) {
         double changed = 0.0;
         for (int i = c.tid; i < n; i += c.nthr) {
@@ -105,7 +107,7 @@ KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
     }
     for (int i = c.tid; i < n; i += c.nthr) scout[i] = mk(dsc[i], 0.0);
 
-    // ---------------------------------------------------------------- 2. Hessenberg reduction
+    // ---- Householder reduction (zgehd2 / zlarfg conventions: H_k = I - tau v v^H, A <- H_k^H A H_k)
     for (int k = 0; k + 2 < n; ++k) {
         double part = 0.0;
         for (int i = k + 2 + c.tid; i < n; i += c.nthr) part += cabs2(HH(i, k));
@@ -153,29 +155,58 @@ KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
         c.sync();
     }
 
-    // ---------------------------------------------------------------- 3. shifted QR iteration
+    if (a.use_smem)
+        for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * a.Hw.ld + j] = HH(i, j); }
+#undef HH
+#undef ZT
+}
+
+// ============================================================================ 2. shifted QR on the packed Hessenberg matrix
+// packed row-major upper Hessenberg: row i holds columns max(i-1,0) .. n-1; HQ(i,j) = Hp[hp_off(i) + j]
+KH_HD int hp_off(int i, int n) { return i * n - ((i - 1) * i) / 2; }
+KH_HD int hp_size(int n) { return hp_off(n - 1, n) + n + 3; }
+
+template <bool PACKED>
+KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
+    const int n = a.n, b = c.bx;
+    cd* Hg = mat_ptr(a.Hw, b);
+    cd* Zt = mat_ptr(a.Zt, b);
+    const int ldz = a.Zt.ld, ldg = a.Hw.ld;
+    cd* wout = a.w + (long long)b * a.w_stride;
+    // shared: [gs n cd][gc n dbl][ctl 8 int][packed H]  (H stays in global memory, full storage, when it does not fit)
+    cd* gs = (cd*)c.smem;
+    double* gc = (double*)(gs + n);
+    int* ctl = (int*)(gc + n);
+    cd* Hp = (cd*)(((uintptr_t)(ctl + 8) + 15) & ~(uintptr_t)15);
+    const bool packed = PACKED;
+#define HQ(i, j) (*(PACKED ? (Hp + hp_off((i), n) + (j)) : (Hg + (long long)(i) * ldg + (j))))
+#define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
+    if (packed)
+        for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; if (j >= i - 1) HQ(i, j) = Hg[(long long)i * ldg + j]; }
+    c.sync();
+
     const double smlnum = ZGEEV_SAFMIN * ((double)n / ZGEEV_EPS);
     const int itmax = 30 * (n > 10 ? n : 10);
     int fail = 0;
     int iact = n - 1, its = 0;
     while (iact >= 0) {
-        // locate the active block [l, iact]
+        // ---- locate the active block [l, iact] (zlahqr deflation criterion)
         if (c.tid == 0) ctl[0] = 0;
         c.sync();
         for (int k = iact - c.tid; k >= 1; k -= c.nthr) {
-            cd hs = HH(k, k - 1);
+            cd hs = HQ(k, k - 1);
             bool negl = false;
             if (cabs1(hs) <= smlnum) negl = true;
             else {
-                double tst = cabs1(HH(k - 1, k - 1)) + cabs1(HH(k, k));
+                double tst = cabs1(HQ(k - 1, k - 1)) + cabs1(HQ(k, k));
                 if (tst == 0.0) {
-                    if (k - 2 >= 0) tst += cabs1(HH(k - 1, k - 2));
-                    if (k + 1 <= n - 1) tst += cabs1(HH(k + 1, k));
+                    if (k - 2 >= 0) tst += cabs1(HQ(k - 1, k - 2));
+                    if (k + 1 <= n - 1) tst += cabs1(HQ(k + 1, k));
                 }
                 if (cabs1(hs) <= ZGEEV_EPS * tst) {
-                    double h12 = cabs1(HH(k - 1, k)), h21 = cabs1(hs);
+                    double h12 = cabs1(HQ(k - 1, k)), h21 = cabs1(hs);
                     double ab = fmax(h21, h12), ba = fmin(h21, h12);
-                    double d1 = cabs1(HH(k, k)), d2 = cabs1(HH(k - 1, k - 1) - HH(k, k));
+                    double d1 = cabs1(HQ(k, k)), d2 = cabs1(HQ(k - 1, k - 1) - HQ(k, k));
                     double aa = fmax(d1, d2), bb = fmin(d1, d2);
                     double s = aa + ab;
                     if (ba * (ab / s) <= fmax(smlnum, ZGEEV_EPS * (bb * (aa / s)))) negl = true;
@@ -186,25 +217,25 @@ KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
         c.sync();
         const int l = ctl[0];
         c.sync();
-        if (l > 0 && c.tid == 0) HH(l, l - 1) = mk(0.0, 0.0);
+        if (l > 0 && c.tid == 0) HQ(l, l - 1) = mk(0.0, 0.0);
         if (l >= iact) {                       // one eigenvalue converged
-            if (c.tid == 0) wout[iact] = HH(iact, iact);
+            if (c.tid == 0) wout[iact] = HQ(iact, iact);
             iact -= 1; its = 0;
             c.sync();
             continue;
         }
         its += 1;
         if (its > itmax) { fail = iact + 1; break; }
-        // shift
+        // ---- shift (zlahqr)
         cd t;
-        if (its % 10 == 0 && (its / 10) % 2 == 1) t = HH(l, l) + mk(0.75 * cabs1(HH(l + 1, l)), 0.0);
-        else if (its % 10 == 0) t = HH(iact, iact) + mk(0.75 * cabs1(HH(iact, iact - 1)), 0.0);
+        if (its % 10 == 0 && (its / 10) % 2 == 1) t = HQ(l, l) + mk(0.75 * cabs1(HQ(l + 1, l)), 0.0);
+        else if (its % 10 == 0) t = HQ(iact, iact) + mk(0.75 * cabs1(HQ(iact, iact - 1)), 0.0);
         else {
-            t = HH(iact, iact);
-            cd u = csqrt_(HH(iact - 1, iact)) * csqrt_(HH(iact, iact - 1));
+            t = HQ(iact, iact);
+            cd u = csqrt_(HQ(iact - 1, iact)) * csqrt_(HQ(iact, iact - 1));
             double s = cabs1(u);
             if (s != 0.0) {
-                cd x = 0.5 * (HH(iact - 1, iact - 1) - t);
+                cd x = 0.5 * (HQ(iact - 1, iact - 1) - t);
                 double sx = cabs1(x);
                 s = fmax(s, sx);
                 cd xs = (1.0 / s) * x, us = (1.0 / s) * u;
@@ -216,57 +247,129 @@ KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
                 t = t - u * (u / (x + y));
             }
         }
-        cd f = HH(l, l) - t, g = HH(l + 1, l);
-        c.sync();   // all threads have read H before the sweep starts writing
-        // one implicit single-shift QR sweep over the active block (two barriers per rotation)
+        // ---- one implicit single-shift sweep over the window [l, iact], one barrier per rotation.
+        // R(k): rows k,k+1 <- G_k (window columns);  C(k): columns k,k+1 <- . G_k^H (window rows <= k+2).
+        kh_givens G = make_givens(HQ(l, l) - t, HQ(l + 1, l));
+        c.sync();                                   // everyone has read H before the sweep writes
+        for (int j = l + c.tid; j <= iact; j += c.nthr) {          // R(l)
+            cd h0 = HQ(l, j), h1 = HQ(l + 1, j);
+            HQ(l, j) = G.c * h0 + G.s * h1;
+            HQ(l + 1, j) = G.c * h1 - cconj(G.s) * h0;
+        }
+        if (c.tid == 0) { gc[l] = G.c; gs[l] = G.s; }
+        c.sync();
+        // register-carried corner state: sub = H[k+1][k] after R(k); pend_* = entries of row k (its
+        // sub-diagonal and diagonal after R(k)) that are known to every thread but not stored yet
+        cd sub = HQ(l + 1, l);
+        cd pend_sub = mk(0, 0), pend_diag = mk(0, 0);
         for (int k = l; k < iact; ++k) {
-            kh_givens G = make_givens(f, g);
-            // rows k, k+1 over columns k..n-1
-            for (int j = k + c.tid; j < n; j += c.nthr) {
-                cd h0 = HH(k, j), h1 = HH(k + 1, j);
-                HH(k, j) = G.c * h0 + G.s * h1;
-                HH(k + 1, j) = G.c * h1 - cconj(G.s) * h0;
+            const bool more = (k + 1 < iact);
+            const cd cb = HQ(k + 1, k + 1);
+            const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;     // C(k) on row k+1
+            kh_givens Gn; Gn.c = 1.0; Gn.s = mk(0, 0); Gn.r = a1;
+            cd newdiag = b1, nextsub = mk(0, 0);
+            if (more) {
+                const cd hd = HQ(k + 2, k + 1);             // H[k+2][k] is zero: C(k) creates the bulge there
+                const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;
+                Gn = make_givens(a1, c1);                   // G(k+1) annihilates the bulge
+                newdiag = Gn.c * b1 + Gn.s * d1;            // H[k+1][k+1] after R(k+1)
+                nextsub = Gn.c * d1 - cconj(Gn.s) * b1;     // H[k+2][k+1] after R(k+1)
             }
-            c.sync();
-            // columns k, k+1 over rows 0..min(k+2, iact); the same columns of Z; bulge bookkeeping
-            if (k > l && c.tid == 0) { HH(k, k - 1) = G.r; HH(k + 1, k - 1) = mk(0.0, 0.0); }
-            const int rmax = (k + 2 < iact) ? k + 2 : iact;
-            for (int r = c.tid; r < 2 * n; r += c.nthr) {
-                if (r < n) {
-                    if (r <= rmax) {
-                        cd h0 = HH(r, k), h1 = HH(r, k + 1);
-                        HH(r, k) = G.c * h0 + cconj(G.s) * h1;
-                        HH(r, k + 1) = G.c * h1 - G.s * h0;
-                    }
+            // M(k) = C(k) on rows l..k  ||  R(k+1) on columns k+2..iact   (disjoint entries)
+            const int nC = k - l + 1, nR = more ? iact - k - 1 : 0;
+            for (int t2 = c.tid; t2 < nC + nR; t2 += c.nthr) {
+                if (t2 < nC) {
+                    const int r = l + t2;
+                    cd h0 = HQ(r, k), h1 = HQ(r, k + 1);
+                    if (r == k && k > l) { h0 = pend_diag; HQ(k, k - 1) = pend_sub; }   // row k: stored now, nobody reads it earlier
+                    HQ(r, k) = G.c * h0 + cconj(G.s) * h1;
+                    HQ(r, k + 1) = G.c * h1 - G.s * h0;
                 } else {
-                    int i = r - n;
-                    cd z0 = ZT(k, i), z1 = ZT(k + 1, i);
-                    ZT(k, i) = G.c * z0 + cconj(G.s) * z1;
-                    ZT(k + 1, i) = G.c * z1 - G.s * z0;
+                    const int j = k + 2 + (t2 - nC);
+                    cd h0 = HQ(k + 1, j), h1 = HQ(k + 2, j);
+                    HQ(k + 1, j) = Gn.c * h0 + Gn.s * h1;
+                    HQ(k + 2, j) = Gn.c * h1 - cconj(Gn.s) * h0;
                 }
             }
+            if (more && c.tid == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; }
+            pend_sub = Gn.r; pend_diag = newdiag; sub = nextsub; G = Gn;
             c.sync();
-            if (k + 1 < iact) { f = HH(k + 1, k); g = HH(k + 2, k); }   // the bulge for the next rotation
         }
+        if (c.tid == 0) { HQ(iact, iact - 1) = pend_sub; HQ(iact, iact) = pend_diag; }
+        // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
+        {
+            const int nAbove = l, nRight = n - 1 - iact;
+            for (int t2 = c.tid; t2 < nAbove + nRight + n; t2 += c.nthr) {
+                if (t2 < nAbove) {                                  // rows above the window: column rotations
+                    const int r = t2;
+                    cd h0 = HQ(r, l);
+                    for (int k = l; k < iact; ++k) {
+                        cd h1 = HQ(r, k + 1);
+                        HQ(r, k) = gc[k] * h0 + cconj(gs[k]) * h1;
+                        h0 = gc[k] * h1 - gs[k] * h0;
+                    }
+                    HQ(r, iact) = h0;
+                } else if (t2 < nAbove + nRight) {                  // columns right of the window: row rotations
+                    const int j = iact + 1 + (t2 - nAbove);
+                    cd h0 = HQ(l, j);
+                    for (int k = l; k < iact; ++k) {
+                        cd h1 = HQ(k + 1, j);
+                        HQ(k, j) = gc[k] * h0 + gs[k] * h1;
+                        h0 = gc[k] * h1 - cconj(gs[k]) * h0;
+                    }
+                    HQ(iact, j) = h0;
+                } else {                                            // Z columns l..iact (rows of Zt), coalesced over i
+                    const int i = t2 - nAbove - nRight;
+                    cd z0 = ZT(l, i);
+                    for (int k = l; k < iact; ++k) {
+                        cd z1 = ZT(k + 1, i);
+                        ZT(k, i) = gc[k] * z0 + cconj(gs[k]) * z1;
+                        z0 = gc[k] * z1 - gs[k] * z0;
+                    }
+                    ZT(iact, i) = z0;
+                }
+            }
+        }
+        c.sync();
     }
     c.sync();
+    if (packed)
+        for (int e = c.tid; e < n * n; e += c.nthr) {
+            int i = e / n, j = e - i * n;
+            Hg[(long long)i * ldg + j] = (j >= i) ? HQ(i, j) : mk(0.0, 0.0);
+        }
+    if (a.info && c.tid == 0) a.info[b] = fail;
+#undef HQ
+#undef ZT
+}
 
-    // ---------------------------------------------------------------- 4. eigenvectors of T
+KH_DEV void zqr_packed_body(const Cta& c, const zgeev_args& a) { zqr_body_t<true>(c, a); }
+KH_DEV void zqr_global_body(const Cta& c, const zgeev_args& a) { zqr_body_t<false>(c, a); }
+
+// ============================================================================ 3. eigenvectors of the triangular factor
+KH_DEV void ztrevc_body(const Cta& c, const zgeev_args& a) {
+    const int n = a.n, b = c.bx;
+    const cd* T = mat_ptr(a.Hw, b);
+    cd* X = mat_ptr(a.X, b);
+    const int ldt = a.Hw.ld, ldx = a.X.ld;
+    const double smlnum = ZGEEV_SAFMIN * ((double)n / ZGEEV_EPS);
+#define TT(i, j) T[(long long)(i) * ldt + (j)]
+#define XX(i, j) X[(long long)(i) * ldx + (j)]
     for (int e = c.tid; e < n * n; e += c.nthr) {
         int i = e / n, k = e - i * n;
-        XX(i, k) = (i < k) ? -HH(i, k) : mk(i == k ? 1.0 : 0.0, 0.0);
+        XX(i, k) = (i < k) ? -TT(i, k) : mk(i == k ? 1.0 : 0.0, 0.0);
     }
     c.sync();
     for (int k = c.tid; k < n; k += c.nthr) {
-        cd tkk = HH(k, k);
+        cd tkk = TT(k, k);
         double smin = fmax(ZGEEV_EPS * cabs1(tkk), smlnum);
         for (int j = n - 2; j >= 0; --j) {
             if (j < k) {
-                cd d = HH(j, j) - tkk;
+                cd d = TT(j, j) - tkk;
                 if (cabs1(d) < smin) d = mk(smin, 0.0);
                 cd xj = XX(j, k) / d;
                 XX(j, k) = xj;
-                for (int i = 0; i < j; ++i) { cd v = XX(i, k); cfms(v, xj, HH(i, j)); XX(i, k) = v; }
+                for (int i = 0; i < j; ++i) { cd v = XX(i, k); cfms(v, xj, TT(i, j)); XX(i, k) = v; }
             }
         }
         double emax = 0.0;
@@ -274,22 +377,33 @@ KH_DEV void zgeev_body(const Cta& c, const zgeev_args& a) {
         double r = 1.0 / emax;
         for (int i = 0; i <= k; ++i) XX(i, k) = r * XX(i, k);
     }
-    if (a.info && c.tid == 0) a.info[b] = fail;
-#undef HH
-#undef ZT
+#undef TT
 #undef XX
 }
 
-static inline size_t zgeev_smem_bytes(int n, int ld_s, int use_smem) {
-    size_t s = (size_t)2 * n * sizeof(cd) + 128 * sizeof(double) + (size_t)n * sizeof(double) + 8 * sizeof(int) + 16;
+static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
+    size_t s = (size_t)2 * n * sizeof(cd) + 192 * sizeof(double) + (size_t)n * sizeof(double) + 16;
     if (use_smem) s += (size_t)n * ld_s * sizeof(cd);
+    return s;
+}
+static inline size_t zqr_smem_bytes(int n, int use_smem) {
+    size_t s = (size_t)n * sizeof(cd) + (size_t)n * sizeof(double) + 8 * sizeof(int) + 16;
+    if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
     return s;
 }
 
 static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     if (batch <= 0 || a.n <= 0) return 0;
-    a.ld_s = a.n | 1;
-    a.use_smem = zgeev_smem_bytes(a.n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
-    int threads = a.n <= 64 ? 128 : 256;
-    return kh_launch<zgeev_args, zgeev_body>(dim3(batch), threads, zgeev_smem_bytes(a.n, a.ld_s, a.use_smem), st, a, "zgeev", 100.0 * a.n * a.n * a.n * batch);
+    const int n = a.n;
+    const double work = 100.0 * n * n * n * batch;          // nominal zgeev count, SURVEY.md 8(d)
+    a.ld_s = n | 1;
+    a.use_smem = zhess_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
+    int e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 64 ? 128 : 256, zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
+    if (e) return e;
+    zgeev_args q = a;
+    q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
+    if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body>(dim3(batch), n <= 126 ? 128 : 256, zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
+    else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
+    if (e) return e;
+    return kh_launch<zgeev_args, ztrevc_body>(dim3(batch), n <= 128 ? 128 : 256, 0, st, a, "zgeev_trevc", 0.25 * work);
 }
