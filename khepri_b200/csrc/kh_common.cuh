@@ -78,6 +78,14 @@ KH_HD cd cexp_(cd z) {
     return mk(e * c, e * s);
 }
 
+KH_HD double kh_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // ------------------------------------------------------------------ CTA context
 struct Cta {
     int tid, nthr;           // thread index / threads per CTA
@@ -97,7 +105,8 @@ struct dim3 {
 };
 struct KhProf { long long launches; };
 static KhProf g_prof = {0};
-template <class Args, void (*Body)(const Cta&, const Args&)>
+#define KH_SMEM(c) ((c).smem)
+template <class Args, void (*Body)(const Cta&, const Args&), int MAXT = 0, int MINB = 1>
 static inline int kh_launch(dim3 grid, int /*block*/, size_t smem, kh_stream_t, const Args& a, const char* = "", double = 0.0) {
     g_prof.launches++;
     unsigned char* buf = (unsigned char*)malloc(smem + 64);
@@ -113,9 +122,16 @@ static inline int kh_launch(dim3 grid, int /*block*/, size_t smem, kh_stream_t, 
 #define KH_ATOMIC_MAX(ptr, v) (*(ptr) = std::max(*(ptr), (v)))
 #define KH_ATOMIC_OR(ptr, v) (*(ptr) |= (v))
 #else
+extern __shared__ __align__(16) unsigned char kh_smem[];
+// KH_SMEM(c): dynamic shared memory with its address space known to the compiler (LDS/STS, not generic LD/ST)
+#define KH_SMEM(c) kh_smem
 template <class Args, void (*Body)(const Cta&, const Args&)>
 __global__ void kh_entry(const __grid_constant__ Args a) {
-    extern __shared__ __align__(16) unsigned char kh_smem[];
+    Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
+    Body(c, a);
+}
+template <class Args, void (*Body)(const Cta&, const Args&), int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) kh_entry_lb(const __grid_constant__ Args a) {
     Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
     Body(c, a);
 }
@@ -133,12 +149,15 @@ static inline cudaEvent_t kh_prof_event() {
     if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-template <class Args, void (*Body)(const Cta&, const Args&)>
+template <class Args, void (*Body)(const Cta&, const Args&), int MAXT = 0, int MINB = 1>
 static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, const Args& a, const char* name = "", double work = 0.0) {
     if (grid.x == 0 || grid.y == 0) return 0;
+    void (*kern)(const Args);
+    if constexpr (MAXT == 0) kern = kh_entry<Args, Body>;           // no launch bounds
+    else kern = kh_entry_lb<Args, Body, MAXT, MINB>;
     static size_t configured = 0;            // per-instantiation opt-in to > 48 KB dynamic smem
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kh_entry<Args, Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
@@ -146,11 +165,11 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
     if (g_prof.on) {
         KhProfRec r{name, work, kh_prof_event(), kh_prof_event()};
         cudaEventRecord(r.e0, st);
-        kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+        kern<<<grid, block, smem, st>>>(a);
         cudaEventRecord(r.e1, st);
         g_prof.recs.push_back(r);
     } else {
-        kh_entry<Args, Body><<<grid, block, smem, st>>>(a);
+        kern<<<grid, block, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
 }

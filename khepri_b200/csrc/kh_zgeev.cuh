@@ -36,20 +36,21 @@ struct zgeev_args {
 
 struct kh_givens { double c; cd s, r; };
 KH_DEV kh_givens make_givens(cd f, cd g) {
+    // G = [[c, s], [-conj(s), c]],  G [f; g] = [r; 0];  c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = sqrt(|f|^2+|g|^2).
+    // Two reciprocal square roots and no division: the rotation sits on the critical path of the sweep.
     kh_givens G;
-    double g2 = cabs2(g);
+    const double g2 = cabs2(g), f2 = cabs2(f);
     if (g2 == 0.0) { G.c = 1.0; G.s = mk(0, 0); G.r = f; return G; }
-    double f2 = cabs2(f);
     if (f2 == 0.0) {
-        double ga = sqrt(g2);
-        G.c = 0.0; G.s = (1.0 / ga) * cconj(g); G.r = mk(ga, 0);
+        const double ig = kh_rsqrt(g2);
+        G.c = 0.0; G.s = ig * cconj(g); G.r = mk(g2 * ig, 0);
         return G;
     }
-    double f1 = sqrt(f2), nrm = sqrt(f2 + g2);
-    cd fu = (1.0 / f1) * f;
-    G.c = f1 / nrm;
-    G.s = (1.0 / nrm) * (fu * cconj(g));
-    G.r = nrm * fu;
+    const double h2 = f2 + g2;
+    const double p = kh_rsqrt(f2), q = kh_rsqrt(h2), pq = p * q;
+    G.c = f2 * pq;
+    G.s = pq * (f * cconj(g));
+    G.r = (p * (h2 * q)) * f;
     return G;
 }
 
@@ -62,7 +63,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     const int ldz = a.Zt.ld;
     cd* scout = a.scale + (long long)b * a.scale_stride;
     // shared: [vv n][uu n][scratch 192 dbl][dsc n dbl][H]
-    cd* vv = (cd*)c.smem;
+    cd* vv = (cd*)KH_SMEM(c);
     cd* uu = vv + n;
     double* scratch = (double*)(uu + n);
     double* dsc = scratch + 192;
@@ -174,7 +175,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int ldz = a.Zt.ld, ldg = a.Hw.ld;
     cd* wout = a.w + (long long)b * a.w_stride;
     // shared: [gs n cd][gc n dbl][ctl 8 int][packed H]  (H stays in global memory, full storage, when it does not fit)
-    cd* gs = (cd*)c.smem;
+    cd* gs = (cd*)KH_SMEM(c);
     double* gc = (double*)(gs + n);
     int* ctl = (int*)(gc + n);
     cd* Hp = (cd*)(((uintptr_t)(ctl + 8) + 15) & ~(uintptr_t)15);
@@ -321,7 +322,19 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 } else {                                            // Z columns l..iact (rows of Zt), coalesced over i
                     const int i = t2 - nAbove - nRight;
                     cd z0 = ZT(l, i);
-                    for (int k = l; k < iact; ++k) {
+                    int k = l;
+                    for (; k + 8 <= iact; k += 8) {                  // 8 independent loads in flight hide the L2 latency
+                        cd zn[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) zn[u] = ZT(k + 1 + u, i);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const double cc = gc[k + u]; const cd ss = gs[k + u];
+                            ZT(k + u, i) = cc * z0 + cconj(ss) * zn[u];
+                            z0 = cc * zn[u] - ss * z0;
+                        }
+                    }
+                    for (; k < iact; ++k) {
                         cd z1 = ZT(k + 1, i);
                         ZT(k, i) = gc[k] * z0 + cconj(gs[k]) * z1;
                         z0 = gc[k] * z1 - gs[k] * z0;

@@ -23,13 +23,9 @@ struct zgemm_args {
     int cs_divide;              // 1: divide by colscale instead of multiplying
 };
 
-#define ZG_BM 64
-#define ZG_BN 64
 #define ZG_BK 16
 #define ZG_LDA 20
-#define ZG_LDB 66
-#define ZG_THREADS 256
-#define ZG_SMEM (2 * (ZG_BM * ZG_LDA + ZG_BK * ZG_LDB) * (int)sizeof(cd))
+#define ZG_EMU_TILE 64
 
 KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc) {
     cd v = a.alpha * acc;
@@ -54,10 +50,14 @@ __device__ __forceinline__ void kh_cp_async_commit() { asm volatile("cp.async.co
 template <int N> __device__ __forceinline__ void kh_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
-KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
+// NW warps x NT column tiles: CTA tile (8 NW) x (8 NT).  (8,8) = 64x64 for general shapes; (7,7) = 56x56
+// wastes less padding at n = 50 (one tile) and n = 98 (2x2 tiles).
+template <int NW, int NT>
+KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
+    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, THREADS = 32 * NW;
     const int b = c.bx;
-    const int tiles_n = (a.N + ZG_BN - 1) / ZG_BN;
-    const int m0 = (c.by / tiles_n) * ZG_BM, n0 = (c.by % tiles_n) * ZG_BN;
+    const int tiles_n = (a.N + BN - 1) / BN;
+    const int m0 = (c.by / tiles_n) * BM, n0 = (c.by % tiles_n) * BN;
     const cd* A = mat_ptr(a.A, b);
     const cd* B = mat_ptr(a.B, b);
     const cd* Cin = mat_ptr(a.Cin, b);
@@ -65,8 +65,8 @@ KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
     const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
     const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
 #ifdef KH_HOST_EMU
-    for (int i = m0; i < m0 + ZG_BM && i < a.M; ++i)
-        for (int j = n0; j < n0 + ZG_BN && j < a.N; ++j) {
+    for (int i = m0; i < m0 + BM && i < a.M; ++i)
+        for (int j = n0; j < n0 + BN && j < a.N; ++j) {
             cd acc = mk(0, 0);
             for (int k = 0; k < a.K; ++k) {
                 cd av = a.transA ? A[(long long)k * a.A.ld + i] : A[(long long)i * a.A.ld + k];
@@ -75,65 +75,62 @@ KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
             Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc);
         }
 #else
-    cd* As = (cd*)c.smem;                               // [2][BM][LDA]
-    cd* Bs = As + 2 * ZG_BM * ZG_LDA;                   // [2][BK][LDB]
+    cd* As = (cd*)KH_SMEM(c);                           // [2][BM][LDA]
+    cd* Bs = As + 2 * BM * ZG_LDA;                      // [2][BK][LDB]
     const int warp = c.tid >> 5, lane = c.tid & 31;
     const int lr = lane >> 2, lk = lane & 3;
-    double cr[8][2], ci[8][2];
+    double cr[NT][2], ci[NT][2];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
+    for (int t = 0; t < NT; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
     const int nk = (a.K + ZG_BK - 1) / ZG_BK;
-    const int nt = min(8, (a.N - n0 + 7) >> 3);
+    const int nt = min(NT, (a.N - n0 + 7) >> 3);
     const bool warp_active = (m0 + warp * 8) < a.M;
 
     auto stage = [&](int buf, int kc) {
         const int k0 = kc * ZG_BK;
-        cd* as = As + buf * ZG_BM * ZG_LDA;
-        cd* bs = Bs + buf * ZG_BK * ZG_LDB;
+        cd* as = As + buf * BM * ZG_LDA;
+        cd* bs = Bs + buf * ZG_BK * LDB;
         if (!a.transA) {
-#pragma unroll
-            for (int e = c.tid; e < ZG_BM * ZG_BK; e += ZG_THREADS) {
+            for (int e = c.tid; e < BM * ZG_BK; e += THREADS) {
                 int m = e >> 4, k = e & 15;
                 bool ok = (m0 + m) < a.M && (k0 + k) < a.K;
                 kh_cp_async16(as + m * ZG_LDA + k, ok ? A + (long long)(m0 + m) * a.A.ld + k0 + k : A, ok);
             }
         } else {
-#pragma unroll
-            for (int e = c.tid; e < ZG_BM * ZG_BK; e += ZG_THREADS) {
-                int k = e >> 6, m = e & 63;
+            for (int e = c.tid; e < BM * ZG_BK; e += THREADS) {
+                int k = e / BM, m = e - k * BM;
                 bool ok = (m0 + m) < a.M && (k0 + k) < a.K;
                 kh_cp_async16(as + m * ZG_LDA + k, ok ? A + (long long)(k0 + k) * a.A.ld + m0 + m : A, ok);
             }
         }
-#pragma unroll
-        for (int e = c.tid; e < ZG_BK * ZG_BN; e += ZG_THREADS) {
-            int k = e >> 6, n = e & 63;
+        for (int e = c.tid; e < ZG_BK * BN; e += THREADS) {
+            int k = e / BN, n = e - k * BN;
             bool ok = (k0 + k) < a.K && (n0 + n) < a.N;
-            kh_cp_async16(bs + k * ZG_LDB + n, ok ? B + (long long)(k0 + k) * a.B.ld + n0 + n : B, ok);
+            kh_cp_async16(bs + k * LDB + n, ok ? B + (long long)(k0 + k) * a.B.ld + n0 + n : B, ok);
         }
         kh_cp_async_commit();
     };
 
-    stage(0, 0);
+    if (nk > 0) stage(0, 0);
     for (int kc = 0; kc < nk; ++kc) {
         const int buf = kc & 1;
         if (kc + 1 < nk) { stage(buf ^ 1, kc + 1); kh_cp_async_wait<1>(); }
         else kh_cp_async_wait<0>();
         __syncthreads();
         if (warp_active) {
-            const cd* as = As + buf * ZG_BM * ZG_LDA + (warp * 8 + lr) * ZG_LDA + lk;
-            const cd* bs = Bs + buf * ZG_BK * ZG_LDB + lk * ZG_LDB + lr;
+            const cd* as = As + buf * BM * ZG_LDA + (warp * 8 + lr) * ZG_LDA + lk;
+            const cd* bs = Bs + buf * ZG_BK * LDB + lk * LDB + lr;
 #pragma unroll
             for (int kk = 0; kk < ZG_BK / 4; ++kk) {
                 cd av = as[kk * 4];
                 double nai = -av.y;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
+                for (int t = 0; t < NT; ++t) {
                     if (t < nt) {
-                        cd bv = bs[kk * 4 * ZG_LDB + t * 8];
+                        cd bv = bs[kk * 4 * LDB + t * 8];
                         kh_dmma(cr[t][0], cr[t][1], av.x, bv.x);
-                        kh_dmma(cr[t][0], cr[t][1], nai, bv.y);
                         kh_dmma(ci[t][0], ci[t][1], av.x, bv.y);
+                        kh_dmma(cr[t][0], cr[t][1], nai, bv.y);
                         kh_dmma(ci[t][0], ci[t][1], av.y, bv.x);
                     }
                 }
@@ -145,7 +142,7 @@ KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
         const int row = m0 + warp * 8 + lr;
         if (row < a.M) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < NT; ++t) {
                 if (t < nt) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -159,11 +156,21 @@ KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) {
     }
 #endif
 }
+KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<8, 8>(c, a); }
+KH_DEV void zgemm56_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<7, 7>(c, a); }
 
+static inline long long zgemm_padded(int M, int N, int T) { return (long long)((M + T - 1) / T) * T * ((N + T - 1) / T) * T; }
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
-    int tiles = ((a.M + ZG_BM - 1) / ZG_BM) * ((a.N + ZG_BN - 1) / ZG_BN);
-    return kh_launch<zgemm_args, zgemm_body>(dim3(batch, tiles), ZG_THREADS, ZG_SMEM, st, a, "zgemm", 8.0 * a.M * a.N * a.K * batch);
+    const double work = 8.0 * a.M * a.N * a.K * batch;
+    if (zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64)) {
+        int tiles = ((a.M + 55) / 56) * ((a.N + 55) / 56);
+        size_t sm = (size_t)2 * (56 * ZG_LDA + ZG_BK * 58) * sizeof(cd);
+        return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(batch, tiles), 224, sm, st, a, "zgemm", work);
+    }
+    int tiles = ((a.M + 63) / 64) * ((a.N + 63) / 64);
+    size_t sm = (size_t)2 * (64 * ZG_LDA + ZG_BK * 66) * sizeof(cd);
+    return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(batch, tiles), 256, sm, st, a, "zgemm", work);
 }
 
 // convenience builder: plain C = alpha*A*B (+ beta*Cin) on [batch, n, n] row-major stacks

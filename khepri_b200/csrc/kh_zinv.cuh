@@ -21,7 +21,7 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
     const cd* A = mat_ptr(a.A, b);
     cd* Out = mat_ptr(a.Ainv, b);
     // shared layout: [colk n][rowk n][scratch 128 dbl][piv n ints][matrix]
-    cd* colk = (cd*)c.smem;
+    cd* colk = (cd*)KH_SMEM(c);
     cd* rowk = colk + n;
     double* scratch = (double*)(rowk + n);
     int* piv = (int*)(scratch + 128);
@@ -101,6 +101,137 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
     if (a.info && c.tid == 0) a.info[b] = bad;
 }
 
+
+#ifndef KH_HOST_EMU
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for n <= 100 (the 5x5 and 7x7 harmonic bases): the whole matrix lives
+// in the register file, each thread owning a 2 x 5 tile; per elimination step only the pivot column
+// and the two rows involved in the interchange travel through shared memory (double buffered, two
+// barriers per step), and the rank-1 update is pure register DFMA work.
+#define ZIR_TC 5
+template <int ZIR_TR>
+__device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) {
+    const int n = a.n, b = c.bx, tid = c.tid;
+    const cd* A = mat_ptr(a.A, b);
+    cd* Out = mat_ptr(a.Ainv, b);
+    const int TXN = (n + ZIR_TC - 1) / ZIR_TC, TYN = (n + ZIR_TR - 1) / ZIR_TR;
+    const bool live = tid < TXN * TYN;
+    const int ty = live ? tid / TXN : 0, tx = live ? tid % TXN : 0;
+    const int i0 = ty * ZIR_TR, j0 = tx * ZIR_TC;
+    // shared: colk[2][n], rowK[2][n], rowP[2][n], piv[n] ints, dest[n] ints
+    cd* colk = (cd*)KH_SMEM(c);
+    cd* rowK = colk + 2 * n;
+    cd* rowP = rowK + 2 * n;
+    int* piv = (int*)(rowP + 2 * n);
+    int* dest = piv + n;
+    cd r[ZIR_TR][ZIR_TC];
+#pragma unroll
+    for (int p = 0; p < ZIR_TR; ++p)
+#pragma unroll
+        for (int q = 0; q < ZIR_TC; ++q) {
+            const int i = i0 + p, j = j0 + q;
+            r[p][q] = (live && i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(0, 0);
+        }
+    int bad = 0;
+    const int lane = tid & 31;
+    for (int k = 0; k < n; ++k) {
+        const int pb = k & 1;
+        cd* ck = colk + pb * n; cd* rK = rowK + pb * n; cd* rP = rowP + pb * n;
+        // A: owners of column k publish it; owners of row k publish the row
+        if (live && k >= j0 && k < j0 + ZIR_TC) {
+            const int q = k - j0;
+#pragma unroll
+            for (int p = 0; p < ZIR_TR; ++p) if (i0 + p < n) ck[i0 + p] = (q == 0) ? r[p][0] : (q == 1) ? r[p][1] : (q == 2) ? r[p][2] : (q == 3) ? r[p][3] : r[p][4];
+        }
+        if (live && k >= i0 && k < i0 + ZIR_TR) {
+            const int p = k - i0;
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) {
+                cd v = r[0][q];
+#pragma unroll
+                for (int pp = 1; pp < ZIR_TR; ++pp) if (p == pp) v = r[pp][q];
+                if (j0 + q < n) rK[j0 + q] = v;
+            }
+        }
+        __syncthreads();
+        // B: every warp finds the pivot row (izamax over rows k..n-1, ties -> smallest index)
+        double best = -1.0; int bi = k;
+        for (int i = k + lane; i < n; i += 32) { double v = cabs1(ck[i]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        const int pr = bi;
+        if (tid == 0) piv[k] = pr;
+        if (live && pr != k && pr >= i0 && pr < i0 + ZIR_TR) {
+            const int p = pr - i0;
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) {
+                cd v = r[0][q];
+#pragma unroll
+                for (int pp = 1; pp < ZIR_TR; ++pp) if (p == pp) v = r[pp][q];
+                if (j0 + q < n) rP[j0 + q] = v;
+            }
+        }
+        __syncthreads();
+        // C: eliminate.  After the interchange row k holds old row pr, row pr holds old row k.
+        const cd* prow = (pr == k) ? rK : rP;
+        const cd pv = ck[pr];
+        if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
+        const cd d = crecip(pv);
+        if (live) {
+            const bool own_k = (k >= i0 && k < i0 + ZIR_TR), own_p = (pr != k && pr >= i0 && pr < i0 + ZIR_TR);
+            cd f[ZIR_TR];
+#pragma unroll
+            for (int p = 0; p < ZIR_TR; ++p) { const int i = i0 + p; f[p] = (i < n) ? ((i == pr) ? ck[k] : ck[i]) : mk(0, 0); }
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) {
+                const int j = j0 + q;
+                if (j >= n) continue;
+                const cd pj = (j == k) ? d : prow[j] * d;           // scaled pivot row entry
+                cd oldk = mk(0, 0);
+                if (own_p) oldk = rK[j];                            // old row k moves to row pr
+#pragma unroll
+                for (int p = 0; p < ZIR_TR; ++p) {
+                    const int i = i0 + p;
+                    if (i >= n) continue;
+                    if (own_k && i == k) { r[p][q] = pj; continue; }
+                    cd v = (own_p && i == pr) ? oldk : r[p][q];
+                    if (j == k) v = -(f[p] * d);
+                    else cfms(v, f[p], pj);
+                    r[p][q] = v;
+                }
+            }
+        }
+        // (no barrier: the next step writes the other buffer set)
+    }
+    __syncthreads();
+    // undo the row interchanges as column interchanges (reverse order) -> destination column of every stored column
+    if (tid == 0) {
+        for (int j = 0; j < n; ++j) dest[j] = j;                  // dest doubles as col_at first
+        for (int k = n - 1; k >= 0; --k) { int p = piv[k]; int t = dest[k]; dest[k] = dest[p]; dest[p] = t; }
+        // dest[pos] = stored column sitting at pos; invert in place through piv as scratch
+        for (int pos = 0; pos < n; ++pos) piv[dest[pos]] = pos;
+        for (int j = 0; j < n; ++j) dest[j] = piv[j];
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int p = 0; p < ZIR_TR; ++p)
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) {
+                const int i = i0 + p, j = j0 + q;
+                if (i < n && j < n) Out[(long long)i * a.Ainv.ld + dest[j]] = r[p][q];
+            }
+    }
+    if (a.info && tid == 0) a.info[b] = bad;
+}
+__device__ __forceinline__ void zinv_reg_small_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
+__device__ __forceinline__ void zinv_reg_mid_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
+__device__ __forceinline__ void zinv_reg_large_body(const Cta& c, const zinv_args& a) { zinv_reg_body<4>(c, a); }
+#endif
+
 static inline size_t zinv_smem_bytes(int n, int ld_s, int use_smem) {
     size_t s = (size_t)2 * n * sizeof(cd) + 128 * sizeof(double) + (size_t)n * sizeof(int) + 16;
     if (use_smem) s += (size_t)n * ld_s * sizeof(cd);
@@ -111,6 +242,18 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
     if (batch <= 0 || n <= 0) return 0;
     zinv_args a;
     a.n = n; a.A = A; a.Ainv = Ainv; a.info = info;
+#ifndef KH_HOST_EMU
+    if (n <= 100) {
+        a.use_smem = 0; a.ld_s = 0;
+        const int txn = (n + ZIR_TC - 1) / ZIR_TC;
+        const int tiles2 = txn * ((n + 1) / 2), tiles4 = txn * ((n + 3) / 4);
+        const size_t sm = (size_t)6 * n * sizeof(cd) + (size_t)2 * n * sizeof(int) + 16;
+        const double work = 8.0 * n * n * n * batch;
+        if (tiles2 <= 256) return kh_launch<zinv_args, zinv_reg_small_body, 256, 2>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
+        if (tiles2 <= 512) return kh_launch<zinv_args, zinv_reg_mid_body, 512, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
+        return kh_launch<zinv_args, zinv_reg_large_body, 512, 1>(dim3(batch), ((tiles4 + 31) / 32) * 32, sm, st, a, "zinv", work);
+    }
+#endif
     a.ld_s = n | 1;
     a.use_smem = zinv_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
     int threads = n <= 64 ? 256 : 512;
