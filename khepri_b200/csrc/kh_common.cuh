@@ -235,6 +235,18 @@ KH_DEV int cta_argmax(const Cta& c, double v, int idx, double* scratch) {
 #endif
 }
 
+// warp-level all-reduce (emulation: one virtual lane)
+#ifdef KH_HOST_EMU
+#define KH_WARP 1
+KH_DEV double kh_warp_allsum(double v) { return v; }
+#else
+#define KH_WARP 32
+KH_DEV double kh_warp_allsum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
 // batch addressing with two levels: matrix b lives at base + (b / inner) * so + (b % inner) * si
 struct MatRef {
     cd* p;

@@ -66,9 +66,9 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     cd* vv = (cd*)KH_SMEM(c);
     cd* uu = vv + n;
     double* scratch = (double*)(uu + n);
-    double* dsc = scratch + 192;
+    double* dsc = scratch + 192;       // [n] balancing factors; the region is 4n doubles and is reused as q / zu afterwards
     cd* H; int ld;
-    if (a.use_smem) { H = (cd*)(((uintptr_t)(dsc + n) + 15) & ~(uintptr_t)15); ld = a.ld_s; }
+    if (a.use_smem) { H = (cd*)(((uintptr_t)(dsc + 4 * n) + 15) & ~(uintptr_t)15); ld = a.ld_s; }
     else { H = Hg; ld = a.Hw.ld; }
 #define HH(i, j) H[(long long)(i) * ld + (j)]
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
@@ -108,54 +108,92 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     }
     for (int i = c.tid; i < n; i += c.nthr) scout[i] = mk(dsc[i], 0.0);
 
-    // ---- Householder reduction (zgehd2 / zlarfg conventions: H_k = I - tau v v^H, A <- H_k^H A H_k)
+    // ---- Householder reduction (zgehd2 / zlarfg conventions: H_k = I - tau v v^H, A <- H_k^H A H_k), written
+    // as ONE rank-2 update per step:  A -= pt conj(v)^T + (conj(tau) v) q^T  with p = A v, q^T = v^H A, s = v^H p,
+    // pt = tau p - |tau|^2 s v;  Z -= (tau Z v) conj(v)^T.   Three barriers per step, all threads busy.
+    cd* pp_ = uu;                      // p  [n]
+    cd* qq_ = (cd*)dsc;                // q  [n]   (dsc is dead after balancing: its n doubles are followed by n more below)
+    cd* zu_ = qq_ + n;                 // tau * Z v [n]
+    const int lane = c.tid % KH_WARP;
     for (int k = 0; k + 2 < n; ++k) {
+        // every warp computes the column norm redundantly (no CTA-wide reduction)
         double part = 0.0;
-        for (int i = k + 2 + c.tid; i < n; i += c.nthr) part += cabs2(HH(i, k));
-        double xn2 = cta_sum(c, part, scratch);
-        cd alpha = HH(k + 1, k);
-        c.sync();
-        if (xn2 == 0.0 && alpha.y == 0.0) continue;          // already reduced: H_k = I
-        double beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
-        cd tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
-        cd sc = crecip(alpha - mk(beta, 0.0));
+        for (int i = k + 2 + lane; i < n; i += KH_WARP) part += cabs2(HH(i, k));
+        const double xn2 = kh_warp_allsum(part);
+        const cd alpha = HH(k + 1, k);
+        if (xn2 == 0.0 && alpha.y == 0.0) continue;          // already reduced: H_k = I   (uniform across the CTA)
+        const double beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
+        const cd tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+        const cd sc = crecip(alpha - mk(beta, 0.0));
+        c.sync();                                              // all warps have read column k
         for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
             vv[i] = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
             HH(i, k) = (i == k + 1) ? mk(beta, 0.0) : mk(0.0, 0.0);
         }
         c.sync();
-        // left: H[k+1:, k+1:] <- (I - conj(tau) v v^H) H[k+1:, k+1:]
-        for (int j = k + 1 + c.tid; j < n; j += c.nthr) {
-            cd w0 = mk(0, 0), w1 = mk(0, 0);
-            int i = k + 1;
-            for (; i + 1 < n; i += 2) { cfma(w0, cconj(vv[i]), HH(i, j)); cfma(w1, cconj(vv[i + 1]), HH(i + 1, j)); }
-            if (i < n) cfma(w0, cconj(vv[i]), HH(i, j));
-            cd wj = cconj(tau) * (w0 + w1);
-            for (i = k + 1; i < n; ++i) cfms(HH(i, j), vv[i], wj);
-        }
-        c.sync();
-        // right: H[:, k+1:] <- H[:, k+1:] (I - tau v v^H)   and the same for Z (rows of Zt)
-        for (int r = c.tid; r < 2 * n; r += c.nthr) {
-            if (r < n) {
-                cd u0 = mk(0, 0), u1 = mk(0, 0);
+        // p = A v (one thread per row), q = v^H A (one thread per column), zu = tau Z v (one thread per row of Z)
+        for (int t = c.tid; t < 3 * n; t += c.nthr) {
+            cd a0 = mk(0, 0), a1 = mk(0, 0);
+            if (t < n) {
+                const int r = t;
                 int j = k + 1;
-                for (; j + 1 < n; j += 2) { cfma(u0, HH(r, j), vv[j]); cfma(u1, HH(r, j + 1), vv[j + 1]); }
-                if (j < n) cfma(u0, HH(r, j), vv[j]);
-                cd ur = tau * (u0 + u1);
-                for (j = k + 1; j < n; ++j) cfms(HH(r, j), ur, cconj(vv[j]));
+                for (; j + 1 < n; j += 2) { cfma(a0, HH(r, j), vv[j]); cfma(a1, HH(r, j + 1), vv[j + 1]); }
+                if (j < n) cfma(a0, HH(r, j), vv[j]);
+                pp_[r] = a0 + a1;
+            } else if (t < 2 * n) {
+                const int j = t - n;
+                if (j > k) {
+                    int i = k + 1;
+                    for (; i + 1 < n; i += 2) { cfma(a0, cconj(vv[i]), HH(i, j)); cfma(a1, cconj(vv[i + 1]), HH(i + 1, j)); }
+                    if (i < n) cfma(a0, cconj(vv[i]), HH(i, j));
+                }
+                qq_[j] = a0 + a1;
             } else {
-                int i = r - n;
-                cd u0 = mk(0, 0), u1 = mk(0, 0);
+                const int i = t - 2 * n;
+                cd a2 = mk(0, 0), a3 = mk(0, 0);
                 int j = k + 1;
-                for (; j + 1 < n; j += 2) { cfma(u0, ZT(j, i), vv[j]); cfma(u1, ZT(j + 1, i), vv[j + 1]); }
-                if (j < n) cfma(u0, ZT(j, i), vv[j]);
-                cd ur = tau * (u0 + u1);
-                for (j = k + 1; j < n; ++j) cfms(ZT(j, i), ur, cconj(vv[j]));
+                for (; j + 3 < n; j += 4) {
+                    const cd z0 = ZT(j, i), z1 = ZT(j + 1, i), z2 = ZT(j + 2, i), z3 = ZT(j + 3, i);
+                    cfma(a0, z0, vv[j]); cfma(a1, z1, vv[j + 1]); cfma(a2, z2, vv[j + 2]); cfma(a3, z3, vv[j + 3]);
+                }
+                for (; j < n; ++j) cfma(a0, ZT(j, i), vv[j]);
+                zu_[i] = tau * ((a0 + a1) + (a2 + a3));
             }
         }
         c.sync();
+        // s = v^H p, redundantly per warp
+        double sr = 0.0, si = 0.0;
+        for (int i = k + 1 + lane; i < n; i += KH_WARP) { const cd w = cconj(vv[i]) * pp_[i]; sr += w.x; si += w.y; }
+        const cd sv = mk(kh_warp_allsum(sr), kh_warp_allsum(si));
+        const cd t2s = cabs2(tau) * sv;
+        const cd ctau = cconj(tau);
+        // rank-2 update of H (rows 0..n-1, columns k+1..n-1): thread = (row, residue class of columns)
+        const int ncol = n - k - 1;
+        const int nseg = (ncol + 3) / 4;
+        for (int e = c.tid; e < n * nseg; e += c.nthr) {
+            const int i = e / nseg, sg = e - i * nseg;
+            cd pt = tau * pp_[i], tv = mk(0, 0);
+            if (i > k) { tv = ctau * vv[i]; pt = pt - t2s * vv[i]; }
+            for (int j = k + 1 + sg; j < n; j += nseg) {
+                cd h = HH(i, j);
+                cfms(h, pt, cconj(vv[j]));
+                cfms(h, tv, qq_[j]);
+                HH(i, j) = h;
+            }
+        }
+        // Z -= zu conj(v)^T   (rows k+1.. of Zt, coalesced over i; independent loads, unrolled)
+        for (int i = c.tid; i < n; i += c.nthr) {
+            const cd zi = zu_[i];
+            int j = k + 1;
+            for (; j + 3 < n; j += 4) {
+                cd z0 = ZT(j, i), z1 = ZT(j + 1, i), z2 = ZT(j + 2, i), z3 = ZT(j + 3, i);
+                cfms(z0, zi, cconj(vv[j])); cfms(z1, zi, cconj(vv[j + 1])); cfms(z2, zi, cconj(vv[j + 2])); cfms(z3, zi, cconj(vv[j + 3]));
+                ZT(j, i) = z0; ZT(j + 1, i) = z1; ZT(j + 2, i) = z2; ZT(j + 3, i) = z3;
+            }
+            for (; j < n; ++j) { cd z0 = ZT(j, i); cfms(z0, zi, cconj(vv[j])); ZT(j, i) = z0; }
+        }
+        c.sync();
     }
-
     if (a.use_smem)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * a.Hw.ld + j] = HH(i, j); }
 #undef HH
@@ -180,7 +218,10 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     int* ctl = (int*)(gc + n);
     cd* Hp = (cd*)(((uintptr_t)(ctl + 8) + 15) & ~(uintptr_t)15);
     const bool packed = PACKED;
-#define HQ(i, j) (*(PACKED ? (Hp + hp_off((i), n) + (j)) : (Hg + (long long)(i) * ldg + (j))))
+    cd* const Hb = PACKED ? Hp : Hg;
+#define ROWOFF(i) (PACKED ? hp_off((i), n) : (i) * ldg)
+#define ROWSTEP(i) (PACKED ? (n - (i)) : ldg)          /* ROWOFF(i+1) - ROWOFF(i) */
+#define HQ(i, j) Hb[ROWOFF(i) + (j)]
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
     if (packed)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; if (j >= i - 1) HQ(i, j) = Hg[(long long)i * ldg + j]; }
@@ -250,6 +291,8 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         }
         // ---- one implicit single-shift sweep over the window [l, iact], one barrier per rotation.
         // R(k): rows k,k+1 <- G_k (window columns);  C(k): columns k,k+1 <- . G_k^H (window rows <= k+2).
+        // Thread t owns index m = l + t: it applies the row steps to column m+1 while k < m and the column
+        // steps to row m once k >= m, so its addresses advance by running offsets (no multiplies in the loop).
         kh_givens G = make_givens(HQ(l, l) - t, HQ(l + 1, l));
         c.sync();                                   // everyone has read H before the sweep writes
         for (int j = l + c.tid; j <= iact; j += c.nthr) {          // R(l)
@@ -263,37 +306,38 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         // sub-diagonal and diagonal after R(k)) that are known to every thread but not stored yet
         cd sub = HQ(l + 1, l);
         cd pend_sub = mk(0, 0), pend_diag = mk(0, 0);
+        int o1 = ROWOFF(l + 1);                     // offset of row k+1 (running)
         for (int k = l; k < iact; ++k) {
             const bool more = (k + 1 < iact);
-            const cd cb = HQ(k + 1, k + 1);
+            const int o2 = o1 + ROWSTEP(k + 1);     // offset of row k+2
+            const cd cb = Hb[o1 + k + 1];
             const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;     // C(k) on row k+1
             kh_givens Gn; Gn.c = 1.0; Gn.s = mk(0, 0); Gn.r = a1;
             cd newdiag = b1, nextsub = mk(0, 0);
             if (more) {
-                const cd hd = HQ(k + 2, k + 1);             // H[k+2][k] is zero: C(k) creates the bulge there
+                const cd hd = Hb[o2 + k + 1];               // H[k+2][k] is zero: C(k) creates the bulge there
                 const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;
                 Gn = make_givens(a1, c1);                   // G(k+1) annihilates the bulge
                 newdiag = Gn.c * b1 + Gn.s * d1;            // H[k+1][k+1] after R(k+1)
                 nextsub = Gn.c * d1 - cconj(Gn.s) * b1;     // H[k+2][k+1] after R(k+1)
             }
             // M(k) = C(k) on rows l..k  ||  R(k+1) on columns k+2..iact   (disjoint entries)
-            const int nC = k - l + 1, nR = more ? iact - k - 1 : 0;
-            for (int t2 = c.tid; t2 < nC + nR; t2 += c.nthr) {
-                if (t2 < nC) {
-                    const int r = l + t2;
-                    cd h0 = HQ(r, k), h1 = HQ(r, k + 1);
-                    if (r == k && k > l) { h0 = pend_diag; HQ(k, k - 1) = pend_sub; }   // row k: stored now, nobody reads it earlier
-                    HQ(r, k) = G.c * h0 + cconj(G.s) * h1;
-                    HQ(r, k + 1) = G.c * h1 - G.s * h0;
-                } else {
-                    const int j = k + 2 + (t2 - nC);
-                    cd h0 = HQ(k + 1, j), h1 = HQ(k + 2, j);
-                    HQ(k + 1, j) = Gn.c * h0 + Gn.s * h1;
-                    HQ(k + 2, j) = Gn.c * h1 - cconj(Gn.s) * h0;
+            for (int m = l + c.tid; m <= iact; m += c.nthr) {
+                if (m <= k) {
+                    cd* hr = Hb + ROWOFF(m) + k;
+                    cd h0 = hr[0], h1 = hr[1];
+                    if (m == k && k > l) { h0 = pend_diag; hr[-1] = pend_sub; }   // row k: stored now, nobody reads it earlier
+                    hr[0] = G.c * h0 + cconj(G.s) * h1;
+                    hr[1] = G.c * h1 - G.s * h0;
+                } else if (more && m < iact) {
+                    const int j = m + 1;
+                    cd h0 = Hb[o1 + j], h1 = Hb[o2 + j];
+                    Hb[o1 + j] = Gn.c * h0 + Gn.s * h1;
+                    Hb[o2 + j] = Gn.c * h1 - cconj(Gn.s) * h0;
                 }
             }
             if (more && c.tid == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; }
-            pend_sub = Gn.r; pend_diag = newdiag; sub = nextsub; G = Gn;
+            pend_sub = Gn.r; pend_diag = newdiag; sub = nextsub; G = Gn; o1 = o2;
             c.sync();
         }
         if (c.tid == 0) { HQ(iact, iact - 1) = pend_sub; HQ(iact, iact) = pend_diag; }
@@ -353,6 +397,8 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         }
     if (a.info && c.tid == 0) a.info[b] = fail;
 #undef HQ
+#undef ROWOFF
+#undef ROWSTEP
 #undef ZT
 }
 
@@ -395,7 +441,7 @@ KH_DEV void ztrevc_body(const Cta& c, const zgeev_args& a) {
 }
 
 static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
-    size_t s = (size_t)2 * n * sizeof(cd) + 192 * sizeof(double) + (size_t)n * sizeof(double) + 16;
+    size_t s = (size_t)2 * n * sizeof(cd) + 192 * sizeof(double) + (size_t)4 * n * sizeof(double) + 32;
     if (use_smem) s += (size_t)n * ld_s * sizeof(cd);
     return s;
 }
@@ -411,7 +457,7 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     const double work = 100.0 * n * n * n * batch;          // nominal zgeev count, SURVEY.md 8(d)
     a.ld_s = n | 1;
     a.use_smem = zhess_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
-    int e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 64 ? 128 : 256, zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
+    int e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
     if (e) return e;
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;

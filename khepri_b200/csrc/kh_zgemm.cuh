@@ -122,6 +122,7 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
             const cd* bs = Bs + buf * ZG_BK * LDB + lk * LDB + lr;
 #pragma unroll
             for (int kk = 0; kk < ZG_BK / 4; ++kk) {
+                if (kc * ZG_BK + kk * 4 >= a.K) break;           // ragged K: skip the all-zero MMA steps
                 cd av = as[kk * 4];
                 double nai = -av.y;
 #pragma unroll

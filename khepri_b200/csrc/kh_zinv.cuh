@@ -105,120 +105,118 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
 #ifndef KH_HOST_EMU
 // ---------------------------------------------------------------------------------------------
 // Register-resident variant for n <= 100 (the 5x5 and 7x7 harmonic bases): the whole matrix lives
-// in the register file, each thread owning a 2 x 5 tile; per elimination step only the pivot column
-// and the two rows involved in the interchange travel through shared memory (double buffered, two
-// barriers per step), and the rank-1 update is pure register DFMA work.
+// in the register file, each thread owning a TR x 5 tile (the matrix is padded with identity rows /
+// columns up to the tile grid, so the elimination loop has no bounds checks).  Per step only the
+// pivot column and the two rows of the interchange travel through shared memory (double buffered:
+// two barriers per step); the rank-1 update is pure register DFMA work.
 #define ZIR_TC 5
-template <int ZIR_TR>
+template <int TR>
+__device__ __forceinline__ cd zir_pick_row(const cd (&r)[TR][ZIR_TC], int p, int q) {     // r[p][q] with runtime p, static q
+    cd v = r[0][q];
+#pragma unroll
+    for (int pp = 1; pp < TR; ++pp) if (p == pp) v = r[pp][q];
+    return v;
+}
+template <int TR>
 __device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) {
-    const int n = a.n, b = c.bx, tid = c.tid;
+    const int n = a.n, b = c.bx, tid = c.tid, lane = tid & 31;
     const cd* A = mat_ptr(a.A, b);
     cd* Out = mat_ptr(a.Ainv, b);
-    const int TXN = (n + ZIR_TC - 1) / ZIR_TC, TYN = (n + ZIR_TR - 1) / ZIR_TR;
+    const int TXN = (n + ZIR_TC - 1) / ZIR_TC, TYN = (n + TR - 1) / TR;
+    const int NP = max(TXN * ZIR_TC, TYN * TR);
     const bool live = tid < TXN * TYN;
-    const int ty = live ? tid / TXN : 0, tx = live ? tid % TXN : 0;
-    const int i0 = ty * ZIR_TR, j0 = tx * ZIR_TC;
-    // shared: colk[2][n], rowK[2][n], rowP[2][n], piv[n] ints, dest[n] ints
-    cd* colk = (cd*)KH_SMEM(c);
-    cd* rowK = colk + 2 * n;
-    cd* rowP = rowK + 2 * n;
-    int* piv = (int*)(rowP + 2 * n);
-    int* dest = piv + n;
-    cd r[ZIR_TR][ZIR_TC];
+    const int ty = live ? tid / TXN : 0, tx = live ? tid - ty * TXN : 0;
+    const int i0 = ty * TR, j0 = tx * ZIR_TC;
+    cd* colk = (cd*)KH_SMEM(c);               // [2][NP]
+    cd* rowK = colk + 2 * NP;                 // [2][NP]
+    cd* rowP = rowK + 2 * NP;                 // [2][NP]
+    int* piv = (int*)(rowP + 2 * NP);         // [n]
+    int* dest = piv + n;                      // [n]
+    cd r[TR][ZIR_TC];
 #pragma unroll
-    for (int p = 0; p < ZIR_TR; ++p)
+    for (int p = 0; p < TR; ++p)
 #pragma unroll
         for (int q = 0; q < ZIR_TC; ++q) {
             const int i = i0 + p, j = j0 + q;
-            r[p][q] = (live && i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(0, 0);
+            r[p][q] = (live && i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk((i == j) ? 1.0 : 0.0, 0.0);
         }
     int bad = 0;
-    const int lane = tid & 31;
     for (int k = 0; k < n; ++k) {
-        const int pb = k & 1;
-        cd* ck = colk + pb * n; cd* rK = rowK + pb * n; cd* rP = rowP + pb * n;
-        // A: owners of column k publish it; owners of row k publish the row
-        if (live && k >= j0 && k < j0 + ZIR_TC) {
-            const int q = k - j0;
+        cd* ck = colk + (k & 1) * NP; cd* rK = rowK + (k & 1) * NP; cd* rP = rowP + (k & 1) * NP;
+        const int kq = k - j0, kp = k - i0;
+        const bool own_col = live && (unsigned)kq < (unsigned)ZIR_TC, own_row = live && (unsigned)kp < (unsigned)TR;
+        // A: publish column k and row k
+        if (own_col) {
 #pragma unroll
-            for (int p = 0; p < ZIR_TR; ++p) if (i0 + p < n) ck[i0 + p] = (q == 0) ? r[p][0] : (q == 1) ? r[p][1] : (q == 2) ? r[p][2] : (q == 3) ? r[p][3] : r[p][4];
-        }
-        if (live && k >= i0 && k < i0 + ZIR_TR) {
-            const int p = k - i0;
+            for (int p = 0; p < TR; ++p) {
+                cd v = r[p][0];
 #pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) {
-                cd v = r[0][q];
-#pragma unroll
-                for (int pp = 1; pp < ZIR_TR; ++pp) if (p == pp) v = r[pp][q];
-                if (j0 + q < n) rK[j0 + q] = v;
+                for (int qq = 1; qq < ZIR_TC; ++qq) if (kq == qq) v = r[p][qq];
+                ck[i0 + p] = v;
             }
+        }
+        if (own_row) {
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) rK[j0 + q] = zir_pick_row<TR>(r, kp, q);
         }
         __syncthreads();
         // B: every warp finds the pivot row (izamax over rows k..n-1, ties -> smallest index)
-        double best = -1.0; int bi = k;
-        for (int i = k + lane; i < n; i += 32) { double v = cabs1(ck[i]); if (v > best) { best = v; bi = i; } }
+        double best = -1.0; int pr = k;
+        for (int i = k + lane; i < n; i += 32) { const double v = cabs1(ck[i]); if (v > best) { best = v; pr = i; } }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, pr, o);
+            if (ov > best || (ov == best && oi < pr)) { best = ov; pr = oi; }
         }
-        const int pr = bi;
+        const int pp = pr - i0;
+        const bool own_prow = live && pr != k && (unsigned)pp < (unsigned)TR;
+        if (own_prow) {
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) rP[j0 + q] = zir_pick_row<TR>(r, pp, q);
+        }
         if (tid == 0) piv[k] = pr;
-        if (live && pr != k && pr >= i0 && pr < i0 + ZIR_TR) {
-            const int p = pr - i0;
-#pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) {
-                cd v = r[0][q];
-#pragma unroll
-                for (int pp = 1; pp < ZIR_TR; ++pp) if (p == pp) v = r[pp][q];
-                if (j0 + q < n) rP[j0 + q] = v;
-            }
-        }
         __syncthreads();
-        // C: eliminate.  After the interchange row k holds old row pr, row pr holds old row k.
+        // C: interchange + eliminate.  Row k becomes the scaled pivot row; row pr receives the old row k.
         const cd* prow = (pr == k) ? rK : rP;
         const cd pv = ck[pr];
         if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
         const cd d = crecip(pv);
-        if (live) {
-            const bool own_k = (k >= i0 && k < i0 + ZIR_TR), own_p = (pr != k && pr >= i0 && pr < i0 + ZIR_TR);
-            cd f[ZIR_TR];
+        cd f[TR];
 #pragma unroll
-            for (int p = 0; p < ZIR_TR; ++p) { const int i = i0 + p; f[p] = (i < n) ? ((i == pr) ? ck[k] : ck[i]) : mk(0, 0); }
+        for (int p = 0; p < TR; ++p) f[p] = ck[i0 + p];
+        if (own_prow) {
 #pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) {
-                const int j = j0 + q;
-                if (j >= n) continue;
-                const cd pj = (j == k) ? d : prow[j] * d;           // scaled pivot row entry
-                cd oldk = mk(0, 0);
-                if (own_p) oldk = rK[j];                            // old row k moves to row pr
+            for (int p = 0; p < TR; ++p) if (p == pp) {
+                f[p] = ck[k];
 #pragma unroll
-                for (int p = 0; p < ZIR_TR; ++p) {
-                    const int i = i0 + p;
-                    if (i >= n) continue;
-                    if (own_k && i == k) { r[p][q] = pj; continue; }
-                    cd v = (own_p && i == pr) ? oldk : r[p][q];
-                    if (j == k) v = -(f[p] * d);
-                    else cfms(v, f[p], pj);
-                    r[p][q] = v;
-                }
+                for (int q = 0; q < ZIR_TC; ++q) r[p][q] = rK[j0 + q];
             }
         }
-        // (no barrier: the next step writes the other buffer set)
+#pragma unroll
+        for (int q = 0; q < ZIR_TC; ++q) {
+            const bool kcol = own_col && (q == kq);
+            const cd pj = kcol ? d : prow[j0 + q] * d;
+#pragma unroll
+            for (int p = 0; p < TR; ++p) {
+                cd v = kcol ? mk(0.0, 0.0) : r[p][q];
+                cfms(v, f[p], pj);
+                r[p][q] = (own_row && p == kp) ? pj : v;
+            }
+        }
+        // (no barrier here: the next step writes the other buffer set)
     }
     __syncthreads();
     // undo the row interchanges as column interchanges (reverse order) -> destination column of every stored column
     if (tid == 0) {
-        for (int j = 0; j < n; ++j) dest[j] = j;                  // dest doubles as col_at first
-        for (int k = n - 1; k >= 0; --k) { int p = piv[k]; int t = dest[k]; dest[k] = dest[p]; dest[p] = t; }
-        // dest[pos] = stored column sitting at pos; invert in place through piv as scratch
-        for (int pos = 0; pos < n; ++pos) piv[dest[pos]] = pos;
+        for (int j = 0; j < n; ++j) dest[j] = j;                  // dest[pos] = stored column sitting at pos
+        for (int k = n - 1; k >= 0; --k) { const int p = piv[k]; const int t = dest[k]; dest[k] = dest[p]; dest[p] = t; }
+        for (int pos = 0; pos < n; ++pos) piv[dest[pos]] = pos;   // invert (piv is free now)
         for (int j = 0; j < n; ++j) dest[j] = piv[j];
     }
     __syncthreads();
     if (live) {
 #pragma unroll
-        for (int p = 0; p < ZIR_TR; ++p)
+        for (int p = 0; p < TR; ++p)
 #pragma unroll
             for (int q = 0; q < ZIR_TC; ++q) {
                 const int i = i0 + p, j = j0 + q;
@@ -247,7 +245,7 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
         a.use_smem = 0; a.ld_s = 0;
         const int txn = (n + ZIR_TC - 1) / ZIR_TC;
         const int tiles2 = txn * ((n + 1) / 2), tiles4 = txn * ((n + 3) / 4);
-        const size_t sm = (size_t)6 * n * sizeof(cd) + (size_t)2 * n * sizeof(int) + 16;
+        const size_t sm = (size_t)6 * (n + 8) * sizeof(cd) + (size_t)2 * n * sizeof(int) + 16;
         const double work = 8.0 * n * n * n * batch;
         if (tiles2 <= 256) return kh_launch<zinv_args, zinv_reg_small_body, 256, 2>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
         if (tiles2 <= 512) return kh_launch<zinv_args, zinv_reg_mid_body, 512, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
