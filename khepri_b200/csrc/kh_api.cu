@@ -111,6 +111,76 @@ static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& 
 }
 #define STAR_TMP_SLABS 7
 
+static int bdmul(kh_stream_t st, int Bc, int N, int side, const cd* bd, int blk, MatRef M, MatRef out, double alpha = 1.0,
+                 const MatRef* Cin = nullptr, double beta = 0.0, double diag = 0.0, const cd* addbd = nullptr, int addblk = 0) {
+    bdmul_args a;
+    a.B = Bc; a.N = N; a.side = side; a.bd = bd; a.blk = blk; a.M = M; a.out = out;
+    a.Cin = Cin ? *Cin : mref(nullptr, 0, 0);
+    a.addbd = addbd; a.addblk = addblk; a.alpha = alpha; a.beta = beta; a.diag = diag;
+    return kh_launch<bdmul_args, bdmul_body>(dim3(Bc, 4), 256, 0, st, a, "bdmul");
+}
+
+// star product with a BD (uniform layer / half space) LEFT operand: 5 GEMMs + 1 inverse + O(n^2) kernels
+static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef& B, cd* out, cd* tmp, int* info) {
+    const int n = 2 * N;
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
+    MatRef U = mref(tmp + 4 * slab, n2, n), Z = mref(tmp + 5 * slab, n2, n), Vt = mref(tmp + 6 * slab, n2, n);
+    SRef O = sref_dense(out, n);
+    int e;
+    if ((e = bdmul(st, Bc, N, 0, A, 3, B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;           // F = I - A22 B11
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X))) return e;                                          // X = F^-1 A21
+    if ((e = bdmul(st, Bc, N, 1, A, 3, Fi, Y))) return e;                                          // Y = F^-1 A22
+    if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                                    // S21 = B21 X
+    if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                           // U = B11 X
+    if ((e = bdmul(st, Bc, N, 0, A, 1, U, O.blk[0], 1.0, nullptr, 0.0, 0.0, A, 0))) return e;      // S11 = A11 + A12 U
+    if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                           // Z = Y B12
+    if ((e = gemm(st, Bc, n, B.blk[2], Z, O.blk[3], 1.0, &B.blk[3], 1.0))) return e;               // S22 = B22 + B21 Z
+    if ((e = gemm(st, Bc, n, B.blk[0], Z, Vt, 1.0, &B.blk[1], 1.0))) return e;                     // Vt = B12 + B11 Z
+    if ((e = bdmul(st, Bc, N, 0, A, 1, Vt, O.blk[1]))) return e;                                   // S12 = A12 Vt
+    return 0;
+}
+// star product with a BD RIGHT operand: 4 GEMMs + 1 inverse + O(n^2) kernels
+static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info) {
+    const int n = 2 * N;
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
+    MatRef U = mref(tmp + 4 * slab, n2, n), Z = mref(tmp + 5 * slab, n2, n), Vt = mref(tmp + 6 * slab, n2, n);
+    SRef O = sref_dense(out, n);
+    int e;
+    if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                          // X = F^-1 A21
+    if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
+    if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                                   // S21 = B21 X
+    if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U))) return e;                                          // U = B11 X
+    if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;               // S11 = A11 + A12 U
+    if ((e = bdmul(st, Bc, N, 1, Bd, 1, Y, Z))) return e;                                          // Z = Y B12
+    if ((e = bdmul(st, Bc, N, 0, Bd, 2, Z, O.blk[3], 1.0, nullptr, 0.0, 0.0, Bd, 3))) return e;    // S22 = B22 + B21 Z
+    if ((e = bdmul(st, Bc, N, 0, Bd, 0, Z, Vt, 1.0, nullptr, 0.0, 0.0, Bd, 1))) return e;          // Vt = B12 + B11 Z
+    if ((e = gemm(st, Bc, n, A.blk[1], Vt, O.blk[1]))) return e;                                   // S12 = A12 Vt
+    return 0;
+}
+
+
+// S = A (*) B for any mix of dense / BD operands.  The result goes to out_bd when both are BD, else to out_dense.
+static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res) {
+    const int n = 2 * N;
+    if (A.bd && B.bd) {
+        bd_star_args a{Bc, N, A.bdp, B.bdp, out_bd};
+        int e = kh_launch<bd_star_args, bd_star_body>(dim3(Bc), 128, 0, st, a, "bd_star");
+        res = sref_bd(out_bd);
+        return e;
+    }
+    int e;
+    if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info);
+    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info);
+    else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info);
+    res = sref_dense(out_dense, n);
+    return e;
+}
+
 // ---------------------------------------------------------------------------- plan
 struct kh_plan {
     int P, Q, N, n;
@@ -356,27 +426,57 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         if (want_fields) KH_TRY(keep_eigenspace_bd(st, p, Bc, cb, out, b0));
 
         // ---- forward chain (layer.py:41-47).  The reference starts from the identity S-matrix,
-        // and identity (*) S0 == S0 exactly, so the chain starts at the first layer.
-        SRef acc = S[p->stack[0]];
+        // and identity (*) S0 == S0 exactly, so the chain starts at the first layer.  The star product is
+        // associative: without field outputs, runs of consecutive BD layers (uniform layers / half spaces)
+        // are first collapsed analytically (O(N) each) and only then combined with the dense operands.
+        SRef acc; acc.bd = false; acc.bdp = nullptr;
+        bool have_acc = false;
         cd* acc_full = nullptr;                 // set when acc is a contiguous dense [Bc][4][n][n] stack
         int pd = 0, pb = 0;
-        if (want_fields) KH_TRY(materialise(st, Bc, N, acc, (cd*)out->prefix_dev + ((long long)b0 * Ls + 0) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
-        for (int i = 1; i < Ls; ++i) {
-            const SRef& R = S[p->stack[i]];
-            if (acc.bd && R.bd) {
-                bd_star_args a{Bc, N, acc.bdp, R.bdp, cb.accB[pb]};
-                KH_TRY((kh_launch<bd_star_args, bd_star_body>(dim3(Bc), 128, 0, st, a)));
-                acc = sref_bd(cb.accB[pb]); pb ^= 1;
-            } else {
-                SRef Ad = acc, Rd = R;
-                if (acc.bd) { KH_TRY(materialise(st, Bc, N, acc, cb.expA, 4 * n2, nullptr)); Ad = sref_dense(cb.expA, n); }
-                if (R.bd) { KH_TRY(materialise(st, Bc, N, R, cb.expB, 4 * n2, nullptr)); Rd = sref_dense(cb.expB, n); }
-                KH_TRY(dense_star(st, Bc, n, Ad, Rd, cb.accD[pd], cb.pool, cb.vec.info_inv + 2 * Bc));
-                if (info_out) { info_args ia{Bc, nullptr, cb.vec.info_inv + 2 * Bc, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
-                acc = sref_dense(cb.accD[pd], n); acc_full = cb.accD[pd]; pd ^= 1;
+        int* sinfo = cb.vec.info_inv + 2 * Bc;
+        auto note_info = [&]() -> int {
+            if (!info_out) return 0;
+            info_args ia{Bc, nullptr, sinfo, info_out};
+            return kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia);
+        };
+        auto combine = [&](const SRef& A, const SRef& Bm, SRef& res) -> int {
+            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res);
+            if (e) return e;
+            if (res.bd) pb ^= 1;
+            else { acc_full = cb.accD[pd]; pd ^= 1; e = note_info(); }
+            return e;
+        };
+        if (want_fields) {
+            for (int i = 0; i < Ls; ++i) {
+                const SRef& R = S[p->stack[i]];
+                if (!have_acc) { acc = R; have_acc = true; }
+                else { SRef r2; KH_TRY(combine(acc, R, r2)); acc = r2; }
+                KH_TRY(materialise(st, Bc, N, acc, (cd*)out->prefix_dev + ((long long)b0 * Ls + i) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
             }
-            if (want_fields) KH_TRY(materialise(st, Bc, N, acc, (cd*)out->prefix_dev + ((long long)b0 * Ls + i) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
+        } else {
+            SRef pend; pend.bd = true; pend.bdp = nullptr;
+            bool have_pend = false;
+            for (int i = 0; i < Ls; ++i) {
+                const SRef& R = S[p->stack[i]];
+                if (R.bd) {
+                    if (!have_pend) { pend = R; have_pend = true; }
+                    else { SRef r2; KH_TRY(combine(pend, R, r2)); pend = r2; }
+                } else {
+                    if (have_pend) {
+                        if (!have_acc) { acc = pend; have_acc = true; }
+                        else { SRef r2; KH_TRY(combine(acc, pend, r2)); acc = r2; }
+                        have_pend = false;
+                    }
+                    if (!have_acc) { acc = R; have_acc = true; }
+                    else { SRef r2; KH_TRY(combine(acc, R, r2)); acc = r2; }
+                }
+            }
+            if (have_pend) {
+                if (!have_acc) { acc = pend; have_acc = true; }
+                else { SRef r2; KH_TRY(combine(acc, pend, r2)); acc = r2; }
+            }
         }
+        if (!acc.bd && acc.blk[0].p != acc_full) acc_full = nullptr;      // acc still refers to a layer table
         if (acc.bd || !acc_full) { KH_TRY(materialise(st, Bc, N, acc, cb.accD[pd], 4 * n2, nullptr)); acc_full = cb.accD[pd]; }
         cd* final_dst = acc_full;
         if (out->Stot_dev) {

@@ -78,9 +78,17 @@ KH_HD cd cexp_(cd z) {
     return mk(e * c, e * s);
 }
 
+// 1/sqrt(x) for normal positive x: hardware seed (MUFU.RSQ64H) + two Newton steps, branch free.
+// Used on the critical path of the Givens rotations (library rsqrt()/sqrt()/division carry slow-path branches).
 KH_HD double kh_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
 #else
     return 1.0 / sqrt(x);
 #endif

@@ -120,17 +120,10 @@ static int reverse_chain(kh_stream_t st, const kh_plan* p, int Bc, const std::ve
         KH_TRY(materialise(st, Bc, N, acc, (cd*)out->suffix_dev + ((long long)b0 * Ls + i) * 4 * n2, (long long)Ls * 4 * n2, cb.expA));
         if (i == 0) break;
         const SRef& L = S[p->stack[i]];
-        if (acc.bd && L.bd) {
-            bd_star_args a{Bc, N, L.bdp, acc.bdp, cb.accB[pb]};
-            KH_TRY((kh_launch<bd_star_args, bd_star_body>(dim3(Bc), 128, 0, st, a)));
-            acc = sref_bd(cb.accB[pb]); pb ^= 1;
-        } else {
-            SRef Ld = L, Ad = acc;
-            if (L.bd) { KH_TRY(materialise(st, Bc, N, L, cb.expA, 4 * n2, nullptr)); Ld = sref_dense(cb.expA, n); }
-            if (acc.bd) { KH_TRY(materialise(st, Bc, N, acc, cb.expB, 4 * n2, nullptr)); Ad = sref_dense(cb.expB, n); }
-            KH_TRY(dense_star(st, Bc, n, Ld, Ad, cb.accR[pd], cb.pool, cb.vec.info_inv + 2 * Bc));
-            acc = sref_dense(cb.accR[pd], n); pd ^= 1;
-        }
+        SRef r2;
+        KH_TRY(star_any(st, Bc, N, L, acc, cb.accR[pd], cb.accB[pb], cb.pool, cb.vec.info_inv + 2 * Bc, r2));
+        if (r2.bd) pb ^= 1; else pd ^= 1;
+        acc = r2;
     }
     return 0;
 }

@@ -202,6 +202,37 @@ KH_DEV void bd_expand_body(const Cta& c, const bd_expand_args& a) {
     }
 }
 
+// dense (x) BD products, O(n^2):  out = alpha * (BD . M | M . BD) + beta * Cin + diag * I + expand(addbd)
+// (used by the star products whose left or right operand is a uniform layer / half space)
+struct bdmul_args {
+    int B, N, side;                 // side 0: BD . M ; side 1: M . BD
+    const cd* bd; int blk;          // BD table [B][4][4][N], block index
+    MatRef M, Cin, out;             // Cin.p may be null
+    const cd* addbd; int addblk;    // optional BD block added to the result
+    double alpha, beta, diag;
+};
+KH_DEV void bdmul_body(const Cta& c, const bdmul_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const cd* bd = a.bd + (long long)b * 16 * N + (long long)a.blk * 4 * N;
+    const cd* ad = a.addbd ? a.addbd + (long long)b * 16 * N + (long long)a.addblk * 4 * N : (const cd*)0;
+    const cd* M = mat_ptr(a.M, b);
+    const cd* Cin = mat_ptr(a.Cin, b);
+    cd* out = mat_ptr(a.out, b);
+    const int rows_per = (n + 3) / 4, r0 = c.by * rows_per, r1 = (r0 + rows_per < n) ? r0 + rows_per : n;
+    for (int e = r0 * n + c.tid; e < r1 * n; e += c.nthr) {
+        const int i = e / n, j = e - i * n;
+        const int hi = i >= N, gi = i - hi * N, hj = j >= N, gj = j - hj * N;
+        cd v;
+        if (a.side == 0) v = bd[(hi * 2 + 0) * N + gi] * M[(long long)gi * a.M.ld + j] + bd[(hi * 2 + 1) * N + gi] * M[(long long)(N + gi) * a.M.ld + j];
+        else v = M[(long long)i * a.M.ld + gj] * bd[(0 * 2 + hj) * N + gj] + M[(long long)i * a.M.ld + N + gj] * bd[(1 * 2 + hj) * N + gj];
+        v = a.alpha * v;
+        if (Cin) v = v + a.beta * Cin[(long long)i * a.Cin.ld + j];
+        if (i == j) v.x += a.diag;
+        if (ad && gi == gj) v = v + ad[(hi * 2 + hj) * N + gi];
+        out[(long long)i * a.out.ld + j] = v;
+    }
+}
+
 // ------------------------------------------------------------------ patterned layer: P, Q (alternative.py:158-171)
 struct pq_args {
     int B, N;

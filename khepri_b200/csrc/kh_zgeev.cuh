@@ -37,20 +37,16 @@ struct zgeev_args {
 struct kh_givens { double c; cd s, r; };
 KH_DEV kh_givens make_givens(cd f, cd g) {
     // G = [[c, s], [-conj(s), c]],  G [f; g] = [r; 0];  c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = sqrt(|f|^2+|g|^2).
-    // Two reciprocal square roots and no division: the rotation sits on the critical path of the sweep.
+    // With y = 1/sqrt(|f|^2 h^2):  c = |f|^2 y,  s = y f conj(g),  r = (h^2 y) f  -- ONE reciprocal square root, no
+    // division, no branch (the degenerate cases are selects): the rotation sits on the critical path of the sweep.
     kh_givens G;
-    const double g2 = cabs2(g), f2 = cabs2(f);
-    if (g2 == 0.0) { G.c = 1.0; G.s = mk(0, 0); G.r = f; return G; }
-    if (f2 == 0.0) {
-        const double ig = kh_rsqrt(g2);
-        G.c = 0.0; G.s = ig * cconj(g); G.r = mk(g2 * ig, 0);
-        return G;
-    }
-    const double h2 = f2 + g2;
-    const double p = kh_rsqrt(f2), q = kh_rsqrt(h2), pq = p * q;
-    G.c = f2 * pq;
-    G.s = pq * (f * cconj(g));
-    G.r = (p * (h2 * q)) * f;
+    const double g2 = cabs2(g), f2 = cabs2(f), h2 = f2 + g2;
+    const bool f0 = (f2 == 0.0), g0 = (g2 == 0.0);
+    const double y = kh_rsqrt(f0 ? g2 : f2 * h2);
+    const cd fg = f * cconj(g);
+    G.c = g0 ? 1.0 : (f0 ? 0.0 : f2 * y);
+    G.s = g0 ? mk(0, 0) : (f0 ? y * cconj(g) : y * fg);
+    G.r = g0 ? f : (f0 ? mk(g2 * y, 0.0) : (h2 * y) * f);
     return G;
 }
 
@@ -307,6 +303,8 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         cd sub = HQ(l + 1, l);
         cd pend_sub = mk(0, 0), pend_diag = mk(0, 0);
         int o1 = ROWOFF(l + 1);                     // offset of row k+1 (running)
+        const int m0 = l + c.tid, moff = ROWOFF(m0 < n ? m0 : 0);
+        const bool one_idx = PACKED && c.nthr >= n;
         for (int k = l; k < iact; ++k) {
             const bool more = (k + 1 < iact);
             const int o2 = o1 + ROWSTEP(k + 1);     // offset of row k+2
@@ -322,9 +320,9 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 nextsub = Gn.c * d1 - cconj(Gn.s) * b1;     // H[k+2][k+1] after R(k+1)
             }
             // M(k) = C(k) on rows l..k  ||  R(k+1) on columns k+2..iact   (disjoint entries)
-            for (int m = l + c.tid; m <= iact; m += c.nthr) {
+            for (int m = m0; m <= iact; m += c.nthr) {
                 if (m <= k) {
-                    cd* hr = Hb + ROWOFF(m) + k;
+                    cd* hr = Hb + (one_idx ? moff : ROWOFF(m)) + k;
                     cd h0 = hr[0], h1 = hr[1];
                     if (m == k && k > l) { h0 = pend_diag; hr[-1] = pend_sub; }   // row k: stored now, nobody reads it earlier
                     hr[0] = G.c * h0 + cconj(G.s) * h1;
@@ -335,6 +333,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     Hb[o1 + j] = Gn.c * h0 + Gn.s * h1;
                     Hb[o2 + j] = Gn.c * h1 - cconj(Gn.s) * h0;
                 }
+                if (one_idx) break;                  // packed path on the GPU: nthr >= n, one index per thread
             }
             if (more && c.tid == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; }
             pend_sub = Gn.r; pend_diag = newdiag; sub = nextsub; G = Gn; o1 = o2;
