@@ -64,7 +64,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     double* scratch = (double*)(uu + n);
     double* dsc = scratch + 192;       // [n] balancing factors; the region is 4n doubles and is reused as q / zu afterwards
     cd* H; int ld;
-    if (a.use_smem) { H = (cd*)(((uintptr_t)(dsc + 4 * n) + 15) & ~(uintptr_t)15); ld = a.ld_s; }
+    if (a.use_smem) { H = (cd*)(KH_SMEM(c) + (((2 * n * 16 + 192 * 8 + 4 * n * 8) + 15) & ~15)); ld = a.ld_s; }   // offset arithmetic keeps the shared address space
     else { H = Hg; ld = a.Hw.ld; }
 #define HH(i, j) H[(long long)(i) * ld + (j)]
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
@@ -212,7 +212,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     cd* gs = (cd*)KH_SMEM(c);
     double* gc = (double*)(gs + n);
     int* ctl = (int*)(gc + n);
-    cd* Hp = (cd*)(((uintptr_t)(ctl + 8) + 15) & ~(uintptr_t)15);
+    cd* Hp = (cd*)(KH_SMEM(c) + (((n * 16 + n * 8 + 8 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
     const bool packed = PACKED;
     cd* const Hb = PACKED ? Hp : Hg;
 #define ROWOFF(i) (PACKED ? hp_off((i), n) : (i) * ldg)

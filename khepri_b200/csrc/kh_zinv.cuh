@@ -28,7 +28,7 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
     cd* W;
     int ld;
     if (a.use_smem) {
-        W = (cd*)(((uintptr_t)(piv + n) + 15) & ~(uintptr_t)15);
+        W = (cd*)(KH_SMEM(c) + (((2 * n * 16 + 128 * 8 + n * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
         ld = a.ld_s;
     } else {
         W = Out;
