@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads and exports every symbol include/khepri_b200.h declares; host-side
+logic (expansion, k-vectors, sources, error behaviour) mirrors the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import rcwa_oracle as orc
+from tests.util import ROOT
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "khepri_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kh_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = header_symbols()
+    for must in ("kh_convmat", "kh_toeplitz_gather", "kh_zgemm_batched", "kh_zinv_batched", "kh_zgeev_batched", "kh_plan_create",
+                 "kh_solve_batch", "kh_star_batch", "kh_flux_batch", "kh_fields_batch"):
+        assert must in syms
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    """No compute call is made (there is no GPU here) -- only that the product .so loads and binds."""
+    from khepri_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/khepri_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(header_symbols())
+    bound = _lib.bind()
+    assert bound.kh_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    from khepri_b200 import Crystal, Engine, KhepriError
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(KhepriError):
+        Engine()
+    cl = Crystal((3, 3))
+    cl.add_layer_uniform("U", 2.0, 0.1)
+    cl.set_device(["U"])
+    cl.set_source(1.0)
+    with pytest.raises(KhepriError):
+        cl.solve()                       # the product path fails loudly instead of computing on the CPU
+    with pytest.raises(KhepriError):
+        from khepri_b200 import _lib
+        _lib.bind("/nonexistent/libkhepri_b200.so")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "khepri_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|\boracle\.[a-z_]+\(|rcwa_oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_expansion_matches_oracle_and_reference_conventions():
+    from khepri_b200 import Expansion
+    from khepri_b200.expansion import generate_expansion_indices
+    with pytest.raises(AssertionError):
+        generate_expansion_indices((4, 3))                        # odd pw asserted (expansion.py:10-11)
+    lat = 0.9 * np.array([[np.sqrt(3) / 2, 0.5], [np.sqrt(3) / 2, -0.5]])
+    e = Expansion((5, 3), lat)
+    assert np.array_equal(e.expansion_indices, orc.harmonic_indices((5, 3)))
+    assert np.allclose(e.g_vectors, orc.g_vectors((5, 3), lat), rtol=0, atol=0)
+    kv = e.k_vectors((0.3 + 0j, -0.2 + 0j), 1.3, 2.25 - 0.1j)
+    ko = orc.k_vectors(orc.g_vectors((5, 3), lat), (0.3 + 0j, -0.2 + 0j), 1.3, 2.25 - 0.1j)
+    assert np.array_equal(kv, np.stack(ko))
+    e1, e2 = Expansion((3, 3)), Expansion((3, 3))
+    e1.rotate(0.1)
+    e2.rotate(-0.1)
+    m = e1 + e2
+    assert m.pw == (9, 9) and m.expansion_lhs is e1 and m.expansion_rhs is e2
+    assert np.allclose(m.g_vectors, orc.minkowski_sum(e1.g_vectors, e2.g_vectors))
+
+
+def test_source_and_incident_vector():
+    from khepri_b200 import Crystal
+    from khepri_b200.alternative import incident
+    from khepri_b200.tools import compute_kplanar
+    cl = Crystal((3, 3), epsi=1.44)
+    cl.set_source(1.3, 0.6, 0.8, theta=20.0, phi=35.0)
+    assert np.allclose(cl.kp, orc.kplanar(1.44, 1.3, 20.0, 35.0))
+    assert np.allclose(compute_kplanar(1.44, 1.3, 20.0, 35.0), orc.kplanar(1.44, 1.3, 20.0, 35.0))
+    kv = (cl.kp[0], cl.kp[1], cl.kzi)
+    assert np.allclose(incident((3, 3), 0.6, 0.8, kv), orc.incident_vector((3, 3), 0.6, 0.8, kv))
+    cl.set_source(0.9, kp=(0.1, 0.2))
+    assert cl.kp == (0.1, 0.2)
+    with pytest.raises(NotImplementedError):
+        Crystal((3, 3), lattice="kagome")
+    with pytest.raises(NotImplementedError):
+        cl.add_layer_analytical("a", [], 1.0, 0.1)
+
+
+def test_set_device_adds_half_spaces_like_the_reference():
+    from khepri_b200 import Crystal, Formulation
+    cl = Crystal((3, 3), epsi=2.0, epse=3.0)
+    cl.add_layer_uniform("U", 2.0, 0.1)
+    cl.add_layer_pixmap("P", np.ones((8, 8)) + np.eye(8), 0.2)
+    cl.set_device(["U", "P", "U"], [True, False, True])
+    assert cl.global_stacking == ["Sref", "U", "P", "U", "Strans"]
+    assert cl.stack_retain_mask == [True, True, False, True, True]
+    assert cl.layers["Sref"].formulation == Formulation.HALF_SPACE_INC and cl.layers["Sref"].epsilon == 2.0
+    assert cl.layers["Strans"].formulation == Formulation.HALF_SPACE_TRN and cl.layers["Strans"].epsilon == 3.0
+    assert cl.layers["U"].fields and not cl.layers["P"].fields
+    assert cl.depth == pytest.approx(0.4) and not cl.solved and not cl.source_defined

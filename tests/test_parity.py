@@ -239,3 +239,51 @@ def test_energy_conservation_and_batch_invariance(backend):
     assert np.array_equal(R2, R[perm]) and np.array_equal(T2, T[perm])
     R0, T0 = cl.solve_batch(np.zeros(0), kps=np.zeros((0, 2)))
     assert R0.shape == (0,) and T0.shape == (0,)
+
+
+# ----------------------------------------------------------------------------- sizes beyond shared memory / full-size properties
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_large_matrices_take_the_global_memory_paths(backend):
+    """n > 118 does not fit in shared memory: inverse and eigensolver run on HBM/L2-resident matrices."""
+    eng = engine(backend)
+    rng = np.random.default_rng(7)
+    n = 130 if backend == "cuda" else 122
+    A = rng.standard_normal((2, n, n)) + 1j * rng.standard_normal((2, n, n))
+    Ai = eng.zinv(A).cpu().numpy()
+    assert np.abs(Ai @ A - np.eye(n)).max() <= 1e-10
+    w, W, info = eng.zgeev(A[:1])
+    assert int(info.max().item()) == 0
+    w, W = w.cpu().numpy(), W.cpu().numpy()
+    assert np.abs(A[0] @ W[0] - W[0] * w[0][None, :]).max() <= 1e-10 * np.abs(A[0]).max() * np.abs(W[0]).max()
+
+
+@pytest.mark.gpu
+def test_full_size_bzi_step_properties():
+    """BASELINE configs[1] at bench size (16 k-points x 101 wavelengths, 7x7): lossless stack -> R + T = 1;
+    the chunked run equals the single-pass run bit for bit; a sample of solves matches the oracle."""
+    eng = engine("cuda")
+    st = cases.bzi_structure((7, 7))
+    kg = cases.bzi_kgrid((64, 64)).reshape(2, -1)
+    wls = 1 / np.linspace(0.8, 1.0, 101)
+    ks = kg[:, 100:116]
+    wl = np.tile(wls, 16)
+    kp = np.repeat(ks.T, 101, axis=0)
+    cl = build_crystal(st, eng)
+    R, T = cl.solve_batch(wl, kps=kp, te=1.0, tm=1.0)
+    assert np.isfinite(R).all() and np.abs(R + T - 1).max() < 1e-9
+    R2, T2 = cl.solve_batch(wl, kps=kp, te=1.0, tm=1.0, chunk=300)
+    assert np.array_equal(R, R2) and np.array_equal(T, T2)
+    for i in (0, 517, 1615):
+        ref = orc.solve_rt(st, wl[i], 1.0, 1.0, kp=(complex(kp[i, 0]), complex(kp[i, 1])))
+        rt_close([R[i], T[i]], ref)
+
+
+@pytest.mark.gpu
+def test_convmat_512_and_batch_of_layers():
+    eng = engine("cuda")
+    pm = cases.disc_pixmap((512, 512), 12, (0.0, 0.0), 0.4, 1.0)
+    pm2 = cases.rect_pixmap((512, 512), 1, (0.1, -0.2), (0.3, 0.6), 9.0)
+    C = eng.convmat(np.stack([pm, pm2]), (15, 15)).cpu().numpy()
+    for k, p in enumerate((pm, pm2)):
+        ref = orc.convolution_matrix(p, (15, 15))
+        assert np.abs(C[k] - ref).max() <= 1e-14 * np.abs(ref).max()
