@@ -35,6 +35,9 @@ struct zgeev_args {
 #define ZGEEV_SAFMIN 2.2250738585072014e-308
 
 struct kh_givens { double c; cd s, r; };
+#ifndef KH_HOST_EMU
+__device__ __forceinline__ cd kh_shfl_cd(cd v, int src) { return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+#endif
 KH_DEV kh_givens make_givens(cd f, cd g) {
     // G = [[c, s], [-conj(s), c]],  G [f; g] = [r; 0];  c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = sqrt(|f|^2+|g|^2).
     // With y = 1/sqrt(|f|^2 h^2):  c = |f|^2 y,  s = y f conj(g),  r = (h^2 y) f  -- ONE reciprocal square root, no
@@ -210,9 +213,11 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     cd* wout = a.w + (long long)b * a.w_stride;
     // shared: [gs n cd][gc n dbl][ctl 8 int][packed H]  (H stays in global memory, full storage, when it does not fit)
     cd* gs = (cd*)KH_SMEM(c);
-    double* gc = (double*)(gs + n);
-    int* ctl = (int*)(gc + n);
-    cd* Hp = (cd*)(KH_SMEM(c) + (((n * 16 + n * 8 + 8 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
+    cd* qsub = gs + n;                 // queue of the warp-specialised sweep: row k's sub-diagonal / diagonal after R(k)
+    cd* qdiag = qsub + n;
+    double* gc = (double*)(qdiag + n);
+    int* ctl = (int*)(gc + n);         // [0] deflation scan, [1] published-rotation counter, [2] error flag
+    cd* Hp = (cd*)(KH_SMEM(c) + (((3 * n * 16 + n * 8 + 8 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
     const bool packed = PACKED;
     cd* const Hb = PACKED ? Hp : Hg;
 #define ROWOFF(i) (PACKED ? hp_off((i), n) : (i) * ldg)
@@ -221,6 +226,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
     if (packed)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; if (j >= i - 1) HQ(i, j) = Hg[(long long)i * ldg + j]; }
+    if (c.tid == 0) ctl[2] = 0;
     c.sync();
 
     const double smlnum = ZGEEV_SAFMIN * ((double)n / ZGEEV_EPS);
@@ -289,7 +295,103 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         // R(k): rows k,k+1 <- G_k (window columns);  C(k): columns k,k+1 <- . G_k^H (window rows <= k+2).
         // Thread t owns index m = l + t: it applies the row steps to column m+1 while k < m and the column
         // steps to row m once k >= m, so its addresses advance by running offsets (no multiplies in the loop).
-        kh_givens G = make_givens(HQ(l, l) - t, HQ(l + 1, l));
+        const cd f_first = HQ(l, l) - t, g_first = HQ(l + 1, l);
+#ifndef KH_HOST_EMU
+        if (PACKED && c.nthr == 128) {
+            // ===== warp-specialised sweep (GPU, packed path).  Warp 0 (the driver) runs the whole dependent chain --
+            // corner, Givens rotation, row steps on every window column (lane q owns columns l+lane+32q, the bottom
+            // entry of each column stays in a register) -- using shuffles only, and publishes every rotation into a
+            // shared-memory queue.  Warps 1-3 (followers) apply the column steps to the rows they own, lagging behind.
+            // No block-wide barrier is on the critical path.
+            volatile int* prog = ctl + 1;              // rotations with index < *prog are published
+            if (c.tid == 0) *prog = l;
+            __syncthreads();                           // (also: everyone has read H before the sweep writes)
+            const int warp = c.tid >> 5, lane = c.tid & 31;
+            if (warp == 0) {
+                kh_givens G = make_givens(f_first, g_first);
+                cd carry[4];
+                const int ol = ROWOFF(l);
+                int o1 = ol + ROWSTEP(l);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                          // R(l)
+                    const int j = l + lane + 32 * q;
+                    carry[q] = mk(0, 0);
+                    if (j <= iact) {
+                        const cd h0 = Hb[ol + j], h1 = Hb[o1 + j];
+                        Hb[ol + j] = G.c * h0 + G.s * h1;
+                        carry[q] = G.c * h1 - cconj(G.s) * h0;
+                    }
+                }
+                cd sub = kh_shfl_cd(carry[0], 0), cb = kh_shfl_cd(carry[0], 1);     // H[l+1][l], H[l+1][l+1] after R(l)
+                if (lane == 0) { gc[l] = G.c; gs[l] = G.s; }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); *prog = l + 1; }
+                for (int k = l; k < iact; ++k) {
+                    const int o2 = o1 + ROWSTEP(k + 1);
+                    const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;      // C(k) on row k+1
+                    if (k + 1 < iact) {
+                        const cd hd = Hb[o2 + k + 1];            // H[k+2][k] is zero: C(k) creates the bulge there
+                        const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;
+                        const kh_givens Gn = make_givens(a1, c1);
+                        const cd newdiag = Gn.c * b1 + Gn.s * d1, nextsub = Gn.c * d1 - cconj(Gn.s) * b1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {              // R(k+1) on the owned columns >= k+2
+                            const int j = l + lane + 32 * q;
+                            if (j >= k + 2 && j <= iact) {
+                                const cd h1 = Hb[o2 + j], h0 = carry[q];
+                                Hb[o1 + j] = Gn.c * h0 + Gn.s * h1;
+                                carry[q] = Gn.c * h1 - cconj(Gn.s) * h0;
+                            }
+                        }
+                        const int src = k + 2 - l;                  // column k+2 carries the next corner diagonal
+                        cd v = carry[0];
+                        if ((src >> 5) == 1) v = carry[1];
+                        if ((src >> 5) == 2) v = carry[2];
+                        if ((src >> 5) == 3) v = carry[3];
+                        cb = kh_shfl_cd(v, src & 31);
+                        if (lane == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; qsub[k + 1] = Gn.r; qdiag[k + 1] = newdiag; }
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); *prog = k + 2; }
+                        sub = nextsub; G = Gn; o1 = o2;
+                    } else if (lane == 0) {
+                        Hb[o1 + k] = a1; Hb[o1 + k + 1] = b1;     // row iact: H[iact][iact-1], H[iact][iact]
+                    }
+                }
+            } else {
+                const int r0 = l + (c.tid - 32), r1 = r0 + 96;      // rows owned by this follower
+                const int rmin = l + (warp - 1) * 32;
+                const int or0 = (r0 < n) ? ROWOFF(r0) : 0, or1 = (r1 < n) ? ROWOFF(r1) : 0;
+                cd car0 = mk(0, 0), car1 = mk(0, 0);
+                if (rmin < iact) {
+                    for (int k = rmin; k < iact; ++k) {
+                        int spins = 0;
+                        while (*prog <= k) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } }
+                        __threadfence_block();
+                        const double cc = gc[k]; const cd ss = gs[k];
+                        if (r0 <= k) {
+                            cd h0 = car0;
+                            if (r0 == k) { if (k > l) { h0 = qdiag[k]; Hb[or0 + k - 1] = qsub[k]; } else h0 = Hb[or0 + k]; }
+                            const cd h1 = Hb[or0 + k + 1];
+                            Hb[or0 + k] = cc * h0 + cconj(ss) * h1;
+                            car0 = cc * h1 - ss * h0;
+                        }
+                        if (r1 <= k) {
+                            cd h0 = car1;
+                            if (r1 == k) { h0 = qdiag[k]; Hb[or1 + k - 1] = qsub[k]; }
+                            const cd h1 = Hb[or1 + k + 1];
+                            Hb[or1 + k] = cc * h0 + cconj(ss) * h1;
+                            car1 = cc * h1 - ss * h0;
+                        }
+                    }
+                    if (r0 < iact) Hb[or0 + iact] = car0;
+                    if (r1 < iact) Hb[or1 + iact] = car1;
+                }
+            }
+            __syncthreads();
+        } else
+#endif
+        {
+        kh_givens G = make_givens(f_first, g_first);
         c.sync();                                   // everyone has read H before the sweep writes
         for (int j = l + c.tid; j <= iact; j += c.nthr) {          // R(l)
             cd h0 = HQ(l, j), h1 = HQ(l + 1, j);
@@ -340,6 +442,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             c.sync();
         }
         if (c.tid == 0) { HQ(iact, iact - 1) = pend_sub; HQ(iact, iact) = pend_diag; }
+        }
         // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
         {
             const int nAbove = l, nRight = n - 1 - iact;
@@ -394,7 +497,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             int i = e / n, j = e - i * n;
             Hg[(long long)i * ldg + j] = (j >= i) ? HQ(i, j) : mk(0.0, 0.0);
         }
-    if (a.info && c.tid == 0) a.info[b] = fail;
+    if (a.info && c.tid == 0) a.info[b] = (fail == 0 && ctl[2] != 0) ? n + 1 : fail;
 #undef HQ
 #undef ROWOFF
 #undef ROWSTEP
@@ -445,7 +548,7 @@ static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
     return s;
 }
 static inline size_t zqr_smem_bytes(int n, int use_smem) {
-    size_t s = (size_t)n * sizeof(cd) + (size_t)n * sizeof(double) + 8 * sizeof(int) + 16;
+    size_t s = (size_t)3 * n * sizeof(cd) + (size_t)n * sizeof(double) + 8 * sizeof(int) + 16;
     if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
     return s;
 }
