@@ -660,3 +660,7 @@ extern "C" int kh_profile_end(char* buf, size_t len) {
 #endif
     return 0;
 }
+
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+extern "C" int kh_qr_timing(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, kh_qr_dbg, 16 * sizeof(long long)); }
+#endif

@@ -84,8 +84,7 @@ KH_HD double kh_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
+    double hx = 0.5 * x;                      // seed ~ 2^-20 relative: two Newton steps reach double precision
     y = y * fma(-hx * y, y, 1.5);
     y = y * fma(-hx * y, y, 1.5);
     return y;

@@ -204,6 +204,16 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
 KH_HD int hp_off(int i, int n) { return i * n - ((i - 1) * i) / 2; }
 KH_HD int hp_size(int n) { return hp_off(n - 1, n) + n + 3; }
 
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+__device__ long long kh_qr_dbg[16];
+#define QT_DECL long long qt0 = clock64(), qt_scan = 0, qt_shift = 0, qt_sweep = 0, qt_delay = 0, qt_n = 0, qt_rot = 0, qt_t
+#define QT_MARK() (qt_t = clock64())
+#define QT_ADD(v) do { long long _n = clock64(); (v) += _n - qt_t; qt_t = _n; } while (0)
+#else
+#define QT_DECL
+#define QT_MARK()
+#define QT_ADD(v)
+#endif
 template <bool PACKED>
 KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int n = a.n, b = c.bx;
@@ -233,7 +243,9 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int itmax = 30 * (n > 10 ? n : 10);
     int fail = 0;
     int iact = n - 1, its = 0;
+    QT_DECL;
     while (iact >= 0) {
+        QT_MARK();
         // ---- locate the active block [l, iact] (zlahqr deflation criterion)
         if (c.tid == 0) ctl[0] = 0;
         c.sync();
@@ -270,6 +282,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         }
         its += 1;
         if (its > itmax) { fail = iact + 1; break; }
+        QT_ADD(qt_scan);
         // ---- shift (zlahqr)
         cd t;
         if (its % 10 == 0 && (its / 10) % 2 == 1) t = HQ(l, l) + mk(0.75 * cabs1(HQ(l + 1, l)), 0.0);
@@ -296,8 +309,9 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         // Thread t owns index m = l + t: it applies the row steps to column m+1 while k < m and the column
         // steps to row m once k >= m, so its addresses advance by running offsets (no multiplies in the loop).
         const cd f_first = HQ(l, l) - t, g_first = HQ(l + 1, l);
+        QT_ADD(qt_shift);
 #ifndef KH_HOST_EMU
-        if (PACKED && c.nthr == 128) {
+        if (PACKED && c.nthr >= 128 && n <= 128) {     // the driver's lanes own at most four columns each
             // ===== warp-specialised sweep (GPU, packed path).  Warp 0 (the driver) runs the whole dependent chain --
             // corner, Givens rotation, row steps on every window column (lane q owns columns l+lane+32q, the bottom
             // entry of each column stays in a register) -- using shuffles only, and publishes every rotation into a
@@ -357,7 +371,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                         Hb[o1 + k] = a1; Hb[o1 + k + 1] = b1;     // row iact: H[iact][iact-1], H[iact][iact]
                     }
                 }
-            } else {
+            } else if (warp < 4) {
                 const int r0 = l + (c.tid - 32), r1 = r0 + 96;      // rows owned by this follower
                 const int rmin = l + (warp - 1) * 32;
                 const int or0 = (r0 < n) ? ROWOFF(r0) : 0, or1 = (r1 < n) ? ROWOFF(r1) : 0;
@@ -443,6 +457,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         }
         if (c.tid == 0) { HQ(iact, iact - 1) = pend_sub; HQ(iact, iact) = pend_diag; }
         }
+        QT_ADD(qt_sweep);
         // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
         {
             const int nAbove = l, nRight = n - 1 - iact;
@@ -469,15 +484,26 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     const int i = t2 - nAbove - nRight;
                     cd z0 = ZT(l, i);
                     int k = l;
-                    for (; k + 8 <= iact; k += 8) {                  // 8 independent loads in flight hide the L2 latency
-                        cd zn[8];
+                    if (k + 8 <= iact) {                             // software pipeline: the next 8 rows of Zt are in flight
+                        cd zn[8], zp[8];                             // while the current 8 rotations are applied (hides the L2 latency)
 #pragma unroll
                         for (int u = 0; u < 8; ++u) zn[u] = ZT(k + 1 + u, i);
+                        for (; k + 8 <= iact; k += 8) {
+                            const bool nxt = (k + 16 <= iact);
+                            if (nxt) {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const double cc = gc[k + u]; const cd ss = gs[k + u];
-                            ZT(k + u, i) = cc * z0 + cconj(ss) * zn[u];
-                            z0 = cc * zn[u] - ss * z0;
+                                for (int u = 0; u < 8; ++u) zp[u] = ZT(k + 9 + u, i);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const double cc = gc[k + u]; const cd ss = gs[k + u];
+                                ZT(k + u, i) = cc * z0 + cconj(ss) * zn[u];
+                                z0 = cc * zn[u] - ss * z0;
+                            }
+                            if (nxt) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) zn[u] = zp[u];
+                            }
                         }
                     }
                     for (; k < iact; ++k) {
@@ -490,6 +516,10 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             }
         }
         c.sync();
+        QT_ADD(qt_delay);
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+        qt_n += 1; qt_rot += iact - l;
+#endif
     }
     c.sync();
     if (packed)
@@ -497,6 +527,12 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             int i = e / n, j = e - i * n;
             Hg[(long long)i * ldg + j] = (j >= i) ? HQ(i, j) : mk(0.0, 0.0);
         }
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    if (c.tid == 0 && b == 0) {
+        kh_qr_dbg[0] = clock64() - qt0; kh_qr_dbg[1] = qt_scan; kh_qr_dbg[2] = qt_shift; kh_qr_dbg[3] = qt_sweep;
+        kh_qr_dbg[4] = qt_delay; kh_qr_dbg[5] = qt_n; kh_qr_dbg[6] = qt_rot;
+    }
+#endif
     if (a.info && c.tid == 0) a.info[b] = (fail == 0 && ctl[2] != 0) ? n + 1 : fail;
 #undef HQ
 #undef ROWOFF
@@ -553,6 +589,9 @@ static inline size_t zqr_smem_bytes(int n, int use_smem) {
     return s;
 }
 
+#ifndef KH_QR_THREADS
+#define KH_QR_THREADS(n) ((n) <= 64 ? 128 : 256)
+#endif
 static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     if (batch <= 0 || a.n <= 0) return 0;
     const int n = a.n;
@@ -563,7 +602,8 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     if (e) return e;
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
-    if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body>(dim3(batch), n <= 126 ? 128 : 256, zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
+    // 256 threads when the delayed updates have more than 128 independent jobs (rows of Z + rows above + columns right)
+    if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), KH_QR_THREADS(n), zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
     else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
     if (e) return e;
     return kh_launch<zgeev_args, ztrevc_body>(dim3(batch), n <= 128 ? 128 : 256, 0, st, a, "zgeev_trevc", 0.25 * work);

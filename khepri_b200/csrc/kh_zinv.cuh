@@ -108,17 +108,99 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
 // in the register file, each thread owning a TR x 5 tile (the matrix is padded with identity rows /
 // columns up to the tile grid, so the elimination loop has no bounds checks).  Per step only the
 // pivot column and the two rows of the interchange travel through shared memory (double buffered:
-// two barriers per step); the rank-1 update is pure register DFMA work.
+// two barriers per step); the rank-1 update is pure register DFMA work.  Because tiles are aligned,
+// the pivot column / row of step k sit in register slot (k mod 5, k mod TR) of their owners, so the
+// step loop is unrolled by lcm(TR, 5) and every register index is a compile-time constant.
 #define ZIR_TC 5
-template <int TR>
-__device__ __forceinline__ cd zir_pick_row(const cd (&r)[TR][ZIR_TC], int p, int q) {     // r[p][q] with runtime p, static q
-    cd v = r[0][q];
+template <int TR, int KQ, int KP>
+__device__ __forceinline__ void zir_step(int k, int n, int NP, int tid, int lane, bool live, int i0, int j0, int tx, int ty,
+                                         cd (&r)[TR][ZIR_TC], cd* colk, cd* rowK, cd* rowP, int* piv, int& bad) {
+    cd* ck = colk + (k & 1) * NP; cd* rK = rowK + (k & 1) * NP; cd* rP = rowP + (k & 1) * NP;
+    const bool own_col = live && (j0 + KQ == k), own_row = live && (i0 + KP == k);
+    // A: publish column k and row k
+    if (own_col) {
 #pragma unroll
-    for (int pp = 1; pp < TR; ++pp) if (p == pp) v = r[pp][q];
-    return v;
+        for (int p = 0; p < TR; ++p) ck[i0 + p] = r[p][KQ];
+    }
+    if (own_row) {
+#pragma unroll
+        for (int q = 0; q < ZIR_TC; ++q) rK[j0 + q] = r[KP][q];
+    }
+    __syncthreads();
+    // B: every warp finds the pivot row (izamax over rows k..n-1, ties -> smallest index)
+    double best = -1.0; int pr = k;
+    for (int i = k + lane; i < n; i += 32) { const double v = cabs1(ck[i]); if (v > best) { best = v; pr = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, pr, o);
+        if (ov > best || (ov == best && oi < pr)) { best = ov; pr = oi; }
+    }
+    const int pp = pr - i0;
+    const bool own_prow = live && pr != k && (unsigned)pp < (unsigned)TR;
+    if (__any_sync(0xffffffffu, own_prow)) {                 // rare per warp: a real branch
+        if (own_prow) {
+#pragma unroll
+            for (int q = 0; q < ZIR_TC; ++q) {
+                cd v = r[0][q];
+#pragma unroll
+                for (int p2 = 1; p2 < TR; ++p2) if (pp == p2) v = r[p2][q];
+                rP[j0 + q] = v;
+            }
+        }
+    }
+    if (tid == 0) piv[k] = pr;
+    __syncthreads();
+    // C: interchange + eliminate.  Row k becomes the scaled pivot row; row pr receives the old row k.
+    const cd* prow = (pr == k) ? rK : rP;
+    const cd pv = ck[pr];
+    if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
+    const cd d = crecip(pv);
+    cd f[TR];
+#pragma unroll
+    for (int p = 0; p < TR; ++p) f[p] = ck[i0 + p];
+    if (__any_sync(0xffffffffu, own_prow)) {
+        if (own_prow) {
+#pragma unroll
+            for (int p = 0; p < TR; ++p) if (p == pp) {
+                f[p] = ck[k];
+#pragma unroll
+                for (int q = 0; q < ZIR_TC; ++q) r[p][q] = rK[j0 + q];
+            }
+        }
+    }
+    if (own_col) {
+#pragma unroll
+        for (int p = 0; p < TR; ++p) r[p][KQ] = mk(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < ZIR_TC; ++q) {
+        cd pj = prow[j0 + q] * d;
+        if (q == KQ && own_col) pj = d;
+#pragma unroll
+        for (int p = 0; p < TR; ++p) cfms(r[p][q], f[p], pj);
+        if (own_row) r[KP][q] = pj;
+    }
+    // (no barrier here: the next step writes the other buffer set)
 }
+
+template <int TR, int U, int L>
+struct zir_unroll {
+    static __device__ __forceinline__ void run(int kb, int n, int NP, int tid, int lane, bool live, int i0, int j0, int tx, int ty,
+                                               cd (&r)[TR][ZIR_TC], cd* colk, cd* rowK, cd* rowP, int* piv, int& bad) {
+        if (kb + U < n) {
+            zir_step<TR, U % ZIR_TC, U % TR>(kb + U, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
+            zir_unroll<TR, U + 1, L>::run(kb, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
+        }
+    }
+};
+template <int TR, int L>
+struct zir_unroll<TR, L, L> {
+    static __device__ __forceinline__ void run(int, int, int, int, int, bool, int, int, int, int, cd (&)[TR][ZIR_TC], cd*, cd*, cd*, int*, int&) {}
+};
+
 template <int TR>
 __device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) {
+    constexpr int L = (TR == 2) ? 10 : 20;             // lcm(TR, 5)
     const int n = a.n, b = c.bx, tid = c.tid, lane = tid & 31;
     const cd* A = mat_ptr(a.A, b);
     cd* Out = mat_ptr(a.Ainv, b);
@@ -141,70 +223,8 @@ __device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) 
             r[p][q] = (live && i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk((i == j) ? 1.0 : 0.0, 0.0);
         }
     int bad = 0;
-    for (int k = 0; k < n; ++k) {
-        cd* ck = colk + (k & 1) * NP; cd* rK = rowK + (k & 1) * NP; cd* rP = rowP + (k & 1) * NP;
-        const int kq = k - j0, kp = k - i0;
-        const bool own_col = live && (unsigned)kq < (unsigned)ZIR_TC, own_row = live && (unsigned)kp < (unsigned)TR;
-        // A: publish column k and row k
-        if (own_col) {
-#pragma unroll
-            for (int p = 0; p < TR; ++p) {
-                cd v = r[p][0];
-#pragma unroll
-                for (int qq = 1; qq < ZIR_TC; ++qq) if (kq == qq) v = r[p][qq];
-                ck[i0 + p] = v;
-            }
-        }
-        if (own_row) {
-#pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) rK[j0 + q] = zir_pick_row<TR>(r, kp, q);
-        }
-        __syncthreads();
-        // B: every warp finds the pivot row (izamax over rows k..n-1, ties -> smallest index)
-        double best = -1.0; int pr = k;
-        for (int i = k + lane; i < n; i += 32) { const double v = cabs1(ck[i]); if (v > best) { best = v; pr = i; } }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, pr, o);
-            if (ov > best || (ov == best && oi < pr)) { best = ov; pr = oi; }
-        }
-        const int pp = pr - i0;
-        const bool own_prow = live && pr != k && (unsigned)pp < (unsigned)TR;
-        if (own_prow) {
-#pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) rP[j0 + q] = zir_pick_row<TR>(r, pp, q);
-        }
-        if (tid == 0) piv[k] = pr;
-        __syncthreads();
-        // C: interchange + eliminate.  Row k becomes the scaled pivot row; row pr receives the old row k.
-        const cd* prow = (pr == k) ? rK : rP;
-        const cd pv = ck[pr];
-        if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
-        const cd d = crecip(pv);
-        cd f[TR];
-#pragma unroll
-        for (int p = 0; p < TR; ++p) f[p] = ck[i0 + p];
-        if (own_prow) {
-#pragma unroll
-            for (int p = 0; p < TR; ++p) if (p == pp) {
-                f[p] = ck[k];
-#pragma unroll
-                for (int q = 0; q < ZIR_TC; ++q) r[p][q] = rK[j0 + q];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < ZIR_TC; ++q) {
-            const bool kcol = own_col && (q == kq);
-            const cd pj = kcol ? d : prow[j0 + q] * d;
-#pragma unroll
-            for (int p = 0; p < TR; ++p) {
-                cd v = kcol ? mk(0.0, 0.0) : r[p][q];
-                cfms(v, f[p], pj);
-                r[p][q] = (own_row && p == kp) ? pj : v;
-            }
-        }
-        // (no barrier here: the next step writes the other buffer set)
-    }
+    for (int kb = 0; kb < n; kb += L)
+        zir_unroll<TR, 0, L>::run(kb, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
     __syncthreads();
     // undo the row interchanges as column interchanges (reverse order) -> destination column of every stored column
     if (tid == 0) {
