@@ -150,7 +150,7 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     st, wl, kp, pol = make_workload(args.workload, 0, 0, args.kpoints)
     n = 2 * st["pw"][0] * st["pw"][1]
-    per_step = max(ncores, min(4 * ncores, int(args.cpu_solves or 2 * ncores)))
+    per_step = max(ncores, int(args.cpu_solves or 8 * ncores))
     vals = []
     for step in range(args.warmup + args.steps):
         v, dt = cpu_time_sample(st, wl, kp, pol, per_step, ncores)
@@ -273,8 +273,14 @@ def run_gpu(args):
         roof = None
         if gem:
             ach = gem["work"] / (gem["ms"] * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_zgemm_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("workload") == args.workload and tj.get("solves_per_step_per_gpu") == B:
+                    traffic = tj["dram_bytes_per_launch"]
             roof = {"bound": "tensor", "kernel": "zgemm (batched complex128 DMMA GEMM)", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp64_peak, "traffic": None,
+                    "frac": ach / fp64_peak, "traffic": traffic,
                     "peak_source": f"FP64 peak measured live by kh_fp64_peak (DFMA {peak['dfma']:.1f}, DMMA {peak['dmma']:.1f} TFLOP/s); MEASURED_PEAKS.json has no FP64 entry",
                     "launches": gem["count"], "avg_launch_ms": gem["ms"] / gem["count"], "share_of_kernel_time": gem["ms"] / tot_kernel_ms,
                     "dominant_by_time": dom, "profiled_ms_per_step": ms_prof / args.steps,
@@ -283,7 +289,7 @@ def run_gpu(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             ncores = os.cpu_count() or 1
-            per = max(ncores, min(4 * ncores, int(args.cpu_solves or 2 * ncores)))
+            per = max(ncores, int(args.cpu_solves or 16 * ncores))
             v, dt = cpu_time_sample(st, host_in[0][0], host_in[0][1], host_in[0][2], per, ncores)
             cpu = {"value": v, "unit": "solves/s", "cores": ncores, "kind": "port",
                    "sample": f"{per} solves spread over one step's sources in {dt:.1f} s, Pool({ncores}) x 1 BLAS thread (oracle = numpy/LAPACK restatement of the reference)"}
