@@ -221,7 +221,7 @@ extern "C" void kh_plan_destroy(kh_plan* plan) { delete plan; }
 
 // ---------------------------------------------------------------------------- patterned-layer solve
 #define LAYER_TMP_SLABS 17
-struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; int* info_eig; int* info_inv; };
+struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; cd* tau; int* info_eig; int* info_inv; };
 
 // Solves one patterned layer for Bc solves of dimension n = 2N (alternative.py:158-195):
 // P, Q -> Omega^2 -> eig -> W, lambda, V -> A, B, X -> S11, S12 (written to Sout [Bc][2][n][n]).
@@ -237,25 +237,29 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
     KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q
     {   zgeev_args a;
         a.n = n; a.A = M(2); a.Hw = M(2); a.Zt = M(3); a.X = M(4);
-        a.w = v.w; a.w_stride = n; a.scale = v.scale; a.scale_stride = n; a.info = v.info_eig;
+        a.w = v.w; a.w_stride = n; a.scale = v.scale; a.scale_stride = n; a.tau = v.tau; a.tau_stride = n; a.info = v.info_eig;
         KH_TRY(zgeev_launch(st, Bc, a)); }
     {   zgemm_args g = zgemm_make(n, n, n, M(3), M(4), M(5));                    // W = diag(scale) Z X
         g.transA = 1; g.rowscale = v.scale; g.rs_stride = n; g.rs_group = 1;
         KH_TRY(zgemm_launch(st, Bc, g)); }
-    {   lam_args a{Bc, n, depth, v.w, k0, v.lam, v.xexp};
+    {   lam_args a{Bc, n, depth, v.w, k0, v.lam, v.xexp, v.tau};                // v.tau is free after the eigensolver: 1/lambda
         KH_TRY((kh_launch<lam_args, lam_body>(dim3(Bc), 128, 0, st, a))); }
-    {   zgemm_args g = zgemm_make(n, n, n, M(1), M(5), M(6));                    // V = Q W / lambda
+    if (Wkeep) {                                                                 // V = Q W / lambda is only needed for field maps
+        zgemm_args g = zgemm_make(n, n, n, M(1), M(5), M(6));
         g.colscale = v.lam; g.cs_stride = n; g.cs_group = 1; g.cs_divide = 1;
-        KH_TRY(zgemm_launch(st, Bc, g)); }
-    if (Wkeep) {
+        KH_TRY(zgemm_launch(st, Bc, g));
         copyv_args cw{n2, S(5), n2, Wkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cw)));
         copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
         copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
     }
-    // W^-1 and V^-1 in one launch over 2*Bc matrices (slabs 5,6 -> 7,8)
-    KH_TRY(zinv_launch(st, 2 * Bc, n, mref(S(5), slab, n, Bc, n2), mref(S(7), slab, n, Bc, n2), v.info_inv));
-    {   ab_args a{Bc, N, S(7), S(8), Kx, Ky, v.xexp, S(0), S(11), S(9), S(10)};  // A->0, B->11, XB->9, XA->10
-        KH_TRY((kh_launch<ab_args, ab_body>(dim3(Bc), 256, 0, st, a))); }
+    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_inv));                     // W^-1 -> 7
+    {   pv0_args a{Bc, N, S(0), Kx, Ky, S(6)};                                   // P V0 -> 6
+        KH_TRY((kh_launch<pv0_args, pv0_body>(dim3(Bc), 256, 0, st, a))); }
+    {   zgemm_args g = zgemm_make(n, n, n, M(7), M(6), M(8));                    // V^-1 V0 = L^-1 (W^-1 (P V0)) -> 8
+        g.rowscale = v.tau; g.rs_stride = n; g.rs_group = 1;
+        KH_TRY(zgemm_launch(st, Bc, g)); }
+    {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
+        KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
     KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv));                     // A^-1 -> 1
     // [M1|M2|M3] = A^-1 [XB|XA|B]   (slabs 9..11 -> 12..14)
     KH_TRY(gemm(st, 3 * Bc, n, mref(S(1), 0, n, Bc, n2), mref(S(9), slab, n, Bc, n2), mref(S(12), slab, n, Bc, n2)));
@@ -309,7 +313,7 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
     (void)any_dense;
     cb.pool = b.get<cd>((size_t)LAYER_TMP_SLABS * Bc * n2);
     cb.vec.w = b.get<cd>((size_t)Bc * n); cb.vec.lam = b.get<cd>((size_t)Bc * n);
-    cb.vec.xexp = b.get<cd>((size_t)Bc * n); cb.vec.scale = b.get<cd>((size_t)Bc * n);
+    cb.vec.xexp = b.get<cd>((size_t)Bc * n); cb.vec.scale = b.get<cd>((size_t)Bc * n); cb.vec.tau = b.get<cd>((size_t)Bc * n);
     cb.vec.info_eig = b.get<int>(Bc); cb.vec.info_inv = b.get<int>((size_t)3 * Bc);
     for (int i = 0; i < 2; ++i) { cb.accD[i] = b.get<cd>((size_t)Bc * 4 * n2); cb.accB[i] = b.get<cd>((size_t)Bc * 16 * N); }
     cb.expA = b.get<cd>((size_t)Bc * 4 * n2); cb.expB = b.get<cd>((size_t)Bc * 4 * n2);
@@ -322,7 +326,7 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
         const size_t Be = (size_t)Bc * Nb, nb2 = (size_t)nb * nb;
         cb.eKx = b.get<cd>(Be * Nb); cb.eKy = b.get<cd>(Be * Nb); cb.ek0 = b.get<double>(Be);
         cb.epool = b.get<cd>((size_t)LAYER_TMP_SLABS * Be * nb2);
-        cb.evec.w = b.get<cd>(Be * nb); cb.evec.lam = b.get<cd>(Be * nb); cb.evec.xexp = b.get<cd>(Be * nb); cb.evec.scale = b.get<cd>(Be * nb);
+        cb.evec.w = b.get<cd>(Be * nb); cb.evec.lam = b.get<cd>(Be * nb); cb.evec.xexp = b.get<cd>(Be * nb); cb.evec.scale = b.get<cd>(Be * nb); cb.evec.tau = b.get<cd>(Be * nb);
         cb.evec.info_eig = b.get<int>(Be); cb.evec.info_inv = b.get<int>(3 * Be);
         cb.eS = b.get<cd>(Be * 2 * nb2); cb.ebd = b.get<cd>(Be * 16 * Nb);
         cb.ewl = b.get<double>(Be); cb.ekp = b.get<cd>(Be * 2);
@@ -535,7 +539,7 @@ extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int*
     return 0;
 }
 extern "C" size_t kh_zgeev_work_bytes(int batch, int n) {
-    return (size_t)batch * ((size_t)3 * n * n + n) * sizeof(cd) + 4096;
+    return (size_t)batch * ((size_t)3 * n * n + 2 * n) * sizeof(cd) + 4096;
 }
 extern "C" int kh_zgeev_batched(int batch, int n, const void* A, void* w, void* W, void* work, size_t work_bytes, int* info, void* stream) {
     if (batch < 0 || n < 1 || !A || !w || !W || !work) return fail(KH_EINVAL, "kh_zgeev_batched: bad arguments");
@@ -543,11 +547,11 @@ extern "C" int kh_zgeev_batched(int batch, int n, const void* A, void* w, void* 
     if (batch == 0) return 0;
     Bump b{(char*)work, work_bytes, 0};
     const size_t n2 = (size_t)n * n;
-    cd* H = b.get<cd>(batch * n2); cd* Zt = b.get<cd>(batch * n2); cd* X = b.get<cd>(batch * n2); cd* sc = b.get<cd>((size_t)batch * n);
+    cd* H = b.get<cd>(batch * n2); cd* Zt = b.get<cd>(batch * n2); cd* X = b.get<cd>(batch * n2); cd* sc = b.get<cd>((size_t)batch * n); cd* tau = b.get<cd>((size_t)batch * n);
     kh_stream_t st = (kh_stream_t)stream;
     zgeev_args a;
     a.n = n; a.A = mref(A, n2, n); a.Hw = mref(H, n2, n); a.Zt = mref(Zt, n2, n); a.X = mref(X, n2, n);
-    a.w = (cd*)w; a.w_stride = n; a.scale = sc; a.scale_stride = n; a.info = info;
+    a.w = (cd*)w; a.w_stride = n; a.scale = sc; a.scale_stride = n; a.tau = tau; a.tau_stride = n; a.info = info;
     KH_TRY(zgeev_launch(st, batch, a));
     zgemm_args g = zgemm_make(n, n, n, a.Zt, a.X, mref(W, n2, n));
     g.transA = 1; g.rowscale = sc; g.rs_stride = n; g.rs_group = 1;

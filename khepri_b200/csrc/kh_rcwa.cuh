@@ -267,7 +267,7 @@ KH_DEV void pq_body(const Cta& c, const pq_args& a) {
 }
 
 // lambda = sqrt(lambda^2 + 0j), X = exp(-lambda d k0)   (alternative.py:173, 186)
-struct lam_args { int B, n; double depth; const cd* w; const double* k0; cd* lam; cd* xexp; };
+struct lam_args { int B, n; double depth; const cd* w; const double* k0; cd* lam; cd* xexp; cd* ilam; };
 KH_DEV void lam_body(const Cta& c, const lam_args& a) {
     const int b = c.bx;
     for (int i = c.tid; i < a.n; i += c.nthr) {
@@ -275,6 +275,7 @@ KH_DEV void lam_body(const Cta& c, const lam_args& a) {
         cd l = csqrt_(mk(w.x + 0.0, w.y + 0.0));
         a.lam[(long long)b * a.n + i] = l;
         a.xexp[(long long)b * a.n + i] = cexp_((-a.depth * a.k0[b]) * l);
+        if (a.ilam) a.ilam[(long long)b * a.n + i] = crecip(l);
     }
 }
 
@@ -302,6 +303,36 @@ KH_DEV void ab_body(const Cta& c, const ab_args& a) {
         a.A[o1] = a1; a.A[o2] = a2; a.Bm[o1] = b1; a.Bm[o2] = b2;
         a.XB[o1] = x[i] * b1; a.XB[o2] = x[i] * b2;
         a.XA[o1] = x[i] * a1; a.XA[o2] = x[i] * a2;
+    }
+}
+
+// PV0 = P . V0 (V0 = free-space H modes, 2x2 blocks of diagonals).  Since Omega^2 = P Q = W L^2 W^-1 and
+// V = Q W L^-1, one has V^-1 = L^-1 W^-1 P, so  V^-1 V0 = L^-1 (W^-1 (P V0)):  a GEMM instead of an inverse.
+struct pv0_args { int B, N; const cd* P; const cd* Kx; const cd* Ky; cd* out; };
+KH_DEV void pv0_body(const Cta& c, const pv0_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const long long off = (long long)b * n * n;
+    const cd* kx = a.Kx + (long long)b * N;
+    const cd* ky = a.Ky + (long long)b * N;
+    for (int e = c.tid; e < n * N; e += c.nthr) {
+        const int i = e / N, g = e - i * N;
+        const m22 V0 = v0_block(kx[g], ky[g]);
+        const cd p1 = a.P[off + (long long)i * n + g], p2 = a.P[off + (long long)i * n + N + g];
+        a.out[off + (long long)i * n + g] = p1 * V0.a + p2 * V0.c;
+        a.out[off + (long long)i * n + N + g] = p1 * V0.b + p2 * V0.d;
+    }
+}
+// A = W^-1 + t2 ; B = W^-1 - t2 ; XB = X B ; XA = X A   with t2 = V^-1 V0 given   (alternative.py:182-186; W0 = I)
+struct ab2_args { int B, n; const cd* Winv; const cd* t2; const cd* xexp; cd* A; cd* Bm; cd* XB; cd* XA; };
+KH_DEV void ab2_body(const Cta& c, const ab2_args& a) {
+    const int n = a.n, b = c.bx;
+    const long long off = (long long)b * n * n;
+    const cd* x = a.xexp + (long long)b * n;
+    for (int e = c.tid; e < n * n; e += c.nthr) {
+        const int i = e / n;
+        const cd w = a.Winv[off + e], t = a.t2[off + e];
+        const cd av = w + t, bv = w - t;
+        a.A[off + e] = av; a.Bm[off + e] = bv; a.XB[off + e] = x[i] * bv; a.XA[off + e] = x[i] * av;
     }
 }
 

@@ -27,6 +27,7 @@ struct zgeev_args {
     MatRef X;          // out: eigenvectors of T (upper triangular)
     cd* w; long long w_stride;          // out: eigenvalues
     cd* scale; long long scale_stride;  // out: balancing factors as complex (imag 0)
+    cd* tau; long long tau_stride;      // work: Householder scalars of the Hessenberg reduction
     int* info;         // out: 0 ok, >0 = QR iteration failed to converge at that index+1
     int use_smem, ld_s;
 };
@@ -61,6 +62,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     cd* Zt = mat_ptr(a.Zt, b);
     const int ldz = a.Zt.ld;
     cd* scout = a.scale + (long long)b * a.scale_stride;
+    cd* tauout = a.tau + (long long)b * a.tau_stride;
     // shared: [vv n][uu n][scratch 192 dbl][dsc n dbl][H]
     cd* vv = (cd*)KH_SMEM(c);
     cd* uu = vv + n;
@@ -73,8 +75,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
 #define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
     if (a.use_smem || H != A)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; HH(i, j) = A[(long long)i * a.A.ld + j]; }
-    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; ZT(i, j) = mk(i == j ? 1.0 : 0.0, 0.0); }
-    for (int i = c.tid; i < n; i += c.nthr) dsc[i] = 1.0;
+    for (int i = c.tid; i < n; i += c.nthr) { dsc[i] = 1.0; tauout[i] = mk(0.0, 0.0); }
     c.sync();
 
     // ---- balancing (Jacobi-style sweeps of the EISPACK balanc criterion; powers of two, so exact)
@@ -109,14 +110,13 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
 
     // ---- Householder reduction (zgehd2 / zlarfg conventions: H_k = I - tau v v^H, A <- H_k^H A H_k), written
     // as ONE rank-2 update per step:  A -= pt conj(v)^T + (conj(tau) v) q^T  with p = A v, q^T = v^H A, s = v^H p,
-    // pt = tau p - |tau|^2 s v;  Z -= (tau Z v) conj(v)^T.   Three barriers per step, all threads busy.
+    // pt = tau p - |tau|^2 s v.  Three barriers per step, everything in shared memory.  The reflectors stay below
+    // the sub-diagonal (LAPACK layout); Z = H_0 H_1 ... is formed afterwards by zunghr, also in shared memory.
     cd* pp_ = uu;                      // p  [n]
-    cd* qq_ = (cd*)dsc;                // q  [n]   (dsc is dead after balancing: its n doubles are followed by n more below)
-    cd* zu_ = qq_ + n;                 // tau * Z v [n]
+    cd* qq_ = (cd*)dsc;                // q  [n]   (dsc is dead after balancing)
     const int lane = c.tid % KH_WARP;
     for (int k = 0; k + 2 < n; ++k) {
-        // every warp computes the column norm redundantly (no CTA-wide reduction)
-        double part = 0.0;
+        double part = 0.0;                                   // every warp computes the column norm redundantly
         for (int i = k + 2 + lane; i < n; i += KH_WARP) part += cabs2(HH(i, k));
         const double xn2 = kh_warp_allsum(part);
         const cd alpha = HH(k + 1, k);
@@ -126,12 +126,14 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
         const cd sc = crecip(alpha - mk(beta, 0.0));
         c.sync();                                              // all warps have read column k
         for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
-            vv[i] = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
-            HH(i, k) = (i == k + 1) ? mk(beta, 0.0) : mk(0.0, 0.0);
+            const cd vi = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
+            vv[i] = vi;
+            HH(i, k) = (i == k + 1) ? mk(beta, 0.0) : vi;     // reflector kept in place
         }
+        if (c.tid == 0) tauout[k] = tau;
         c.sync();
-        // p = A v (one thread per row), q = v^H A (one thread per column), zu = tau Z v (one thread per row of Z)
-        for (int t = c.tid; t < 3 * n; t += c.nthr) {
+        // p = A v (one thread per row), q = v^H A (one thread per column)
+        for (int t = c.tid; t < 2 * n; t += c.nthr) {
             cd a0 = mk(0, 0), a1 = mk(0, 0);
             if (t < n) {
                 const int r = t;
@@ -139,7 +141,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
                 for (; j + 1 < n; j += 2) { cfma(a0, HH(r, j), vv[j]); cfma(a1, HH(r, j + 1), vv[j + 1]); }
                 if (j < n) cfma(a0, HH(r, j), vv[j]);
                 pp_[r] = a0 + a1;
-            } else if (t < 2 * n) {
+            } else {
                 const int j = t - n;
                 if (j > k) {
                     int i = k + 1;
@@ -147,29 +149,17 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
                     if (i < n) cfma(a0, cconj(vv[i]), HH(i, j));
                 }
                 qq_[j] = a0 + a1;
-            } else {
-                const int i = t - 2 * n;
-                cd a2 = mk(0, 0), a3 = mk(0, 0);
-                int j = k + 1;
-                for (; j + 3 < n; j += 4) {
-                    const cd z0 = ZT(j, i), z1 = ZT(j + 1, i), z2 = ZT(j + 2, i), z3 = ZT(j + 3, i);
-                    cfma(a0, z0, vv[j]); cfma(a1, z1, vv[j + 1]); cfma(a2, z2, vv[j + 2]); cfma(a3, z3, vv[j + 3]);
-                }
-                for (; j < n; ++j) cfma(a0, ZT(j, i), vv[j]);
-                zu_[i] = tau * ((a0 + a1) + (a2 + a3));
             }
         }
         c.sync();
-        // s = v^H p, redundantly per warp
-        double sr = 0.0, si = 0.0;
+        double sr = 0.0, si = 0.0;                           // s = v^H p, redundantly per warp
         for (int i = k + 1 + lane; i < n; i += KH_WARP) { const cd w = cconj(vv[i]) * pp_[i]; sr += w.x; si += w.y; }
         const cd sv = mk(kh_warp_allsum(sr), kh_warp_allsum(si));
         const cd t2s = cabs2(tau) * sv;
         const cd ctau = cconj(tau);
-        // rank-2 update of H (rows 0..n-1, columns k+1..n-1): thread = (row, residue class of columns)
         const int ncol = n - k - 1;
         const int nseg = (ncol + 3) / 4;
-        for (int e = c.tid; e < n * nseg; e += c.nthr) {
+        for (int e = c.tid; e < n * nseg; e += c.nthr) {      // rank-2 update: thread = (row, residue class of columns)
             const int i = e / nseg, sg = e - i * nseg;
             cd pt = tau * pp_[i], tv = mk(0, 0);
             if (i > k) { tv = ctau * vv[i]; pt = pt - t2s * vv[i]; }
@@ -180,23 +170,56 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
                 HH(i, j) = h;
             }
         }
-        // Z -= zu conj(v)^T   (rows k+1.. of Zt, coalesced over i; independent loads, unrolled)
-        for (int i = c.tid; i < n; i += c.nthr) {
-            const cd zi = zu_[i];
-            int j = k + 1;
-            for (; j + 3 < n; j += 4) {
-                cd z0 = ZT(j, i), z1 = ZT(j + 1, i), z2 = ZT(j + 2, i), z3 = ZT(j + 3, i);
-                cfms(z0, zi, cconj(vv[j])); cfms(z1, zi, cconj(vv[j + 1])); cfms(z2, zi, cconj(vv[j + 2])); cfms(z3, zi, cconj(vv[j + 3]));
-                ZT(j, i) = z0; ZT(j + 1, i) = z1; ZT(j + 2, i) = z2; ZT(j + 3, i) = z3;
-            }
-            for (; j < n; ++j) { cd z0 = ZT(j, i); cfms(z0, zi, cconj(vv[j])); ZT(j, i) = z0; }
-        }
         c.sync();
     }
     if (a.use_smem)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * a.Hw.ld + j] = HH(i, j); }
 #undef HH
 #undef ZT
+}
+
+// ============================================================================ 1b. Z = H_0 H_1 ... H_{n-3} (zunghr), backward accumulation
+KH_DEV void zunghr_body(const Cta& c, const zgeev_args& a) {
+    const int n = a.n, b = c.bx;
+    const cd* Hg = mat_ptr(a.Hw, b);
+    cd* Ztg = mat_ptr(a.Zt, b);
+    const int ldg = a.Hw.ld, ldz = a.Zt.ld;
+    const cd* taus = a.tau + (long long)b * a.tau_stride;
+    // shared: [vv n][ww n][Z n x ld]   (Z stays in global memory, transposed, when it does not fit)
+    cd* vv = (cd*)KH_SMEM(c);
+    cd* ww = vv + n;
+    cd* Z; int ld; bool tr;            // tr: Z is addressed transposed (global Zt)
+    if (a.use_smem) { Z = ww + n; ld = a.ld_s; tr = false; }
+    else { Z = Ztg; ld = ldz; tr = true; }
+#define ZZ(i, j) Z[tr ? ((long long)(j) * ld + (i)) : ((long long)(i) * ld + (j))]
+    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; ZZ(i, j) = mk(i == j ? 1.0 : 0.0, 0.0); }
+    c.sync();
+    for (int k = n - 3; k >= 0; --k) {
+        const cd tau = taus[k];
+        if (tau.x == 0.0 && tau.y == 0.0) continue;                       // uniform
+        for (int i = k + 1 + c.tid; i < n; i += c.nthr) vv[i] = (i == k + 1) ? mk(1.0, 0.0) : Hg[(long long)i * ldg + k];
+        c.sync();
+        // w = v^H Z[k+1:, k+1:]  (one thread per column), then Z[k+1:, k+1:] -= tau v w
+        for (int j = k + 1 + c.tid; j < n; j += c.nthr) {
+            cd a0 = mk(0, 0), a1 = mk(0, 0);
+            int i = k + 1;
+            for (; i + 1 < n; i += 2) { cfma(a0, cconj(vv[i]), ZZ(i, j)); cfma(a1, cconj(vv[i + 1]), ZZ(i + 1, j)); }
+            if (i < n) cfma(a0, cconj(vv[i]), ZZ(i, j));
+            ww[j] = tau * (a0 + a1);
+        }
+        c.sync();
+        const int m = n - k - 1;
+        for (int e = c.tid; e < m * m; e += c.nthr) {
+            const int i = k + 1 + e / m, j = k + 1 + (e - (e / m) * m);
+            cd z = ZZ(i, j);
+            cfms(z, vv[i], ww[j]);
+            ZZ(i, j) = z;
+        }
+        c.sync();
+    }
+    if (a.use_smem)
+        for (int e = c.tid; e < n * n; e += c.nthr) { int j = e / n, i = e - j * n; Ztg[(long long)j * ldz + i] = ZZ(i, j); }
+#undef ZZ
 }
 
 // ============================================================================ 2. shifted QR on the packed Hessenberg matrix
@@ -600,6 +623,11 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     a.use_smem = zhess_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
     int e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
     if (e) return e;
+    {   zgeev_args u = a;
+        const size_t usm = (size_t)2 * n * sizeof(cd) + (size_t)n * u.ld_s * sizeof(cd) + 16;
+        u.use_smem = usm <= (size_t)KH_SMEM_MAX;
+        e = kh_launch<zgeev_args, zunghr_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), u.use_smem ? usm : (size_t)2 * n * sizeof(cd) + 16, st, u, "zgeev_hess", 0.0);
+        if (e) return e; }
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
     // 256 threads when the delayed updates have more than 128 independent jobs (rows of Z + rows above + columns right)
