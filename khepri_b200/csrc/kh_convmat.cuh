@@ -42,23 +42,31 @@ KH_DEV void dft1_body(const Cta& c, const dft1_args& a) {
         row[j] = a.is_complex ? ((const cd*)a.pix)[off] : mk(((const double*)a.pix)[off], 0.0);
     }
     c.sync();
+    // twiddle index (l*y) mod Ny advances by a constant step: no integer division in the inner loop
+    const int wlanes = KH_WARP;
 #ifdef KH_HOST_EMU
-    for (int li = 0; li < nl; ++li) {
-        int l = li - (a.Q - 1);
-        cd acc = mk(0, 0);
-        for (int y = 0; y < Ny; ++y) { int idx = (int)((((long long)l * y) % Ny + Ny) % Ny); cfma(acc, row[y], tw[idx]); }
-        a.G[((long long)lay * a.Nx + x) * nl + li] = acc;
-    }
+    const int warp = 0, lane = 0, nw = 1;
 #else
     const int warp = c.tid >> 5, lane = c.tid & 31, nw = c.nthr >> 5;
+#endif
     for (int li = warp; li < nl; li += nw) {
-        int l = li - (a.Q - 1);
-        cd acc = mk(0, 0);
-        for (int y = lane; y < Ny; y += 32) { int idx = (int)((((long long)l * y) % Ny + Ny) % Ny); cfma(acc, row[y], tw[idx]); }
-        for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+        const int l = li - (a.Q - 1);
+        const int lm = ((l % Ny) + Ny) % Ny;                                  // l mod Ny in [0, Ny)
+        int idx = (int)(((long long)lm * lane) % Ny);
+        const int step = (int)(((long long)lm * wlanes) % Ny);
+        cd acc0 = mk(0, 0), acc1 = mk(0, 0);
+        int y = lane;
+        for (; y + wlanes < Ny; y += 2 * wlanes) {
+            int idx2 = idx + step; if (idx2 >= Ny) idx2 -= Ny;
+            cfma(acc0, row[y], tw[idx]);
+            cfma(acc1, row[y + wlanes], tw[idx2]);
+            idx = idx2 + step; if (idx >= Ny) idx -= Ny;
+        }
+        if (y < Ny) cfma(acc0, row[y], tw[idx]);
+        cd acc = acc0 + acc1;
+        acc.x = kh_warp_allsum(acc.x); acc.y = kh_warp_allsum(acc.y);
         if (lane == 0) a.G[((long long)lay * a.Nx + x) * nl + li] = acc;
     }
-#endif
 }
 
 struct dft2_args {
