@@ -38,6 +38,10 @@ struct zgeev_args {
 struct kh_givens { double c; cd s, r; };
 #ifndef KH_HOST_EMU
 __device__ __forceinline__ cd kh_shfl_cd(cd v, int src) { return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+// release store to a shared-memory flag (publishes everything the warp wrote before the preceding __syncwarp)
+__device__ __forceinline__ void kh_st_release_shared(int* p, int v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 #endif
 KH_DEV kh_givens make_givens(cd f, cd g) {
     // G = [[c, s], [-conj(s), c]],  G [f; g] = [r; 0];  c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = sqrt(|f|^2+|g|^2).
@@ -244,13 +248,14 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     cd* Zt = mat_ptr(a.Zt, b);
     const int ldz = a.Zt.ld, ldg = a.Hw.ld;
     cd* wout = a.w + (long long)b * a.w_stride;
-    // shared: [gs n cd][gc n dbl][ctl 8 int][packed H]  (H stays in global memory, full storage, when it does not fit)
+    // shared: [gs, qsub, qdiag, qnsub: n cd each][gc n dbl][ctl 16 int][packed H]  (H stays in global memory, full storage, when it does not fit)
     cd* gs = (cd*)KH_SMEM(c);
     cd* qsub = gs + n;                 // queue of the warp-specialised sweep: row k's sub-diagonal / diagonal after R(k)
     cd* qdiag = qsub + n;
-    double* gc = (double*)(qdiag + n);
-    int* ctl = (int*)(gc + n);         // [0] deflation scan, [1] published-rotation counter, [2] error flag
-    cd* Hp = (cd*)(KH_SMEM(c) + (((3 * n * 16 + n * 8 + 8 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
+    cd* qnsub = qdiag + n;             // H[t+1][t] after R(t): handed to the warp that takes the chain over
+    double* gc = (double*)(qnsub + n);
+    int* ctl = (int*)(gc + n);         // [0] deflation scan, [2] error flag, [4..7] per-column-warp progress counters
+    cd* Hp = (cd*)(KH_SMEM(c) + (((4 * n * 16 + n * 8 + 16 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
     const bool packed = PACKED;
     cd* const Hb = PACKED ? Hp : Hg;
 #define ROWOFF(i) (PACKED ? hp_off((i), n) : (i) * ldg)
@@ -334,94 +339,127 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         const cd f_first = HQ(l, l) - t, g_first = HQ(l + 1, l);
         QT_ADD(qt_shift);
 #ifndef KH_HOST_EMU
-        if (PACKED && c.nthr >= 128 && n <= 128) {     // the driver's lanes own at most four columns each
-            // ===== warp-specialised sweep (GPU, packed path).  Warp 0 (the driver) runs the whole dependent chain --
-            // corner, Givens rotation, row steps on every window column (lane q owns columns l+lane+32q, the bottom
-            // entry of each column stays in a register) -- using shuffles only, and publishes every rotation into a
-            // shared-memory queue.  Warps 1-3 (followers) apply the column steps to the rows they own, lagging behind.
-            // No block-wide barrier is on the critical path.
-            volatile int* prog = ctl + 1;              // rotations with index < *prog are published
-            if (c.tid == 0) *prog = l;
+        if (PACKED && c.nthr >= 64 && n <= 32 * (c.nthr >> 6)) {
+            // ===== warp-specialised RELAY sweep (GPU, packed path).  The first half of the warps own the window columns
+            // (thread <-> column l + 32 w + lane, the running bottom entry of the column stays in a register), the second
+            // half own the window rows.  Rotation t is GENERATED by the warp that owns column t: it has the corner
+            // H[t][t] in a lane, runs the dependent chain (corner -> Givens -> own column -> shuffle) without any block
+            // barrier, and publishes (c, s, r, diagonal, sub-diagonal) in a shared-memory queue.  Column warps to the right
+            // FOLLOW (apply the published rotations to their columns) until the corner reaches them and they take over
+            // the chain; row warps apply the column steps C(t), lagging behind.  prg[w] = number of rotations column warp
+            // w has applied (and, inside its own range, generated); every wait is on an earlier index, so no deadlock.
+            volatile int* prg = ctl + 4;
+            const int CW = c.nthr >> 6;                // column warps; the same number of row warps
+            if (c.tid < 4) prg[c.tid] = l;
             __syncthreads();                           // (also: everyone has read H before the sweep writes)
             const int warp = c.tid >> 5, lane = c.tid & 31;
-            if (warp == 0) {
-                kh_givens G = make_givens(f_first, g_first);
-                cd carry[4];
-                const int ol = ROWOFF(l);
-                int o1 = ol + ROWSTEP(l);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {                          // R(l)
-                    const int j = l + lane + 32 * q;
-                    carry[q] = mk(0, 0);
-                    if (j <= iact) {
-                        const cd h0 = Hb[ol + j], h1 = Hb[o1 + j];
-                        Hb[ol + j] = G.c * h0 + G.s * h1;
-                        carry[q] = G.c * h1 - cconj(G.s) * h0;
+            if (warp < CW) {
+                const int w = warp, j = l + 32 * w + lane;
+                if (l + 32 * w <= iact) {
+                    const int jl = j < n ? j : n - 1;                   // clamped for the unconditional loads
+                    const bool mine = (j <= iact);
+                    kh_givens G = make_givens(f_first, g_first);       // G(l), computed redundantly by every column warp
+                    int ot = ROWOFF(l);                                 // row t
+                    int ot1 = ot + ROWSTEP(l);                          // row t+1
+                    cd carry = Hb[ot + jl];                             // H[t][j] before R(t)
+                    cd h1 = Hb[ot1 + jl];                               // H[t+1][j]   (untouched by this sweep)
+                    {   // R(l) on the own column (column l included: the shift makes its bottom entry the first bulge)
+                        const cd top = G.c * carry + G.s * h1, bot = G.c * h1 - cconj(G.s) * carry;
+                        if (mine) { Hb[ot + j] = top; carry = bot; }
+                    }
+                    cd sub = mk(0, 0);
+                    if (w == 0) { sub = kh_shfl_cd(carry, 0); if (lane == 0) { gc[l] = G.c; gs[l] = G.s; } }
+                    __syncwarp();
+                    if (lane == 0) kh_st_release_shared(ctl + 4 + w, l + 1);
+                    const int tlast = (iact - 1 < l + 32 * w + 31) ? iact - 1 : l + 32 * w + 31;    // last rotation handled here
+                    const int tgen = (w == 0) ? l + 1 : l + 32 * w;     // first rotation generated here
+                    int t = l + 1;
+                    ot = ot1; ot1 = ot + ROWSTEP(l + 1);
+                    int spins = 0;
+                    // ---- follower mode: rotations generated by the warps to the left
+                    while (t < tgen && t <= tlast) {
+                        const int wg = (t - l) >> 5;
+                        int avail = prg[wg];
+                        if (avail <= t) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } continue; }
+                        __threadfence_block();
+                        int tend = l + 32 * (wg + 1);                   // generation range of warp wg ends here
+                        if (tend > avail) tend = avail;
+                        if (tend > tgen) tend = tgen;
+                        if (tend > tlast + 1) tend = tlast + 1;
+                        h1 = Hb[ot1 + jl];
+                        for (; t < tend; ++t) {
+                            const double cc = gc[t]; const cd ss = gs[t];
+                            const int ot2 = ot1 + ROWSTEP(t + 1);
+                            const cd h1n = Hb[ot2 + jl];                // next row, in flight while this rotation is applied
+                            const cd top = cc * carry + ss * h1;
+                            carry = cc * h1 - cconj(ss) * carry;
+                            if (mine) Hb[ot + j] = top;
+                            h1 = h1n; ot = ot1; ot1 = ot2;
+                        }
+                        G.c = gc[t - 1]; G.s = gs[t - 1]; sub = qnsub[t - 1];
+                        __syncwarp();
+                        if (lane == 0) kh_st_release_shared(ctl + 4 + w, t);
+                    }
+                    // ---- driver mode: this warp owns the corner column
+                    if (t >= tgen && t <= tlast && ctl[2] == 0) {
+                        cd hd = Hb[ot1 + t];                            // H[t+1][t]
+                        h1 = Hb[ot1 + jl];
+                        for (; t <= tlast; ++t) {
+                            const int ot2 = ot1 + ROWSTEP(t + 1);
+                            const cd hdn = Hb[ot2 + t + 1];             // operands of the next iteration, loaded ahead
+                            const cd h1n = Hb[ot2 + jl];                // (row t+2 is at most one past the last row: padded)
+                            const cd cb = kh_shfl_cd(carry, (t - l) & 31);                            // H[t][t] after R(t-1)
+                            const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;      // C(t-1) on row t
+                            const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;                              // C(t-1) on row t+1: bulge
+                            const kh_givens Gn = make_givens(a1, c1);                                  // G(t) annihilates it
+                            const cd ncs = cconj(Gn.s);
+                            const cd top = Gn.c * carry + Gn.s * h1, bot = Gn.c * h1 - ncs * carry;    // R(t) on the own column
+                            const cd newdiag = Gn.c * b1 + Gn.s * d1, nextsub = Gn.c * d1 - ncs * b1;
+                            if (j > t && mine) { Hb[ot + j] = top; carry = bot; }
+                            if (lane == 0) { gc[t] = Gn.c; gs[t] = Gn.s; qsub[t] = Gn.r; qdiag[t] = newdiag; qnsub[t] = nextsub; }
+                            __syncwarp();
+                            if (lane == 0) kh_st_release_shared(ctl + 4 + w, t + 1);
+                            G = Gn; sub = nextsub; hd = hdn; h1 = h1n; ot = ot1; ot1 = ot2;
+                        }
+                    }
+                    // ---- the warp that owns column iact finishes row iact: C(iact-1) on its two entries
+                    if (((iact - l) >> 5) == w && ctl[2] == 0) {
+                        const cd cb = kh_shfl_cd(carry, (iact - l) & 31);
+                        if (lane == 0) {
+                            const int oi = ROWOFF(iact);
+                            Hb[oi + iact - 1] = G.c * sub + cconj(G.s) * cb;
+                            Hb[oi + iact] = G.c * cb - G.s * sub;
+                        }
                     }
                 }
-                cd sub = kh_shfl_cd(carry[0], 0), cb = kh_shfl_cd(carry[0], 1);     // H[l+1][l], H[l+1][l+1] after R(l)
-                if (lane == 0) { gc[l] = G.c; gs[l] = G.s; }
-                __syncwarp();
-                if (lane == 0) { __threadfence_block(); *prog = l + 1; }
-                for (int k = l; k < iact; ++k) {
-                    const int o2 = o1 + ROWSTEP(k + 1);
-                    const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;      // C(k) on row k+1
-                    if (k + 1 < iact) {
-                        const cd hd = Hb[o2 + k + 1];            // H[k+2][k] is zero: C(k) creates the bulge there
-                        const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;
-                        const kh_givens Gn = make_givens(a1, c1);
-                        const cd newdiag = Gn.c * b1 + Gn.s * d1, nextsub = Gn.c * d1 - cconj(Gn.s) * b1;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {              // R(k+1) on the owned columns >= k+2
-                            const int j = l + lane + 32 * q;
-                            if (j >= k + 2 && j <= iact) {
-                                const cd h1 = Hb[o2 + j], h0 = carry[q];
-                                Hb[o1 + j] = Gn.c * h0 + Gn.s * h1;
-                                carry[q] = Gn.c * h1 - cconj(Gn.s) * h0;
+            } else {
+                // ---- row warps: C(t) on row r for t >= r (rows t+1, t+2 are handled inside the chain)
+                const int r = l + (c.tid - 32 * CW);
+                const int rmin = l + (warp - CW) * 32;
+                const int orow = (r < n) ? ROWOFF(r) : 0;
+                cd car = mk(0, 0);
+                if (rmin < iact) {
+                    int t = rmin, spins = 0;
+                    while (t < iact) {
+                        const int wq = (t + 1 - l) >> 5;               // owner of column t+1 must have applied R(<= t) to it
+                        int avail = prg[wq];
+                        if (avail <= t) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } continue; }
+                        __threadfence_block();
+                        int tend = l + 32 * (wq + 1) - 1;
+                        if (tend > avail) tend = avail;
+                        if (tend > iact) tend = iact;
+                        for (; t < tend; ++t) {
+                            const double cc = gc[t]; const cd ss = gs[t];
+                            if (r <= t) {
+                                cd h0 = car;
+                                if (r == t) { if (t > l) { h0 = qdiag[t]; Hb[orow + t - 1] = qsub[t]; } else h0 = Hb[orow + t]; }
+                                const cd h1 = Hb[orow + t + 1];
+                                Hb[orow + t] = cc * h0 + cconj(ss) * h1;
+                                car = cc * h1 - ss * h0;
                             }
                         }
-                        const int src = k + 2 - l;                  // column k+2 carries the next corner diagonal
-                        cd v = carry[0];
-                        if ((src >> 5) == 1) v = carry[1];
-                        if ((src >> 5) == 2) v = carry[2];
-                        if ((src >> 5) == 3) v = carry[3];
-                        cb = kh_shfl_cd(v, src & 31);
-                        if (lane == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; qsub[k + 1] = Gn.r; qdiag[k + 1] = newdiag; }
-                        __syncwarp();
-                        if (lane == 0) { __threadfence_block(); *prog = k + 2; }
-                        sub = nextsub; G = Gn; o1 = o2;
-                    } else if (lane == 0) {
-                        Hb[o1 + k] = a1; Hb[o1 + k + 1] = b1;     // row iact: H[iact][iact-1], H[iact][iact]
                     }
-                }
-            } else if (warp < 4) {
-                const int r0 = l + (c.tid - 32), r1 = r0 + 96;      // rows owned by this follower
-                const int rmin = l + (warp - 1) * 32;
-                const int or0 = (r0 < n) ? ROWOFF(r0) : 0, or1 = (r1 < n) ? ROWOFF(r1) : 0;
-                cd car0 = mk(0, 0), car1 = mk(0, 0);
-                if (rmin < iact) {
-                    for (int k = rmin; k < iact; ++k) {
-                        int spins = 0;
-                        while (*prog <= k) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } }
-                        __threadfence_block();
-                        const double cc = gc[k]; const cd ss = gs[k];
-                        if (r0 <= k) {
-                            cd h0 = car0;
-                            if (r0 == k) { if (k > l) { h0 = qdiag[k]; Hb[or0 + k - 1] = qsub[k]; } else h0 = Hb[or0 + k]; }
-                            const cd h1 = Hb[or0 + k + 1];
-                            Hb[or0 + k] = cc * h0 + cconj(ss) * h1;
-                            car0 = cc * h1 - ss * h0;
-                        }
-                        if (r1 <= k) {
-                            cd h0 = car1;
-                            if (r1 == k) { h0 = qdiag[k]; Hb[or1 + k - 1] = qsub[k]; }
-                            const cd h1 = Hb[or1 + k + 1];
-                            Hb[or1 + k] = cc * h0 + cconj(ss) * h1;
-                            car1 = cc * h1 - ss * h0;
-                        }
-                    }
-                    if (r0 < iact) Hb[or0 + iact] = car0;
-                    if (r1 < iact) Hb[or1 + iact] = car1;
+                    if (r < iact) Hb[orow + iact] = car;
                 }
             }
             __syncthreads();
@@ -607,7 +645,7 @@ static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
     return s;
 }
 static inline size_t zqr_smem_bytes(int n, int use_smem) {
-    size_t s = (size_t)3 * n * sizeof(cd) + (size_t)n * sizeof(double) + 8 * sizeof(int) + 16;
+    size_t s = (size_t)4 * n * sizeof(cd) + (size_t)n * sizeof(double) + 16 * sizeof(int) + 16;
     if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
     return s;
 }
