@@ -30,6 +30,11 @@ struct zgeev_args {
     cd* tau; long long tau_stride;      // work: Householder scalars of the Hessenberg reduction
     int* info;         // out: 0 ok, >0 = QR iteration failed to converge at that index+1
     int use_smem, ld_s;
+    // Optional rotation log (work space, doubles).  When set, the QR kernel does not touch Z: it records every sweep
+    // (window + rotations) and zrot_apply replays the log on Z afterwards, with Z resident in shared memory.
+    // Per matrix: [0] header (int2: sweeps, rotations) [2 .. 2+sw_cap) sweep descriptors (int2: l | iact << 16, first
+    // rotation) [2+sw_cap ..) rotations (c, re s, im s).
+    double* rlog = nullptr; long long rlog_stride = 0; int rot_cap = 0, sw_cap = 0;
 };
 
 #define ZGEEV_EPS 2.220446049250313e-16   /* LAPACK ulp = eps*base */
@@ -42,7 +47,16 @@ __device__ __forceinline__ cd kh_shfl_cd(cd v, int src) { return mk(__shfl_sync(
 __device__ __forceinline__ void kh_st_release_shared(int* p, int v) {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
+// explicit 32-bit shared-memory addressing for the sweep's inner loops (running addresses, immediate offsets)
+__device__ __forceinline__ unsigned kh_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ cd kh_lds_cd(unsigned a) { cd v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ double kh_lds_d(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void kh_sts_cd(unsigned a, cd v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+__device__ __forceinline__ void kh_sts_d(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void kh_st_release_saddr(unsigned a, int v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 #endif
+// one entry of the rotation queue of a sweep (shared memory): G(t) = (c, s), and the corner entries after R(t)
+struct alignas(16) kh_qrot { double c, pad; cd s, r, diag, nsub; };     // r = H[t][t-1], diag = H[t][t], nsub = H[t+1][t]
 KH_DEV kh_givens make_givens(cd f, cd g) {
     // G = [[c, s], [-conj(s), c]],  G [f; g] = [r; 0];  c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = sqrt(|f|^2+|g|^2).
     // With y = 1/sqrt(|f|^2 h^2):  c = |f|^2 y,  s = y f conj(g),  r = (h^2 y) f  -- ONE reciprocal square root, no
@@ -57,6 +71,22 @@ KH_DEV kh_givens make_givens(cd f, cd g) {
     G.r = g0 ? f : (f0 ? mk(g2 * y, 0.0) : (h2 * y) * f);
     return G;
 }
+#ifndef KH_HOST_EMU
+// Same rotation for the generic case f != 0, g != 0 (the caller branches, warp-uniformly, to make_givens otherwise):
+// no selects, and the reciprocal square root refined by ONE third-order step  y1 = y0 (1 + e/2 + 3e^2/8),
+// e = 1 - x y0^2  (seed error 2^-20 -> 2^-58), four dependent operations instead of six.
+__device__ __forceinline__ kh_givens make_givens_fast(cd f, cd g, double f2, double g2) {
+    kh_givens G;
+    const double h2 = f2 + g2, x = f2 * h2;
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-(x * y0), y0, 1.0);
+    const double y = fma(y0 * e, fma(0.375, e, 0.5), y0);
+    const cd fg = f * cconj(g);
+    G.c = f2 * y; G.s = y * fg; G.r = (h2 * y) * f;
+    return G;
+}
+#endif
 
 // ============================================================================ 1. balance + Hessenberg
 KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
@@ -248,14 +278,10 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     cd* Zt = mat_ptr(a.Zt, b);
     const int ldz = a.Zt.ld, ldg = a.Hw.ld;
     cd* wout = a.w + (long long)b * a.w_stride;
-    // shared: [gs, qsub, qdiag, qnsub: n cd each][gc n dbl][ctl 16 int][packed H]  (H stays in global memory, full storage, when it does not fit)
-    cd* gs = (cd*)KH_SMEM(c);
-    cd* qsub = gs + n;                 // queue of the warp-specialised sweep: row k's sub-diagonal / diagonal after R(k)
-    cd* qdiag = qsub + n;
-    cd* qnsub = qdiag + n;             // H[t+1][t] after R(t): handed to the warp that takes the chain over
-    double* gc = (double*)(qnsub + n);
-    int* ctl = (int*)(gc + n);         // [0] deflation scan, [2] error flag, [4..7] per-column-warp progress counters
-    cd* Hp = (cd*)(KH_SMEM(c) + (((4 * n * 16 + n * 8 + 16 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
+    // shared: [Q: n rotation-queue entries][ctl 16 int][packed H]  (H stays in global memory, full storage, when it does not fit)
+    kh_qrot* Q = (kh_qrot*)KH_SMEM(c); // rotation queue of the current sweep
+    int* ctl = (int*)(Q + n);          // [0] deflation scan, [2] error flag, [4..7] per-column-warp progress counters
+    cd* Hp = (cd*)(KH_SMEM(c) + (((n * (int)sizeof(kh_qrot) + 16 * 4) + 15) & ~15));   // offset arithmetic keeps the shared address space
     const bool packed = PACKED;
     cd* const Hb = PACKED ? Hp : Hg;
 #define ROWOFF(i) (PACKED ? hp_off((i), n) : (i) * ldg)
@@ -271,6 +297,10 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int itmax = 30 * (n > 10 ? n : 10);
     int fail = 0;
     int iact = n - 1, its = 0;
+    double* const rl = a.rlog ? a.rlog + (long long)b * a.rlog_stride : nullptr;
+    int* const rl_sw = rl ? (int*)(rl + 2) : nullptr;
+    double* const rl_rot = rl ? rl + 2 + a.sw_cap : nullptr;
+    int nsw = 0, nrot = 0;             // logged sweeps / rotations (uniform)
     QT_DECL;
     while (iact >= 0) {
         QT_MARK();
@@ -348,33 +378,37 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             // FOLLOW (apply the published rotations to their columns) until the corner reaches them and they take over
             // the chain; row warps apply the column steps C(t), lagging behind.  prg[w] = number of rotations column warp
             // w has applied (and, inside its own range, generated); every wait is on an earlier index, so no deadlock.
+            // A warp issues in order, so every instruction in the driver loop costs time: addresses are running 32-bit
+            // shared addresses and the operands of iteration t+1 are loaded during iteration t.
             volatile int* prg = ctl + 4;
             const int CW = c.nthr >> 6;                // column warps; the same number of row warps
             if (c.tid < 4) prg[c.tid] = l;
             __syncthreads();                           // (also: everyone has read H before the sweep writes)
             const int warp = c.tid >> 5, lane = c.tid & 31;
+            const unsigned sH = kh_saddr(Hb), sQ = kh_saddr(Q);
             if (warp < CW) {
                 const int w = warp, j = l + 32 * w + lane;
                 if (l + 32 * w <= iact) {
                     const int jl = j < n ? j : n - 1;                   // clamped for the unconditional loads
                     const bool mine = (j <= iact);
+                    const unsigned sP = kh_saddr(ctl + 4 + w);
                     kh_givens G = make_givens(f_first, g_first);       // G(l), computed redundantly by every column warp
-                    int ot = ROWOFF(l);                                 // row t
-                    int ot1 = ot + ROWSTEP(l);                          // row t+1
-                    cd carry = Hb[ot + jl];                             // H[t][j] before R(t)
-                    cd h1 = Hb[ot1 + jl];                               // H[t+1][j]   (untouched by this sweep)
+                    unsigned a_t = sH + 16u * (unsigned)(ROWOFF(l) + jl);   // &H[t][j]
+                    int rs = ROWSTEP(l);                                // elements from row t to row t+1
+                    cd carry = kh_lds_cd(a_t);                          // H[t][j] before R(t)
+                    cd h1 = kh_lds_cd(a_t + 16u * rs);                  // H[t+1][j]   (untouched by this sweep)
                     {   // R(l) on the own column (column l included: the shift makes its bottom entry the first bulge)
                         const cd top = G.c * carry + G.s * h1, bot = G.c * h1 - cconj(G.s) * carry;
-                        if (mine) { Hb[ot + j] = top; carry = bot; }
+                        if (mine) { kh_sts_cd(a_t, top); carry = bot; }
                     }
                     cd sub = mk(0, 0);
-                    if (w == 0) { sub = kh_shfl_cd(carry, 0); if (lane == 0) { gc[l] = G.c; gs[l] = G.s; } }
+                    if (w == 0) { sub = kh_shfl_cd(carry, 0); if (lane == 0) { Q[l].c = G.c; Q[l].s = G.s; } }
                     __syncwarp();
-                    if (lane == 0) kh_st_release_shared(ctl + 4 + w, l + 1);
+                    if (lane == 0) kh_st_release_saddr(sP, l + 1);
                     const int tlast = (iact - 1 < l + 32 * w + 31) ? iact - 1 : l + 32 * w + 31;    // last rotation handled here
                     const int tgen = (w == 0) ? l + 1 : l + 32 * w;     // first rotation generated here
                     int t = l + 1;
-                    ot = ot1; ot1 = ot + ROWSTEP(l + 1);
+                    a_t += 16u * rs; rs -= 1;
                     int spins = 0;
                     // ---- follower mode: rotations generated by the warps to the left
                     while (t < tgen && t <= tlast) {
@@ -386,40 +420,53 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                         if (tend > avail) tend = avail;
                         if (tend > tgen) tend = tgen;
                         if (tend > tlast + 1) tend = tlast + 1;
-                        h1 = Hb[ot1 + jl];
+                        h1 = kh_lds_cd(a_t + 16u * rs);
+                        unsigned aq = sQ + (unsigned)sizeof(kh_qrot) * t;
                         for (; t < tend; ++t) {
-                            const double cc = gc[t]; const cd ss = gs[t];
-                            const int ot2 = ot1 + ROWSTEP(t + 1);
-                            const cd h1n = Hb[ot2 + jl];                // next row, in flight while this rotation is applied
+                            const double cc = kh_lds_d(aq); const cd ss = kh_lds_cd(aq + 16);
+                            const unsigned a_t1 = a_t + 16u * rs;
+                            const cd h1n = kh_lds_cd(a_t1 + 16u * (rs - 1));   // next row, in flight while this rotation is applied
                             const cd top = cc * carry + ss * h1;
                             carry = cc * h1 - cconj(ss) * carry;
-                            if (mine) Hb[ot + j] = top;
-                            h1 = h1n; ot = ot1; ot1 = ot2;
+                            if (mine) kh_sts_cd(a_t, top);
+                            h1 = h1n; a_t = a_t1; rs -= 1; aq += (unsigned)sizeof(kh_qrot);
                         }
-                        G.c = gc[t - 1]; G.s = gs[t - 1]; sub = qnsub[t - 1];
+                        G.c = kh_lds_d(aq - 80); G.s = kh_lds_cd(aq - 64); sub = kh_lds_cd(aq - 16);
                         __syncwarp();
-                        if (lane == 0) kh_st_release_shared(ctl + 4 + w, t);
+                        if (lane == 0) kh_st_release_saddr(sP, t);
                     }
                     // ---- driver mode: this warp owns the corner column
                     if (t >= tgen && t <= tlast && ctl[2] == 0) {
-                        cd hd = Hb[ot1 + t];                            // H[t+1][t]
-                        h1 = Hb[ot1 + jl];
+                        unsigned a_hd = sH + 16u * (unsigned)(ROWOFF(t + 1) + t);          // &H[t+1][t]
+                        unsigned aq = sQ + (unsigned)sizeof(kh_qrot) * t;
+                        int lc = (t - l) & 31;                          // lane of the corner column t
+                        cd hd = kh_lds_cd(a_hd);
+                        h1 = kh_lds_cd(a_t + 16u * rs);
+#pragma unroll 2
                         for (; t <= tlast; ++t) {
-                            const int ot2 = ot1 + ROWSTEP(t + 1);
-                            const cd hdn = Hb[ot2 + t + 1];             // operands of the next iteration, loaded ahead
-                            const cd h1n = Hb[ot2 + jl];                // (row t+2 is at most one past the last row: padded)
-                            const cd cb = kh_shfl_cd(carry, (t - l) & 31);                            // H[t][t] after R(t-1)
+                            const unsigned a_t1 = a_t + 16u * rs;
+                            a_hd += 16u * rs;
+                            const cd hdn = kh_lds_cd(a_hd);             // operands of the next iteration, loaded ahead
+                            const cd h1n = kh_lds_cd(a_t1 + 16u * (rs - 1));   // (row t+2 is at most one past the last row: padded)
+                            const cd cb = kh_shfl_cd(carry, lc);                                      // H[t][t] after R(t-1)
                             const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;      // C(t-1) on row t
                             const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;                              // C(t-1) on row t+1: bulge
-                            const kh_givens Gn = make_givens(a1, c1);                                  // G(t) annihilates it
+                            const double f2 = cabs2(a1), g2 = cabs2(c1);
+                            kh_givens Gn;                                                              // G(t) annihilates it
+                            if (f2 == 0.0 || g2 == 0.0) Gn = make_givens(a1, c1);                      // (warp-uniform, rare)
+                            else Gn = make_givens_fast(a1, c1, f2, g2);
                             const cd ncs = cconj(Gn.s);
                             const cd top = Gn.c * carry + Gn.s * h1, bot = Gn.c * h1 - ncs * carry;    // R(t) on the own column
                             const cd newdiag = Gn.c * b1 + Gn.s * d1, nextsub = Gn.c * d1 - ncs * b1;
-                            if (j > t && mine) { Hb[ot + j] = top; carry = bot; }
-                            if (lane == 0) { gc[t] = Gn.c; gs[t] = Gn.s; qsub[t] = Gn.r; qdiag[t] = newdiag; qnsub[t] = nextsub; }
+                            if (j > t && mine) { kh_sts_cd(a_t, top); carry = bot; }
+                            if (lane == 0) {
+                                kh_sts_d(aq, Gn.c); kh_sts_cd(aq + 16, Gn.s); kh_sts_cd(aq + 32, Gn.r);
+                                kh_sts_cd(aq + 48, newdiag); kh_sts_cd(aq + 64, nextsub);
+                            }
                             __syncwarp();
-                            if (lane == 0) kh_st_release_shared(ctl + 4 + w, t + 1);
-                            G = Gn; sub = nextsub; hd = hdn; h1 = h1n; ot = ot1; ot1 = ot2;
+                            if (lane == 0) kh_st_release_saddr(sP, t + 1);
+                            G = Gn; sub = nextsub; hd = hdn; h1 = h1n; a_t = a_t1; rs -= 1;
+                            aq += (unsigned)sizeof(kh_qrot); lc = (lc + 1) & 31;
                         }
                     }
                     // ---- the warp that owns column iact finishes row iact: C(iact-1) on its two entries
@@ -436,7 +483,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 // ---- row warps: C(t) on row r for t >= r (rows t+1, t+2 are handled inside the chain)
                 const int r = l + (c.tid - 32 * CW);
                 const int rmin = l + (warp - CW) * 32;
-                const int orow = (r < n) ? ROWOFF(r) : 0;
+                const unsigned a_row = sH + 16u * (unsigned)((r < n) ? ROWOFF(r) : 0);
                 cd car = mk(0, 0);
                 if (rmin < iact) {
                     int t = rmin, spins = 0;
@@ -448,18 +495,21 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                         int tend = l + 32 * (wq + 1) - 1;
                         if (tend > avail) tend = avail;
                         if (tend > iact) tend = iact;
+                        unsigned aq = sQ + (unsigned)sizeof(kh_qrot) * t;
+                        unsigned a_e = a_row + 16u * t;                  // &H[r][t]
                         for (; t < tend; ++t) {
-                            const double cc = gc[t]; const cd ss = gs[t];
+                            const double cc = kh_lds_d(aq); const cd ss = kh_lds_cd(aq + 16);
                             if (r <= t) {
                                 cd h0 = car;
-                                if (r == t) { if (t > l) { h0 = qdiag[t]; Hb[orow + t - 1] = qsub[t]; } else h0 = Hb[orow + t]; }
-                                const cd h1 = Hb[orow + t + 1];
-                                Hb[orow + t] = cc * h0 + cconj(ss) * h1;
+                                if (r == t) { if (t > l) { h0 = kh_lds_cd(aq + 48); kh_sts_cd(a_e - 16, kh_lds_cd(aq + 32)); } else h0 = kh_lds_cd(a_e); }
+                                const cd h1 = kh_lds_cd(a_e + 16);
+                                kh_sts_cd(a_e, cc * h0 + cconj(ss) * h1);
                                 car = cc * h1 - ss * h0;
                             }
+                            aq += (unsigned)sizeof(kh_qrot); a_e += 16;
                         }
                     }
-                    if (r < iact) Hb[orow + iact] = car;
+                    if (r < iact) Hb[ROWOFF(r) + iact] = car;
                 }
             }
             __syncthreads();
@@ -473,7 +523,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             HQ(l, j) = G.c * h0 + G.s * h1;
             HQ(l + 1, j) = G.c * h1 - cconj(G.s) * h0;
         }
-        if (c.tid == 0) { gc[l] = G.c; gs[l] = G.s; }
+        if (c.tid == 0) { Q[l].c = G.c; Q[l].s = G.s; }
         c.sync();
         // register-carried corner state: sub = H[k+1][k] after R(k); pend_* = entries of row k (its
         // sub-diagonal and diagonal after R(k)) that are known to every thread but not stored yet
@@ -512,7 +562,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 }
                 if (one_idx) break;                  // packed path on the GPU: nthr >= n, one index per thread
             }
-            if (more && c.tid == 0) { gc[k + 1] = Gn.c; gs[k + 1] = Gn.s; }
+            if (more && c.tid == 0) { Q[k + 1].c = Gn.c; Q[k + 1].s = Gn.s; }
             pend_sub = Gn.r; pend_diag = newdiag; sub = nextsub; G = Gn; o1 = o2;
             c.sync();
         }
@@ -522,14 +572,45 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
         {
             const int nAbove = l, nRight = n - 1 - iact;
-            for (int t2 = c.tid; t2 < nAbove + nRight + n; t2 += c.nthr) {
+            int nZ = n;
+            if (rl) {
+                // Z is updated later by zrot_apply: only record the sweep.  A full log is first replayed on Z here
+                // (slow, rare), so the order of the rotations is preserved.
+                const int cnt = iact - l;
+                if (nsw >= a.sw_cap || nrot + cnt > a.rot_cap) {
+                    c.sync();
+                    for (int i = c.tid; i < n; i += c.nthr)
+                        for (int sw = 0; sw < nsw; ++sw) {
+                            const int l0 = rl_sw[2 * sw] & 0xffff, i0 = rl_sw[2 * sw] >> 16;
+                            const double* rr = rl_rot + 3LL * rl_sw[2 * sw + 1];
+                            cd z0 = ZT(l0, i);
+                            for (int k = l0; k < i0; ++k, rr += 3) {
+                                const double cc = rr[0]; const cd ss = mk(rr[1], rr[2]);
+                                const cd z1 = ZT(k + 1, i);
+                                ZT(k, i) = cc * z0 + cconj(ss) * z1;
+                                z0 = cc * z1 - ss * z0;
+                            }
+                            ZT(i0, i) = z0;
+                        }
+                    c.sync();
+                    nsw = 0; nrot = 0;
+                }
+                for (int k = l + c.tid; k < iact; k += c.nthr) {
+                    double* rr = rl_rot + 3LL * (nrot + k - l);
+                    rr[0] = Q[k].c; rr[1] = Q[k].s.x; rr[2] = Q[k].s.y;
+                }
+                if (c.tid == 0) { rl_sw[2 * nsw] = l | (iact << 16); rl_sw[2 * nsw + 1] = nrot; }
+                nsw += 1; nrot += cnt;
+                nZ = 0;
+            }
+            for (int t2 = c.tid; t2 < nAbove + nRight + nZ; t2 += c.nthr) {
                 if (t2 < nAbove) {                                  // rows above the window: column rotations
                     const int r = t2;
                     cd h0 = HQ(r, l);
                     for (int k = l; k < iact; ++k) {
                         cd h1 = HQ(r, k + 1);
-                        HQ(r, k) = gc[k] * h0 + cconj(gs[k]) * h1;
-                        h0 = gc[k] * h1 - gs[k] * h0;
+                        HQ(r, k) = Q[k].c * h0 + cconj(Q[k].s) * h1;
+                        h0 = Q[k].c * h1 - Q[k].s * h0;
                     }
                     HQ(r, iact) = h0;
                 } else if (t2 < nAbove + nRight) {                  // columns right of the window: row rotations
@@ -537,8 +618,8 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     cd h0 = HQ(l, j);
                     for (int k = l; k < iact; ++k) {
                         cd h1 = HQ(k + 1, j);
-                        HQ(k, j) = gc[k] * h0 + gs[k] * h1;
-                        h0 = gc[k] * h1 - cconj(gs[k]) * h0;
+                        HQ(k, j) = Q[k].c * h0 + Q[k].s * h1;
+                        h0 = Q[k].c * h1 - cconj(Q[k].s) * h0;
                     }
                     HQ(iact, j) = h0;
                 } else {                                            // Z columns l..iact (rows of Zt), coalesced over i
@@ -557,7 +638,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                             }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
-                                const double cc = gc[k + u]; const cd ss = gs[k + u];
+                                const double cc = Q[k + u].c; const cd ss = Q[k + u].s;
                                 ZT(k + u, i) = cc * z0 + cconj(ss) * zn[u];
                                 z0 = cc * zn[u] - ss * z0;
                             }
@@ -569,8 +650,8 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     }
                     for (; k < iact; ++k) {
                         cd z1 = ZT(k + 1, i);
-                        ZT(k, i) = gc[k] * z0 + cconj(gs[k]) * z1;
-                        z0 = gc[k] * z1 - gs[k] * z0;
+                        ZT(k, i) = Q[k].c * z0 + cconj(Q[k].s) * z1;
+                        z0 = Q[k].c * z1 - Q[k].s * z0;
                     }
                     ZT(iact, i) = z0;
                 }
@@ -594,6 +675,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         kh_qr_dbg[4] = qt_delay; kh_qr_dbg[5] = qt_n; kh_qr_dbg[6] = qt_rot;
     }
 #endif
+    if (rl && c.tid == 0) { ((int*)rl)[0] = nsw; ((int*)rl)[1] = nrot; }
     if (a.info && c.tid == 0) a.info[b] = (fail == 0 && ctl[2] != 0) ? n + 1 : fail;
 #undef HQ
 #undef ROWOFF
@@ -603,6 +685,82 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
 
 KH_DEV void zqr_packed_body(const Cta& c, const zgeev_args& a) { zqr_body_t<true>(c, a); }
 KH_DEV void zqr_global_body(const Cta& c, const zgeev_args& a) { zqr_body_t<false>(c, a); }
+
+// ============================================================================ 2b. replay of the rotation log on Z
+// One CTA per matrix: Zt (n x n, transposed Schur vectors) is staged in shared memory, thread i owns column i of Zt
+// (= row i of Z) and applies every logged rotation to it (one LDS + one STS per rotation, the running entry stays in a
+// register); the rotations of the next sweep are fetched from the log while the current sweep is applied.
+struct zrot_args { int n; MatRef Zt; const double* rlog; long long rlog_stride; int sw_cap; };
+KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
+    const int n = a.n, b = c.bx;
+    cd* Ztg = mat_ptr(a.Zt, b);
+    const int ldz = a.Zt.ld;
+    const double* rl = a.rlog + (long long)b * a.rlog_stride;
+    const int nsw = ((const int*)rl)[0];
+    const int* swg = (const int*)(rl + 2);
+    const double* rot = rl + 2 + a.sw_cap;
+    // shared: [Zs n x n cd][rb 2 x n x 3 dbl][sw 2 x sw_cap int]
+    cd* Zs = (cd*)KH_SMEM(c);
+    double* rb = (double*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd));
+    int* sws = (int*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd) + (size_t)6 * n * sizeof(double));
+    if (nsw == 0) return;                                            // uniform
+    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Zs[e] = Ztg[(long long)k * ldz + i]; }
+    for (int e = c.tid; e < 2 * nsw; e += c.nthr) sws[e] = swg[e];
+    c.sync();
+    {   const int l0 = sws[0] & 0xffff, i0 = sws[0] >> 16, cnt = i0 - l0;
+        const double* rr = rot + 3LL * sws[1];
+        for (int e = c.tid; e < 3 * cnt; e += c.nthr) rb[e] = rr[e]; }
+    c.sync();
+    for (int sw = 0; sw < nsw; ++sw) {
+        const int l = sws[2 * sw] & 0xffff, iact = sws[2 * sw] >> 16;
+        const double* cur = rb + (sw & 1) * 3 * n;
+        double* nxt = rb + ((sw + 1) & 1) * 3 * n;
+        // fetch the next sweep's rotations (asynchronous copies, in flight while this sweep is applied)
+        if (sw + 1 < nsw) {
+            const int cnt = (sws[2 * sw + 2] >> 16) - (sws[2 * sw + 2] & 0xffff);
+            const double* rr = rot + 3LL * sws[2 * sw + 3];
+            for (int e = c.tid; e < 3 * cnt; e += c.nthr) {
+#ifdef KH_HOST_EMU
+                nxt[e] = rr[e];
+#else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(nxt + e)), "l"(rr + e));
+#endif
+            }
+        }
+        for (int i = c.tid; i < n; i += c.nthr) {
+            cd* zp = Zs + (long long)l * n + i;
+            cd z0 = zp[0];
+            int k = l;
+            for (; k + 4 <= iact; k += 4) {                          // rows k+1..k+4 are read before this sweep writes them
+                const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
+                const double* q = cur + 3 * (k - l);
+                const double c0 = q[0], c1 = q[3], c2 = q[6], c3 = q[9];
+                const cd s0 = mk(q[1], q[2]), s1 = mk(q[4], q[5]), s2 = mk(q[7], q[8]), s3 = mk(q[10], q[11]);
+                zp[0] = c0 * z0 + cconj(s0) * z1; z0 = c0 * z1 - s0 * z0;
+                zp[n] = c1 * z0 + cconj(s1) * z2; z0 = c1 * z2 - s1 * z0;
+                zp[2 * n] = c2 * z0 + cconj(s2) * z3; z0 = c2 * z3 - s2 * z0;
+                zp[3 * n] = c3 * z0 + cconj(s3) * z4; z0 = c3 * z4 - s3 * z0;
+                zp += 4 * n;
+            }
+            for (; k < iact; ++k) {
+                const cd z1 = zp[n];
+                const double* q = cur + 3 * (k - l);
+                const double cc = q[0]; const cd ss = mk(q[1], q[2]);
+                zp[0] = cc * z0 + cconj(ss) * z1; z0 = cc * z1 - ss * z0;
+                zp += n;
+            }
+            zp[0] = z0;
+        }
+#ifndef KH_HOST_EMU
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+        c.sync();
+    }
+    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Ztg[(long long)k * ldz + i] = Zs[e]; }
+}
+static inline size_t zrot_smem_bytes(int n, int sw_cap) { return (size_t)n * n * sizeof(cd) + (size_t)6 * n * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
+// work space (doubles per matrix) the log needs for the given capacities
+static inline long long zgeev_rlog_doubles(int rot_cap, int sw_cap) { return 2LL + sw_cap + 3LL * rot_cap; }
 
 // ============================================================================ 3. eigenvectors of the triangular factor
 KH_DEV void ztrevc_body(const Cta& c, const zgeev_args& a) {
@@ -645,7 +803,7 @@ static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
     return s;
 }
 static inline size_t zqr_smem_bytes(int n, int use_smem) {
-    size_t s = (size_t)4 * n * sizeof(cd) + (size_t)n * sizeof(double) + 16 * sizeof(int) + 16;
+    size_t s = (size_t)n * sizeof(kh_qrot) + 16 * sizeof(int) + 16;
     if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
     return s;
 }
@@ -668,9 +826,16 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
         if (e) return e; }
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
+    if (!(q.use_smem && q.rlog && q.rot_cap >= n && q.sw_cap >= 1 && q.sw_cap < 65536 && n < 65536 &&
+          zrot_smem_bytes(n, q.sw_cap) <= (size_t)KH_SMEM_MAX)) q.rlog = nullptr;
     // 256 threads when the delayed updates have more than 128 independent jobs (rows of Z + rows above + columns right)
     if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), KH_QR_THREADS(n), zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
     else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
     if (e) return e;
+    if (q.rlog) {
+        zrot_args z{n, a.Zt, q.rlog, q.rlog_stride, q.sw_cap};
+        e = kh_launch<zrot_args, zrot_apply_body>(dim3(batch), 128, zrot_smem_bytes(n, q.sw_cap), st, z, "zgeev_zrot", 0.0);
+        if (e) return e;
+    }
     return kh_launch<zgeev_args, ztrevc_body>(dim3(batch), n <= 128 ? 128 : 256, 0, st, a, "zgeev_trevc", 0.25 * work);
 }
