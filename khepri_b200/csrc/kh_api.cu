@@ -238,9 +238,10 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
     {   zgeev_args a;
         a.n = n; a.A = M(2); a.Hw = M(2); a.Zt = M(3); a.X = M(4);
         a.w = v.w; a.w_stride = n; a.scale = v.scale; a.scale_stride = n; a.tau = v.tau; a.tau_stride = n; a.info = v.info_eig;
-        // rotation log of the QR sweeps: slabs 5..8 are free until W is formed (4 n^2 complex = 8 n^2 doubles per solve)
-        a.rlog = (double*)S(5); a.rlog_stride = 8 * n2; a.sw_cap = 6 * n;
+        // rotation log of the QR sweeps: slabs 5..12 are free until W is formed (8 n^2 complex = 16 n^2 doubles per solve)
+        a.rlog = (double*)S(5); a.rlog_stride = 16 * n2; a.sw_cap = 8 * n;     // slabs 5..12
         a.rot_cap = (int)((a.rlog_stride - 2 - a.sw_cap) / 3);
+        a.istate = v.info_inv + Bc;                                           // (middle third of the info block: unused elsewhere)
         KH_TRY(zgeev_launch(st, Bc, a)); }
     {   zgemm_args g = zgemm_make(n, n, n, M(3), M(4), M(5));                    // W = diag(scale) Z X
         g.transA = 1; g.rowscale = v.scale; g.rs_stride = n; g.rs_group = 1;
@@ -542,7 +543,7 @@ extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int*
     return 0;
 }
 extern "C" size_t kh_zgeev_work_bytes(int batch, int n) {
-    return (size_t)batch * ((size_t)7 * n * n + 2 * n) * sizeof(cd) + 4096;      // H, Zt, X, scale, tau + the rotation log (4 n^2)
+    return (size_t)batch * ((size_t)11 * n * n + 2 * n) * sizeof(cd) + (size_t)batch * sizeof(int) + 8192;      // H, Zt, X, scale, tau + the rotation log (8 n^2) + phase state
 }
 extern "C" int kh_zgeev_batched(int batch, int n, const void* A, void* w, void* W, void* work, size_t work_bytes, int* info, void* stream) {
     if (batch < 0 || n < 1 || !A || !w || !W || !work) return fail(KH_EINVAL, "kh_zgeev_batched: bad arguments");
@@ -551,12 +552,13 @@ extern "C" int kh_zgeev_batched(int batch, int n, const void* A, void* w, void* 
     Bump b{(char*)work, work_bytes, 0};
     const size_t n2 = (size_t)n * n;
     cd* H = b.get<cd>(batch * n2); cd* Zt = b.get<cd>(batch * n2); cd* X = b.get<cd>(batch * n2); cd* sc = b.get<cd>((size_t)batch * n); cd* tau = b.get<cd>((size_t)batch * n);
-    cd* rlog = b.get<cd>(batch * 4 * n2);
+    cd* rlog = b.get<cd>(batch * 8 * n2); int* istate = b.get<int>(batch);
     kh_stream_t st = (kh_stream_t)stream;
     zgeev_args a;
     a.n = n; a.A = mref(A, n2, n); a.Hw = mref(H, n2, n); a.Zt = mref(Zt, n2, n); a.X = mref(X, n2, n);
     a.w = (cd*)w; a.w_stride = n; a.scale = sc; a.scale_stride = n; a.tau = tau; a.tau_stride = n; a.info = info;
-    a.rlog = (double*)rlog; a.rlog_stride = 8 * (long long)n2; a.sw_cap = 6 * n; a.rot_cap = (int)((a.rlog_stride - 2 - a.sw_cap) / 3);
+    a.rlog = (double*)rlog; a.rlog_stride = 16 * (long long)n2; a.sw_cap = 8 * n; a.rot_cap = (int)((a.rlog_stride - 2 - a.sw_cap) / 3);
+    a.istate = istate;
     KH_TRY(zgeev_launch(st, batch, a));
     zgemm_args g = zgemm_make(n, n, n, a.Zt, a.X, mref(W, n2, n));
     g.transA = 1; g.rowscale = sc; g.rs_stride = n; g.rs_group = 1;
@@ -671,5 +673,10 @@ extern "C" int kh_profile_end(char* buf, size_t len) {
 }
 
 #if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
-extern "C" int kh_qr_timing(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, kh_qr_dbg, 16 * sizeof(long long)); }
+extern "C" int kh_qr_timing(long long* out16) {          // returns the counters accumulated since the last call and clears them
+    cudaError_t e = cudaMemcpyFromSymbol(out16, kh_qr_dbg, 16 * sizeof(long long));
+    long long zero[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(kh_qr_dbg, zero, sizeof(zero));
+    return (int)e;
+}
 #endif

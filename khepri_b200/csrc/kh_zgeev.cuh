@@ -35,6 +35,10 @@ struct zgeev_args {
     // Per matrix: [0] header (int2: sweeps, rotations) [2 .. 2+sw_cap) sweep descriptors (int2: l | iact << 16, first
     // rotation) [2+sw_cap ..) rotations (c, re s, im s).
     double* rlog = nullptr; long long rlog_stride = 0; int rot_cap = 0, sw_cap = 0;
+    // Phases of the QR iteration (only with a log).  With everything outside the active window deferred to the log, the
+    // kernel only needs the leading na x na block: later phases run with a smaller shared-memory footprint and more
+    // CTAs per SM.  A phase starts from istate[b] (phase > 0) and stops once iact < iact_stop.
+    int na = 0, iact_stop = 0, phase = 0; int* istate = nullptr;
 };
 
 #define ZGEEV_EPS 2.220446049250313e-16   /* LAPACK ulp = eps*base */
@@ -273,7 +277,13 @@ __device__ long long kh_qr_dbg[16];
 #endif
 template <bool PACKED>
 KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
-    const int n = a.n, b = c.bx;
+    const int nfull = a.n, n = (a.na > 0 && a.na < a.n) ? a.na : a.n, b = c.bx;     // n: leading block this phase works on
+    int iact = n - 1;
+    if (a.phase > 0) {                                                // continue where the previous phase stopped
+        iact = a.istate[b];
+        if (iact < a.iact_stop || iact < 0) return;                   // nothing left for this phase (uniform)
+        if (iact > n - 1) iact = n - 1;
+    }
     cd* Hg = mat_ptr(a.Hw, b);
     cd* Zt = mat_ptr(a.Zt, b);
     const int ldz = a.Zt.ld, ldg = a.Hw.ld;
@@ -293,16 +303,18 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     if (c.tid == 0) ctl[2] = 0;
     c.sync();
 
-    const double smlnum = ZGEEV_SAFMIN * ((double)n / ZGEEV_EPS);
-    const int itmax = 30 * (n > 10 ? n : 10);
+    const double smlnum = ZGEEV_SAFMIN * ((double)nfull / ZGEEV_EPS);
+    const int itmax = 30 * (nfull > 10 ? nfull : 10);
     int fail = 0;
-    int iact = n - 1, its = 0;
+    int its = 0;
     double* const rl = a.rlog ? a.rlog + (long long)b * a.rlog_stride : nullptr;
     int* const rl_sw = rl ? (int*)(rl + 2) : nullptr;
     double* const rl_rot = rl ? rl + 2 + a.sw_cap : nullptr;
     int nsw = 0, nrot = 0;             // logged sweeps / rotations (uniform)
+    if (rl && a.phase > 0) { nsw = ((const int*)rl)[0]; nrot = ((const int*)rl)[1]; }
+    const int istop = a.iact_stop > 0 ? a.iact_stop : 0;
     QT_DECL;
-    while (iact >= 0) {
+    while (iact >= istop) {
         QT_MARK();
         // ---- locate the active block [l, iact] (zlahqr deflation criterion)
         if (c.tid == 0) ctl[0] = 0;
@@ -572,38 +584,21 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
         {
             const int nAbove = l, nRight = n - 1 - iact;
-            int nZ = n;
+            int nZ = n, nR = nRight;
             if (rl) {
-                // Z is updated later by zrot_apply: only record the sweep.  A full log is first replayed on Z here
-                // (slow, rare), so the order of the rotations is preserved.
+                // Z and the columns of H right of the window only ever RECEIVE rotations (no later sweep reads them), so
+                // they are updated after the iteration by zrot_apply: only record the sweep.
                 const int cnt = iact - l;
-                if (nsw >= a.sw_cap || nrot + cnt > a.rot_cap) {
-                    c.sync();
-                    for (int i = c.tid; i < n; i += c.nthr)
-                        for (int sw = 0; sw < nsw; ++sw) {
-                            const int l0 = rl_sw[2 * sw] & 0xffff, i0 = rl_sw[2 * sw] >> 16;
-                            const double* rr = rl_rot + 3LL * rl_sw[2 * sw + 1];
-                            cd z0 = ZT(l0, i);
-                            for (int k = l0; k < i0; ++k, rr += 3) {
-                                const double cc = rr[0]; const cd ss = mk(rr[1], rr[2]);
-                                const cd z1 = ZT(k + 1, i);
-                                ZT(k, i) = cc * z0 + cconj(ss) * z1;
-                                z0 = cc * z1 - ss * z0;
-                            }
-                            ZT(i0, i) = z0;
-                        }
-                    c.sync();
-                    nsw = 0; nrot = 0;
-                }
+                if (nsw >= a.sw_cap || nrot + cnt > a.rot_cap) { fail = nfull + 2; break; }     // log full: reported like a convergence failure
                 for (int k = l + c.tid; k < iact; k += c.nthr) {
                     double* rr = rl_rot + 3LL * (nrot + k - l);
                     rr[0] = Q[k].c; rr[1] = Q[k].s.x; rr[2] = Q[k].s.y;
                 }
                 if (c.tid == 0) { rl_sw[2 * nsw] = l | (iact << 16); rl_sw[2 * nsw + 1] = nrot; }
                 nsw += 1; nrot += cnt;
-                nZ = 0;
+                nZ = 0; nR = 0;
             }
-            for (int t2 = c.tid; t2 < nAbove + nRight + nZ; t2 += c.nthr) {
+            for (int t2 = c.tid; t2 < nAbove + nR + nZ; t2 += c.nthr) {
                 if (t2 < nAbove) {                                  // rows above the window: column rotations
                     const int r = t2;
                     cd h0 = HQ(r, l);
@@ -613,7 +608,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                         h0 = Q[k].c * h1 - Q[k].s * h0;
                     }
                     HQ(r, iact) = h0;
-                } else if (t2 < nAbove + nRight) {                  // columns right of the window: row rotations
+                } else if (t2 < nAbove + nR) {                      // columns right of the window: row rotations
                     const int j = iact + 1 + (t2 - nAbove);
                     cd h0 = HQ(l, j);
                     for (int k = l; k < iact; ++k) {
@@ -623,7 +618,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     }
                     HQ(iact, j) = h0;
                 } else {                                            // Z columns l..iact (rows of Zt), coalesced over i
-                    const int i = t2 - nAbove - nRight;
+                    const int i = t2 - nAbove - nR;
                     cd z0 = ZT(l, i);
                     int k = l;
                     if (k + 8 <= iact) {                             // software pipeline: the next 8 rows of Zt are in flight
@@ -667,16 +662,18 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     if (packed)
         for (int e = c.tid; e < n * n; e += c.nthr) {
             int i = e / n, j = e - i * n;
-            Hg[(long long)i * ldg + j] = (j >= i) ? HQ(i, j) : mk(0.0, 0.0);
+            Hg[(long long)i * ldg + j] = (j >= i - 1) ? HQ(i, j) : mk(0.0, 0.0);      // deflated sub-diagonals are exact zeros
         }
 #if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
     if (c.tid == 0 && b == 0) {
-        kh_qr_dbg[0] = clock64() - qt0; kh_qr_dbg[1] = qt_scan; kh_qr_dbg[2] = qt_shift; kh_qr_dbg[3] = qt_sweep;
-        kh_qr_dbg[4] = qt_delay; kh_qr_dbg[5] = qt_n; kh_qr_dbg[6] = qt_rot;
+        kh_qr_dbg[0] += clock64() - qt0; kh_qr_dbg[1] += qt_scan; kh_qr_dbg[2] += qt_shift; kh_qr_dbg[3] += qt_sweep;
+        kh_qr_dbg[4] += qt_delay; kh_qr_dbg[5] += qt_n; kh_qr_dbg[6] += qt_rot;
     }
 #endif
     if (rl && c.tid == 0) { ((int*)rl)[0] = nsw; ((int*)rl)[1] = nrot; }
-    if (a.info && c.tid == 0) a.info[b] = (fail == 0 && ctl[2] != 0) ? n + 1 : fail;
+    if (fail == 0 && ctl[2] != 0) fail = nfull + 1;
+    if (a.istate && c.tid == 0) a.istate[b] = fail ? -1 : iact;
+    if (a.info && c.tid == 0 && (fail || a.phase == 0)) a.info[b] = fail;
 #undef HQ
 #undef ROWOFF
 #undef ROWSTEP
@@ -686,79 +683,116 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
 KH_DEV void zqr_packed_body(const Cta& c, const zgeev_args& a) { zqr_body_t<true>(c, a); }
 KH_DEV void zqr_global_body(const Cta& c, const zgeev_args& a) { zqr_body_t<false>(c, a); }
 
-// ============================================================================ 2b. replay of the rotation log on Z
-// One CTA per matrix: Zt (n x n, transposed Schur vectors) is staged in shared memory, thread i owns column i of Zt
-// (= row i of Z) and applies every logged rotation to it (one LDS + one STS per rotation, the running entry stays in a
-// register); the rotations of the next sweep are fetched from the log while the current sweep is applied.
-struct zrot_args { int n; MatRef Zt; const double* rlog; long long rlog_stride; int sw_cap; };
+// ============================================================================ 2b. replay of the rotation log
+// Two CTAs per matrix.  by = 0: Zt (transposed Schur vectors) is staged in shared memory, thread i owns column i of Zt
+// (= row i of Z) and applies every logged rotation to it.  by = 1: the triangular factor T is staged, thread j owns
+// column j and applies the row rotations of every sweep whose window ended above row j (iact < j).  One LDS + one STS per
+// rotation, the running entry stays in a register; the log is streamed through shared memory in chunks of whole
+// sweeps (asynchronous copies, next chunk in flight while the current one is applied), one barrier per chunk.
+struct zrot_args { int n; MatRef Zt, T; const double* rlog; long long rlog_stride; int sw_cap, chunk; };
 KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
-    const int n = a.n, b = c.bx;
-    cd* Ztg = mat_ptr(a.Zt, b);
-    const int ldz = a.Zt.ld;
+    const int n = a.n, b = c.bx, mode = c.by, CH = a.chunk;
+    const MatRef M = mode ? a.T : a.Zt;
+    cd* Mg = mat_ptr(M, b);
+    const int ldm = M.ld;
     const double* rl = a.rlog + (long long)b * a.rlog_stride;
     const int nsw = ((const int*)rl)[0];
     const int* swg = (const int*)(rl + 2);
     const double* rot = rl + 2 + a.sw_cap;
-    // shared: [Zs n x n cd][rb 2 x n x 3 dbl][sw 2 x sw_cap int]
-    cd* Zs = (cd*)KH_SMEM(c);
+    // shared: [Ms n x n cd][rb 2 x CH x 4 dbl][sw 2 x sw_cap int]
+    cd* Ms = (cd*)KH_SMEM(c);
     double* rb = (double*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd));
-    int* sws = (int*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd) + (size_t)6 * n * sizeof(double));
+    int* sws = (int*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd) + (size_t)8 * CH * sizeof(double));
     if (nsw == 0) return;                                            // uniform
-    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Zs[e] = Ztg[(long long)k * ldz + i]; }
+    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Ms[e] = Mg[(long long)k * ldm + i]; }
     for (int e = c.tid; e < 2 * nsw; e += c.nthr) sws[e] = swg[e];
     c.sync();
-    {   const int l0 = sws[0] & 0xffff, i0 = sws[0] >> 16, cnt = i0 - l0;
-        const double* rr = rot + 3LL * sws[1];
-        for (int e = c.tid; e < 3 * cnt; e += c.nthr) rb[e] = rr[e]; }
-    c.sync();
-    for (int sw = 0; sw < nsw; ++sw) {
-        const int l = sws[2 * sw] & 0xffff, iact = sws[2 * sw] >> 16;
-        const double* cur = rb + (sw & 1) * 3 * n;
-        double* nxt = rb + ((sw + 1) & 1) * 3 * n;
-        // fetch the next sweep's rotations (asynchronous copies, in flight while this sweep is applied)
-        if (sw + 1 < nsw) {
-            const int cnt = (sws[2 * sw + 2] >> 16) - (sws[2 * sw + 2] & 0xffff);
-            const double* rr = rot + 3LL * sws[2 * sw + 3];
-            for (int e = c.tid; e < 3 * cnt; e += c.nthr) {
+    const int nrot = sws[2 * nsw - 1] + ((sws[2 * nsw - 2] >> 16) - (sws[2 * nsw - 2] & 0xffff));
+    // chunk [s0, s1): whole sweeps, at most CH rotations (every sweep has fewer than n <= CH rotations)
+    auto chunk_end = [&](int s0) {
+        int s1 = s0 + 1;
+        while (s1 < nsw && ((s1 + 1 < nsw ? sws[2 * s1 + 3] : nrot) - sws[2 * s0 + 1]) <= CH) ++s1;
+        return s1;
+    };
+    auto stage = [&](int s0, int s1, double* dst) {
+        const int r0 = sws[2 * s0 + 1], r1 = (s1 < nsw) ? sws[2 * s1 + 1] : nrot;
+        const double* src = rot + 3LL * r0;
+        for (int e = c.tid; e < 3 * (r1 - r0); e += c.nthr) {
+            const int q = e / 3, comp = e - 3 * q;
 #ifdef KH_HOST_EMU
-                nxt[e] = rr[e];
+            dst[4 * q + comp] = src[e];
 #else
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(nxt + e)), "l"(rr + e));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst + 4 * q + comp)), "l"(src + e));
 #endif
-            }
         }
+    };
+    int s0 = 0, s1 = chunk_end(0), buf = 0;
+    stage(s0, s1, rb);
+#ifndef KH_HOST_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    c.sync();
+    while (s0 < nsw) {
+        const int s2 = (s1 < nsw) ? chunk_end(s1) : s1;
+        if (s1 < nsw) stage(s1, s2, rb + (buf ^ 1) * 4 * CH);
+        const double* cur = rb + buf * 4 * CH;
+        const int rbase = sws[2 * s0 + 1];
         for (int i = c.tid; i < n; i += c.nthr) {
-            cd* zp = Zs + (long long)l * n + i;
-            cd z0 = zp[0];
-            int k = l;
-            for (; k + 4 <= iact; k += 4) {                          // rows k+1..k+4 are read before this sweep writes them
-                const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
-                const double* q = cur + 3 * (k - l);
-                const double c0 = q[0], c1 = q[3], c2 = q[6], c3 = q[9];
-                const cd s0 = mk(q[1], q[2]), s1 = mk(q[4], q[5]), s2 = mk(q[7], q[8]), s3 = mk(q[10], q[11]);
-                zp[0] = c0 * z0 + cconj(s0) * z1; z0 = c0 * z1 - s0 * z0;
-                zp[n] = c1 * z0 + cconj(s1) * z2; z0 = c1 * z2 - s1 * z0;
-                zp[2 * n] = c2 * z0 + cconj(s2) * z3; z0 = c2 * z3 - s2 * z0;
-                zp[3 * n] = c3 * z0 + cconj(s3) * z4; z0 = c3 * z4 - s3 * z0;
-                zp += 4 * n;
+            for (int sw = s0; sw < s1; ++sw) {
+                const int l = sws[2 * sw] & 0xffff, iact = sws[2 * sw] >> 16;
+                if (mode && iact >= i) continue;
+                const double* q = cur + 4 * (sws[2 * sw + 1] - rbase);
+                cd* zp = Ms + (long long)l * n + i;
+                cd z0 = zp[0];
+                int k = l;
+                if (mode == 0) {
+                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * n) {      // rows k+1..k+4 are read before this sweep writes them
+                        const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
+                        const double c0 = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
+                        const cd t0 = mk(q[1], q[2]), t1 = mk(q[5], q[6]), t2 = mk(q[9], q[10]), t3 = mk(q[13], q[14]);
+                        zp[0] = c0 * z0 + cconj(t0) * z1; z0 = c0 * z1 - t0 * z0;
+                        zp[n] = c1 * z0 + cconj(t1) * z2; z0 = c1 * z2 - t1 * z0;
+                        zp[2 * n] = c2 * z0 + cconj(t2) * z3; z0 = c2 * z3 - t2 * z0;
+                        zp[3 * n] = c3 * z0 + cconj(t3) * z4; z0 = c3 * z4 - t3 * z0;
+                    }
+                    for (; k < iact; ++k, q += 4, zp += n) {
+                        const cd z1 = zp[n];
+                        const double cc = q[0]; const cd ss = mk(q[1], q[2]);
+                        zp[0] = cc * z0 + cconj(ss) * z1; z0 = cc * z1 - ss * z0;
+                    }
+                } else {
+                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * n) {
+                        const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
+                        const double c0 = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
+                        const cd t0 = mk(q[1], q[2]), t1 = mk(q[5], q[6]), t2 = mk(q[9], q[10]), t3 = mk(q[13], q[14]);
+                        zp[0] = c0 * z0 + t0 * z1; z0 = c0 * z1 - cconj(t0) * z0;
+                        zp[n] = c1 * z0 + t1 * z2; z0 = c1 * z2 - cconj(t1) * z0;
+                        zp[2 * n] = c2 * z0 + t2 * z3; z0 = c2 * z3 - cconj(t2) * z0;
+                        zp[3 * n] = c3 * z0 + t3 * z4; z0 = c3 * z4 - cconj(t3) * z0;
+                    }
+                    for (; k < iact; ++k, q += 4, zp += n) {
+                        const cd z1 = zp[n];
+                        const double cc = q[0]; const cd ss = mk(q[1], q[2]);
+                        zp[0] = cc * z0 + ss * z1; z0 = cc * z1 - cconj(ss) * z0;
+                    }
+                }
+                zp[0] = z0;
             }
-            for (; k < iact; ++k) {
-                const cd z1 = zp[n];
-                const double* q = cur + 3 * (k - l);
-                const double cc = q[0]; const cd ss = mk(q[1], q[2]);
-                zp[0] = cc * z0 + cconj(ss) * z1; z0 = cc * z1 - ss * z0;
-                zp += n;
-            }
-            zp[0] = z0;
         }
 #ifndef KH_HOST_EMU
         asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
         c.sync();
+        s0 = s1; s1 = s2; buf ^= 1;
     }
-    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Ztg[(long long)k * ldz + i] = Zs[e]; }
+    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Mg[(long long)k * ldm + i] = Ms[e]; }
 }
-static inline size_t zrot_smem_bytes(int n, int sw_cap) { return (size_t)n * n * sizeof(cd) + (size_t)6 * n * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
+static inline int zrot_chunk(int n, int sw_cap) {                     // rotations per staged chunk that fit beside the matrix
+    const long long room = (long long)KH_SMEM_MAX - (long long)n * n * (long long)sizeof(cd) - 2LL * sw_cap * (long long)sizeof(int) - 64;
+    long long ch = room / (2 * 4 * (long long)sizeof(double));
+    return ch > 4096 ? 4096 : (int)ch;
+}
+static inline size_t zrot_smem_bytes(int n, int sw_cap, int chunk) { return (size_t)n * n * sizeof(cd) + (size_t)8 * chunk * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
 // work space (doubles per matrix) the log needs for the given capacities
 static inline long long zgeev_rlog_doubles(int rot_cap, int sw_cap) { return 2LL + sw_cap + 3LL * rot_cap; }
 
@@ -827,14 +861,32 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
     if (!(q.use_smem && q.rlog && q.rot_cap >= n && q.sw_cap >= 1 && q.sw_cap < 65536 && n < 65536 &&
-          zrot_smem_bytes(n, q.sw_cap) <= (size_t)KH_SMEM_MAX)) q.rlog = nullptr;
-    // 256 threads when the delayed updates have more than 128 independent jobs (rows of Z + rows above + columns right)
-    if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), KH_QR_THREADS(n), zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
+          zrot_chunk(n, q.sw_cap) >= n)) q.rlog = nullptr;
+    if (q.use_smem && q.rlog && q.istate) {
+        // Phased iteration on the shrinking leading block: (na, launch shape) chosen so that 2 / 4 / 8 CTAs share an SM.
+        auto fit = [&](size_t budget) { int m = n; while (m > 8 && zqr_smem_bytes(m, 1) > budget) --m; return m; };
+        const int na2 = fit((size_t)KH_SMEM_MAX / 4 - 1024), na3 = fit((size_t)KH_SMEM_MAX / 8 - 1024);
+        int phase = 0;
+        auto run = [&](int na, int stop) {
+            zgeev_args r = q;
+            r.na = na; r.iact_stop = stop; r.phase = phase++;
+            const size_t sm = zqr_smem_bytes(na, 1);
+            const int thr = na <= 64 ? 128 : (na <= 96 ? 192 : 256);
+            if (na <= na3 && na <= 64) return kh_launch<zgeev_args, zqr_packed_body, 128, 8>(dim3(batch), thr, sm, st, r, "zgeev_qr", phase == 1 ? 0.5 * work : 0.0);
+            if (na <= na2 && na <= 96) return kh_launch<zgeev_args, zqr_packed_body, 192, 4>(dim3(batch), thr, sm, st, r, "zgeev_qr", phase == 1 ? 0.5 * work : 0.0);
+            return kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), thr, sm, st, r, "zgeev_qr", phase == 1 ? 0.5 * work : 0.0);
+        };
+        if (n > na2 + 8) { e = run(n, na2); if (e) return e; }
+        if (n > na3 + 8) { e = run(n < na2 ? n : (phase ? na2 : n), na3); if (e) return e; }
+        e = run(phase ? na3 : n, 0);
+    }
+    else if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), KH_QR_THREADS(n), zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
     else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
     if (e) return e;
     if (q.rlog) {
-        zrot_args z{n, a.Zt, q.rlog, q.rlog_stride, q.sw_cap};
-        e = kh_launch<zrot_args, zrot_apply_body>(dim3(batch), 128, zrot_smem_bytes(n, q.sw_cap), st, z, "zgeev_zrot", 0.0);
+        const int ch = zrot_chunk(n, q.sw_cap);
+        zrot_args z{n, a.Zt, a.Hw, q.rlog, q.rlog_stride, q.sw_cap, ch};
+        e = kh_launch<zrot_args, zrot_apply_body>(dim3(batch, 2), 128, zrot_smem_bytes(n, q.sw_cap, ch), st, z, "zgeev_zrot", 0.0);
         if (e) return e;
     }
     return kh_launch<zgeev_args, ztrevc_body>(dim3(batch), n <= 128 ? 128 : 256, 0, st, a, "zgeev_trevc", 0.25 * work);

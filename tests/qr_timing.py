@@ -8,9 +8,10 @@ eng = Engine(lib_path=__import__("os").environ.get("KH_TLIB", "tests/hostemu/lib
 st = cases.bzi_structure((7, 7))
 cl = build_crystal(st, eng)
 wl = 1 / np.linspace(0.8, 1.0, 8)
-R, T = cl.solve_batch(wl, kps=np.tile([[0.3, 0.2]], (8, 1)), te=1.0, tm=1.0)
 out = (C.c_longlong * 16)()
 eng.lib.kh_qr_timing.argtypes = [C.POINTER(C.c_longlong)]
+eng.lib.kh_qr_timing(out)            # clear
+R, T = cl.solve_batch(wl, kps=np.tile([[0.3, 0.2]], (8, 1)), te=1.0, tm=1.0)
 eng.lib.kh_qr_timing(out)
 names = ["total", "scan", "shift", "sweep", "delayed", "sweeps", "rotations"]
 print({k: int(v) for k, v in zip(names, out)})
