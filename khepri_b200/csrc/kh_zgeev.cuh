@@ -92,6 +92,16 @@ __device__ __forceinline__ kh_givens make_givens_fast(cd f, cd g, double f2, dou
 }
 #endif
 
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+__device__ long long kh_qr_dbg[16];
+#define QT_DECL long long qt0 = clock64(), qt_scan = 0, qt_shift = 0, qt_sweep = 0, qt_delay = 0, qt_n = 0, qt_rot = 0, qt_t
+#define QT_MARK() (qt_t = clock64())
+#define QT_ADD(v) do { long long _n = clock64(); (v) += _n - qt_t; qt_t = _n; } while (0)
+#else
+#define QT_DECL
+#define QT_MARK()
+#define QT_ADD(v)
+#endif
 // ============================================================================ 1. balance + Hessenberg
 KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     const int n = a.n, b = c.bx;
@@ -153,6 +163,12 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     cd* pp_ = uu;                      // p  [n]
     cd* qq_ = (cd*)dsc;                // q  [n]   (dsc is dead after balancing)
     const int lane = c.tid % KH_WARP;
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    long long ht = clock64(), h_norm = 0, h_v = 0, h_mv = 0, h_upd = 0, h_n;
+#define HT_ADD(v) do { h_n = clock64(); (v) += h_n - ht; ht = h_n; } while (0)
+#else
+#define HT_ADD(v)
+#endif
     for (int k = 0; k + 2 < n; ++k) {
         double part = 0.0;                                   // every warp computes the column norm redundantly
         for (int i = k + 2 + lane; i < n; i += KH_WARP) part += cabs2(HH(i, k));
@@ -163,6 +179,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
         const cd tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
         const cd sc = crecip(alpha - mk(beta, 0.0));
         c.sync();                                              // all warps have read column k
+        HT_ADD(h_norm);
         for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
             const cd vi = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
             vv[i] = vi;
@@ -170,6 +187,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
         }
         if (c.tid == 0) tauout[k] = tau;
         c.sync();
+        HT_ADD(h_v);
         // p = A v (one thread per row), q = v^H A (one thread per column)
         for (int t = c.tid; t < 2 * n; t += c.nthr) {
             cd a0 = mk(0, 0), a1 = mk(0, 0);
@@ -190,6 +208,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
             }
         }
         c.sync();
+        HT_ADD(h_mv);
         double sr = 0.0, si = 0.0;                           // s = v^H p, redundantly per warp
         for (int i = k + 1 + lane; i < n; i += KH_WARP) { const cd w = cconj(vv[i]) * pp_[i]; sr += w.x; si += w.y; }
         const cd sv = mk(kh_warp_allsum(sr), kh_warp_allsum(si));
@@ -209,11 +228,234 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
             }
         }
         c.sync();
+        HT_ADD(h_upd);
     }
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    if (c.tid == 0 && b == 0) { kh_qr_dbg[8] += h_norm; kh_qr_dbg[9] += h_v; kh_qr_dbg[10] += h_mv; kh_qr_dbg[11] += h_upd; }
+#endif
     if (a.use_smem)
         for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * a.Hw.ld + j] = HH(i, j); }
 #undef HH
 #undef ZT
+}
+
+// ============================================================================ 1a. fused shared-memory variant
+// Balance + Hessenberg reduction + formation of Z in ONE kernel with the matrix resident in shared memory (n <= ~117).
+// Per reduction step three barriers: [norm, v] | [p = A v, q = v^H A with several threads per dot product, s = v^H p] |
+// [rank-2 update, thread <-> row so that its coefficients stay in registers, four columns in flight].  Z is then
+// accumulated IN PLACE (LAPACK zunghr/zung2r layout: reflector k sits in column k+1 until step k consumes it), two
+// barriers per step and no global-memory access inside the loop.
+KH_DEV void zhessz_body(const Cta& c, const zgeev_args& a) {
+    const int n = a.n, b = c.bx, ld = a.ld_s;
+    const cd* A = mat_ptr(a.A, b);
+    cd* Hg = mat_ptr(a.Hw, b);
+    cd* Ztg = mat_ptr(a.Zt, b);
+    const int ldz = a.Zt.ld, ldg = a.Hw.ld;
+    cd* scout = a.scale + (long long)b * a.scale_stride;
+    // shared: [vv n][pp n][scratch 192 dbl][qq 2n cd (balancing factors first)][H n x ld]
+    cd* vv = (cd*)KH_SMEM(c);
+    cd* pp = vv + n;
+    double* scratch = (double*)(pp + n);
+    double* dsc = scratch + 192;
+    cd* vq = (cd*)dsc;                  // [n][2]: (conj v_j, q_j) interleaved for the update
+    cd* Hs = (cd*)(KH_SMEM(c) + (((2 * n * 16 + 192 * 8 + 4 * n * 8) + 15) & ~15));
+    cd* spart = (cd*)scratch;           // [<= 32] per-warp partial sums of s = v^H p
+    cd* tauout = a.tau + (long long)b * a.tau_stride;
+#define HH(i, j) Hs[(i) * ld + (j)]
+    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; HH(i, j) = A[(long long)i * a.A.ld + j]; }
+    for (int i = c.tid; i < n; i += c.nthr) { dsc[i] = 1.0; tauout[i] = mk(0.0, 0.0); }
+    c.sync();
+    // ---- balancing (Jacobi-style sweeps of the EISPACK balanc criterion; powers of two, so exact)
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double changed = 0.0;
+        for (int i = c.tid; i < n; i += c.nthr) {
+            double cn = 0.0, rn = 0.0;
+            for (int j = 0; j < n; ++j) if (j != i) { cn += cabs1(HH(j, i)); rn += cabs1(HH(i, j)); }
+            double f = 1.0;
+            if (cn != 0.0 && rn != 0.0 && cn <= 1e300 && rn <= 1e300) {      // (NaN/inf rows are left alone)
+                double g = rn * 0.5, s = cn + rn, cc = cn;
+                for (int q = 0; q < 1100 && cc < g; ++q) { f *= 2.0; cc *= 4.0; }
+                g = rn * 2.0;
+                for (int q = 0; q < 1100 && cc >= g; ++q) { f *= 0.5; cc *= 0.25; }
+                if ((cc + rn) / f >= 0.95 * s) f = 1.0;
+            }
+            pp[i].x = f;
+            if (f != 1.0) changed = 1.0;
+        }
+        changed = cta_max(c, changed, scratch);
+        c.sync();
+        if (changed == 0.0) break;
+        for (int e = c.tid; e < n * n; e += c.nthr) {
+            int i = e / n, j = e - i * n;
+            double f = pp[j].x / pp[i].x;
+            if (f != 1.0) HH(i, j) = f * HH(i, j);
+        }
+        for (int i = c.tid; i < n; i += c.nthr) dsc[i] *= pp[i].x;
+        c.sync();
+    }
+    for (int i = c.tid; i < n; i += c.nthr) scout[i] = mk(dsc[i], 0.0);
+    c.sync();
+
+    const int lane = c.tid % KH_WARP, warp = c.tid / KH_WARP, nw = (c.nthr + KH_WARP - 1) / KH_WARP;
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    long long ht = clock64(), h_norm = 0, h_mv = 0, h_upd = 0, h_out = 0, h_zb = 0, h_zc = 0, h_n;
+#define HT_ADD(v) do { h_n = clock64(); (v) += h_n - ht; ht = h_n; } while (0)
+#else
+#define HT_ADD(v)
+#endif
+    // update phase: RG row groups of RPG rows (thread <-> row), CB interleaved column classes
+    const int RG = (n + 31) / 32, RPG = (n + RG - 1) / RG;
+#ifdef KH_HOST_EMU
+    const int CB = 1, VT = RG * 32;
+#else
+    const int CB = (nw / RG) > 0 ? (nw / RG) : 1, VT = RG * CB * 32;
+#endif
+    for (int k = 0; k + 2 < n; ++k) {
+        // ---- phase 1: norm of the column below the sub-diagonal (every warp redundantly), Householder scalars, v
+        double part = 0.0;
+        for (int i = k + 2 + lane; i < n; i += KH_WARP) part += cabs2(HH(i, k));
+        const double xn2 = kh_warp_allsum(part);
+        const cd alpha = HH(k + 1, k);
+        if (xn2 == 0.0 && alpha.y == 0.0) continue;          // already reduced: H_k = I   (uniform across the CTA)
+        const double beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
+        const double rbeta = 1.0 / beta;
+        const cd tau = mk((beta - alpha.x) * rbeta, -alpha.y * rbeta);
+        const cd sc = crecip(alpha - mk(beta, 0.0));
+        const cd ctau = cconj(tau);
+        for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
+            const cd vi = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
+            vv[i] = vi;
+            vq[2 * i] = cconj(vi);
+        }
+        if (c.tid == 0) tauout[k] = tau;
+        c.sync();
+        HT_ADD(h_norm);
+        // ---- phase 2: p = A v (jobs 0..n-1, one per row), q = v^H A (jobs n.., one per column > k), TPJ threads per job
+        const int m = n - k - 1, J = n + m;
+#ifdef KH_HOST_EMU
+        const int TPJ = 1;
+#else
+        const int TPJ = (4 * J <= c.nthr) ? 4 : ((2 * J <= c.nthr) ? 2 : 1);
+#endif
+        cd contrib = mk(0, 0);
+        const int jpp = c.nthr / TPJ, sub = c.tid % TPJ;
+        for (int jb = 0; jb < J; jb += jpp) {
+            const int job = jb + c.tid / TPJ;
+            cd a0 = mk(0, 0), a1 = mk(0, 0);
+            if (job < n) {
+                const cd* hr = &HH(job, 0);
+                int j = k + 1 + sub;
+                for (; j + TPJ < n; j += 2 * TPJ) { cfma(a0, hr[j], vv[j]); cfma(a1, hr[j + TPJ], vv[j + TPJ]); }
+                if (j < n) cfma(a0, hr[j], vv[j]);
+            } else if (job < J) {
+                const int jc = job - n + k + 1;
+                const cd* hc = &HH(0, jc);
+                int i = k + 1 + sub;
+                for (; i + TPJ < n; i += 2 * TPJ) { cfma(a0, vq[2 * i], hc[i * ld]); cfma(a1, vq[2 * (i + TPJ)], hc[(i + TPJ) * ld]); }
+                if (i < n) cfma(a0, vq[2 * i], hc[i * ld]);
+            }
+            cd acc = a0 + a1;
+#ifndef KH_HOST_EMU
+            for (int o = TPJ >> 1; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+#endif
+            if (sub == 0) {
+                if (job < n) { pp[job] = acc; if (job > k) contrib = contrib + vq[2 * job] * acc; }
+                else if (job < J) vq[2 * (job - n + k + 1) + 1] = acc;
+            }
+        }
+        contrib.x = kh_warp_allsum(contrib.x); contrib.y = kh_warp_allsum(contrib.y);
+        if (lane == 0) spart[warp] = contrib;
+        c.sync();
+        HT_ADD(h_mv);
+        // ---- phase 3: A -= pt conj(v)^T + (conj(tau) v) q^T,  pt = tau p - |tau|^2 s v ; the reflector goes into column k
+        cd sv = mk(0, 0);
+        for (int w = 0; w < nw; ++w) sv = sv + spart[w];
+        const cd t2s = cabs2(tau) * sv;
+        for (int vt = c.tid; vt < VT; vt += c.nthr) {
+            const int vw = vt >> 5, vl = vt & 31, rg = vw % RG, cb = vw / RG;
+            const int i = rg * RPG + vl;
+            if (vl >= RPG || i >= n) continue;
+            cd pt = tau * pp[i], tv = mk(0, 0);
+            if (i > k) { const cd vi = vv[i]; tv = ctau * vi; pt = pt - t2s * vi; }
+            cd* hr = &HH(i, 0);
+            int j = k + 1 + cb;
+            for (; j + 3 * CB < n; j += 4 * CB) {
+                cd h0 = hr[j], h1 = hr[j + CB], h2 = hr[j + 2 * CB], h3 = hr[j + 3 * CB];
+                cfms(h0, pt, vq[2 * j]); cfms(h1, pt, vq[2 * (j + CB)]); cfms(h2, pt, vq[2 * (j + 2 * CB)]); cfms(h3, pt, vq[2 * (j + 3 * CB)]);
+                cfms(h0, tv, vq[2 * j + 1]); cfms(h1, tv, vq[2 * (j + CB) + 1]); cfms(h2, tv, vq[2 * (j + 2 * CB) + 1]); cfms(h3, tv, vq[2 * (j + 3 * CB) + 1]);
+                hr[j] = h0; hr[j + CB] = h1; hr[j + 2 * CB] = h2; hr[j + 3 * CB] = h3;
+            }
+            for (; j < n; j += CB) { cd h = hr[j]; cfms(h, pt, vq[2 * j]); cfms(h, tv, vq[2 * j + 1]); hr[j] = h; }
+            if (cb == 0 && i > k) hr[k] = (i == k + 1) ? mk(beta, 0.0) : vv[i];       // reflector kept in place
+        }
+        c.sync();
+        HT_ADD(h_upd);
+    }
+    // ---- Hessenberg matrix out (the QR kernel reads j >= i-1 only)
+    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * ldg + j] = (j >= i - 1) ? HH(i, j) : mk(0.0, 0.0); }
+    c.sync();
+    // ---- Z = H_0 H_1 ... H_{n-3} in place: shift the reflectors one column to the right, identity elsewhere
+    for (int i = c.tid; i < n; i += c.nthr) {
+        for (int j = n - 1; j >= 0; --j)
+            HH(i, j) = (j >= 1 && j <= i - 1) ? HH(i, j - 1) : mk(i == j ? 1.0 : 0.0, 0.0);
+        vq[i] = tauout[i];                                                  // (written by this CTA; vq is free now)
+    }
+    c.sync();
+    HT_ADD(h_out);
+    for (int k = n - 3; k >= 0; --k) {
+        const cd tau = vq[k];
+        if (tau.x == 0.0 && tau.y == 0.0) continue;                       // uniform
+        // w_j = v^H Z[k+1:, j] for j >= k+2 (v = [1; column k+1 below the diagonal]); Z[k+1][j] is still zero there
+        const int m = n - k - 2;
+#ifdef KH_HOST_EMU
+        const int TPJ = 1;
+#else
+        const int TPJ = (4 * m <= c.nthr) ? 4 : ((2 * m <= c.nthr) ? 2 : 1);
+#endif
+        const int jpp = c.nthr / TPJ, sub = c.tid % TPJ;
+        for (int i = k + 1 + c.tid; i < n; i += c.nthr) vv[i] = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k + 1);
+        for (int jb = 0; jb < m; jb += jpp) {
+            const int job = jb + c.tid / TPJ;
+            cd a0 = mk(0, 0), a1 = mk(0, 0);
+            if (job < m) {
+                const cd* zc = &HH(0, k + 2 + job);
+                const cd* vc = &HH(0, k + 1);
+                int i = k + 2 + sub;
+                for (; i + TPJ < n; i += 2 * TPJ) { cfma(a0, cconj(vc[i * ld]), zc[i * ld]); cfma(a1, cconj(vc[(i + TPJ) * ld]), zc[(i + TPJ) * ld]); }
+                if (i < n) cfma(a0, cconj(vc[i * ld]), zc[i * ld]);
+            }
+            cd acc = a0 + a1;
+#ifndef KH_HOST_EMU
+            for (int o = TPJ >> 1; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+#endif
+            if (sub == 0 && job < m) pp[k + 2 + job] = tau * acc;
+        }
+        c.sync();
+        HT_ADD(h_zb);
+        // Z[i][j] -= v_i (tau w_j) for i >= k+1, j >= k+2 ; column k+1 becomes e_{k+1} - tau v
+        for (int vt = c.tid; vt < VT; vt += c.nthr) {
+            const int vw = vt >> 5, vl = vt & 31, rg = vw % RG, cb = vw / RG;
+            const int i = rg * RPG + vl;
+            if (vl >= RPG || i >= n || i <= k) continue;
+            const cd vi = vv[i];
+            cd* zr = &HH(i, 0);
+            int j = k + 2 + cb;
+            for (; j + 3 * CB < n; j += 4 * CB) {
+                cd z0 = zr[j], z1 = zr[j + CB], z2 = zr[j + 2 * CB], z3 = zr[j + 3 * CB];
+                cfms(z0, vi, pp[j]); cfms(z1, vi, pp[j + CB]); cfms(z2, vi, pp[j + 2 * CB]); cfms(z3, vi, pp[j + 3 * CB]);
+                zr[j] = z0; zr[j + CB] = z1; zr[j + 2 * CB] = z2; zr[j + 3 * CB] = z3;
+            }
+            for (; j < n; j += CB) { cd z = zr[j]; cfms(z, vi, pp[j]); zr[j] = z; }
+            if (cb == 0) zr[k + 1] = (i == k + 1) ? mk(1.0 - tau.x, -tau.y) : mk(0, 0) - tau * vi;
+        }
+        c.sync();
+        HT_ADD(h_zc);
+    }
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    if (c.tid == 0 && b == 0) { kh_qr_dbg[8] += h_norm; kh_qr_dbg[9] += h_mv; kh_qr_dbg[10] += h_upd; kh_qr_dbg[11] += h_out; kh_qr_dbg[12] += h_zb; kh_qr_dbg[13] += h_zc; }
+#endif
+    for (int e = c.tid; e < n * n; e += c.nthr) { int j = e / n, i = e - j * n; Ztg[(long long)j * ldz + i] = HH(i, j); }
+#undef HH
 }
 
 // ============================================================================ 1b. Z = H_0 H_1 ... H_{n-3} (zunghr), backward accumulation
@@ -265,16 +507,6 @@ KH_DEV void zunghr_body(const Cta& c, const zgeev_args& a) {
 KH_HD int hp_off(int i, int n) { return i * n - ((i - 1) * i) / 2; }
 KH_HD int hp_size(int n) { return hp_off(n - 1, n) + n + 3; }
 
-#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
-__device__ long long kh_qr_dbg[16];
-#define QT_DECL long long qt0 = clock64(), qt_scan = 0, qt_shift = 0, qt_sweep = 0, qt_delay = 0, qt_n = 0, qt_rot = 0, qt_t
-#define QT_MARK() (qt_t = clock64())
-#define QT_ADD(v) do { long long _n = clock64(); (v) += _n - qt_t; qt_t = _n; } while (0)
-#else
-#define QT_DECL
-#define QT_MARK()
-#define QT_ADD(v)
-#endif
 template <bool PACKED>
 KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int nfull = a.n, n = (a.na > 0 && a.na < a.n) ? a.na : a.n, b = c.bx;     // n: leading block this phase works on
@@ -851,9 +1083,11 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     const double work = 100.0 * n * n * n * batch;          // nominal zgeev count, SURVEY.md 8(d)
     a.ld_s = n | 1;
     a.use_smem = zhess_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
-    int e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
+    int e;
+    if (a.use_smem) e = kh_launch<zgeev_args, zhessz_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, 1), st, a, "zgeev_hess", 0.25 * work);
+    else e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
     if (e) return e;
-    {   zgeev_args u = a;
+    if (!a.use_smem) {   zgeev_args u = a;
         const size_t usm = (size_t)2 * n * sizeof(cd) + (size_t)n * u.ld_s * sizeof(cd) + 16;
         u.use_smem = usm <= (size_t)KH_SMEM_MAX;
         e = kh_launch<zgeev_args, zunghr_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), u.use_smem ? usm : (size_t)2 * n * sizeof(cd) + 16, st, u, "zgeev_hess", 0.0);

@@ -15,4 +15,5 @@ R, T = cl.solve_batch(wl, kps=np.tile([[0.3, 0.2]], (8, 1)), te=1.0, tm=1.0)
 eng.lib.kh_qr_timing(out)
 names = ["total", "scan", "shift", "sweep", "delayed", "sweeps", "rotations"]
 print({k: int(v) for k, v in zip(names, out)})
+print("zhessz phases (balance+norm+v, matvec, update, out+shift, z-dots, z-update):", [int(out[i]) for i in range(8, 14)])
 print("cycles/rotation in sweep:", out[3] / max(1, out[6]), " cycles/sweep fixed (scan+shift):", (out[1] + out[2]) / max(1, out[5]))
