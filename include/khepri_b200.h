@@ -79,8 +79,12 @@ int kh_zgemm_batched(int batch, int M, int N, int K, int transA,
                      const void* A_dev, int lda, long long strideA,
                      const void* B_dev, int ldb, long long strideB,
                      void* C_dev, int ldc, long long strideC, double alpha, void* stream);
-/* numpy.linalg.inv / solve: Ainv[b] = A[b]^-1 (n x n, contiguous stacks); info_dev [batch] optional */
-int kh_zinv_batched(int batch, int n, const void* A_dev, void* Ainv_dev, int* info_dev, void* stream);
+/* numpy.linalg.inv / solve: Ainv[b] = A[b]^-1 (n x n, contiguous stacks); info_dev [batch] optional.
+   Matrices beyond shared memory (kh_zinv_work_bytes > 0) use the blocked Gauss-Jordan + DMMA GEMM
+   variant and need that much DEVICE work space; work_dev may be NULL when the size is 0. */
+size_t kh_zinv_work_bytes(int batch, int n);
+int kh_zinv_batched(int batch, int n, const void* A_dev, void* Ainv_dev, int* info_dev,
+                    void* work_dev, size_t work_bytes, void* stream);
 /* numpy.linalg.eig (alternative.py:172): w[b] eigenvalues [n], W[b] right eigenvectors [n][n] (columns) */
 size_t kh_zgeev_work_bytes(int batch, int n);
 int kh_zgeev_batched(int batch, int n, const void* A_dev, void* w_dev, void* W_dev,

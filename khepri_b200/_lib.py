@@ -36,7 +36,8 @@ SIGNATURES = {
     "kh_convmat": (i32, [i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, sz, vp]),
     "kh_toeplitz_gather": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "kh_zgemm_batched": (i32, [i32, i32, i32, i32, i32, vp, i32, i64, vp, i32, i64, vp, i32, i64, f64, vp]),
-    "kh_zinv_batched": (i32, [i32, i32, vp, vp, vp, vp]),
+    "kh_zinv_work_bytes": (sz, [i32, i32]),
+    "kh_zinv_batched": (i32, [i32, i32, vp, vp, vp, vp, sz, vp]),
     "kh_zgeev_work_bytes": (sz, [i32, i32]),
     "kh_zgeev_batched": (i32, [i32, i32, vp, vp, vp, vp, sz, vp, vp]),
     "kh_plan_create": (i32, [C.POINTER(vp), i32, i32, vp, f64, f64, f64, f64, i32, C.POINTER(LayerDesc), i32,

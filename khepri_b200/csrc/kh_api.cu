@@ -97,7 +97,7 @@ static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& 
     SRef O = sref_dense(out, n);
     int e;
     if ((e = gemm(st, Bc, n, A.blk[3], B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;     // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
     if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                    // X = F^-1 A21
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                    // Y = F^-1 A22
     if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                              // S21 = B21 X
@@ -129,7 +129,7 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     SRef O = sref_dense(out, n);
     int e;
     if ((e = bdmul(st, Bc, N, 0, A, 3, B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;           // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
     if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X))) return e;                                          // X = F^-1 A21
     if ((e = bdmul(st, Bc, N, 1, A, 3, Fi, Y))) return e;                                          // Y = F^-1 A22
     if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                                    // S21 = B21 X
@@ -150,7 +150,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
     SRef O = sref_dense(out, n);
     int e;
     if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info))) return e;
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
     if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                          // X = F^-1 A21
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                                   // S21 = B21 X
@@ -256,7 +256,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
         copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
     }
-    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_inv));                     // W^-1 -> 7
+    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_inv, S(8), slab));                     // W^-1 -> 7
     {   pv0_args a{Bc, N, S(0), Kx, Ky, S(6)};                                   // P V0 -> 6
         KH_TRY((kh_launch<pv0_args, pv0_body>(dim3(Bc), 256, 0, st, a))); }
     {   zgemm_args g = zgemm_make(n, n, n, M(7), M(6), M(8));                    // V^-1 V0 = L^-1 (W^-1 (P V0)) -> 8
@@ -264,7 +264,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(zgemm_launch(st, Bc, g)); }
     {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
         KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
-    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv));                     // A^-1 -> 1
+    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv, S(12), slab));                     // A^-1 -> 1
     // [M1|M2|M3] = A^-1 [XB|XA|B]   (slabs 9..11 -> 12..14)
     KH_TRY(gemm(st, 3 * Bc, n, mref(S(1), 0, n, Bc, n2), mref(S(9), slab, n, Bc, n2), mref(S(12), slab, n, Bc, n2)));
     {   MatRef A = M(0), Bm = M(11);
@@ -273,7 +273,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         zgemm_args g = zgemm_make(n, n, n, M(11), M(14), M(16), -1.0);           // R2 = X (A - B M3)
         g.Cin = A; g.beta = 1.0; g.rowscale = v.xexp; g.rs_stride = n; g.rs_group = 1;
         KH_TRY(zgemm_launch(st, Bc, g)); }
-    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv));                     // T^-1 -> 3
+    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv, S(4), slab));                     // T^-1 -> 3
     // [S11|S12] = T^-1 [R1|R2]
     KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
     return 0;
@@ -537,9 +537,15 @@ extern "C" int kh_zgemm_batched(int batch, int M, int N, int K, int transA, cons
     KH_TRY(zgemm_launch((kh_stream_t)stream, batch, g));
     return 0;
 }
-extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int* info, void* stream) {
+extern "C" size_t kh_zinv_work_bytes(int batch, int n) {
+    return n >= KH_ZINV_BLOCKED_MIN ? (size_t)batch * (size_t)zinv_work_cd(n) * sizeof(cd) : 0;
+}
+extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int* info, void* work, size_t work_bytes, void* stream) {
     if (batch < 0 || n < 1 || !A || !Ainv) return fail(KH_EINVAL, "kh_zinv_batched: bad arguments");
-    KH_TRY(zinv_launch((kh_stream_t)stream, batch, n, mref(A, (long long)n * n, n), mref(Ainv, (long long)n * n, n), info));
+    if (n >= KH_ZINV_BLOCKED_MIN && (!work || work_bytes < kh_zinv_work_bytes(batch, n)))
+        return fail(KH_ENOMEM, "kh_zinv_batched: workspace too small (kh_zinv_work_bytes)");
+    KH_TRY(zinv_launch((kh_stream_t)stream, batch, n, mref(A, (long long)n * n, n), mref(Ainv, (long long)n * n, n), info,
+                       (cd*)work, (long long)(work_bytes / sizeof(cd))));
     return 0;
 }
 extern "C" size_t kh_zgeev_work_bytes(int batch, int n) {

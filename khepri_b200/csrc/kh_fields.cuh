@@ -159,6 +159,7 @@ KH_DEV void fld_phase_body(const Cta& c, const fld_phase_args& a) {
 struct FieldBufs {
     cd *Kx, *Ky; double* k0; cd* c1p; cd* Fm; cd* Finv; cd* y12; cd* m12; cd* Winv; cd* Vinv; cd* Sall; cd* Ph;
     int* zpos; int* zlayer; double* zdist; const cd** ICp; cd* ICs; int* info;
+    cd* zwork; long long zwork_cd;      // work space of the blocked inverse (n beyond shared memory)
 };
 static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, FieldBufs& f) {
     const size_t N = p->N, n = p->n, n2 = n * n, nL = p->layers.size(), Ls = p->stack.size();
@@ -169,6 +170,8 @@ static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, Fi
     f.Sall = b.get<cd>((size_t)B * nz * 6 * N); f.Ph = b.get<cd>((size_t)B * N * npts);
     f.zpos = b.get<int>(nz); f.zlayer = b.get<int>(nz); f.zdist = b.get<double>(nz);
     f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * B);
+    f.zwork_cd = (int)n >= KH_ZINV_BLOCKED_MIN ? (long long)B * zinv_work_cd((int)n) : 0;
+    f.zwork = b.get<cd>((size_t)f.zwork_cd);
 }
 
 extern "C" size_t kh_fields_workspace_bytes(const kh_plan* plan, int B, int npts, int nz) {
@@ -247,8 +250,8 @@ extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev,
     cd* Wd = (cd*)solved->W_dev; cd* Vd = (cd*)solved->V_dev;
     for (int li = 0; li < nL; ++li) {
         if (!lay_active[li]) continue;
-        KH_TRY(zinv_launch(st, B, n, mref(Wd + (long long)li * n2, (long long)nL * n2, n), mref(f.Winv + (long long)li * B * n2, n2, n), f.info));
-        KH_TRY(zinv_launch(st, B, n, mref(Vd + (long long)li * n2, (long long)nL * n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.info + B));
+        KH_TRY(zinv_launch(st, B, n, mref(Wd + (long long)li * n2, (long long)nL * n2, n), mref(f.Winv + (long long)li * B * n2, n2, n), f.info, f.zwork, f.zwork_cd));
+        KH_TRY(zinv_launch(st, B, n, mref(Vd + (long long)li * n2, (long long)nL * n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.info + B, f.zwork, f.zwork_cd));
     }
     cd* pre = (cd*)solved->prefix_dev; cd* suf = (cd*)solved->suffix_dev;
     const long long sstride = (long long)Ls * 4 * n2;
@@ -258,7 +261,7 @@ extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev,
         MatRef Sr11 = mref(suf + ((long long)i * 4 + 0) * n2, sstride, n);
         MatRef Fm = mref(f.Fm, n2, n), Fi = mref(f.Finv, n2, n);
         KH_TRY(gemm(st, B, n, Sl22, Sr11, Fm, -1.0, nullptr, 0.0, 1.0));
-        KH_TRY(zinv_launch(st, B, n, Fm, Fi, f.info));
+        KH_TRY(zinv_launch(st, B, n, Fm, Fi, f.info, f.zwork, f.zwork_cd));
         {   fld_amp_args a{B, N, Fi, Sl21, Sr11, f.c1p, f.Kx, f.Ky, f.y12};
             KH_TRY((kh_launch<fld_amp_args, fld_amp_body>(dim3(B), 256, (size_t)3 * n * sizeof(cd), st, a))); }
         const int li = p->stack[i];

@@ -18,6 +18,7 @@
 // Eigenvalue order / eigenvector scaling are free: parity is on physical outputs.
 #pragma once
 #include "kh_common.cuh"
+#include "kh_zgeev_tiled.cuh"
 
 struct zgeev_args {
     int n;
@@ -1084,10 +1085,12 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     a.ld_s = n | 1;
     a.use_smem = zhess_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;
     int e;
-    if (a.use_smem) e = kh_launch<zgeev_args, zhessz_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, 1), st, a, "zgeev_hess", 0.25 * work);
+    const bool tiled_hess = !a.use_smem && a.rlog && a.rlog_stride / 2 >= zhb_work_cd(n);
+    if (tiled_hess) e = zhess_blocked_launch(st, batch, n, a.A, a.Hw, a.Zt, a.X, (cd*)a.rlog, a.rlog_stride / 2, a.scale, a.scale_stride, a.tau, a.tau_stride, 0.25 * work);
+    else if (a.use_smem) e = kh_launch<zgeev_args, zhessz_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, 1), st, a, "zgeev_hess", 0.25 * work);
     else e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
     if (e) return e;
-    if (!a.use_smem) {   zgeev_args u = a;
+    if (!a.use_smem && !tiled_hess) {   zgeev_args u = a;
         const size_t usm = (size_t)2 * n * sizeof(cd) + (size_t)n * u.ld_s * sizeof(cd) + 16;
         u.use_smem = usm <= (size_t)KH_SMEM_MAX;
         e = kh_launch<zgeev_args, zunghr_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), u.use_smem ? usm : (size_t)2 * n * sizeof(cd) + 16, st, u, "zgeev_hess", 0.0);

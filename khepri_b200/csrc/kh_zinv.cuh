@@ -7,6 +7,7 @@
 // becomes inverse + DMMA GEMM here; pivot choice follows LAPACK's izamax (|re|+|im|).
 #pragma once
 #include "kh_common.cuh"
+#include "kh_zgemm.cuh"
 
 struct zinv_args {
     int n;
@@ -250,14 +251,183 @@ __device__ __forceinline__ void zinv_reg_mid_body(const Cta& c, const zinv_args&
 __device__ __forceinline__ void zinv_reg_large_body(const Cta& c, const zinv_args& a) { zinv_reg_body<4>(c, a); }
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// Tiled variant for matrices that do not fit in shared memory (n > ~118: the 9x9 ... 15x15 harmonic
+// bases and the extended-RCWA supercells): BLOCKED in-place Gauss-Jordan.  Per block column of nb
+// pivots:
+//   panel kernel (one CTA per matrix): the n x nb block column is staged in shared memory and
+//     eliminated there with partial pivoting (pivot rows from the diagonal block downwards), which
+//     turns it into the block column  P' = [-A01 A11^-1; A11^-1; -A21 A11^-1]  of the Gauss-Jordan
+//     transformation.  The row interchanges are then applied to the rest of the matrix, the nb pivot
+//     rows R (all other columns) are moved to a side buffer and zeroed in place;
+//   two DMMA GEMMs:  A[:, left] += P' R[:, left],  A[:, right] += P' R[:, right]   (M = n, K = nb).
+// All 8 n^3 flops of the inversion run on the tensor pipe; HBM traffic is one read+write of the
+// matrix per block column.  A final kernel undoes the row interchanges as one column gather.
+struct zinvb_args {
+    int n, k0, nb;
+    MatRef A;                         // in-place matrix
+    cd* R; long long r_stride;        // [batch][nb][n] pivot rows of the current step
+    int* piv; long long piv_stride;   // [batch][n] pivot rows (absolute)
+    int* info;
+    int lds;
+};
+
+KH_DEV void zinvb_panel_body(const Cta& c, const zinvb_args& a) {
+    const int n = a.n, b = c.bx, k0 = a.k0, lds = a.lds;
+    const int nb = (a.nb < n - k0) ? a.nb : n - k0;
+    cd* A = mat_ptr(a.A, b);
+    const int ld = a.A.ld;
+    cd* R = a.R + (long long)b * a.r_stride;
+    int* pivg = a.piv + (long long)b * a.piv_stride;
+    // shared: [colk n][rowk 32][scratch 128 dbl][pivs 32 int][panel n x lds]
+    cd* colk = (cd*)KH_SMEM(c);
+    cd* rowk = colk + n;
+    double* scratch = (double*)(rowk + 32);
+    int* pivs = (int*)(scratch + 128);
+    cd* Ps = (cd*)(KH_SMEM(c) + (((n * 16 + 32 * 16 + 128 * 8 + 32 * 4) + 15) & ~15));
+    for (int e = c.tid; e < n * nb; e += c.nthr) { int i = e / nb, j = e - i * nb; Ps[i * lds + j] = A[(long long)i * ld + k0 + j]; }
+    c.sync();
+    int bad = 0;
+    for (int s = 0; s < nb; ++s) {
+        const int k = k0 + s;
+        double best = -1.0; int bi = k;
+        for (int i = k + c.tid; i < n; i += c.nthr) {
+            double v = cabs1(Ps[i * lds + s]);
+            if (v > best) { best = v; bi = i; }
+        }
+        const int p = cta_argmax(c, best, bi, scratch);
+        if (c.tid == 0) pivs[s] = p;
+        if (p != k)
+            for (int j = c.tid; j < nb; j += c.nthr) { cd t = Ps[k * lds + j]; Ps[k * lds + j] = Ps[p * lds + j]; Ps[p * lds + j] = t; }
+        c.sync();
+        const cd pv = Ps[k * lds + s];
+        if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
+        const cd d = crecip(pv);
+        for (int i = c.tid; i < n; i += c.nthr) colk[i] = Ps[i * lds + s];
+        for (int j = c.tid; j < nb; j += c.nthr) rowk[j] = (j == s) ? d : Ps[k * lds + j] * d;
+        c.sync();
+        for (int e = c.tid; e < n * nb; e += c.nthr) {
+            const int i = e / nb, j = e - i * nb;
+            cd v;
+            if (i == k) v = rowk[j];
+            else if (j == s) v = -(colk[i] * d);
+            else { v = Ps[i * lds + j]; cfms(v, colk[i], rowk[j]); }
+            Ps[i * lds + j] = v;
+        }
+        c.sync();
+    }
+    // row interchanges on the columns outside the panel (sequential: later swaps may touch the same rows)
+    const int nout = n - nb;
+    for (int s = 0; s < nb; ++s) {
+        const int k = k0 + s, p = pivs[s];
+        if (p != k) {
+            for (int t = c.tid; t < nout; t += c.nthr) {
+                const int j = t < k0 ? t : t + nb;
+                cd x = A[(long long)k * ld + j]; A[(long long)k * ld + j] = A[(long long)p * ld + j]; A[(long long)p * ld + j] = x;
+            }
+            c.sync();
+        }
+    }
+    // panel out; pivot rows to the side buffer, zero in place
+    for (int e = c.tid; e < n * nb; e += c.nthr) { int i = e / nb, j = e - i * nb; A[(long long)i * ld + k0 + j] = Ps[i * lds + j]; }
+    for (int e = c.tid; e < nb * nout; e += c.nthr) {
+        const int s = e / nout, t = e - s * nout, j = t < k0 ? t : t + nb;
+        R[(long long)s * n + j] = A[(long long)(k0 + s) * ld + j];
+        A[(long long)(k0 + s) * ld + j] = mk(0.0, 0.0);
+    }
+    for (int s = c.tid; s < nb; s += c.nthr) pivg[k0 + s] = pivs[s];
+    if (a.info && c.tid == 0) { if (k0 == 0) a.info[b] = bad; else if (bad && a.info[b] == 0) a.info[b] = bad; }
+}
+
+// undo the row interchanges: out[:, j] = in[:, src[j]] with src = the column swaps (k <-> piv[k]) applied for k = n-1 .. 0
+KH_DEV void zinvb_unpermute_body(const Cta& c, const zinvb_args& a) {
+    const int n = a.n, b = c.bx;
+    cd* A = mat_ptr(a.A, b);
+    const int ld = a.A.ld;
+    const int* pivg = a.piv + (long long)b * a.piv_stride;
+    int* src = (int*)KH_SMEM(c);
+    const int nw = (c.nthr + KH_WARP - 1) / KH_WARP, warp = c.tid / KH_WARP, lane = c.tid % KH_WARP;
+    cd* rows = (cd*)(KH_SMEM(c) + (((n * 4) + 15) & ~15));           // one row buffer per warp
+    for (int j = c.tid; j < n; j += c.nthr) src[j] = j;
+    c.sync();
+    if (c.tid == 0)
+        for (int k = n - 1; k >= 0; --k) { const int p = pivg[k]; if (p != k) { int t = src[k]; src[k] = src[p]; src[p] = t; } }
+    c.sync();
+    cd* buf = rows + (long long)warp * n;
+    for (int i = warp; i < n; i += nw) {
+        for (int j = lane; j < n; j += KH_WARP) buf[j] = A[(long long)i * ld + j];
+#ifndef KH_HOST_EMU
+        __syncwarp();
+#endif
+        for (int j = lane; j < n; j += KH_WARP) A[(long long)i * ld + j] = buf[src[j]];
+#ifndef KH_HOST_EMU
+        __syncwarp();
+#endif
+    }
+}
+
+struct zcopym_args { int n; MatRef src, dst; };
+KH_DEV void zcopym_body(const Cta& c, const zcopym_args& a) {
+    const cd* s = mat_ptr(a.src, c.bx); cd* d = mat_ptr(a.dst, c.bx);
+    for (int e = c.tid; e < a.n * a.n; e += c.nthr) { int i = e / a.n, j = e - i * a.n; d[(long long)i * a.dst.ld + j] = s[(long long)i * a.src.ld + j]; }
+}
+
+static inline int zinvb_nb(int n) {
+    int nb = 32;
+    while (nb > 4 && (size_t)n * (nb + 1) * sizeof(cd) + (size_t)n * 16 + 4096 > (size_t)200 * 1024) nb >>= 1;
+    return nb;
+}
+// work space of the blocked variant, in complex elements per matrix (pivot rows + pivot indices)
+static inline long long zinv_work_cd(int n) { return (long long)zinvb_nb(n) * n + (n + 3) / 4 + 4; }
+#ifndef KH_ZINV_BLOCKED_MIN
+#define KH_ZINV_BLOCKED_MIN 119
+#endif
+
+static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work) {
+    int e;
+    if (A.p != Ainv.p) {
+        zcopym_args cp{n, A, Ainv};
+        if ((e = kh_launch<zcopym_args, zcopym_body>(dim3(batch), 256, 0, st, cp, "zinv", 0.0))) return e;
+    }
+    const int nb = zinvb_nb(n);
+    const long long wstride = zinv_work_cd(n);
+    zinvb_args a;
+    a.n = n; a.nb = nb; a.A = Ainv; a.R = work; a.r_stride = wstride; a.info = info; a.lds = nb + 1;
+    a.piv = (int*)(work + (long long)nb * n); a.piv_stride = wstride * 4;
+    const size_t sm = (size_t)n * 16 + 32 * 16 + 128 * 8 + 32 * 4 + 16 + (size_t)n * a.lds * sizeof(cd);
+    for (int k0 = 0; k0 < n; k0 += nb) {
+        a.k0 = k0;
+        const int nbk = nb < n - k0 ? nb : n - k0;
+        if ((e = kh_launch<zinvb_args, zinvb_panel_body>(dim3(batch), 512, sm, st, a, "zinv", 0.0))) return e;
+        MatRef Pm = Ainv; Pm.p = Ainv.p + k0;
+        MatRef Rm = mref(work, wstride, n);
+        if (k0 > 0) {
+            zgemm_args g = zgemm_make(n, k0, nbk, Pm, Rm, Ainv);
+            g.Cin = Ainv; g.beta = 1.0;
+            if ((e = zgemm_launch(st, batch, g))) return e;
+        }
+        if (k0 + nbk < n) {
+            MatRef Rr = Rm; Rr.p = work + k0 + nbk;
+            MatRef Cr = Ainv; Cr.p = Ainv.p + k0 + nbk;
+            zgemm_args g = zgemm_make(n, n - k0 - nbk, nbk, Pm, Rr, Cr);
+            g.Cin = Cr; g.beta = 1.0;
+            if ((e = zgemm_launch(st, batch, g))) return e;
+        }
+    }
+    const int uthr = 256;
+    const size_t usm = (size_t)((n * 4 + 15) & ~15) + (size_t)(uthr / 32) * n * sizeof(cd) + 16;
+    return kh_launch<zinvb_args, zinvb_unpermute_body>(dim3(batch), uthr, usm, st, a, "zinv", 0.0);
+}
+
 static inline size_t zinv_smem_bytes(int n, int ld_s, int use_smem) {
     size_t s = (size_t)2 * n * sizeof(cd) + 128 * sizeof(double) + (size_t)n * sizeof(int) + 16;
     if (use_smem) s += (size_t)n * ld_s * sizeof(cd);
     return s;
 }
 
-static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info) {
+static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work = nullptr, long long work_cd = 0) {
     if (batch <= 0 || n <= 0) return 0;
+    if (n >= KH_ZINV_BLOCKED_MIN && work && work_cd >= (long long)batch * zinv_work_cd(n)) return zinv_blocked_launch(st, batch, n, A, Ainv, info, work);
     zinv_args a;
     a.n = n; a.A = A; a.Ainv = Ainv; a.info = info;
 #ifndef KH_HOST_EMU

@@ -188,7 +188,9 @@ class Engine:
         batch, n, _ = A.shape
         out = torch.empty_like(A)
         info = torch.zeros(batch, dtype=torch.int32, device=self.device)
-        check(self.lib, self.lib.kh_zinv_batched(batch, n, _ptr(A), _ptr(out), _ptr(info), self.stream()), "kh_zinv_batched")
+        wb = self.lib.kh_zinv_work_bytes(batch, n)
+        ws = torch.empty(max(wb, 16), dtype=torch.uint8, device=self.device)
+        check(self.lib, self.lib.kh_zinv_batched(batch, n, _ptr(A), _ptr(out), _ptr(info), _ptr(ws), wb, self.stream()), "kh_zinv_batched")
         out = out[0] if squeeze else out
         return (out, info) if return_info else out
 
