@@ -508,6 +508,103 @@ KH_DEV void zunghr_body(const Cta& c, const zgeev_args& a) {
 KH_HD int hp_off(int i, int n) { return i * n - ((i - 1) * i) / 2; }
 KH_HD int hp_size(int n) { return hp_off(n - 1, n) + n + 3; }
 
+// ---- tiled sweep for a Hessenberg matrix in global memory (n beyond shared memory).  The rotations of a sweep are
+// generated in groups of ZQT_W: the diagonal tile that determines them (rows ks..ke+1, columns ks-1..ke+1) is staged in
+// shared memory and chased there by ONE warp (lanes <-> tile columns for the row steps, tile rows for the column steps,
+// warp-level synchronisation only); the rest of the window then receives the whole group in bulk - one thread per column
+// right of the tile (row rotations) and one thread per row above it (column rotations, all rows 0..ks-1 so nothing above
+// the window is left for later), each element loaded and stored once per group instead of once per rotation.
+#define ZQT_W 28
+#define ZQT_LD 33
+KH_DEV void zqr_tiled_sweep(const Cta& c, cd* Hg, int ldg, int l, int iact, cd f_first, cd g_first, kh_qrot* Q, cd* D) {
+    const int lane = c.tid % KH_WARP, warp = c.tid / KH_WARP;
+    for (int ks = l; ks < iact; ks += ZQT_W) {
+        const int ke = (ks + ZQT_W < iact) ? ks + ZQT_W : iact;          // rotations ks .. ke-1
+        const int rA = ks, rB = (ke + 1 < iact) ? ke + 1 : iact;
+        const int cA = (ks - 1 > l) ? ks - 1 : l, cB = rB;
+        const int nr = rB - rA + 1, nc = cB - cA + 1;
+        for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; D[i * ZQT_LD + j] = Hg[(long long)(rA + i) * ldg + cA + j]; }
+        c.sync();
+        if (warp == 0) {
+#define DT(i, j) D[((i) - rA) * ZQT_LD + ((j) - cA)]
+            for (int k = ks; k < ke; ++k) {
+                kh_givens G;
+                if (k == l) G = make_givens(f_first, g_first);
+                else {
+                    G = make_givens(DT(k, k - 1), DT(k + 1, k - 1));       // annihilates the bulge
+#ifndef KH_HOST_EMU
+                    __syncwarp();
+#endif
+                    if (lane == 0) { DT(k, k - 1) = G.r; DT(k + 1, k - 1) = mk(0.0, 0.0); }
+                }
+                const cd cs = cconj(G.s);
+                for (int j = k + lane; j <= cB; j += KH_WARP) {           // R(k)
+                    const cd h0 = DT(k, j), h1 = DT(k + 1, j);
+                    DT(k, j) = G.c * h0 + G.s * h1;
+                    DT(k + 1, j) = G.c * h1 - cs * h0;
+                }
+#ifndef KH_HOST_EMU
+                __syncwarp();
+#endif
+                const int rl = (k + 2 < rB) ? k + 2 : rB;
+                for (int r = rA + lane; r <= rl; r += KH_WARP) {          // C(k)
+                    const cd h0 = DT(r, k), h1 = DT(r, k + 1);
+                    DT(r, k) = G.c * h0 + cs * h1;
+                    DT(r, k + 1) = G.c * h1 - G.s * h0;
+                }
+                if (lane == 0) { Q[k].c = G.c; Q[k].s = G.s; }
+#ifndef KH_HOST_EMU
+                __syncwarp();
+#endif
+            }
+#undef DT
+        }
+        c.sync();
+        for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; Hg[(long long)(rA + i) * ldg + cA + j] = D[i * ZQT_LD + j]; }
+        const int nRight = iact - cB, nUp = rA;
+        for (int t = c.tid; t < nRight + nUp; t += c.nthr) {
+            if (t < nRight) {                                              // row rotations on a column right of the tile
+                cd* hp = Hg + (long long)ks * ldg + (cB + 1 + t);
+                cd h0 = hp[0];
+                int k = ks;
+                for (; k + 4 <= ke; k += 4, hp += 4LL * ldg) {
+                    const cd h1 = hp[ldg], h2 = hp[2LL * ldg], h3 = hp[3LL * ldg], h4 = hp[4LL * ldg];
+                    const double c0 = Q[k].c, c1 = Q[k + 1].c, c2 = Q[k + 2].c, c3 = Q[k + 3].c;
+                    const cd s0 = Q[k].s, s1 = Q[k + 1].s, s2 = Q[k + 2].s, s3 = Q[k + 3].s;
+                    hp[0] = c0 * h0 + s0 * h1; h0 = c0 * h1 - cconj(s0) * h0;
+                    hp[ldg] = c1 * h0 + s1 * h2; h0 = c1 * h2 - cconj(s1) * h0;
+                    hp[2LL * ldg] = c2 * h0 + s2 * h3; h0 = c2 * h3 - cconj(s2) * h0;
+                    hp[3LL * ldg] = c3 * h0 + s3 * h4; h0 = c3 * h4 - cconj(s3) * h0;
+                }
+                for (; k < ke; ++k, hp += ldg) {
+                    const cd h1 = hp[ldg];
+                    hp[0] = Q[k].c * h0 + Q[k].s * h1; h0 = Q[k].c * h1 - cconj(Q[k].s) * h0;
+                }
+                hp[0] = h0;
+            } else {                                                       // column rotations on a row above the tile
+                cd* hp = Hg + (long long)(t - nRight) * ldg + ks;
+                cd h0 = hp[0];
+                int k = ks;
+                for (; k + 4 <= ke; k += 4, hp += 4) {
+                    const cd h1 = hp[1], h2 = hp[2], h3 = hp[3], h4 = hp[4];
+                    const double c0 = Q[k].c, c1 = Q[k + 1].c, c2 = Q[k + 2].c, c3 = Q[k + 3].c;
+                    const cd s0 = Q[k].s, s1 = Q[k + 1].s, s2 = Q[k + 2].s, s3 = Q[k + 3].s;
+                    hp[0] = c0 * h0 + cconj(s0) * h1; h0 = c0 * h1 - s0 * h0;
+                    hp[1] = c1 * h0 + cconj(s1) * h2; h0 = c1 * h2 - s1 * h0;
+                    hp[2] = c2 * h0 + cconj(s2) * h3; h0 = c2 * h3 - s2 * h0;
+                    hp[3] = c3 * h0 + cconj(s3) * h4; h0 = c3 * h4 - s3 * h0;
+                }
+                for (; k < ke; ++k, hp += 1) {
+                    const cd h1 = hp[1];
+                    hp[0] = Q[k].c * h0 + cconj(Q[k].s) * h1; h0 = Q[k].c * h1 - Q[k].s * h0;
+                }
+                hp[0] = h0;
+            }
+        }
+        c.sync();
+    }
+}
+
 template <bool PACKED>
 KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
     const int nfull = a.n, n = (a.na > 0 && a.na < a.n) ? a.na : a.n, b = c.bx;     // n: leading block this phase works on
@@ -760,7 +857,10 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
             __syncthreads();
         } else
 #endif
-        {
+        if (!PACKED) {
+            c.sync();                               // everyone has read H before the sweep writes
+            zqr_tiled_sweep(c, Hg, ldg, l, iact, f_first, g_first, Q, Hp);
+        } else {
         kh_givens G = make_givens(f_first, g_first);
         c.sync();                                   // everyone has read H before the sweep writes
         for (int j = l + c.tid; j <= iact; j += c.nthr) {          // R(l)
@@ -816,7 +916,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         QT_ADD(qt_sweep);
         // ---- delayed application of the sweep's rotations outside the window and to Z (no barriers inside)
         {
-            const int nAbove = l, nRight = n - 1 - iact;
+            const int nAbove = PACKED ? l : 0, nRight = n - 1 - iact;     // (the tiled sweep has already updated the rows above)
             int nZ = n, nR = nRight;
             if (rl) {
                 // Z and the columns of H right of the window only ever RECEIVE rotations (no later sweep reads them), so
@@ -922,22 +1022,25 @@ KH_DEV void zqr_global_body(const Cta& c, const zgeev_args& a) { zqr_body_t<fals
 // column j and applies the row rotations of every sweep whose window ended above row j (iact < j).  One LDS + one STS per
 // rotation, the running entry stays in a register; the log is streamed through shared memory in chunks of whole
 // sweeps (asynchronous copies, next chunk in flight while the current one is applied), one barrier per chunk.
-struct zrot_args { int n; MatRef Zt, T; const double* rlog; long long rlog_stride; int sw_cap, chunk; };
+struct zrot_args { int n; MatRef Zt, T; const double* rlog; long long rlog_stride; int sw_cap, chunk, cw; };
+// Matrices beyond shared memory are replayed in column STRIPS of cw columns (grid.y = 2 * strips): the strip stays
+// resident in shared memory for the whole log, so Z and T are read and written exactly once.
 KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
-    const int n = a.n, b = c.bx, mode = c.by, CH = a.chunk;
+    const int n = a.n, b = c.bx, mode = c.by & 1, CH = a.chunk, cw = a.cw;
+    const int c0 = (c.by >> 1) * cw, cols = (cw < n - c0) ? cw : n - c0;
     const MatRef M = mode ? a.T : a.Zt;
-    cd* Mg = mat_ptr(M, b);
+    cd* Mg = mat_ptr(M, b) + c0;
     const int ldm = M.ld;
     const double* rl = a.rlog + (long long)b * a.rlog_stride;
     const int nsw = ((const int*)rl)[0];
     const int* swg = (const int*)(rl + 2);
     const double* rot = rl + 2 + a.sw_cap;
-    // shared: [Ms n x n cd][rb 2 x CH x 4 dbl][sw 2 x sw_cap int]
+    // shared: [Ms n x cw cd][rb 2 x CH x 4 dbl][sw 2 x sw_cap int]
     cd* Ms = (cd*)KH_SMEM(c);
-    double* rb = (double*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd));
-    int* sws = (int*)(KH_SMEM(c) + (size_t)n * n * sizeof(cd) + (size_t)8 * CH * sizeof(double));
-    if (nsw == 0) return;                                            // uniform
-    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Ms[e] = Mg[(long long)k * ldm + i]; }
+    double* rb = (double*)(KH_SMEM(c) + (size_t)n * cw * sizeof(cd));
+    int* sws = (int*)(KH_SMEM(c) + (size_t)n * cw * sizeof(cd) + (size_t)8 * CH * sizeof(double));
+    if (nsw == 0 || cols <= 0) return;                               // uniform
+    for (int e = c.tid; e < n * cols; e += c.nthr) { const int k = e / cols, i = e - k * cols; Ms[k * cw + i] = Mg[(long long)k * ldm + i]; }
     for (int e = c.tid; e < 2 * nsw; e += c.nthr) sws[e] = swg[e];
     c.sync();
     const int nrot = sws[2 * nsw - 1] + ((sws[2 * nsw - 2] >> 16) - (sws[2 * nsw - 2] & 0xffff));
@@ -970,41 +1073,41 @@ KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
         if (s1 < nsw) stage(s1, s2, rb + (buf ^ 1) * 4 * CH);
         const double* cur = rb + buf * 4 * CH;
         const int rbase = sws[2 * s0 + 1];
-        for (int i = c.tid; i < n; i += c.nthr) {
+        for (int i = c.tid; i < cols; i += c.nthr) {
             for (int sw = s0; sw < s1; ++sw) {
                 const int l = sws[2 * sw] & 0xffff, iact = sws[2 * sw] >> 16;
-                if (mode && iact >= i) continue;
+                if (mode && iact >= c0 + i) continue;
                 const double* q = cur + 4 * (sws[2 * sw + 1] - rbase);
-                cd* zp = Ms + (long long)l * n + i;
+                cd* zp = Ms + (long long)l * cw + i;
                 cd z0 = zp[0];
                 int k = l;
                 if (mode == 0) {
-                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * n) {      // rows k+1..k+4 are read before this sweep writes them
-                        const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
-                        const double c0 = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
+                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * cw) {      // rows k+1..k+4 are read before this sweep writes them
+                        const cd z1 = zp[cw], z2 = zp[2 * cw], z3 = zp[3 * cw], z4 = zp[4 * cw];
+                        const double c0_ = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
                         const cd t0 = mk(q[1], q[2]), t1 = mk(q[5], q[6]), t2 = mk(q[9], q[10]), t3 = mk(q[13], q[14]);
-                        zp[0] = c0 * z0 + cconj(t0) * z1; z0 = c0 * z1 - t0 * z0;
-                        zp[n] = c1 * z0 + cconj(t1) * z2; z0 = c1 * z2 - t1 * z0;
-                        zp[2 * n] = c2 * z0 + cconj(t2) * z3; z0 = c2 * z3 - t2 * z0;
-                        zp[3 * n] = c3 * z0 + cconj(t3) * z4; z0 = c3 * z4 - t3 * z0;
+                        zp[0] = c0_ * z0 + cconj(t0) * z1; z0 = c0_ * z1 - t0 * z0;
+                        zp[cw] = c1 * z0 + cconj(t1) * z2; z0 = c1 * z2 - t1 * z0;
+                        zp[2 * cw] = c2 * z0 + cconj(t2) * z3; z0 = c2 * z3 - t2 * z0;
+                        zp[3 * cw] = c3 * z0 + cconj(t3) * z4; z0 = c3 * z4 - t3 * z0;
                     }
-                    for (; k < iact; ++k, q += 4, zp += n) {
-                        const cd z1 = zp[n];
+                    for (; k < iact; ++k, q += 4, zp += cw) {
+                        const cd z1 = zp[cw];
                         const double cc = q[0]; const cd ss = mk(q[1], q[2]);
                         zp[0] = cc * z0 + cconj(ss) * z1; z0 = cc * z1 - ss * z0;
                     }
                 } else {
-                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * n) {
-                        const cd z1 = zp[n], z2 = zp[2 * n], z3 = zp[3 * n], z4 = zp[4 * n];
-                        const double c0 = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
+                    for (; k + 4 <= iact; k += 4, q += 16, zp += 4 * cw) {
+                        const cd z1 = zp[cw], z2 = zp[2 * cw], z3 = zp[3 * cw], z4 = zp[4 * cw];
+                        const double c0_ = q[0], c1 = q[4], c2 = q[8], c3 = q[12];
                         const cd t0 = mk(q[1], q[2]), t1 = mk(q[5], q[6]), t2 = mk(q[9], q[10]), t3 = mk(q[13], q[14]);
-                        zp[0] = c0 * z0 + t0 * z1; z0 = c0 * z1 - cconj(t0) * z0;
-                        zp[n] = c1 * z0 + t1 * z2; z0 = c1 * z2 - cconj(t1) * z0;
-                        zp[2 * n] = c2 * z0 + t2 * z3; z0 = c2 * z3 - cconj(t2) * z0;
-                        zp[3 * n] = c3 * z0 + t3 * z4; z0 = c3 * z4 - cconj(t3) * z0;
+                        zp[0] = c0_ * z0 + t0 * z1; z0 = c0_ * z1 - cconj(t0) * z0;
+                        zp[cw] = c1 * z0 + t1 * z2; z0 = c1 * z2 - cconj(t1) * z0;
+                        zp[2 * cw] = c2 * z0 + t2 * z3; z0 = c2 * z3 - cconj(t2) * z0;
+                        zp[3 * cw] = c3 * z0 + t3 * z4; z0 = c3 * z4 - cconj(t3) * z0;
                     }
-                    for (; k < iact; ++k, q += 4, zp += n) {
-                        const cd z1 = zp[n];
+                    for (; k < iact; ++k, q += 4, zp += cw) {
+                        const cd z1 = zp[cw];
                         const double cc = q[0]; const cd ss = mk(q[1], q[2]);
                         zp[0] = cc * z0 + ss * z1; z0 = cc * z1 - cconj(ss) * z0;
                     }
@@ -1018,14 +1121,26 @@ KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
         c.sync();
         s0 = s1; s1 = s2; buf ^= 1;
     }
-    for (int e = c.tid; e < n * n; e += c.nthr) { const int k = e / n, i = e - k * n; Mg[(long long)k * ldm + i] = Ms[e]; }
+    for (int e = c.tid; e < n * cols; e += c.nthr) { const int k = e / cols, i = e - k * cols; Mg[(long long)k * ldm + i] = Ms[k * cw + i]; }
 }
-static inline int zrot_chunk(int n, int sw_cap) {                     // rotations per staged chunk that fit beside the matrix
-    const long long room = (long long)KH_SMEM_MAX - (long long)n * n * (long long)sizeof(cd) - 2LL * sw_cap * (long long)sizeof(int) - 64;
+// strip width: the whole matrix when it fits beside a chunk buffer of >= n rotations, else equal strips of <= 64 columns
+static inline int zrot_strip(int n, int sw_cap) {
+    const long long fixed = 2LL * sw_cap * (long long)sizeof(int) + 64, ch_min = 2LL * 4 * (long long)sizeof(double) * (n > 256 ? n : 256);
+    if ((long long)n * n * (long long)sizeof(cd) + fixed + 2LL * 4 * (long long)sizeof(double) * n <= (long long)KH_SMEM_MAX) return n;
+    long long room = (long long)KH_SMEM_MAX - fixed - ch_min;
+    if (room <= 0) return 0;
+    long long cw = room / ((long long)n * (long long)sizeof(cd));
+    if (cw > 64) cw = 64;
+    if (cw < 1) return 0;
+    const int strips = (int)((n + cw - 1) / cw);
+    return (n + strips - 1) / strips;
+}
+static inline int zrot_chunk(int n, int sw_cap, int cw) {             // rotations per staged chunk that fit beside the strip
+    const long long room = (long long)KH_SMEM_MAX - (long long)n * cw * (long long)sizeof(cd) - 2LL * sw_cap * (long long)sizeof(int) - 64;
     long long ch = room / (2 * 4 * (long long)sizeof(double));
     return ch > 4096 ? 4096 : (int)ch;
 }
-static inline size_t zrot_smem_bytes(int n, int sw_cap, int chunk) { return (size_t)n * n * sizeof(cd) + (size_t)8 * chunk * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
+static inline size_t zrot_smem_bytes(int n, int sw_cap, int chunk, int cw) { return (size_t)n * cw * sizeof(cd) + (size_t)8 * chunk * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
 // work space (doubles per matrix) the log needs for the given capacities
 static inline long long zgeev_rlog_doubles(int rot_cap, int sw_cap) { return 2LL + sw_cap + 3LL * rot_cap; }
 
@@ -1072,6 +1187,7 @@ static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
 static inline size_t zqr_smem_bytes(int n, int use_smem) {
     size_t s = (size_t)n * sizeof(kh_qrot) + 16 * sizeof(int) + 16;
     if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
+    else s += (size_t)(ZQT_W + 2) * ZQT_LD * sizeof(cd);
     return s;
 }
 
@@ -1097,8 +1213,9 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
         if (e) return e; }
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
-    if (!(q.use_smem && q.rlog && q.rot_cap >= n && q.sw_cap >= 1 && q.sw_cap < 65536 && n < 65536 &&
-          zrot_chunk(n, q.sw_cap) >= n)) q.rlog = nullptr;
+    const int zcw = (q.rlog && q.sw_cap >= 1) ? zrot_strip(n, q.sw_cap) : 0;
+    if (!(q.rlog && q.rot_cap >= n && q.sw_cap >= 1 && q.sw_cap < 65536 && n < 65536 && zcw > 0 &&
+          zrot_chunk(n, q.sw_cap, zcw) >= n)) q.rlog = nullptr;
     if (q.use_smem && q.rlog && q.istate) {
         // Phased iteration on the shrinking leading block: (na, launch shape) chosen so that 2 / 4 / 8 CTAs share an SM.
         auto fit = [&](size_t budget) { int m = n; while (m > 8 && zqr_smem_bytes(m, 1) > budget) --m; return m; };
@@ -1121,9 +1238,9 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
     if (e) return e;
     if (q.rlog) {
-        const int ch = zrot_chunk(n, q.sw_cap);
-        zrot_args z{n, a.Zt, a.Hw, q.rlog, q.rlog_stride, q.sw_cap, ch};
-        e = kh_launch<zrot_args, zrot_apply_body>(dim3(batch, 2), 128, zrot_smem_bytes(n, q.sw_cap, ch), st, z, "zgeev_zrot", 0.0);
+        const int ch = zrot_chunk(n, q.sw_cap, zcw), strips = (n + zcw - 1) / zcw;
+        zrot_args z{n, a.Zt, a.Hw, q.rlog, q.rlog_stride, q.sw_cap, ch, zcw};
+        e = kh_launch<zrot_args, zrot_apply_body>(dim3(batch, 2 * strips), zcw <= 32 ? 32 : (zcw <= 64 ? 64 : 128), zrot_smem_bytes(n, q.sw_cap, ch, zcw), st, z, "zgeev_zrot", 0.0);
         if (e) return e;
     }
     return kh_launch<zgeev_args, ztrevc_body>(dim3(batch), n <= 128 ? 128 : 256, 0, st, a, "zgeev_trevc", 0.25 * work);
