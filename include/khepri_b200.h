@@ -135,6 +135,17 @@ int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void
                     const double* z_host, int nz, const double* zpos_host, void* F_dev,
                     void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Same on a rectangular grid x = xs[ix], y = ys[iy] (fields_volume with meshgrid coordinates):
+ * F_dev [B][nz][6][ny][nx].  Separable inverse transform, 8 (N nx + Q nx ny) flops per map instead of
+ * 8 N nx ny.  Requires a lattice whose reciprocal vector b1 has no y component (ky depends on the q
+ * index only: square / rectangular lattices) and Q <= 16; the caller checks the lattice
+ * (khepri_b200.Crystal does) and falls back to kh_fields_batch otherwise. */
+size_t kh_fields_grid_workspace_bytes(const kh_plan* plan, int B, int nx, int ny, int nz);
+int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                         const kh_outputs* solved, const double* xs_dev, int nx, const double* ys_dev, int ny,
+                         const double* z_host, int nz, const double* zpos_host, void* F_dev,
+                         void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- measurement helper --------------------------------------------------------------------- */
 /* FP64 peak probe on the current device (registers only): mode 0 = DFMA stream, 1 = DMMA m8n8k4
  * stream.  Synchronous; returns TFLOP/s.  Used by bench.py for the roofline denominator that

@@ -328,8 +328,11 @@ class Crystal:
             assert layer.fields, f"Layer at {z} did not store eigenspace."
         plan = self._get_plan(True)
         inc = np.asarray(incident_fields, dtype=np.complex128).reshape(1, 2, plan.n)
+        grid = None
+        if x.ndim == 2 and x.shape == y.shape and np.all(x == x[:1, :]) and np.all(y == y[:, :1]):
+            grid = (x[0, :], y[:, 0])                       # numpy.meshgrid(indexing="xy") coordinates: separable transform
         F = self.engine.fields(plan, self._solved, [self.source.wavelength], [self.kp], inc, x.ravel(), y.ravel(), zs,
-                               self.stack_positions)
+                               self.stack_positions, grid=grid)
         return F[0]
 
     def fields_coords_xy(self, x, y, z, incident_fields=None, kp=None, return_fourier=False):

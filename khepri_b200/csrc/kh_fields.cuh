@@ -156,18 +156,84 @@ KH_DEV void fld_phase_body(const Cta& c, const fld_phase_args& a) {
     }
 }
 
+// ---- separable inverse transform on a rectangular (x, y) grid (fields_volume with meshgrid coordinates) for
+// lattices whose ky depends on the q index only (b1 along x: square / rectangular lattices):
+//     f[iy][ix] = sum_q ( sum_p S[qP+p] exp(i kx_{pq} x_ix) ) exp(i ky_q y_iy)
+// 8 (N nx + Q nx ny) flops per map instead of the 8 N nx ny of the dense phase matrix, which moves the field maps from the
+// FP64 pipe to the HBM roofline (16 B written per Q complex FMAs).  Tables: Xt[b][g][ix], Yt[b][q][iy].
+struct fld_gtab_args { int B, N, P, Q, nx, ny; const cd* kp; const double* g; const double* xs; const double* ys; cd* Xt; cd* Yt; };
+KH_DEV void fld_gtab_body(const Cta& c, const fld_gtab_args& a) {
+    const int b = c.bx, r = c.by;                     // r < N: row g of Xt ; r >= N: row q of Yt
+    if (r < a.N) {
+        const cd kx = mk(a.kp[2 * b].x + a.g[r], a.kp[2 * b].y);
+        cd* o = a.Xt + ((long long)b * a.N + r) * a.nx;
+        for (int i = c.tid; i < a.nx; i += c.nthr) { const cd arg = a.xs[i] * kx; o[i] = cexp_(mk(-arg.y, arg.x)); }
+    } else {
+        const int q = r - a.N;
+        const cd ky = mk(a.kp[2 * b + 1].x + a.g[a.N + q * a.P], a.kp[2 * b + 1].y);
+        cd* o = a.Yt + ((long long)b * a.Q + q) * a.ny;
+        for (int i = c.tid; i < a.ny; i += c.nthr) { const cd arg = a.ys[i] * ky; o[i] = cexp_(mk(-arg.y, arg.x)); }
+    }
+}
+#define FLD_QMAX 16
+struct fld_grid_args { int B, N, P, Q, nx, ny, maps, ysplit; const cd* Sall; const cd* Xt; const cd* Yt; cd* F; };
+KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) {
+    const int b = c.bx, map = c.by / a.ysplit, part = c.by - map * a.ysplit;         // map = iz * 6 + component
+    const int P = a.P, Q = a.Q, N = a.N, nx = a.nx, ny = a.ny;
+    const int y0 = (int)((long long)ny * part / a.ysplit), y1 = (int)((long long)ny * (part + 1) / a.ysplit);
+    // shared: [S N][Y Q x (y1 - y0)]
+    cd* Ss = (cd*)c.smem;
+    cd* Ys = Ss + N;
+    const int nyl = y1 - y0;
+    const cd* S = a.Sall + ((long long)b * a.maps + map) * N;
+    for (int g = c.tid; g < N; g += c.nthr) Ss[g] = S[g];
+    for (int e = c.tid; e < Q * nyl; e += c.nthr) { const int q = e / nyl, i = e - q * nyl; Ys[e] = a.Yt[((long long)b * Q + q) * ny + y0 + i]; }
+    c.sync();
+    cd* out = a.F + ((long long)b * a.maps + map) * ny * nx;
+    for (int ix = c.tid; ix < nx; ix += c.nthr) {
+        cd T[FLD_QMAX];
+#pragma unroll
+        for (int q = 0; q < FLD_QMAX; ++q) {
+            T[q] = mk(0, 0);
+            if (q < Q) {
+                const cd* xr = a.Xt + ((long long)b * N + q * P) * nx + ix;
+                cd acc = mk(0, 0);
+                for (int p = 0; p < P; ++p) cfma(acc, Ss[q * P + p], xr[(long long)p * nx]);
+                T[q] = acc;
+            }
+        }
+        int iy = 0;
+        for (; iy + 2 <= nyl; iy += 2) {
+            cd f0 = mk(0, 0), f1 = mk(0, 0);
+#pragma unroll
+            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) { cfma(f0, T[q], Ys[q * nyl + iy]); cfma(f1, T[q], Ys[q * nyl + iy + 1]); }
+            out[(long long)(y0 + iy) * nx + ix] = f0;
+            out[(long long)(y0 + iy + 1) * nx + ix] = f1;
+        }
+        for (; iy < nyl; ++iy) {
+            cd f0 = mk(0, 0);
+#pragma unroll
+            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) cfma(f0, T[q], Ys[q * nyl + iy]);
+            out[(long long)(y0 + iy) * nx + ix] = f0;
+        }
+    }
+}
+
 struct FieldBufs {
     cd *Kx, *Ky; double* k0; cd* c1p; cd* Fm; cd* Finv; cd* y12; cd* m12; cd* Winv; cd* Vinv; cd* Sall; cd* Ph;
     int* zpos; int* zlayer; double* zdist; const cd** ICp; cd* ICs; int* info;
     cd* zwork; long long zwork_cd;      // work space of the blocked inverse (n beyond shared memory)
+    cd* Xt; cd* Yt;                     // grid path: phase tables
 };
-static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, FieldBufs& f) {
+static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, FieldBufs& f, int nx = 0, int ny = 0) {
     const size_t N = p->N, n = p->n, n2 = n * n, nL = p->layers.size(), Ls = p->stack.size();
     f.Kx = b.get<cd>(B * N); f.Ky = b.get<cd>(B * N); f.k0 = b.get<double>(B);
     f.c1p = b.get<cd>(B * n); f.Fm = b.get<cd>(B * n2); f.Finv = b.get<cd>(B * n2);
     f.y12 = b.get<cd>(B * 2 * n); f.m12 = b.get<cd>(B * Ls * 2 * n);
     f.Winv = b.get<cd>(nL * B * n2); f.Vinv = b.get<cd>(nL * B * n2);
-    f.Sall = b.get<cd>((size_t)B * nz * 6 * N); f.Ph = b.get<cd>((size_t)B * N * npts);
+    f.Sall = b.get<cd>((size_t)B * nz * 6 * N);
+    if (nx > 0) { f.Ph = nullptr; f.Xt = b.get<cd>((size_t)B * N * nx); f.Yt = b.get<cd>((size_t)B * p->Q * ny); }
+    else { f.Ph = b.get<cd>((size_t)B * N * npts); f.Xt = f.Yt = nullptr; }
     f.zpos = b.get<int>(nz); f.zlayer = b.get<int>(nz); f.zdist = b.get<double>(nz);
     f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * B);
     f.zwork_cd = (int)n >= KH_ZINV_BLOCKED_MIN ? (long long)B * zinv_work_cd((int)n) : 0;
@@ -192,10 +258,19 @@ static int kh_h2d(void* dst, const void* src, size_t bytes, kh_stream_t st) {
 #endif
 }
 
-extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
-                               const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts,
-                               const double* z_host, int nz, const double* zpos_host, void* F_dev,
-                               void* ws_dev, size_t ws_bytes, void* stream) {
+extern "C" size_t kh_fields_grid_workspace_bytes(const kh_plan* plan, int B, int nx, int ny, int nz) {
+    if (!plan || B < 1 || nx < 1 || ny < 1 || nz < 1) return 0;
+    Bump b{nullptr, 0, 0};
+    FieldBufs f;
+    layout_fields(plan, B, nx * ny, nz, b, f, nx, ny);
+    return b.off + 256;
+}
+
+// grid = 0: scattered points (x_dev[p], y_dev[p]), p < npts.  grid = 1: x_dev[nx], y_dev[ny] are the axes of a rectangular grid.
+static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                       const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts, int grid, int nx, int ny,
+                       const double* z_host, int nz, const double* zpos_host, void* F_dev,
+                       void* ws_dev, size_t ws_bytes, void* stream) {
     if (!plan || B < 0 || !wl_dev || !kp_dev || !inc_dev || !solved || !x_dev || !y_dev || npts < 1 || !z_host || nz < 1 || !zpos_host || !F_dev || !ws_dev)
         return fail(KH_EINVAL, "kh_fields_batch: bad arguments");
     if (!(solved->prefix_dev && solved->suffix_dev && solved->W_dev && solved->V_dev && solved->L_dev))
@@ -204,13 +279,15 @@ extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev,
     const kh_plan* p = plan;
     if (p->has_ext) return fail(KH_EINVAL, "kh_fields_batch: extended layers are not supported");
     if (p->layers[p->stack[0]].kind != KH_LAYER_HALF_INC) return fail(KH_EINVAL, "kh_fields_batch: the stack must start with the incidence half space");
-    if (ws_bytes < kh_fields_workspace_bytes(p, B, npts, nz)) return fail(KH_ENOMEM, "kh_fields_batch: workspace too small");
+    if (grid && p->Q > FLD_QMAX) return fail(KH_EINVAL, "kh_fields_grid_batch: more than 16 harmonics along y; use kh_fields_batch");
+    if (ws_bytes < (grid ? kh_fields_grid_workspace_bytes(p, B, nx, ny, nz) : kh_fields_workspace_bytes(p, B, npts, nz)))
+        return fail(KH_ENOMEM, "kh_fields_batch: workspace too small");
     kh_stream_t st = (kh_stream_t)stream;
     const int N = p->N, n = p->n, Ls = (int)p->stack.size(), nL = (int)p->layers.size();
     const long long n2 = (long long)n * n;
     Bump bump{(char*)ws_dev, ws_bytes, 0};
     FieldBufs f;
-    layout_fields(p, B, npts, nz, bump, f);
+    layout_fields(p, B, npts, nz, bump, f, grid ? nx : 0, grid ? ny : 0);
 
     // host: locate every depth (crystal.py:208-232) -> stack position, layer, distance to the right face
     std::vector<int> zpos(nz), zlay(nz);
@@ -272,10 +349,37 @@ extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev,
     {   fld_z_args a{B, N, nz, f.zpos, f.zlayer, f.zdist, f.m12, (long long)Ls * 2 * n, 2LL * n,
                      Wd, Vd, (const cd*)solved->L_dev, (long long)nL * n2, nL, f.ICp, f.ICs, f.Kx, f.Ky, f.k0, f.Sall};
         KH_TRY((kh_launch<fld_z_args, fld_z_body>(dim3(B, nz), 256, (size_t)5 * n * sizeof(cd), st, a))); }
+    if (grid) {
+        {   fld_gtab_args a{B, N, p->P, p->Q, nx, ny, (const cd*)kp_dev, p->g_dev, x_dev, y_dev, f.Xt, f.Yt};
+            KH_TRY((kh_launch<fld_gtab_args, fld_gtab_body>(dim3(B, N + p->Q), 256, 0, st, a, "fld_grid"))); }
+        // enough CTAs for a few waves: split the y range when the batch of maps is small
+        int ysplit = 1;
+        while ((long long)B * nz * 6 * ysplit < 4 * 148 && ysplit * 2 <= ny && ysplit < 16) ysplit *= 2;
+        const int nyl = (ny + ysplit - 1) / ysplit + 1;
+        fld_grid_args a{B, N, p->P, p->Q, nx, ny, 6 * nz, ysplit, f.Sall, f.Xt, f.Yt, (cd*)F_dev};
+        const size_t sm = ((size_t)N + (size_t)p->Q * nyl) * sizeof(cd);
+        if (sm > (size_t)KH_SMEM_MAX) return fail(KH_EINVAL, "kh_fields_grid_batch: grid too tall for the phase table in shared memory");
+        const double work = 8.0 * ((double)N * nx + (double)p->Q * nx * ny) * 6.0 * nz * B;
+        return kh_launch<fld_grid_args, fld_grid_body>(dim3(B, 6 * nz * ysplit), nx >= 256 ? 256 : (nx >= 128 ? 128 : 64), sm, st, a, "fld_grid", work);
+    }
     {   fld_phase_args a{B, N, npts, (const cd*)kp_dev, p->g_dev, x_dev, y_dev, f.Ph};
         KH_TRY((kh_launch<fld_phase_args, fld_phase_body>(dim3(B, N), 256, 0, st, a))); }
     {   zgemm_args g = zgemm_make(6 * nz, npts, N, mref(f.Sall, (long long)nz * 6 * N, N), mref(f.Ph, (long long)N * npts, npts),
                                   mref(F_dev, (long long)nz * 6 * npts, npts));
         KH_TRY(zgemm_launch(st, B, g)); }
     return 0;
+}
+
+extern "C" int kh_fields_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                               const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts,
+                               const double* z_host, int nz, const double* zpos_host, void* F_dev,
+                               void* ws_dev, size_t ws_bytes, void* stream) {
+    return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, x_dev, y_dev, npts, 0, 0, 0, z_host, nz, zpos_host, F_dev, ws_dev, ws_bytes, stream);
+}
+extern "C" int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                                    const kh_outputs* solved, const double* xs_dev, int nx, const double* ys_dev, int ny,
+                                    const double* z_host, int nz, const double* zpos_host, void* F_dev,
+                                    void* ws_dev, size_t ws_bytes, void* stream) {
+    if (nx < 1 || ny < 1) return fail(KH_EINVAL, "kh_fields_grid_batch: bad grid");
+    return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, xs_dev, ys_dev, nx * ny, 1, nx, ny, z_host, nz, zpos_host, F_dev, ws_dev, ws_bytes, stream);
 }

@@ -509,100 +509,159 @@ KH_HD int hp_off(int i, int n) { return i * n - ((i - 1) * i) / 2; }
 KH_HD int hp_size(int n) { return hp_off(n - 1, n) + n + 3; }
 
 // ---- tiled sweep for a Hessenberg matrix in global memory (n beyond shared memory).  The rotations of a sweep are
-// generated in groups of ZQT_W: the diagonal tile that determines them (rows ks..ke+1, columns ks-1..ke+1) is staged in
-// shared memory and chased there by ONE warp (lanes <-> tile columns for the row steps, tile rows for the column steps,
-// warp-level synchronisation only); the rest of the window then receives the whole group in bulk - one thread per column
-// right of the tile (row rotations) and one thread per row above it (column rotations, all rows 0..ks-1 so nothing above
-// the window is left for later), each element loaded and stored once per group instead of once per rotation.
+// generated in groups of ZQT_W.  The diagonal tile that determines a group (rows ks..ke, columns ks-1..ke) is staged in
+// shared memory and chased there by ONE warp, lane <-> tile column: the dependent chain
+//     corner (shuffle) -> C(t-1) on rows t, t+1 in registers -> Givens G(t) -> R(t) on the own column
+// runs without any barrier or shared-memory round trip (each lane keeps the running bottom entry of its column in a
+// register, exactly like the relay sweep of the packed kernel); the column steps C(t) on the tile rows above the corner
+// are applied afterwards, lane <-> row, from the queue.  The rest of the window then receives the whole group in bulk:
+// one thread per column right of the tile (row rotations, rows ks..ke) and one thread per row above it (column
+// rotations, ALL rows 0..ks-1, so nothing above the window is left for later) - each element is loaded and stored once
+// per group instead of once per rotation, with eight loads in flight per thread.
+// State between groups: R(t), t < ke, applied everywhere; C(ke-1) still pending on rows ke, ke+1 (the next group's first
+// chain step applies it), H[ke][ke-1] holds the sub-diagonal entry after R(ke-1).
 #define ZQT_W 28
 #define ZQT_LD 33
+template <bool ROWS>      // ROWS: row rotations down a column (stride = ld); else column rotations along a row (stride 1)
+KH_DEV void zqt_bulk_chain(cd* hp, long long stride, const kh_qrot* Q, int ks, int ke) {
+    cd h0 = hp[0];
+    int k = ks;
+    for (; k + 8 <= ke; k += 8, hp += 8 * stride) {
+        cd h[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) h[u] = hp[(u + 1) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double cc = Q[k + u].c; const cd ss = Q[k + u].s;
+            if (ROWS) { hp[u * stride] = cc * h0 + ss * h[u]; h0 = cc * h[u] - cconj(ss) * h0; }
+            else { hp[u * stride] = cc * h0 + cconj(ss) * h[u]; h0 = cc * h[u] - ss * h0; }
+        }
+    }
+    for (; k < ke; ++k, hp += stride) {
+        const cd h1 = hp[stride];
+        const double cc = Q[k].c; const cd ss = Q[k].s;
+        if (ROWS) { hp[0] = cc * h0 + ss * h1; h0 = cc * h1 - cconj(ss) * h0; }
+        else { hp[0] = cc * h0 + cconj(ss) * h1; h0 = cc * h1 - ss * h0; }
+    }
+    hp[0] = h0;
+}
 KH_DEV void zqr_tiled_sweep(const Cta& c, cd* Hg, int ldg, int l, int iact, cd f_first, cd g_first, kh_qrot* Q, cd* D) {
     const int lane = c.tid % KH_WARP, warp = c.tid / KH_WARP;
+#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
+    long long tt = clock64(), tn, t_load = 0, t_chase = 0, t_bulk = 0;
+#define TT_ADD(v) do { tn = clock64(); (v) += tn - tt; tt = tn; } while (0)
+#else
+#define TT_ADD(v)
+#endif
+#ifdef KH_HOST_EMU
+    // ---- host emulation (one virtual thread): same grouping, every group completes its column steps on rows <= k+2
     for (int ks = l; ks < iact; ks += ZQT_W) {
-        const int ke = (ks + ZQT_W < iact) ? ks + ZQT_W : iact;          // rotations ks .. ke-1
+        const int ke = (ks + ZQT_W < iact) ? ks + ZQT_W : iact;
         const int rA = ks, rB = (ke + 1 < iact) ? ke + 1 : iact;
         const int cA = (ks - 1 > l) ? ks - 1 : l, cB = rB;
         const int nr = rB - rA + 1, nc = cB - cA + 1;
+        for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; D[i * (ZQT_LD + 2) + j] = Hg[(long long)(rA + i) * ldg + cA + j]; }
+#define DT(i, j) D[((i) - rA) * (ZQT_LD + 2) + ((j) - cA)]
+        for (int k = ks; k < ke; ++k) {
+            kh_givens G;
+            if (k == l) G = make_givens(f_first, g_first);
+            else { G = make_givens(DT(k, k - 1), DT(k + 1, k - 1)); DT(k, k - 1) = G.r; DT(k + 1, k - 1) = mk(0.0, 0.0); }
+            const cd cs = cconj(G.s);
+            for (int j = k; j <= cB; ++j) { const cd h0 = DT(k, j), h1 = DT(k + 1, j); DT(k, j) = G.c * h0 + G.s * h1; DT(k + 1, j) = G.c * h1 - cs * h0; }
+            const int rl = (k + 2 < rB) ? k + 2 : rB;
+            for (int r = rA; r <= rl; ++r) { const cd h0 = DT(r, k), h1 = DT(r, k + 1); DT(r, k) = G.c * h0 + cs * h1; DT(r, k + 1) = G.c * h1 - G.s * h0; }
+            Q[k].c = G.c; Q[k].s = G.s;
+        }
+#undef DT
+        for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; Hg[(long long)(rA + i) * ldg + cA + j] = D[i * (ZQT_LD + 2) + j]; }
+        for (int t = 0; t < iact - cB; ++t) zqt_bulk_chain<true>(Hg + (long long)ks * ldg + (cB + 1 + t), ldg, Q, ks, ke);
+        for (int t = 0; t < rA; ++t) zqt_bulk_chain<false>(Hg + (long long)t * ldg + ks, 1, Q, ks, ke);
+    }
+#else
+    for (int ks = l; ks < iact; ks += ZQT_W) {
+        const int ke = (ks + ZQT_W < iact) ? ks + ZQT_W : iact;          // rotations ks .. ke-1
+        const int rA = ks, cA = (ks > l) ? ks - 1 : l;                    // tile rows ks..ke, columns cA..ke
+        const int nr = ke - rA + 1, nc = ke - cA + 1;
         for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; D[i * ZQT_LD + j] = Hg[(long long)(rA + i) * ldg + cA + j]; }
-        c.sync();
+        __syncthreads();
+        TT_ADD(t_load);
         if (warp == 0) {
 #define DT(i, j) D[((i) - rA) * ZQT_LD + ((j) - cA)]
-            for (int k = ks; k < ke; ++k) {
-                kh_givens G;
-                if (k == l) G = make_givens(f_first, g_first);
-                else {
-                    G = make_givens(DT(k, k - 1), DT(k + 1, k - 1));       // annihilates the bulge
-#ifndef KH_HOST_EMU
-                    __syncwarp();
-#endif
-                    if (lane == 0) { DT(k, k - 1) = G.r; DT(k + 1, k - 1) = mk(0.0, 0.0); }
-                }
-                const cd cs = cconj(G.s);
-                for (int j = k + lane; j <= cB; j += KH_WARP) {           // R(k)
-                    const cd h0 = DT(k, j), h1 = DT(k + 1, j);
-                    DT(k, j) = G.c * h0 + G.s * h1;
-                    DT(k + 1, j) = G.c * h1 - cs * h0;
-                }
-#ifndef KH_HOST_EMU
+            const int j = cA + lane, jc = (j <= ke) ? j : ke;             // own tile column (clamped for the unconditional loads)
+            const bool own = (j <= ke);
+            kh_givens G;
+            cd sub, carry;
+            int t;
+            if (ks == l) {                                                // first group: G(l) from the shift, R(l) on every column
+                G = make_givens(f_first, g_first);
+                const cd h0 = DT(l, jc), h1 = DT(l + 1, jc);
+                carry = G.c * h1 - cconj(G.s) * h0;
+                if (own) DT(l, j) = G.c * h0 + G.s * h1;
+                sub = kh_shfl_cd(carry, 0);
+                if (lane == 0) { Q[l].c = G.c; Q[l].s = G.s; }
+                t = l + 1;
+            } else {                                                      // continue: G(ks-1) is in the queue
+                G.c = Q[ks - 1].c; G.s = Q[ks - 1].s; G.r = mk(0, 0);
+                carry = DT(ks, jc);
+                sub = DT(ks, ks - 1);
+                t = ks;
+            }
+            for (; t < ke; ++t) {
+                const cd hd = DT(t + 1, t);                                // untouched by this sweep so far
+                const cd h1 = DT(t + 1, jc);
+                const cd cb = kh_shfl_cd(carry, t - cA);                   // H[t][t] after R(t-1)
+                const cd a1 = G.c * sub + cconj(G.s) * cb, b1 = G.c * cb - G.s * sub;      // C(t-1) on row t
+                const cd c1 = cconj(G.s) * hd, d1 = G.c * hd;                              // C(t-1) on row t+1: bulge
+                const double f2 = cabs2(a1), g2 = cabs2(c1);
+                kh_givens Gn;
+                if (f2 == 0.0 || g2 == 0.0) Gn = make_givens(a1, c1);
+                else Gn = make_givens_fast(a1, c1, f2, g2);
+                const cd ncs = cconj(Gn.s);
+                const cd top = Gn.c * carry + Gn.s * h1, bot = Gn.c * h1 - ncs * carry;    // R(t) on the own column
+                const cd newdiag = Gn.c * b1 + Gn.s * d1, nextsub = Gn.c * d1 - ncs * b1;
+                if (own && j > t) { DT(t, j) = top; carry = bot; }
+                if (lane == 0) { Q[t].c = Gn.c; Q[t].s = Gn.s; Q[t].r = Gn.r; Q[t].diag = newdiag; Q[t].nsub = nextsub; }
+                G = Gn; sub = nextsub;
+            }
+            {   const cd cb = kh_shfl_cd(carry, ke - cA);                  // row ke of column ke after R(ke-1)
                 __syncwarp();
-#endif
-                const int rl = (k + 2 < rB) ? k + 2 : rB;
-                for (int r = rA + lane; r <= rl; r += KH_WARP) {          // C(k)
-                    const cd h0 = DT(r, k), h1 = DT(r, k + 1);
-                    DT(r, k) = G.c * h0 + cs * h1;
-                    DT(r, k + 1) = G.c * h1 - G.s * h0;
+                if (lane == 0) {
+                    if (ke == iact) { DT(ke, ke - 1) = G.c * sub + cconj(G.s) * cb; DT(ke, ke) = G.c * cb - G.s * sub; }   // C(iact-1) on row iact
+                    else { DT(ke, ke - 1) = sub; DT(ke, ke) = cb; }
                 }
-                if (lane == 0) { Q[k].c = G.c; Q[k].s = G.s; }
-#ifndef KH_HOST_EMU
-                __syncwarp();
-#endif
+            }
+            __syncwarp();
+            // column steps C(t), t >= r, on the tile rows r < ke (rows t+1, t+2 were handled inside the chain)
+            const int r = rA + lane;
+            if (r < ke) {
+                cd car = mk(0, 0);
+                for (int t2 = r; t2 < ke; ++t2) {
+                    const double cc = Q[t2].c; const cd ss = Q[t2].s;
+                    cd h0 = car;
+                    if (t2 == r) { if (t2 > l) { h0 = Q[t2].diag; DT(r, t2 - 1) = Q[t2].r; } else h0 = DT(r, t2); }
+                    const cd h1 = DT(r, t2 + 1);
+                    DT(r, t2) = cc * h0 + cconj(ss) * h1;
+                    car = cc * h1 - ss * h0;
+                }
+                DT(r, ke) = car;
             }
 #undef DT
         }
-        c.sync();
+        __syncthreads();
+        TT_ADD(t_chase);
         for (int e = c.tid; e < nr * nc; e += c.nthr) { const int i = e / nc, j = e - i * nc; Hg[(long long)(rA + i) * ldg + cA + j] = D[i * ZQT_LD + j]; }
-        const int nRight = iact - cB, nUp = rA;
+        const int nRight = iact - ke, nUp = rA;
         for (int t = c.tid; t < nRight + nUp; t += c.nthr) {
-            if (t < nRight) {                                              // row rotations on a column right of the tile
-                cd* hp = Hg + (long long)ks * ldg + (cB + 1 + t);
-                cd h0 = hp[0];
-                int k = ks;
-                for (; k + 4 <= ke; k += 4, hp += 4LL * ldg) {
-                    const cd h1 = hp[ldg], h2 = hp[2LL * ldg], h3 = hp[3LL * ldg], h4 = hp[4LL * ldg];
-                    const double c0 = Q[k].c, c1 = Q[k + 1].c, c2 = Q[k + 2].c, c3 = Q[k + 3].c;
-                    const cd s0 = Q[k].s, s1 = Q[k + 1].s, s2 = Q[k + 2].s, s3 = Q[k + 3].s;
-                    hp[0] = c0 * h0 + s0 * h1; h0 = c0 * h1 - cconj(s0) * h0;
-                    hp[ldg] = c1 * h0 + s1 * h2; h0 = c1 * h2 - cconj(s1) * h0;
-                    hp[2LL * ldg] = c2 * h0 + s2 * h3; h0 = c2 * h3 - cconj(s2) * h0;
-                    hp[3LL * ldg] = c3 * h0 + s3 * h4; h0 = c3 * h4 - cconj(s3) * h0;
-                }
-                for (; k < ke; ++k, hp += ldg) {
-                    const cd h1 = hp[ldg];
-                    hp[0] = Q[k].c * h0 + Q[k].s * h1; h0 = Q[k].c * h1 - cconj(Q[k].s) * h0;
-                }
-                hp[0] = h0;
-            } else {                                                       // column rotations on a row above the tile
-                cd* hp = Hg + (long long)(t - nRight) * ldg + ks;
-                cd h0 = hp[0];
-                int k = ks;
-                for (; k + 4 <= ke; k += 4, hp += 4) {
-                    const cd h1 = hp[1], h2 = hp[2], h3 = hp[3], h4 = hp[4];
-                    const double c0 = Q[k].c, c1 = Q[k + 1].c, c2 = Q[k + 2].c, c3 = Q[k + 3].c;
-                    const cd s0 = Q[k].s, s1 = Q[k + 1].s, s2 = Q[k + 2].s, s3 = Q[k + 3].s;
-                    hp[0] = c0 * h0 + cconj(s0) * h1; h0 = c0 * h1 - s0 * h0;
-                    hp[1] = c1 * h0 + cconj(s1) * h2; h0 = c1 * h2 - s1 * h0;
-                    hp[2] = c2 * h0 + cconj(s2) * h3; h0 = c2 * h3 - s2 * h0;
-                    hp[3] = c3 * h0 + cconj(s3) * h4; h0 = c3 * h4 - s3 * h0;
-                }
-                for (; k < ke; ++k, hp += 1) {
-                    const cd h1 = hp[1];
-                    hp[0] = Q[k].c * h0 + cconj(Q[k].s) * h1; h0 = Q[k].c * h1 - Q[k].s * h0;
-                }
-                hp[0] = h0;
-            }
+            if (t < nRight) zqt_bulk_chain<true>(Hg + (long long)ks * ldg + (ke + 1 + t), ldg, Q, ks, ke);
+            else zqt_bulk_chain<false>(Hg + (long long)(t - nRight) * ldg + ks, 1, Q, ks, ke);
         }
-        c.sync();
+        __syncthreads();
+        TT_ADD(t_bulk);
     }
+#if defined(KH_QR_TIMING)
+    if (c.tid == 0 && c.bx == 0) { kh_qr_dbg[8] += t_load; kh_qr_dbg[9] += t_chase; kh_qr_dbg[10] += t_bulk; }
+#endif
+#endif
 }
 
 template <bool PACKED>
@@ -1179,6 +1238,9 @@ KH_DEV void ztrevc_body(const Cta& c, const zgeev_args& a) {
 #undef XX
 }
 
+#ifndef KH_ZQT_SMEM_PAD
+#define KH_ZQT_SMEM_PAD 0             /* extra dynamic shared memory: caps the CTAs per SM (L2 residency of the matrices in flight) */
+#endif
 static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
     size_t s = (size_t)2 * n * sizeof(cd) + 192 * sizeof(double) + (size_t)4 * n * sizeof(double) + 32;
     if (use_smem) s += (size_t)n * ld_s * sizeof(cd);
@@ -1187,10 +1249,14 @@ static inline size_t zhess_smem_bytes(int n, int ld_s, int use_smem) {
 static inline size_t zqr_smem_bytes(int n, int use_smem) {
     size_t s = (size_t)n * sizeof(kh_qrot) + 16 * sizeof(int) + 16;
     if (use_smem) s += (size_t)hp_size(n) * sizeof(cd);
-    else s += (size_t)(ZQT_W + 2) * ZQT_LD * sizeof(cd);
+    else s += (size_t)(ZQT_W + 2) * (ZQT_LD + 2) * sizeof(cd) + KH_ZQT_SMEM_PAD;
     return s;
 }
 
+#ifndef KH_ZQT_THREADS
+#define KH_ZQT_THREADS 128       /* tiled QR (global-memory Hessenberg matrix): threads per CTA, CTAs per SM */
+#define KH_ZQT_MINB 4
+#endif
 #ifndef KH_QR_THREADS
 #define KH_QR_THREADS(n) ((n) <= 64 ? 128 : 256)
 #endif
@@ -1235,7 +1301,7 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
         e = run(phase ? na3 : n, 0);
     }
     else if (q.use_smem) e = kh_launch<zgeev_args, zqr_packed_body, 256, 2>(dim3(batch), KH_QR_THREADS(n), zqr_smem_bytes(n, 1), st, q, "zgeev_qr", 0.5 * work);
-    else e = kh_launch<zgeev_args, zqr_global_body>(dim3(batch), 256, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
+    else e = kh_launch<zgeev_args, zqr_global_body, KH_ZQT_THREADS, KH_ZQT_MINB>(dim3(batch), KH_ZQT_THREADS, zqr_smem_bytes(n, 0), st, q, "zgeev_qr", 0.5 * work);
     if (e) return e;
     if (q.rlog) {
         const int ch = zrot_chunk(n, q.sw_cap, zcw), strips = (n + zcw - 1) / zcw;

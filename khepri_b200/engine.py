@@ -37,7 +37,11 @@ class Plan:
         self.Ls = len(self.stack)
         self.nL = len(layers)
         dev = engine.device
-        self.g = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64), device=dev)
+        g_host = np.ascontiguousarray(g, dtype=np.float64)
+        # ky depends on the q index only (b1 has no y component: square / rectangular lattices) -> separable field maps
+        gy = g_host[1].reshape(self.pw[1], self.pw[0]) if g_host.shape == (2, self.N) else None
+        self.grid_separable = bool(gy is not None and self.pw[1] <= 16 and np.all(gy == gy[:, :1]))
+        self.g = torch.as_tensor(g_host, device=dev)
         assert self.g.shape == (2, self.N), "g-vectors must have shape (2, N)"
         self.glhs = torch.as_tensor(np.ascontiguousarray(glhs, dtype=np.float64), device=dev) if glhs is not None else None
         self.grhs = torch.as_tensor(np.ascontiguousarray(grhs, dtype=np.float64), device=dev) if grhs is not None else None
@@ -290,10 +294,14 @@ class Engine:
               "kh_flux_batch")
         return (RT, orders) if want_orders else RT
 
-    def fields(self, plan, solved, wl, kp, inc, x, y, z, stack_positions):
+    def fields(self, plan, solved, wl, kp, inc, x, y, z, stack_positions, grid=None):
         """(Ex,Ey,Ez,Hx,Hy,Hz) at points (x[p], y[p]) and depths z for every solve of a want_fields
-        solve -> DEVICE tensor [B, nz, 6, npts].  inc [B, 2, n] = incident (E, H) Fourier vectors."""
+        solve -> DEVICE tensor [B, nz, 6, npts].  inc [B, 2, n] = incident (E, H) Fourier vectors.
+        grid=(xs, ys): the points are the rectangular grid x = xs[ix], y = ys[iy] (p = iy * nx + ix) and the
+        separable transform is used when the lattice allows it (plan.grid_separable)."""
         B = solved["prefix"].shape[0]
+        if grid is not None and plan.grid_separable:
+            return self._fields_grid(plan, solved, wl, kp, inc, grid[0], grid[1], z, stack_positions)
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
         kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
         inc_d = self.to_dev(np.asarray(inc, dtype=np.complex128).reshape(B, 2, plan.n), _c128)
@@ -314,4 +322,27 @@ class Engine:
         check(self.lib, self.lib.kh_fields_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out), _ptr(x_d), _ptr(y_d), npts,
                                                  z_h.ctypes.data_as(dp), nz, zp_h.ctypes.data_as(dp), _ptr(F), _ptr(ws), ws.numel(), self.stream()),
               "kh_fields_batch")
+        return F
+
+    def _fields_grid(self, plan, solved, wl, kp, inc, xs, ys, z, stack_positions):
+        B = solved["prefix"].shape[0]
+        wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
+        kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
+        inc_d = self.to_dev(np.asarray(inc, dtype=np.complex128).reshape(B, 2, plan.n), _c128)
+        xs_d = self.to_dev(np.asarray(xs, dtype=np.float64).reshape(-1), _f64)
+        ys_d = self.to_dev(np.asarray(ys, dtype=np.float64).reshape(-1), _f64)
+        z_h = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(-1))
+        zp_h = np.ascontiguousarray(np.asarray(stack_positions, dtype=np.float64).reshape(-1))
+        assert zp_h.size == plan.Ls + 1, "stack_positions must hold Ls+1 interface positions"
+        nx, ny, nz = xs_d.numel(), ys_d.numel(), z_h.size
+        F = torch.empty((B, nz, 6, ny * nx), dtype=_c128, device=self.device)
+        out = Outputs()
+        out.prefix_dev, out.suffix_dev = solved["prefix"].data_ptr(), solved["suffix"].data_ptr()
+        out.W_dev, out.V_dev, out.L_dev = solved["W"].data_ptr(), solved["V"].data_ptr(), solved["L"].data_ptr()
+        wb = self.lib.kh_fields_grid_workspace_bytes(plan.handle, B, nx, ny, nz)
+        ws = self.workspace(wb)
+        dp = C.POINTER(C.c_double)
+        check(self.lib, self.lib.kh_fields_grid_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out), _ptr(xs_d), nx, _ptr(ys_d), ny,
+                                                      z_h.ctypes.data_as(dp), nz, zp_h.ctypes.data_as(dp), _ptr(F), _ptr(ws), ws.numel(), self.stream()),
+              "kh_fields_grid_batch")
         return F

@@ -53,7 +53,7 @@ for rep in range(2):
     solved = eng.solve_batch(plan, wl, kp, pol, want_flux=True, want_fields=True)
     e1 = ev()
     eng.lib.kh_profile_begin()
-    F = eng.fields(plan, solved, wl, kp, inc, X.ravel(), Y.ravel(), z, cl.stack_positions)
+    F = eng.fields(plan, solved, wl, kp, inc, X.ravel(), Y.ravel(), z, cl.stack_positions, grid=(x, y))
     e2 = ev()
     torch.cuda.synchronize()
     buf = C.create_string_buffer(1 << 16)

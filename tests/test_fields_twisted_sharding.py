@@ -66,6 +66,32 @@ def test_fields_oracle_explicit_incident_and_oblique(backend):
     assert np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max()
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_fields_grid_path_matches_point_path(backend):
+    """Meshgrid coordinates take the separable transform (kh_fields_grid_batch); scattered points (here: the same grid
+    sheared so that it is no longer a meshgrid, and a hexagonal lattice) take the dense phase matrix.  Same numbers."""
+    eng = engine(backend)
+    st, _, (X, Y, z) = cases.case_fields(5, slices=2, grid=(9, 7, 4))
+    src = dict(wavelength=1.7, te=0.3, tm=0.9, theta=11.0, phi=40.0)
+    cl = build_crystal(st, eng, fields=True)
+    cl.set_source(**src)
+    cl.solve()
+    plan = cl._get_plan(True)
+    assert plan.grid_separable
+    E, H = cl.fields_volume(X, Y, z)                                       # grid path
+    inc = np.hstack(cl.get_source_as_field_vectors()).reshape(1, 2, plan.n)
+    F = eng.fields(plan, cl._solved, [cl.source.wavelength], [cl.kp], inc, X.ravel(), Y.ravel(), [float(v) for v in z],
+                   cl.stack_positions).cpu().numpy()[0].reshape((len(z), 6) + X.shape)        # point path
+    assert np.abs(E - F[:, :3]).max() <= 1e-12 * np.abs(F).max()
+    assert np.abs(H - F[:, 3:]).max() <= 1e-12 * np.abs(F).max()
+    Xs = X + 0.05 * Y                                                      # sheared: not a meshgrid -> point path inside the API
+    E2, H2 = cl.fields_volume(Xs, Y, z)
+    kp = tuple(orc.kplanar(st["epsi"], src["wavelength"], src["theta"], src["phi"]))
+    sol = orc.solve_structure(st, src["wavelength"], kp)
+    Eo, Ho = orc.fields_volume(st, sol, Xs, Y, z, src["te"], src["tm"])
+    assert np.abs(E2 - Eo).max() <= 1e-9 * np.abs(Eo).max() and np.abs(H2 - Ho).max() <= 1e-9 * np.abs(Ho).max()
+
+
 def _twisted(eng, tw, ta):
     from khepri_b200 import Crystal, Expansion, Layer
     e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
