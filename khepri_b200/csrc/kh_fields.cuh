@@ -203,12 +203,15 @@ KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) {
             }
         }
         int iy = 0;
-        for (; iy + 2 <= nyl; iy += 2) {
-            cd f0 = mk(0, 0), f1 = mk(0, 0);
+        for (; iy + 4 <= nyl; iy += 4) {                                   // four independent accumulation chains per thread
+            cd f0 = mk(0, 0), f1 = mk(0, 0), f2 = mk(0, 0), f3 = mk(0, 0);
 #pragma unroll
-            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) { cfma(f0, T[q], Ys[q * nyl + iy]); cfma(f1, T[q], Ys[q * nyl + iy + 1]); }
-            out[(long long)(y0 + iy) * nx + ix] = f0;
-            out[(long long)(y0 + iy + 1) * nx + ix] = f1;
+            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) {
+                const cd* yq = Ys + q * nyl + iy;
+                cfma(f0, T[q], yq[0]); cfma(f1, T[q], yq[1]); cfma(f2, T[q], yq[2]); cfma(f3, T[q], yq[3]);
+            }
+            cd* o = out + (long long)(y0 + iy) * nx + ix;
+            o[0] = f0; o[nx] = f1; o[2LL * nx] = f2; o[3LL * nx] = f3;
         }
         for (; iy < nyl; ++iy) {
             cd f0 = mk(0, 0);

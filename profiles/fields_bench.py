@@ -47,7 +47,9 @@ def inc_vectors():
 
 inc = inc_vectors()
 cl.solve()            # sets stack_positions (crystal.py:196-203)
-for rep in range(2):
+F = None
+for rep in range(3):
+    del F                            # (the 13 GB output of the previous repetition goes back to the caching allocator)
     torch.cuda.synchronize()
     e0 = ev()
     solved = eng.solve_batch(plan, wl, kp, pol, want_flux=True, want_fields=True)
