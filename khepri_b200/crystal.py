@@ -180,7 +180,7 @@ class Crystal:
         f = layer.formulation
         if f == Formulation.UNIFORM:
             return {"kind": _lib.LAYER_UNIFORM, "eps": layer.epsilon, "depth": layer.depth, "retain": retain}
-        if f == Formulation.FFT:
+        if f == Formulation.FFT or f == Formulation.ANALYTICAL:
             Cm, ICm = layer.convmat_device(eng)
             return {"kind": _lib.LAYER_PIXMAP, "depth": layer.depth, "C": Cm, "IC": ICm, "retain": retain}
         if f == Formulation.HALF_SPACE_INC:
@@ -195,7 +195,7 @@ class Crystal:
             layer = self.layers[name]
             base = layer.base if isinstance(layer, EL) else layer
             eps = base.epsilon
-            key.append((name, id(layer), int(base.formulation), float(base.depth), id(eps) if isinstance(eps, np.ndarray) else complex(eps)))
+            key.append((name, id(layer), int(base.formulation), float(base.depth), id(eps) if isinstance(eps, (np.ndarray, list, tuple)) else complex(eps)))
         key.append(self.expansion._g_vectors.tobytes())
         return tuple(key)
 

@@ -23,5 +23,9 @@ class Drawing:
         self._canvas[inside] = epsilon
         self.geometric_description.append({"type": "rectangle", "params": [0.5 + x, 0.5 + y, 0.5 + x + wh[0], 0.5 + y + wh[1]], "epsilon": epsilon})
 
+    def islands(self):
+        """Geometric description for Crystal.add_layer_analytical (draw.py:108-109)."""
+        return self.geometric_description
+
     def canvas(self):
         return self._canvas.copy()

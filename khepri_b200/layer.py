@@ -60,9 +60,14 @@ class Layer:
 
     @classmethod
     def analytical(cls, expansion, islands_description, eps_host, depth):
-        raise NotImplementedError(
-            "add_layer_analytical / Layer.analytical is the next row of the hot-path scope (SURVEY.md 8f.1); "
-            "rasterise the islands to a pixmap and use Layer.pixmap for now.")
+        """layer.py:121-129: islands with closed-form Fourier transforms (Drawing.islands()) in a host medium."""
+        layer = cls()
+        layer.expansion = expansion
+        layer.formulation = Formulation.ANALYTICAL
+        layer.epsilon = islands_description
+        layer.eps_host = eps_host
+        layer.depth = depth
+        return layer
 
     @classmethod
     def half_infinite(cls, expansion, type, epsilon):
@@ -83,7 +88,11 @@ class Layer:
     def convmat_device(self, engine):
         key = (id(self.epsilon), tuple(self.expansion.pw), id(engine))
         if self._cache is None or self._cache[0] != key:
-            Cm = engine.convmat(np.asarray(self.epsilon), self.expansion.pw)[0]
+            if self.formulation == Formulation.ANALYTICAL:         # layer.py:161-168: analytic coefficients -> Toeplitz gather
+                from .fourier import analytical_coefficients
+                Cm = engine.toeplitz_gather(analytical_coefficients(self.expansion, self.epsilon, self.eps_host), self.expansion.pw)
+            else:
+                Cm = engine.convmat(np.asarray(self.epsilon), self.expansion.pw)[0]
             ICm, info = engine.zinv(Cm, return_info=True)
             if int(info.max().item()) != 0:
                 raise np.linalg.LinAlgError("Singular matrix")     # what np.linalg.inv raises in the reference

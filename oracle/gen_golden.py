@@ -40,6 +40,8 @@ def ref_crystal(st, fields=False):
     for name, spec in st["layers"].items():
         if spec[0] == "uniform":
             cl.add_layer_uniform(name, spec[1], spec[2])
+        elif spec[0] == "analytical":
+            cl.add_layer_analytical(name, spec[1], spec[3], spec[2])
         else:
             cl.add_layer_pixmap(name, spec[1], spec[2])
     cl.set_device(st["stack"], [fields] * len(st["stack"]))
@@ -182,5 +184,28 @@ def main():
     print("twisted done")
 
 
+def gen_analytical():
+    """layers from analytic island transforms (Crystal.add_layer_analytical, layer.py:161-174)."""
+    d = Drawing((64, 64), 2.2)
+    d.rectangle((0.1, -0.05), (0.5, 0.3), 6.0)
+    d.disc((-0.2, 0.15), 0.12, 1.0)
+    mine = [cases.rect_island((0.1, -0.05), (0.5, 0.3), 6.0), cases.disc_island((-0.2, 0.15), 0.12, 1.0)]
+    for a, b in zip(d.islands(), mine):
+        assert a["type"] == b["type"] and np.array_equal(np.asarray(a["params"], float), np.asarray(b["params"], float)) and a["epsilon"] == b["epsilon"]
+    out = {}
+    for which in ("tidy", "mixed", "rect"):
+        st, srcs = cases.case_analytical(which)
+        rt, _, cl = sweep(st, srcs)
+        name = [k for k, v in st["layers"].items() if v[0] == "analytical"][0]
+        out["RT_" + which] = rt
+        out["C_" + which] = np.asarray(cl.layers[name].C)
+    np.savez(os.path.join(OUT, "analytical.npz"), **out)
+    print("analytical done", out["RT_tidy"][:2])
+
+
 if __name__ == "__main__":
-    main()
+    if "--analytical" in sys.argv:
+        gen_analytical()
+    else:
+        main()
+        gen_analytical()

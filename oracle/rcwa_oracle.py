@@ -22,7 +22,7 @@ A *structure* is a plain dict::
 
     {"pw": (P, Q), "lattice": 2x2 array (rows = lattice vectors),
      "epsi": eps_incidence, "epse": eps_emergence,
-     "layers": {name: ("uniform", eps, depth) | ("pixmap", eps_xy, depth)},
+     "layers": {name: ("uniform", eps, depth) | ("pixmap", eps_xy, depth) | ("analytical", islands, depth, eps_host, lattice)},
      "stack": [names...]}            # device stack WITHOUT the two half spaces
 
 Each function cites the reference file:line it follows.
@@ -106,6 +106,51 @@ def fourier_coefficients(pixmap):
 def convolution_matrix(pixmap, pw):
     """tools.py:33-56."""
     return toeplitz_gather(fourier_coefficients(pixmap), pw)
+
+
+def _fexpz(z):
+    """fourier.py:8-20: (exp(z) - 1) / z, Horner series for |z| <= 1e-2."""
+    z = np.asarray(z, dtype=complex)
+    big = np.abs(z) > 1e-2
+    r = np.empty_like(z)
+    r[big] = (np.exp(z[big]) - 1.0) / z[big]
+    zs = z[~big]
+    r[~big] = 1 + zs / 2.0 * (1 + zs / 3.0 * (1 + zs / 4.0 * (1 + zs / 5.0 * (1 + zs / 6.0 * (1 + zs / 7)))))
+    return r
+
+
+def island_transform(kind, params, Gx, Gy, sigma):
+    """fourier.py:23-58: analytic Fourier transform of a rectangle / disc island."""
+    if kind == "rectangle":
+        ll0, ll1, ur0, ur1 = params
+        a, b = ur0 - ll0, ur1 - ll1
+        return a * b / sigma * _fexpz(-1j * Gx * a) * _fexpz(-1j * Gy * b) * np.exp(-1j * (ll0 * Gx + ll1 * Gy))
+    if kind == "disc":
+        from scipy import special
+        c0, c1, radius = params
+        norm = np.sqrt(Gx * Gx + Gy * Gy) * radius
+        zero = np.logical_and(np.isclose(Gx, 0.0), np.isclose(Gy, 0.0))
+        out = np.zeros_like(Gx, dtype=complex)
+        out[~zero] = (np.pi * radius ** 2 / sigma * 2 * np.exp(-1j * (c0 * Gx[~zero] + c1 * Gy[~zero]))
+                      * special.jv(1.0, norm[~zero]) / norm[~zero])
+        out[zero] = np.pi * radius ** 2 / sigma
+        return out
+    raise AttributeError(kind)
+
+
+def analytical_convolution_matrix(islands, eps_host, pw, lattice):
+    """layer.py:161-168 with expansion.py:86-92 and fourier.py:145-159: coefficients on the 3x oversampled harmonic
+    grid (flat, p fastest), reshaped to (3P, 3Q) -- the reference's `.T` on the 1-D array is a no-op -- then gathered."""
+    epw = [e * 3 if e > 1 else 1 for e in pw]
+    b = np.asarray(reciprocal_basis(lattice[0], lattice[1]), dtype=float)
+    idx = harmonic_indices(epw)
+    G = b[0][:, None] * idx[0][None, :] + b[1][:, None] * idx[1][None, :]
+    sigma = abs(lattice[0][0] * lattice[1][1] - lattice[0][1] * lattice[1][0])          # tools.unitcellarea
+    eps_g = np.zeros(G.shape[1], dtype=complex)
+    eps_g[(G.shape[1] - 1) // 2] = eps_host
+    for isl in islands:
+        eps_g += (isl["epsilon"] - eps_host) * island_transform(isl["type"], isl["params"], G[0], G[1], sigma)
+    return toeplitz_gather(eps_g.reshape(epw), pw)
 
 
 # --------------------------------------------------------------------------- #
@@ -286,6 +331,11 @@ def solve_layer(spec, g, pw, kp, wl):
     kind = spec[0]
     if kind == "pixmap":
         C = convolution_matrix(spec[1], pw)          # recomputed per solve, as the reference does
+        IC = inv(C)
+        W, V, L = structured_layer_modes(Kx, Ky, C)
+        S = layer_smatrix(W, V, W0, V0, L, spec[2], k0)
+    elif kind == "analytical":                       # ("analytical", islands, eps_host, depth, lattice)
+        C = analytical_convolution_matrix(spec[1], spec[3], pw, spec[4])
         IC = inv(C)
         W, V, L = structured_layer_modes(Kx, Ky, C)
         S = layer_smatrix(W, V, W0, V0, L, spec[2], k0)

@@ -142,3 +142,37 @@ def twisted_case(pw=(3, 3), nf=3, nt=3):
     freqs = np.linspace(0.7, 0.83, 50)[:: 50 // nf][:nf]
     twists = np.deg2rad(np.linspace(0, 45, 50))[3:: 50 // nt][:nt]
     return {"pw": pw, "pixmap": pm, "depths": (0.2, 0.3, 0.2), "freqs": freqs, "twists": twists}
+
+
+def rect_island(center, wh, eps):
+    """khepri/draw.py:46-55 (Drawing.rectangle's geometric description)."""
+    x, y = center[0] - wh[0] / 2, center[1] - wh[1] / 2
+    return {"type": "rectangle", "params": [0.5 + x, 0.5 + y, 0.5 + x + wh[0], 0.5 + y + wh[1]], "epsilon": eps}
+
+
+def disc_island(center, radius, eps):
+    """khepri/draw.py:41-44."""
+    return {"type": "disc", "params": [0.5 + center[0], 0.5 + center[1], radius], "epsilon": eps}
+
+
+def case_analytical(which="tidy"):
+    """Layers from analytic island transforms (Crystal.add_layer_analytical).
+    tidy : test/integration/test_tidy.py:13-31 (square rod eps 4 in air, depth 1, 13 wavelengths, pol (1,1)), 7x7 harmonics
+    mixed: asymmetric rectangle + disc in a host of eps 2.2 over a uniform slab, oblique incidence, 5x5
+    rect : pw = (3, 5), exposes the reference's reshape of the coefficient table for P != Q"""
+    lat = np.eye(2)
+    if which == "tidy":
+        layers = {"1": ("analytical", [rect_island((0, 0), (0.5, 0.5), 4)], 1.0, 1, lat)}
+        st = _st((7, 7), layers, ["1"])
+        srcs = [dict(wavelength=float(w), te=1.0, tm=1.0, theta=0.0, phi=0.0) for w in np.linspace(1.01, 2, 13)]
+    elif which == "mixed":
+        isl = [rect_island((0.1, -0.05), (0.5, 0.3), 6.0), disc_island((-0.2, 0.15), 0.12, 1.0)]
+        layers = {"A": ("analytical", isl, 0.4, 2.2, lat), "U": ("uniform", 1.5, 0.3)}
+        st = _st((5, 5), layers, ["A", "U", "A"], epse=2.0)
+        srcs = [dict(wavelength=float(w), te=0.7, tm=0.4, theta=12.0, phi=33.0) for w in np.linspace(1.2, 1.9, 9)]
+    else:
+        isl = [rect_island((0.05, 0.1), (0.4, 0.6), 5.0)]
+        layers = {"A": ("analytical", isl, 0.5, 1.0, lat)}
+        st = _st((3, 5), layers, ["A"])
+        srcs = [dict(wavelength=float(w), te=1.0, tm=0.5, theta=5.0, phi=10.0) for w in np.linspace(1.3, 1.8, 6)]
+    return st, srcs

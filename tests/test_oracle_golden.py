@@ -128,3 +128,15 @@ def test_twisted_bilayer_extended():
             sol["layers"]["Sref"]["W"] = sol["layers"]["Strans"]["W"] = np.identity(sol["Stot"].shape[-1])
             rt[i, j] = orc.flux_end(st, sol, 1.0, 0.0)
     np.testing.assert_allclose(rt, g["RT"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("which", ["tidy", "mixed", "rect"])
+def test_analytical_layers(which):
+    """add_layer_analytical (analytic island transforms -> Toeplitz gather), layer.py:161-174."""
+    g = gold("analytical")
+    st, srcs = cases.case_analytical(which)
+    name, spec = [(k, v) for k, v in st["layers"].items() if v[0] == "analytical"][0]
+    C = orc.analytical_convolution_matrix(spec[1], spec[3], st["pw"], spec[4])
+    assert np.abs(C - g["C_" + which]).max() <= 1e-14 * np.abs(g["C_" + which]).max()
+    rt = oracle_sweep(st, srcs)
+    assert np.abs(rt - g["RT_" + which]).max() <= 1e-10

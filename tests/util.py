@@ -45,6 +45,8 @@ def build_crystal(st, eng, fields=False):
     for name, spec in st["layers"].items():
         if spec[0] == "uniform":
             cl.add_layer_uniform(name, spec[1], spec[2])
+        elif spec[0] == "analytical":
+            cl.add_layer_analytical(name, spec[1], spec[3], spec[2])
         else:
             cl.add_layer_pixmap(name, spec[1], spec[2])
     cl.set_device(st["stack"], [fields] * len(st["stack"]))
