@@ -99,8 +99,9 @@ def test_source_and_incident_vector():
     assert cl.kp == (0.1, 0.2)
     with pytest.raises(NotImplementedError):
         Crystal((3, 3), lattice="kagome")
-    with pytest.raises(NotImplementedError):
-        cl.add_layer_analytical("a", [], 1.0, 0.1)
+    from khepri_b200 import Formulation
+    cl.add_layer_analytical("a", [{"type": "disc", "params": [0.5, 0.5, 0.2], "epsilon": 2.0}], 1.0, 0.1)     # layer.py:121-129
+    assert cl.layers["a"].formulation == Formulation.ANALYTICAL and cl.layers["a"].eps_host == 1.0
 
 
 def test_set_device_adds_half_spaces_like_the_reference():
