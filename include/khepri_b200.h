@@ -146,6 +146,13 @@ int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl_dev, const
                          const double* z_host, int nz, const double* zpos_host, void* F_dev,
                          void* ws_dev, size_t ws_bytes, void* stream);
 
+/* ---- Brillouin-zone-integration source (beams.py:164-191, amplitudes_from_fields) ---------------- */
+/* amp_dev [B][N][4] c128 = scale * sum_p fields_dev[p][c] exp(-i ((kp[b] + g) . r_p)), c = (Ex, Ey, Hx, Hy);
+ * kp_dev [B][2] c128, g_dev [2][N] f64, x_dev / y_dev [npts] f64, fields_dev [npts][4] c128. */
+size_t kh_beam_amplitudes_work_bytes(int B, int N, int npts);
+int kh_beam_amplitudes(int B, int N, int npts, const void* kp_dev, const double* g_dev, const double* x_dev, const double* y_dev,
+                       const void* fields_dev, double scale, void* amp_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- measurement helper --------------------------------------------------------------------- */
 /* FP64 peak probe on the current device (registers only): mode 0 = DFMA stream, 1 = DMMA m8n8k4
  * stream.  Synchronous; returns TFLOP/s.  Used by bench.py for the roofline denominator that

@@ -6,6 +6,7 @@ package does not need a GPU; constructing an Engine (or solving a Crystal) does,
 without one -- there is no CPU fallback.
 """
 from .crystal import Crystal, Multilayer
+from . import beams
 from .draw import Drawing
 from .engine import Engine
 from .expansion import Expansion
@@ -13,4 +14,4 @@ from .extension import ExtendedLayer
 from .layer import Field, Formulation, Layer
 from ._lib import KhepriError
 
-__all__ = ["Crystal", "Multilayer", "Drawing", "Engine", "Expansion", "ExtendedLayer", "Field", "Formulation", "Layer", "KhepriError"]
+__all__ = ["beams", "Crystal", "Multilayer", "Drawing", "Engine", "Expansion", "ExtendedLayer", "Field", "Formulation", "Layer", "KhepriError"]

@@ -335,6 +335,35 @@ class Crystal:
                                self.stack_positions, grid=grid)
         return F[0]
 
+    def fields_batch_sum(self, wavelengths, kps, incident_fields, x, y, zs, chunk=64):
+        """Sum over a batch of sources of the field maps (Ex,Ey,Ez,Hx,Hy,Hz)(z, y, x): the k-sum of the Brillouin-zone
+        integration loop (examples/bzi/bzi_animation.py:59-80) -- solve with retained eigenspaces, reconstruct with each
+        source's own incident amplitudes [B, 4N] = (Ex_g, Ey_g, Hx_g, Hy_g), accumulate on the device.
+        Returns a DEVICE tensor [nz, 6, ny * nx]."""
+        import torch
+        wl = np.atleast_1d(np.asarray(wavelengths, dtype=np.float64)).reshape(-1)
+        B = wl.size
+        kp = np.asarray(kps, dtype=np.complex128).reshape(B, 2)
+        plan = self._get_plan(True)
+        inc = np.asarray(incident_fields, dtype=np.complex128).reshape(B, 2, plan.n)
+        layer_sizes = [self.layers[name].depth for name in self.global_stacking]
+        pos = list(np.cumsum(layer_sizes))
+        pos[-1] = np.inf
+        if not self.void:
+            pos.insert(0, -np.inf)
+        x, y = ensure_array(x), ensure_array(y)
+        grid = None
+        if x.ndim == 2 and x.shape == y.shape and np.all(x == x[:1, :]) and np.all(y == y[:, :1]):
+            grid = (x[0, :], y[:, 0])
+        total = torch.zeros((len(zs), 6, x.size), dtype=torch.complex128, device=self.engine.device)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            res = self.engine.solve_batch(plan, wl[lo:hi], kp[lo:hi], want_S=False, want_flux=False, want_fields=True)
+            self._check_info(res["info"])
+            F = self.engine.fields(plan, res, wl[lo:hi], kp[lo:hi], inc[lo:hi], x.ravel(), y.ravel(), zs, pos, grid=grid)
+            total += F.sum(dim=0)
+        return total
+
     def fields_coords_xy(self, x, y, z, incident_fields=None, kp=None, return_fourier=False):
         """E and H at the points (x, y) of depth z (crystal.py:297-333) -> [E(3,ny,nx), H(3,ny,nx)]."""
         x, y = ensure_array(x), ensure_array(y)

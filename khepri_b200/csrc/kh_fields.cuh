@@ -145,13 +145,13 @@ KH_DEV void fld_z_body(const Cta& c, const fld_z_args& a) {
 }
 
 // phase matrix Ph[b][g][p] = exp(i (kx_g x_p + ky_g y_p)),  kx_g = kp_x + g_x (not normalised)
-struct fld_phase_args { int B, N, npts; const cd* kp; const double* g; const double* x; const double* y; cd* Ph; };
+struct fld_phase_args { int B, N, npts; const cd* kp; const double* g; const double* x; const double* y; cd* Ph; double sign = 1.0; };
 KH_DEV void fld_phase_body(const Cta& c, const fld_phase_args& a) {
     const int b = c.bx, g = c.by;
     cd kx = mk(a.kp[2 * b].x + a.g[g], a.kp[2 * b].y), ky = mk(a.kp[2 * b + 1].x + a.g[a.N + g], a.kp[2 * b + 1].y);
     cd* o = a.Ph + ((long long)b * a.N + g) * a.npts;
     for (int p = c.tid; p < a.npts; p += c.nthr) {
-        cd arg = a.x[p] * kx + a.y[p] * ky;
+        cd arg = a.sign * (a.x[p] * kx + a.y[p] * ky);
         o[p] = cexp_(mk(-arg.y, arg.x));
     }
 }
@@ -385,4 +385,30 @@ extern "C" int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl
                                     void* ws_dev, size_t ws_bytes, void* stream) {
     if (nx < 1 || ny < 1) return fail(KH_EINVAL, "kh_fields_grid_batch: bad grid");
     return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, xs_dev, ys_dev, nx * ny, 1, nx, ny, z_host, nz, zpos_host, F_dev, ws_dev, ws_bytes, stream);
+}
+
+
+// ---- Brillouin-zone-integration source (khepri/beams.py:164-191, amplitudes_from_fields): Fourier amplitudes of a
+// real-space beam for every k-point of the BZ grid,
+//     amp[b][g][c] = scale * sum_p F[p][c] exp(-i ((kp_x[b] + g_x) x_p + (kp_y[b] + g_y) y_p)),   c = (Ex, Ey, Hx, Hy)
+// (the reference divides the samples by the Bloch phase of k and calls slow_dft per supercell tile; the sum over tiles is
+// one sum over all samples).  Phase matrix by fld_phase (sign -1), then ONE DMMA GEMM  [N x npts] . [npts x 4]  per k-point
+// with the sample matrix shared by the whole batch.
+extern "C" size_t kh_beam_amplitudes_work_bytes(int B, int N, int npts) {
+    return (size_t)B * N * npts * sizeof(cd) + 512;
+}
+extern "C" int kh_beam_amplitudes(int B, int N, int npts, const void* kp_dev, const double* g_dev, const double* x_dev, const double* y_dev,
+                                  const void* fields_dev, double scale, void* amp_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+    if (B < 0 || N < 1 || npts < 1 || !kp_dev || !g_dev || !x_dev || !y_dev || !fields_dev || !amp_dev || !ws_dev)
+        return fail(KH_EINVAL, "kh_beam_amplitudes: bad arguments");
+    if (ws_bytes < kh_beam_amplitudes_work_bytes(B, N, npts)) return fail(KH_ENOMEM, "kh_beam_amplitudes: workspace too small");
+    if (B == 0) return 0;
+    kh_stream_t st = (kh_stream_t)stream;
+    Bump bump{(char*)ws_dev, ws_bytes, 0};
+    cd* Ph = bump.get<cd>((size_t)B * N * npts);
+    {   fld_phase_args a{B, N, npts, (const cd*)kp_dev, g_dev, x_dev, y_dev, Ph, -1.0};
+        KH_TRY((kh_launch<fld_phase_args, fld_phase_body>(dim3(B, N), 256, 0, st, a, "beam_phase"))); }
+    zgemm_args g = zgemm_make(N, 4, npts, mref(Ph, (long long)N * npts, npts), mref(fields_dev, 0, 4), mref(amp_dev, (long long)N * 4, 4), scale);
+    KH_TRY(zgemm_launch(st, B, g));
+    return 0;
 }

@@ -324,6 +324,25 @@ class Engine:
               "kh_fields_batch")
         return F
 
+    def beam_amplitudes(self, kps, g, x, y, fields4, scale):
+        """beams.amplitudes_from_fields for a batch of k-points -> DEVICE [B, N, 4] (Ex, Ey, Hx, Hy per harmonic)."""
+        kp_d = self.to_dev(np.asarray(kps, dtype=np.complex128).reshape(-1, 2), _c128)
+        g_d = self.to_dev(np.ascontiguousarray(g, dtype=np.float64), _f64)
+        x_d = self.to_dev(np.asarray(x, dtype=np.float64).reshape(-1), _f64)
+        y_d = self.to_dev(np.asarray(y, dtype=np.float64).reshape(-1), _f64)
+        f_d = self.to_dev(np.asarray(fields4, dtype=np.complex128).reshape(-1, 4), _c128)
+        B, N, npts = kp_d.shape[0], g_d.shape[1], x_d.numel()
+        assert f_d.shape[0] == npts and y_d.numel() == npts
+        amp = torch.empty((B, N, 4), dtype=_c128, device=self.device)
+        cap = max(1, int((4 << 30) // (N * npts * 16)))               # k-points per call: phase matrix <= 4 GB
+        for lo in range(0, B, cap):
+            hi = min(B, lo + cap)
+            wb = self.lib.kh_beam_amplitudes_work_bytes(hi - lo, N, npts)
+            ws = self.workspace(wb)
+            check(self.lib, self.lib.kh_beam_amplitudes(hi - lo, N, npts, _ptr(kp_d[lo:hi]), _ptr(g_d), _ptr(x_d), _ptr(y_d), _ptr(f_d), float(scale),
+                                                        _ptr(amp[lo:hi]), _ptr(ws), ws.numel(), self.stream()), "kh_beam_amplitudes")
+        return amp
+
     def _fields_grid(self, plan, solved, wl, kp, inc, xs, ys, z, stack_positions):
         B = solved["prefix"].shape[0]
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)

@@ -203,9 +203,40 @@ def gen_analytical():
     print("analytical done", out["RT_tidy"][:2])
 
 
+def gen_bzi_beam():
+    """BZI source amplitudes (beams.amplitudes_from_fields) and the k-summed field maps (bzi_animation.py:41-80)."""
+    from khepri.beams import _paraxial_gaussian_field_fn, shifted_rotated_fields, amplitudes_from_fields
+    st, c = cases.case_bzi_beam()
+    b = c["beam"]
+    X, Y = c["X"], c["Y"]
+    src = shifted_rotated_fields(_paraxial_gaussian_field_fn, X, Y, np.zeros_like(X), b["wl"], b["x0"], b["y0"], b["z0"],
+                                 b["theta"], b["phi"], b["pol"], beam_waist=b["beam_waist"], er=b["er"])
+    src = np.asarray(src)
+    if src.ndim == 5:                                                            # numpy >= 2: solve() keeps a trailing singleton (beams.py:69-71)
+        src = src[..., 0]
+    src = np.swapaxes(np.swapaxes(src, 0, 2), 1, 3)                             # (ny, nx, 2, 3) as in the example
+    e1 = Expansion(st["pw"])
+    xo, yo, zo = c["out"]
+    amps, total = [], None
+    for kp in c["kbz"]:
+        cl = ref_crystal(st, fields=True)
+        cl.set_source(c["wl"], np.nan, np.nan, kp=tuple(kp))
+        cl.solve()
+        F = amplitudes_from_fields(src, e1, c["wl"], tuple(kp), X, Y, c["bz"])
+        amps.append(F)
+        S, U = np.split(F.flatten(), 2)
+        E, H = cl.fields_volume(xo, yo, zo, incident_fields=(S, U))
+        total = np.asarray((E, H)) if total is None else total + np.asarray((E, H))
+    np.savez(os.path.join(OUT, "bzi_beam.npz"), source=src, amplitudes=np.array(amps), fields=total)
+    print("bzi beam done", np.abs(total).max())
+
+
 if __name__ == "__main__":
-    if "--analytical" in sys.argv:
+    if "--bzi-beam" in sys.argv:
+        gen_bzi_beam()
+    elif "--analytical" in sys.argv:
         gen_analytical()
     else:
         main()
         gen_analytical()
+        gen_bzi_beam()

@@ -486,11 +486,14 @@ def fields_fourier_at(st, sol, z, inc_eh):
     return sx, sy, sz, ux, uy, uz
 
 
-def fields_volume(st, sol, x, y, zs, te, tm):
-    """crystal.py:285-343 -> (E, H), each (nz, 3, ny, nx)."""
+def fields_volume(st, sol, x, y, zs, te, tm, incident_fields=None):
+    """crystal.py:285-343 -> (E, H), each (nz, 3, ny, nx).  incident_fields: explicit (E, H) Fourier vectors [4N]."""
     wl, kp, g = sol["wl"], sol["kp"], sol["g"]
-    e = incident_vector(st["pw"], te, tm, (kp[0], kp[1], source_kzi(st, wl, kp)))
-    inc = np.concatenate([e, np.zeros_like(e)])
+    if incident_fields is None:
+        e = incident_vector(st["pw"], te, tm, (kp[0], kp[1], source_kzi(st, wl, kp)))
+        inc = np.concatenate([e, np.zeros_like(e)])
+    else:
+        inc = np.asarray(incident_fields, dtype=complex).reshape(-1)
     Kx, Ky, _ = k_vectors(g, kp, wl)
     k0 = TWO_PI / wl
     out = np.empty((len(zs), 6) + x.shape, dtype=complex)
@@ -499,6 +502,18 @@ def fields_volume(st, sol, x, y, zs, te, tm):
         for c, s in enumerate(comps):
             out[iz, c] = idft(s, k0 * Kx, k0 * Ky, x, y)
     return out[:, :3], out[:, 3:]
+
+
+def beam_amplitudes(fields, g, kp, x, y, bzs):
+    """beams.py:164-191 (amplitudes_from_fields): samples (ny, nx, 2, 3) of a real-space source on the supercell points
+    (x, y), divided by the Bloch phase of kp, transformed tile by tile with slow_dft (fourier.py:93-104) on the harmonics g,
+    each tile normalised by n_tiles * NS (sic) and summed -> (4, N) = (Ex, Ey, Hx, Hy)_g."""
+    fields = np.asarray(fields)
+    ny, nx = fields.shape[:2]
+    NS = ny // bzs[1]
+    F = (fields / np.exp(1j * (kp[0] * x + kp[1] * y))[..., None, None])[..., :2].reshape(ny * nx, 4)
+    ph = np.exp(-1j * (g[0][None, :] * x.reshape(-1, 1) + g[1][None, :] * y.reshape(-1, 1)))        # [pts, N]
+    return (F.T @ ph) / (bzs[0] * bzs[1]) / NS
 
 
 # --------------------------------------------------------------------------- #

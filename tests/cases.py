@@ -176,3 +176,21 @@ def case_analytical(which="tidy"):
         st = _st((3, 5), layers, ["A"])
         srcs = [dict(wavelength=float(w), te=1.0, tm=0.5, theta=5.0, phi=10.0) for w in np.linspace(1.3, 1.8, 6)]
     return st, srcs
+
+
+def case_bzi_beam(bz=(5, 1), NS=7, pw=(3, 1)):
+    """examples/bzi/bzi_animation.py at test size: 1-D grating (pw = (P, 1)), Gaussian beam at 25 degrees sampled on a
+    supercell of bz unit cells with NS x NS samples each, BZ grid of bz k-points shifted by the beam's k-parallel."""
+    wl, theta, eps1, eps2, zmax = 1.1, np.deg2rad(25.0), 1.0, 4.0, 6.0
+    pm = rect_pixmap((64, 64), eps1, (0, 0), (0.5, 1), eps2)
+    layers = {"S1": ("uniform", eps1, 0.99), "S3": ("pixmap", pm, 0.4), "S2": ("uniform", eps2, 2.99)}
+    st = _st(pw, layers, ["S1"] * 2 + ["S3", "S2"], epsi=eps1, epse=eps2)
+    X, Y = np.meshgrid(np.linspace(0, bz[0], NS * bz[0], endpoint=True), np.linspace(0, bz[1], NS * bz[1], endpoint=True))
+    si, sj = 1 / bz[0], 1 / bz[1]
+    i, j = np.meshgrid(np.arange(-0.5 + si / 2, 0.5, si), np.arange(-0.5 + sj / 2, 0.5, sj), indexing="ij")
+    kbz = np.stack([2 * np.pi * i, 2 * np.pi * j]).reshape(2, -1).T.copy()
+    kbz[:, 0] += np.sqrt(eps1) * 2 * np.pi / wl * np.sin(theta)
+    xo, yo = np.meshgrid(np.linspace(0, bz[0], 24), np.linspace(bz[1] / 2, bz[1] / 2, 3), indexing="xy")
+    zo = np.linspace(0.01, zmax, 5)
+    beam = dict(wl=wl, x0=bz[0] / 2, y0=bz[1] / 2, z0=-zmax / 2, theta=theta, phi=0.0, pol=np.pi / 2, beam_waist=2 * wl, er=eps1)
+    return st, dict(wl=wl, bz=bz, NS=NS, X=X, Y=Y, kbz=kbz, beam=beam, out=(xo, yo, zo))

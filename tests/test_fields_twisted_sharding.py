@@ -92,6 +92,34 @@ def test_fields_grid_path_matches_point_path(backend):
     assert np.abs(E2 - Eo).max() <= 1e-9 * np.abs(Eo).max() and np.abs(H2 - Ho).max() <= 1e-9 * np.abs(Ho).max()
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_bzi_beam_source_and_k_summed_fields(backend):
+    """per-k source amplitudes (kh_beam_amplitudes) and the Brillouin-zone sum of the field maps, against the
+    unmodified reference (examples/bzi/bzi_animation.py at test size: 1-D grating pw = (3, 1), 5 k-points)."""
+    from khepri_b200 import Expansion
+    from khepri_b200.beams import amplitudes_from_fields, bzi_fields, paraxial_gaussian_field, shifted_rotated_fields
+    eng = engine(backend)
+    g = gold("bzi_beam")
+    st, c = cases.case_bzi_beam()
+    b = c["beam"]
+    X, Y = c["X"], c["Y"]
+    src = shifted_rotated_fields(paraxial_gaussian_field, X, Y, np.zeros_like(X), b["wl"], b["x0"], b["y0"], b["z0"],
+                                 b["theta"], b["phi"], b["pol"], beam_waist=b["beam_waist"], er=b["er"])
+    src = np.swapaxes(np.swapaxes(np.asarray(src), 0, 2), 1, 3)
+    assert np.abs(src - g["source"]).max() <= 1e-12 * np.abs(g["source"]).max()          # beam synthesis (host)
+    e1 = Expansion(st["pw"])
+    A = amplitudes_from_fields(g["source"], e1, c["wl"], c["kbz"], X, Y, c["bz"], engine=eng)       # [B, 4, N], batched over k
+    assert A.shape == g["amplitudes"].shape
+    assert np.abs(A - g["amplitudes"]).max() <= 1e-11 * np.abs(g["amplitudes"]).max()
+    A0 = amplitudes_from_fields(g["source"], e1, c["wl"], tuple(c["kbz"][0]), X, Y, c["bz"], engine=eng)   # the reference's call
+    assert A0.shape == (4, e1._g_vectors.shape[1]) and np.abs(A0 - A[0]).max() <= 1e-13 * np.abs(A).max()
+    cl = build_crystal(st, eng, fields=True)
+    xo, yo, zo = c["out"]
+    E, H = bzi_fields(cl, c["wl"], c["kbz"], A.reshape(len(c["kbz"]), -1), xo, yo, zo)
+    got = np.asarray((E, H))
+    assert np.abs(got - g["fields"]).max() <= 1e-9 * np.abs(g["fields"]).max()
+
+
 def _twisted(eng, tw, ta):
     from khepri_b200 import Crystal, Expansion, Layer
     e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
@@ -149,8 +177,14 @@ def _rank_main(rank, world, port, out):
     R, T = sweep_sharded(cl, wl, te=1.0, tm=0.0)
     part = torch.full((3,), complex(rank + 1, -rank), dtype=torch.complex128)
     tot = allreduce_sum(part)
+    # Brillouin-zone-integrated field maps: 5 k-points over 2 ranks (3 + 2), partial sums all-reduced
+    from khepri_b200.beams import bzi_fields
+    stb, c = cases.case_bzi_beam()
+    clb = build_crystal(stb, eng, fields=True)
+    xo, yo, zo = c["out"]
+    E, H = bzi_fields(clb, c["wl"], c["kbz"], gold("bzi_beam")["amplitudes"].reshape(len(c["kbz"]), -1), xo, yo, zo)
     if rank == 0:
-        np.savez(out, R=R, T=T, tot=tot.numpy())
+        np.savez(out, R=R, T=T, tot=tot.numpy(), EH=np.asarray((E, H)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -164,6 +198,8 @@ def test_sweep_sharded_two_ranks_gloo(tmp_path):
     g = gold("suh03")
     assert np.abs(np.stack([res["R"], res["T"]], 1) - g["RT"][:7]).max() <= 1e-9
     assert np.allclose(res["tot"], complex(3, -1))
+    gb = gold("bzi_beam")["fields"]
+    assert np.abs(res["EH"] - gb).max() <= 1e-9 * np.abs(gb).max()
 
 
 @pytest.mark.gpu

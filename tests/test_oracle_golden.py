@@ -140,3 +140,19 @@ def test_analytical_layers(which):
     assert np.abs(C - g["C_" + which]).max() <= 1e-14 * np.abs(g["C_" + which]).max()
     rt = oracle_sweep(st, srcs)
     assert np.abs(rt - g["RT_" + which]).max() <= 1e-10
+
+
+def test_bzi_beam_amplitudes_and_summed_fields():
+    """beams.amplitudes_from_fields + the k-sum of fields_volume (examples/bzi/bzi_animation.py:41-80)."""
+    g = gold("bzi_beam")
+    st, c = cases.case_bzi_beam()
+    gv = orc.g_vectors(st["pw"], st["lattice"])
+    xo, yo, zo = c["out"]
+    total = 0
+    for i, kp in enumerate(c["kbz"]):
+        A = orc.beam_amplitudes(g["source"], gv, kp, c["X"], c["Y"], c["bz"])
+        assert np.abs(A - g["amplitudes"][i]).max() <= 1e-12 * np.abs(g["amplitudes"]).max()
+        sol = orc.solve_structure(st, c["wl"], tuple(kp))
+        E, H = orc.fields_volume(st, sol, xo, yo, zo, None, None, incident_fields=A.reshape(-1))
+        total = total + np.asarray((E, H))
+    assert np.abs(total - g["fields"]).max() <= 1e-9 * np.abs(g["fields"]).max()
