@@ -201,7 +201,7 @@ struct zir_unroll<TR, L, L> {
 
 template <int TR>
 __device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) {
-    constexpr int L = (TR == 2) ? 10 : 20;             // lcm(TR, 5)
+    constexpr int L = (TR == 2) ? 10 : ((TR == 3) ? 15 : 20);             // lcm(TR, 5)
     const int n = a.n, b = c.bx, tid = c.tid, lane = tid & 31;
     const cd* A = mat_ptr(a.A, b);
     cd* Out = mat_ptr(a.Ainv, b);
@@ -249,6 +249,8 @@ __device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) 
 __device__ __forceinline__ void zinv_reg_small_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
 __device__ __forceinline__ void zinv_reg_mid_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
 __device__ __forceinline__ void zinv_reg_large_body(const Cta& c, const zinv_args& a) { zinv_reg_body<4>(c, a); }
+__device__ __forceinline__ void zinv_reg_t3_body(const Cta& c, const zinv_args& a) { zinv_reg_body<3>(c, a); }
+__device__ __forceinline__ void zinv_reg_t2x_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -380,7 +382,7 @@ static inline int zinvb_nb(int n) {
 // work space of the blocked variant, in complex elements per matrix (pivot rows + pivot indices)
 static inline long long zinv_work_cd(int n) { return (long long)zinvb_nb(n) * n + (n + 3) / 4 + 4; }
 #ifndef KH_ZINV_BLOCKED_MIN
-#define KH_ZINV_BLOCKED_MIN 119
+#define KH_ZINV_BLOCKED_MIN 101
 #endif
 
 static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work) {
@@ -439,6 +441,12 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
         const double work = 8.0 * n * n * n * batch;
         if (tiles2 <= 256) return kh_launch<zinv_args, zinv_reg_small_body, 256, 2>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
         if (tiles2 <= 512) return kh_launch<zinv_args, zinv_reg_mid_body, 512, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
+#ifndef KH_ZINV_VARIANT
+#define KH_ZINV_VARIANT 0
+#endif
+        const int tiles3 = txn * ((n + 2) / 3);
+        if (KH_ZINV_VARIANT == 1 && tiles3 <= 704) return kh_launch<zinv_args, zinv_reg_t3_body, 704, 1>(dim3(batch), ((tiles3 + 31) / 32) * 32, sm, st, a, "zinv", work);
+        if (KH_ZINV_VARIANT == 2 && tiles2 <= 1024) return kh_launch<zinv_args, zinv_reg_t2x_body, 1024, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
         return kh_launch<zinv_args, zinv_reg_large_body, 512, 1>(dim3(batch), ((tiles4 + 31) / 32) * 32, sm, st, a, "zinv", work);
     }
 #endif

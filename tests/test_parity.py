@@ -260,7 +260,7 @@ def test_energy_conservation_and_batch_invariance(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("n", [119, 150, 242, 450])
+@pytest.mark.parametrize("n", [101, 119, 150, 242, 450])
 def test_zinv_blocked(backend, n):
     """Tiled inverse (blocked Gauss-Jordan panels + DMMA GEMM updates) for matrices beyond shared memory."""
     if backend != "cuda" and n > 150:
