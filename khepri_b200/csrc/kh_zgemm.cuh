@@ -55,9 +55,11 @@ template <int N> __device__ __forceinline__ void kh_cp_async_wait() { asm volati
 template <int NW, int NT>
 KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
     constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, THREADS = 32 * NW;
-    const int b = c.bx;
-    const int tiles_n = (a.N + BN - 1) / BN;
-    const int m0 = (c.by / tiles_n) * BM, n0 = (c.by % tiles_n) * BN;
+    // 1-D grid, tile index fastest: the CTAs that share a matrix's A / B panels are launched next to each other, so the
+    // second reader of a panel finds it in L2 (with the batch index fastest every panel was fetched from HBM once per tile)
+    const int tiles_n = (a.N + BN - 1) / BN, tiles = ((a.M + BM - 1) / BM) * tiles_n;
+    const int b = c.bx / tiles, tile = c.bx - b * tiles;
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
     const cd* A = mat_ptr(a.A, b);
     const cd* B = mat_ptr(a.B, b);
     const cd* Cin = mat_ptr(a.Cin, b);
@@ -167,11 +169,11 @@ static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64)) {
         int tiles = ((a.M + 55) / 56) * ((a.N + 55) / 56);
         size_t sm = (size_t)2 * (56 * ZG_LDA + ZG_BK * 58) * sizeof(cd);
-        return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(batch, tiles), 224, sm, st, a, "zgemm", work);
+        return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3((unsigned)batch * tiles), 224, sm, st, a, "zgemm", work);
     }
     int tiles = ((a.M + 63) / 64) * ((a.N + 63) / 64);
     size_t sm = (size_t)2 * (64 * ZG_LDA + ZG_BK * 66) * sizeof(cd);
-    return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(batch, tiles), 256, sm, st, a, "zgemm", work);
+    return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3((unsigned)batch * tiles), 256, sm, st, a, "zgemm", work);
 }
 
 // convenience builder: plain C = alpha*A*B (+ beta*Cin) on [batch, n, n] row-major stacks

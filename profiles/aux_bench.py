@@ -65,6 +65,16 @@ fr = np.linspace(0.4 / 1.414, 0.65 / 1.414, 200); kxw = np.linspace(0, 0.99 * np
 wlw = np.tile(1 / fr, 4); kpw = np.stack([np.repeat(kxw, 200), np.zeros(800)], 1); polw = np.ones((800, 2))
 sweep_rate("C3 woodpile 11x11 (200 freqs x 4 kx)", cases.woodpile_structure((11, 11)), wlw, kpw, polw, reps=2)
 
+# ---- 13x13 and 15x15 direct bases (the large end of the north-star range; Twisted.ipynb cell 6-8 geometry: two pixmap layers)
+def two_layer_structure(pp, res=256):
+    pm = cases.disc_pixmap((res, res), 4.0, (0.0, 0.0), 0.25, 1.0)
+    layers = {"A": ("pixmap", pm, 0.2), "B": ("pixmap", pm.T.copy() + 0.5 * cases.rect_pixmap((res, res), 0.0, (0.1, 0.0), (0.3, 0.5), 1.0), 0.2), "U": ("uniform", 1.0, 0.3)}
+    return cases._st((pp, pp), layers, ["A", "U", "B"])
+
+for pp, nf in ((13, 120), (15, 60)):
+    fq = np.linspace(0.7, 0.83, nf)
+    sweep_rate(f"direct {pp}x{pp} supercell basis, two pixmap layers ({nf} freqs)", two_layer_structure(pp), 1 / fq, np.zeros((nf, 2)), np.tile([[1.0, 0.0]], (nf, 1)), reps=2)
+
 # ---- C4: twisted bilayer (3,3)+(3,3), n = 162 (extended RCWA)
 tw = cases.twisted_case()
 e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
