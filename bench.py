@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="bzi77", choices=sorted(WORKLOADS))
     ap.add_argument("--kpoints", type=int, default=41, help="k-points per step per GPU (x wavelengths = solves per step)")
-    ap.add_argument("--workspace-gb", type=float, default=32.0)
+    ap.add_argument("--workspace-gb", type=float, default=40.0)
     ap.add_argument("--cpu-solves", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

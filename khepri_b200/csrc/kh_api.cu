@@ -388,6 +388,10 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
     long long chunk = 1 + (long long)((ws_bytes - per1) / (slope + 1024));
     if (chunk > B) chunk = B;
     while (chunk > 1 && kh_solve_workspace_bytes(p, (int)chunk, flags) > ws_bytes) --chunk;
+    if (chunk < B) {                           // balance the chunks: a remainder of a few solves would pay the full latency of every kernel
+        const long long nch = (B + chunk - 1) / chunk;
+        chunk = (B + nch - 1) / nch;
+    }
 
     if (out->info_dev) { zero_int_args z{B, out->info_dev}; KH_TRY((kh_launch<zero_int_args, zero_int_body>(dim3((B + 255) / 256), 256, 0, st, z))); }
 
