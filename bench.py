@@ -316,11 +316,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="bzi77", choices=sorted(WORKLOADS))
-    ap.add_argument("--kpoints", type=int, default=41, help="k-points per step per GPU (x wavelengths = solves per step)")
-    ap.add_argument("--workspace-gb", type=float, default=40.0)
+    ap.add_argument("--kpoints", type=int, default=0, help="k-points per step per GPU (x wavelengths = solves per step); default 41 (bzi77), 64 (suh03), 8 (woodpile1111)")
+    ap.add_argument("--workspace-gb", type=float, default=80.0)
     ap.add_argument("--cpu-solves", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.kpoints <= 0:
+        args.kpoints = {"bzi77": 41, "suh03": 64, "woodpile1111": 8}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

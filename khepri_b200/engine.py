@@ -114,7 +114,7 @@ class Engine:
         if self.device.type == "cuda":
             free, _total = torch.cuda.mem_get_info(self.device)
             held = self._ws.numel() if self._ws is not None else 0
-            return int(min(48 << 30, 0.6 * (free + held)))
+            return int(min(96 << 30, 0.6 * (free + held)))        # of the B200's 180 GB: large chunks keep the latency-bound kernels in full waves
         return 1 << 30
 
     def workspace(self, nbytes):

@@ -300,6 +300,29 @@ def test_zgeev_tiled(backend, n):
         assert np.abs(np.sort_complex(np.linalg.eigvals(A[b])) - np.sort_complex(w[b])).max() <= 1e-7 * np.abs(w[b]).max()
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_new_entry_points_edge_cases(backend):
+    """Empty batches and argument checks of the entry points added for the tiled / grid / BZI rows."""
+    import ctypes as C
+    from khepri_b200 import Expansion
+    eng = engine(backend)
+    lib = eng.lib
+    # blocked inverse: work space is mandatory above the shared-memory sizes, and sized by kh_zinv_work_bytes
+    assert lib.kh_zinv_work_bytes(4, 50) == 0 and lib.kh_zinv_work_bytes(4, 242) >= 4 * 32 * 242 * 16
+    A = eng.to_dev(np.eye(130, dtype=complex)[None], __import__("torch").complex128)
+    out = A.clone()
+    rc = lib.kh_zinv_batched(1, 130, C.c_void_p(A.data_ptr()), C.c_void_p(out.data_ptr()), None, None, 0, eng.stream())
+    assert rc != 0 and b"workspace" in lib.kh_last_error()
+    assert np.array_equal(eng.zinv(np.eye(130, dtype=complex)[None]).cpu().numpy()[0], np.eye(130))        # exact on the identity
+    # beam amplitudes: empty k-batch, and a one-sample "beam" (a single exponential per harmonic)
+    e = Expansion((3, 1))
+    amp = eng.beam_amplitudes(np.zeros((0, 2)), e._g_vectors, np.array([0.3]), np.array([0.2]), np.ones((1, 4)), 1.0)
+    assert tuple(amp.shape) == (0, 3, 4)
+    amp = eng.beam_amplitudes(np.array([[0.5, -0.25]]), e._g_vectors, np.array([0.3]), np.array([0.2]), np.array([[1, 2, 3, 4]], dtype=complex), 0.5).cpu().numpy()
+    ref = 0.5 * np.exp(-1j * ((0.5 + e._g_vectors[0]) * 0.3 + (-0.25 + e._g_vectors[1]) * 0.2))[:, None] * np.array([1, 2, 3, 4])[None, :]
+    assert np.abs(amp[0] - ref).max() <= 1e-14
+
+
 # ----------------------------------------------------------------------------- sizes beyond shared memory / full-size properties
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_large_matrices_take_the_global_memory_paths(backend):
