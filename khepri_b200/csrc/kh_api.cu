@@ -629,7 +629,8 @@ extern "C" int kh_fp64_peak(int mode, int iters, int blocks, double* scratch_dev
     for (int rep = 0; rep < 2; ++rep) {          // first pass warms up
         cudaEventRecord(e0);
         if (mode == 0) kh_peak_dfma<<<blocks, 256>>>(scratch_dev, iters, 1.0);
-        else kh_peak_dmma<<<blocks, 256>>>(scratch_dev, iters, 1.0);
+        else if (mode == 1) kh_peak_dmma<<<blocks, 256>>>(scratch_dev, iters, 1.0);
+        else kh_peak_mixed<<<blocks, 256>>>(scratch_dev, iters, 1.0);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
     }
@@ -638,8 +639,9 @@ extern "C" int kh_fp64_peak(int mode, int iters, int blocks, double* scratch_dev
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail((int)err, "kh_fp64_peak: launch failed");
-    double flops = mode == 0 ? 2.0 * 16 * 256.0 * blocks * (double)iters            // 16 FMA / thread / iter
-                             : 2.0 * 8 * 256.0 * (256.0 / 32.0) * blocks * (double)iters;   // 8 DMMA (8x8x4) / warp / iter
+    const double f_dfma = 2.0 * 16 * 256.0 * blocks * (double)iters;                    // 16 FMA / thread / iter
+    const double f_dmma = 2.0 * 8 * 256.0 * (256.0 / 32.0) * blocks * (double)iters;   // 8 DMMA (8x8x4) / warp / iter
+    double flops = mode == 0 ? f_dfma : (mode == 1 ? f_dmma : f_dfma + f_dmma);
     *tflops_out = flops / (ms * 1e-3) / 1e12;
     return 0;
 #endif

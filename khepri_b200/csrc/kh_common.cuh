@@ -142,6 +142,12 @@ __global__ void __launch_bounds__(MAXT, MINB) kh_entry_lb(const __grid_constant_
     Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
     Body(c, a);
 }
+// register budget given directly (ptxas derives a needlessly low cap from launch bounds whose thread count is not a multiple of 128)
+template <class Args, void (*Body)(const Cta&, const Args&), int MAXREG>
+__global__ void __maxnreg__(MAXREG) kh_entry_mr(const __grid_constant__ Args a) {
+    Cta c{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)blockIdx.y, kh_smem};
+    Body(c, a);
+}
 // launch counter + optional per-kernel CUDA-event profiler (kh_profile_begin / kh_profile_end)
 #include <vector>
 struct KhProfRec { const char* name; double work; cudaEvent_t e0, e1; };
@@ -161,6 +167,7 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
     if (grid.x == 0 || grid.y == 0) return 0;
     void (*kern)(const Args);
     if constexpr (MAXT == 0) kern = kh_entry<Args, Body>;           // no launch bounds
+    else if constexpr (MAXT < 0) kern = kh_entry_mr<Args, Body, MINB>;   // MAXT < 0: MINB is a register cap
     else kern = kh_entry_lb<Args, Body, MAXT, MINB>;
     static size_t configured = 0;            // per-instantiation opt-in to > 48 KB dynamic smem
     if (smem > 48 * 1024 && smem > configured) {

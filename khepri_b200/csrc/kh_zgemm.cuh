@@ -159,21 +159,179 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
     }
 #endif
 }
+
+#ifndef KH_HOST_EMU
+// One full K chunk (4 DMMA k-steps) on NA of the warp's NT column tiles, branch free.
+template <int NT, int NA, int LDB>
+__device__ __forceinline__ void zgemm_mma_chunk(double (&cr)[NT][2], double (&ci)[NT][2], const cd* as, const cd* bs) {
+#pragma unroll
+    for (int kk = 0; kk < ZG_BK / 4; ++kk) {
+        const cd av = as[kk * 4];
+        const double nai = -av.y;
+        constexpr int G = NA > 8 ? (NA + 1) / 2 : NA;      // B fragments held at once (register budget)
+#pragma unroll
+        for (int g0 = 0; g0 < NA; g0 += G) {
+            cd bv[G];
+#pragma unroll
+            for (int t = 0; t < G; ++t) if (g0 + t < NA) bv[t] = bs[kk * 4 * LDB + (g0 + t) * 8];
+#pragma unroll
+            for (int t = 0; t < G; ++t) if (g0 + t < NA) { kh_dmma(cr[g0 + t][0], cr[g0 + t][1], av.x, bv[t].x); kh_dmma(ci[g0 + t][0], ci[g0 + t][1], av.x, bv[t].y); }
+#pragma unroll
+            for (int t = 0; t < G; ++t) if (g0 + t < NA) { kh_dmma(cr[g0 + t][0], cr[g0 + t][1], nai, bv[t].y); kh_dmma(ci[g0 + t][0], ci[g0 + t][1], av.y, bv[t].x); }
+        }
+    }
+}
+#endif
+
+// Pipelined variant (the one the launcher uses): NW == NT, so every staging pass is 4 uniform strides per thread
+// (no per-element index arithmetic), ST cp.async stages with ONE barrier per K chunk, and a branch-free inner
+// loop on interior tiles (the two DMMAs that feed one accumulator are issued NT instructions apart).
+template <int NW, int NT, int ST>
+KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
+#ifdef KH_HOST_EMU
+    zgemm_body_t<NW, NT>(c, a);
+#else
+    static_assert(NW == NT, "staging strides assume a square CTA tile");
+    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, STAGE = BM * ZG_LDA + ZG_BK * LDB;
+    const int tiles_n = (a.N + BN - 1) / BN, tiles = ((a.M + BM - 1) / BM) * tiles_n;
+    const int b = c.bx / tiles, tile = c.bx - b * tiles;
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    const cd* A = mat_ptr(a.A, b);
+    const cd* B = mat_ptr(a.B, b);
+    cd* sm = (cd*)KH_SMEM(c);                           // [ST] x { A tile [BM][LDA], B tile [BK][LDB] }
+    const int tid = c.tid, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int nk = (a.K + ZG_BK - 1) / ZG_BK;
+    const int nt = min(NT, (a.N - n0 + 7) >> 3);
+    const bool warp_active = (m0 + warp * 8) < a.M;
+
+    // staging roles (4 passes each).  A: thread -> (row am + 2NW*i, k ak), or transposed (row am, k ak + 4i).  B: (k bk + 4i, col bn).
+    const int am = a.transA ? tid % BM : tid >> 4, ak = a.transA ? tid / BM : tid & 15;
+    const int bk = tid / BN, bn = tid - bk * BN;
+    const cd* asrc = a.transA ? A + (long long)ak * a.A.ld + m0 + am : A + (long long)(m0 + am) * a.A.ld + ak;
+    const cd* bsrc = B + (long long)bk * a.B.ld + n0 + bn;
+    const int adst = am * ZG_LDA + ak, bdst = BM * ZG_LDA + bk * LDB + bn;
+    const bool bn_ok = (n0 + bn) < a.N;
+    const long long a_pass = a.transA ? 4LL * a.A.ld : 2LL * NW * a.A.ld, b_pass = 4LL * a.B.ld;
+    const long long a_chunk = a.transA ? (long long)ZG_BK * a.A.ld : ZG_BK, b_chunk = (long long)ZG_BK * a.B.ld;
+
+    auto stage = [&](int buf, int kc) {
+        cd* s = sm + buf * STAGE;
+        const int k0 = kc * ZG_BK;
+        if (!a.transA) {
+            const bool kok = (k0 + ak) < a.K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = kok && (m0 + am + 2 * NW * i) < a.M;
+                kh_cp_async16(s + adst + 2 * NW * i * ZG_LDA, ok ? asrc + i * a_pass : A, ok);
+            }
+        } else {
+            const bool mok = (m0 + am) < a.M;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = mok && (k0 + ak + 4 * i) < a.K;
+                kh_cp_async16(s + adst + 4 * i, ok ? asrc + i * a_pass : A, ok);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = bn_ok && (k0 + bk + 4 * i) < a.K;
+            kh_cp_async16(s + bdst + 4 * i * LDB, ok ? bsrc + i * b_pass : B, ok);
+        }
+        asrc += a_chunk; bsrc += b_chunk;
+    };
+
+    double cr[NT][2], ci[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) { if (s < nk) stage(s, s); kh_cp_async_commit(); }
+    int buf = 0, nbuf = ST - 1;
+    for (int kc = 0; kc < nk; ++kc) {
+        kh_cp_async_wait<ST - 2>();
+        __syncthreads();
+        if (kc + ST - 1 < nk) stage(nbuf, kc + ST - 1);
+        kh_cp_async_commit();
+        if (warp_active) {
+            const cd* as = sm + buf * STAGE + (warp * 8 + lr) * ZG_LDA + lk;
+            const cd* bs = sm + buf * STAGE + BM * ZG_LDA + lk * LDB + lr;
+            const int ks = min(ZG_BK / 4, (a.K - kc * ZG_BK + 3) >> 2);
+            if (ks == ZG_BK / 4 && nt == NT) zgemm_mma_chunk<NT, NT, LDB>(cr, ci, as, bs);
+            else if (ks == ZG_BK / 4 && nt == NT - 1) zgemm_mma_chunk<NT, NT - 1, LDB>(cr, ci, as, bs);
+            else {
+                for (int kk = 0; kk < ks; ++kk) {
+                    const cd av = as[kk * 4];
+                    const double nai = -av.y;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        if (t < nt) {
+                            const cd bv = bs[kk * 4 * LDB + t * 8];
+                            kh_dmma(cr[t][0], cr[t][1], av.x, bv.x);
+                            kh_dmma(ci[t][0], ci[t][1], av.x, bv.y);
+                            kh_dmma(cr[t][0], cr[t][1], nai, bv.y);
+                            kh_dmma(ci[t][0], ci[t][1], av.y, bv.x);
+                        }
+                    }
+                }
+            }
+        }
+        buf = (buf + 1 == ST) ? 0 : buf + 1;
+        nbuf = (nbuf + 1 == ST) ? 0 : nbuf + 1;
+    }
+    if (warp_active) {
+        const int row = m0 + warp * 8 + lr;
+        if (row < a.M) {
+            const cd* Cin = mat_ptr(a.Cin, b);
+            cd* Cout = mat_ptr(a.Cout, b);
+            const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
+            const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (t < nt) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int col = n0 + t * 8 + 2 * lk + h;
+                        if (col < a.N)
+                            Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]));
+                    }
+                }
+            }
+        }
+    }
+#endif
+}
+KH_DEV void zgemm56p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<7, 7, 3>(c, a); }
+KH_DEV void zgemm56p2_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<7, 7, 2>(c, a); }
+KH_DEV void zgemm64p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<8, 8, 3>(c, a); }
+KH_DEV void zgemm104p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<13, 13, 3>(c, a); }
 KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<8, 8>(c, a); }
 KH_DEV void zgemm56_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<7, 7>(c, a); }
 
 static inline long long zgemm_padded(int M, int N, int T) { return (long long)((M + T - 1) / T) * T * ((N + T - 1) / T) * T; }
+static inline size_t zgemm_smem(int T, int ST) { return (size_t)ST * (T * ZG_LDA + ZG_BK * (T + 2)) * sizeof(cd); }
+static inline int zgemm_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KH_ZGEMM_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     const double work = 8.0 * a.M * a.N * a.K * batch;
-    if (zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64)) {
-        int tiles = ((a.M + 55) / 56) * ((a.N + 55) / 56);
-        size_t sm = (size_t)2 * (56 * ZG_LDA + ZG_BK * 58) * sizeof(cd);
-        return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3((unsigned)batch * tiles), 224, sm, st, a, "zgemm", work);
+    const int var = zgemm_variant();
+    const bool t56 = zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64);
+    const unsigned g56 = (unsigned)batch * ((a.M + 55) / 56) * ((a.N + 55) / 56), g64 = (unsigned)batch * ((a.M + 63) / 64) * ((a.N + 63) / 64);
+    if (var == 9) {           // previous kernels (double buffer, two barriers per chunk)
+        if (t56) return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 2), st, a, "zgemm", work);
+        return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 2), st, a, "zgemm", work);
     }
-    int tiles = ((a.M + 63) / 64) * ((a.N + 63) / 64);
-    size_t sm = (size_t)2 * (64 * ZG_LDA + ZG_BK * 66) * sizeof(cd);
-    return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3((unsigned)batch * tiles), 256, sm, st, a, "zgemm", work);
+    if (var == 2 && a.M > 56 && a.M <= 104 && a.N > 56 && a.N <= 104)
+        return kh_launch<zgemm_args, zgemm104p3_body, -1, 144>(dim3((unsigned)batch), 416, zgemm_smem(104, 3), st, a, "zgemm", work);
+    if (t56) {
+        if (var == 1) return kh_launch<zgemm_args, zgemm56p2_body, -1, 96>(dim3(g56), 224, zgemm_smem(56, 2), st, a, "zgemm", work);
+        return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, "zgemm", work);
+    }
+    return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, "zgemm", work);
 }
 
 // convenience builder: plain C = alpha*A*B (+ beta*Cin) on [batch, n, n] row-major stacks

@@ -253,6 +253,232 @@ __device__ __forceinline__ void zinv_reg_t3_body(const Cta& c, const zinv_args& 
 __device__ __forceinline__ void zinv_reg_t2x_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
 #endif
 
+#ifndef KH_HOST_EMU
+// ---------------------------------------------------------------------------------------------
+// Shared-memory resident BLOCKED Gauss-Jordan for n <= 104 (the 5x5 and 7x7 harmonic bases): one CTA per
+// matrix, the matrix (padded with identity to a multiple of 8) stays in shared memory for the whole
+// inversion.  Per block column of NB = 16 pivots:
+//   panel  : warps 0-3, thread <-> row, the row's NB panel entries in registers; per pivot a warp-shuffle
+//            argmax + one 4-entry exchange, the pivot row broadcast through shared memory, two 128-thread
+//            named barriers; the eliminated panel is the block column P' of the Gauss-Jordan transformation;
+//   rows   : thread <-> column applies the panel's interchanges to the other columns and moves the NB pivot
+//            rows R to a side buffer (zeroed in place);
+//   update : all 16 warps, A[:, other] += P' R on 8x8 DMMA tiles, C read from / written to shared memory.
+// All 8 n^3 flops of the rank updates run as DMMA (same pipe throughput as DFMA on B200, but 1/8 of the
+// issue slots and no per-pivot CTA-wide barriers), which is what the register-resident variant was short of.
+// 1/z without divisions (FP64 division is a ~25-deep dependent chain at ~20 cycles per op on B200): exact power-of-two
+// scaling, |z|^2, hardware reciprocal seed (20 bits) + two Newton steps.  z = 0 gives NaN/Inf like the division would.
+__device__ __forceinline__ cd kh_crecip_fast(cd z) {
+    const double m = fmax(fabs(z.x), fabs(z.y));
+    const int e = (__double2hiint(m) >> 20) & 0x7ff;
+    const double sc = __hiloint2double((2046 - e) << 20, 0);          // 2^(1023 - e): scaled max magnitude in [1, 2)
+    const double xs = z.x * sc, ys = z.y * sc;
+    const double t = fma(xs, xs, ys * ys);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    r = fma(r, fma(-t, r, 1.0), r);
+    r = fma(r, fma(-t, r, 1.0), r);
+    r *= sc;
+    return mk(xs * r, -(ys * r));
+}
+#define ZID_NB 16
+#define ZID_NMAX 104
+#ifdef ZID_PROFILE
+#define ZID_T(i) { long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; }
+#else
+#define ZID_T(i)
+#endif
+struct zid_slot { cd row[ZID_NB]; cd d; unsigned long long key; int idx; int pad; };
+__device__ __forceinline__ void zid_bar_panel() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// panel factorisation (warps 0-3, thread <-> row): block column k0 .. k0+nbk of As becomes the Gauss-Jordan block column P'
+__device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0, int nbk, zid_slot* slots, int* piv, int& bad, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool rowok = tid < np;
+    cd p[ZID_NB];
+#pragma unroll
+    for (int j = 0; j < ZID_NB; ++j) p[j] = (rowok && j < nbk) ? As[tid * lda + k0 + j] : mk(0.0, 0.0);
+    // speculative per-row quantities of the NEXT pivot column: 1 / entry and the ordering key of |re| + |im|
+    // (bits of a non-negative double order like an unsigned integer; +1 so an eligible zero beats an ineligible row)
+    cd dmine = kh_crecip_fast(p[0]);
+    unsigned long long key = (rowok && tid >= k0) ? (unsigned long long)__double_as_longlong(cabs1(p[0])) + 1ull : 0ull;
+    // The register panel is ROTATED by one column per pivot (the pivot column is always p[0], the next one p[1]) so that the
+    // step is a real loop of ~600 instructions instead of 16 unrolled copies: the unrolled form ran out of the instruction
+    // cache with a single warp per scheduler and nothing to hide the fetches.
+#pragma unroll 1
+    for (int s = 0; s < nbk; ++s) {
+        const int k = k0 + s;
+        zid_slot* sl = slots + (s & 1) * 5;            // 4 warp candidates + the old row k
+        // warp-level argmax (two 32-bit reductions + ballot, ties -> smallest row); the warp's winner publishes its row
+        const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? klo : 0u);
+        const unsigned who = __ballot_sync(0xffffffffu, khi == mhi && klo == mlo);
+        const bool iswin = lane == __ffs(who) - 1;
+        if (iswin || tid == k) {                       // one divergent block for both publishers (row k's copy is only read when pr != k)
+            zid_slot* dst = iswin ? sl + warp : sl + 4;
+#pragma unroll
+            for (int j = 0; j < ZID_NB; ++j) dst->row[j] = p[j];
+            dst->d = dmine; dst->key = key; dst->idx = tid;
+        }
+        zid_bar_panel();
+        unsigned long long bk = sl[0].key; int wbest = 0;
+#pragma unroll
+        for (int w = 1; w < 4; ++w) { const unsigned long long ok = sl[w].key; if (ok > bk) { bk = ok; wbest = w; } }
+        const zid_slot* win = sl + wbest;
+        const int pr = win->idx;
+        const cd d = win->d;
+        if (tid == 0) piv[k] = pr;
+        if (tid == pr && pr != k) {                    // row k's old values: in its warp's slot if it won there, else in slot 4
+            const zid_slot* rk = (sl[k >> 5].idx == k) ? sl + (k >> 5) : sl + 4;
+#pragma unroll
+            for (int j = 0; j < ZID_NB; ++j) p[j] = rk->row[j];
+        }
+        const cd pv = win->row[0];
+        if (pv.x == 0.0 && pv.y == 0.0 && !bad && k < n) bad = k + 1;
+        cd q[ZID_NB];                                  // the row after this step, already rotated
+        if (tid == k) {
+#pragma unroll
+            for (int j = 1; j < ZID_NB; ++j) q[j - 1] = win->row[j] * d;
+            q[ZID_NB - 1] = d;
+            key = 0ull;
+        } else {
+            const cd g = p[0] * d;
+            cd nx = p[1];
+            cfms(nx, g, win->row[1]);                  // next pivot column first, its reciprocal overlaps the rest of the update
+            q[0] = nx;
+            dmine = kh_crecip_fast(nx);
+            key = (rowok && tid > k) ? (unsigned long long)__double_as_longlong(cabs1(nx)) + 1ull : 0ull;
+#pragma unroll
+            for (int j = 2; j < ZID_NB; ++j) { cd v = p[j]; cfms(v, g, win->row[j]); q[j - 1] = v; }
+            q[ZID_NB - 1] = -g;
+        }
+#pragma unroll
+        for (int j = 0; j < ZID_NB; ++j) p[j] = q[j];
+    }
+    if (rowok) {                                       // p[j] holds panel column (j + nbk) mod NB
+#pragma unroll
+        for (int j = 0; j < ZID_NB; ++j) { const int col = (j + nbk) & (ZID_NB - 1); if (col < nbk) As[tid * lda + k0 + col] = p[j]; }
+    }
+}
+// A[:, tile columns outside [skip0, skip1) or inside [only0, only1)] += P' R on 8x8 DMMA tiles; worker w of nwork takes tiles w, w + nwork, ...
+__device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr, int np, int k0, int nbk, int c0, int c1, bool inside,
+                                           int w, int nwork, int lane) {
+    const int lr = lane >> 2, lk = lane & 3;
+    const int nstrip = np >> 3, ncols = inside ? (c1 - c0) : nstrip - (c1 - c0), total = nstrip * ncols;
+    for (int t = w; t < total; t += nwork) {
+        const int strip = t / ncols; int tc = t - strip * ncols;
+        if (inside) tc += c0; else if (tc >= c0) tc += c1 - c0;
+        cd* cp = As + (strip * 8 + lr) * lda + tc * 8 + 2 * lk;
+        const cd* ap = As + (strip * 8 + lr) * lda + k0 + lk;
+        const cd* bp = R + lk * ldr + tc * 8 + lr;
+        const cd c0v = cp[0], c1v = cp[1];
+        double cr0 = c0v.x, cr1 = c1v.x, ci0 = c0v.y, ci1 = c1v.y;
+        if (nbk == ZID_NB) {
+            cd av[4], bv[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) { av[kk] = ap[kk * 4]; bv[kk] = bp[kk * 4 * ldr]; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                kh_dmma(cr0, cr1, av[kk].x, bv[kk].x); kh_dmma(ci0, ci1, av[kk].x, bv[kk].y);
+                kh_dmma(cr0, cr1, -av[kk].y, bv[kk].y); kh_dmma(ci0, ci1, av[kk].y, bv[kk].x);
+            }
+        } else {
+            for (int kk = 0; kk < (nbk >> 2); ++kk) {
+                const cd av = ap[kk * 4], bv = bp[kk * 4 * ldr];
+                kh_dmma(cr0, cr1, av.x, bv.x); kh_dmma(ci0, ci1, av.x, bv.y);
+                kh_dmma(cr0, cr1, -av.y, bv.y); kh_dmma(ci0, ci1, av.y, bv.x);
+            }
+        }
+        cp[0] = mk(cr0, ci0); cp[1] = mk(cr1, ci1);
+    }
+}
+template <int NW, bool LA>
+__device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& a) {
+    const int n = a.n, b = c.bx, tid = c.tid, warp = tid >> 5, lane = tid & 31;
+    const int np = (n + 7) & ~7, lda = np + 4, ldr = np + 2;
+    const cd* A = mat_ptr(a.A, b);
+    cd* Out = mat_ptr(a.Ainv, b);
+    cd* As = (cd*)KH_SMEM(c);                     // [np][lda]
+    cd* R = As + np * lda;                        // [NB][ldr]
+    zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][4 warp candidates + old row k]
+    int* piv = (int*)(slots + 10);                // [np]
+#ifdef ZID_PROFILE
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
+#endif
+    for (int e = tid; e < np * np; e += c.nthr) {
+        const int i = e / np, j = e - i * np;
+        As[i * lda + j] = (i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(i == j ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+    int bad = 0;
+    ZID_T(0)
+    if (warp < 4) zid_panel(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
+    __syncthreads();
+    ZID_T(1)
+    for (int k0 = 0; k0 < np; k0 += ZID_NB) {
+        const int nbk = min(ZID_NB, np - k0);     // 16 or 8
+        const int k1 = k0 + nbk, nbk1 = min(ZID_NB, np - k1);      // next panel (nbk1 <= 0: none)
+        // ---------------- interchanges of panel k0 on the other columns, pivot rows -> R (zeroed in place): thread <-> column
+        {
+            const int j = tid - 128;
+            if (j >= 0 && j < np && (j < k0 || j >= k1)) {
+                for (int s = 0; s < nbk; ++s) {
+                    const int k = k0 + s, pr = piv[k];
+                    if (pr != k) { const cd x = As[k * lda + j]; As[k * lda + j] = As[pr * lda + j]; As[pr * lda + j] = x; }
+                }
+                for (int s = 0; s < nbk; ++s) { R[s * ldr + j] = As[(k0 + s) * lda + j]; As[(k0 + s) * lda + j] = mk(0.0, 0.0); }
+            }
+        }
+        __syncthreads();
+        ZID_T(2)
+        if (!LA) {
+            zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
+            __syncthreads();
+            ZID_T(3)
+            if (nbk1 > 0 && warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
+        } else if (nbk1 > 0) {
+            // ---------------- look-ahead: the next panel's columns first (all warps), then its factorisation by warps 0-3
+            //                  overlaps the rest of this update on the other warps
+            zid_update(As, R, lda, ldr, np, k0, nbk, k1 >> 3, (k1 + nbk1) >> 3, true, warp, NW, lane);
+            __syncthreads();
+            ZID_T(4)
+            if (warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
+            else zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, (k1 + nbk1) >> 3, false, warp - 4, NW - 4, lane);
+        } else {
+            zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
+        }
+        __syncthreads();
+        ZID_T(5)
+    }
+    // undo the row interchanges as column interchanges (reverse order): thread j follows stored column j to its final position
+    int* dest = (int*)R;
+    if (tid < n) {
+        int pos = tid;
+        for (int k = np - 1; k >= 0; --k) { const int pr = piv[k]; pos = (pos == k) ? pr : ((pos == pr) ? k : pos); }
+        dest[tid] = pos;
+    }
+    __syncthreads();
+    ZID_T(6)
+    for (int e = tid; e < n * n; e += c.nthr) {
+        const int i = e / n, j = e - i * n;
+        Out[(long long)i * a.Ainv.ld + dest[j]] = As[i * lda + j];
+    }
+    ZID_T(7)
+#ifdef ZID_PROFILE
+    if ((tid == 0 || tid == 200) && b == 0) printf("zid n=%d LA=%d tid=%d: load %lld panel0 %lld rows %lld upd(noLA) %lld la-part1 %lld panel|rest %lld dest %lld store %lld\n", n, (int)LA, tid, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7]);
+#endif
+    if (a.info && tid == 0) a.info[b] = bad;
+}
+__device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, false>(c, a); }
+__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, false>(c, a); }
+__device__ __forceinline__ void zinv_dmma_la_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, true>(c, a); }
+__device__ __forceinline__ void zinv_dmma8_la_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, true>(c, a); }
+static inline size_t zinv_dmma_smem(int n) {
+    const int np = (n + 7) & ~7;
+    return ((size_t)np * (np + 4) + (size_t)ZID_NB * (np + 2)) * sizeof(cd) + 10 * sizeof(zid_slot) + (size_t)np * 4 + 16;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Tiled variant for matrices that do not fit in shared memory (n > ~118: the 9x9 ... 15x15 harmonic
 // bases and the extended-RCWA supercells): BLOCKED in-place Gauss-Jordan.  Per block column of nb
@@ -433,6 +659,16 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
     zinv_args a;
     a.n = n; a.A = A; a.Ainv = Ainv; a.info = info;
 #ifndef KH_HOST_EMU
+    static int zvar = -1;
+    if (zvar < 0) { const char* e = getenv("KH_ZINV_KERNEL"); zvar = e ? atoi(e) : 0; }   // 1: previous register-resident kernels
+    if (n <= 64 && n >= 16 && zvar == 2)
+        return kh_launch<zinv_args, zinv_dmma8_la_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
+    if (n <= ZID_NMAX && n >= 16 && zvar == 2)
+        return kh_launch<zinv_args, zinv_dmma_la_body, 512, 1>(dim3(batch), 512, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
+    if (n <= 64 && n >= 16 && zvar != 1)
+        return kh_launch<zinv_args, zinv_dmma8_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
+    if (n <= ZID_NMAX && n >= 16 && zvar != 1)
+        return kh_launch<zinv_args, zinv_dmma_body, 512, 1>(dim3(batch), 512, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
     if (n <= 100) {
         a.use_smem = 0; a.ld_s = 0;
         const int txn = (n + ZIR_TC - 1) / ZIR_TC;
