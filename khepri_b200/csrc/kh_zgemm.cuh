@@ -4,9 +4,10 @@
 //
 // tcgen05 has no FP64 kind, so warp-level DMMA is the tensor path for complex128 on sm_100a.
 // A complex product is four real DMMAs per 8x8x4 step (Cr += Ar Br - Ai Bi ; Ci += Ar Bi + Ai Br).
-// CTA tile 64x64, K chunks of 16 staged with cp.async (zero-filled at the ragged edges, so
-// matrices need no padding in HBM), double buffered.  Eight warps; warp w owns rows 8w..8w+7 of
-// the tile and all eight 8-column MMA tiles.  Shared-memory strides (20 / 66 complex) make the
+// CTA tile 64x64 or 56x56, K chunks of 16 staged with cp.async (zero-filled at the ragged edges, so
+// matrices need no padding in HBM) in a 3-stage pipeline with one barrier per chunk.  64x64: eight warps,
+// warp w owns rows 8w..8w+7 of the tile and all eight 8-column MMA tiles.  56x56: the 49 (strip, tile)
+// units are dealt evenly over 8 warps (zgemm_body_u).  Shared-memory strides (20 / 66 complex) make the
 // A- and B-fragment loads bank-conflict free.
 #pragma once
 #include "kh_common.cuh"
@@ -301,10 +302,148 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
     }
 #endif
 }
+#ifndef KH_HOST_EMU
+// CNT (8-row strip, 8-column tile) units of one warp over a full K chunk; runtime smem offsets, B/A fragments in groups of 4
+template <int CNT, int MAXU, int LDB>
+__device__ __forceinline__ void zgemm_mma_units(double (&cr)[MAXU][2], double (&ci)[MAXU][2], const cd* sa, const cd* sb,
+                                                const int (&aoff)[MAXU], const int (&boff)[MAXU], int ks) {
+    constexpr int G = CNT > 4 ? (CNT + 1) / 2 : CNT;
+#pragma unroll
+    for (int kk = 0; kk < ZG_BK / 4; ++kk) {
+        if (kk < ks) {
+#pragma unroll
+            for (int g0 = 0; g0 < CNT; g0 += G) {
+                cd av[G], bv[G];
+#pragma unroll
+                for (int t = 0; t < G; ++t) if (g0 + t < CNT) { av[t] = sa[aoff[g0 + t] + kk * 4]; bv[t] = sb[boff[g0 + t] + kk * 4 * LDB]; }
+#pragma unroll
+                for (int t = 0; t < G; ++t) if (g0 + t < CNT) { kh_dmma(cr[g0 + t][0], cr[g0 + t][1], av[t].x, bv[t].x); kh_dmma(ci[g0 + t][0], ci[g0 + t][1], av[t].x, bv[t].y); }
+#pragma unroll
+                for (int t = 0; t < G; ++t) if (g0 + t < CNT) { kh_dmma(cr[g0 + t][0], cr[g0 + t][1], -av[t].y, bv[t].y); kh_dmma(ci[g0 + t][0], ci[g0 + t][1], av[t].y, bv[t].x); }
+            }
+        }
+    }
+}
+#endif
+
+// Unit-balanced variant: the CTA tile is (8 NW) x (8 NT) as above and NW warps stage it, but NW + 1 warps compute, and the
+// (strip, tile) units of the tile are dealt out evenly over them instead of one 8-row strip per warp.  With NW = 7 a CTA has
+// 8 compute warps = 2 per scheduler, whereas 7 strip-warps leave the 4th scheduler of an SM with half the DMMA work of the
+// others (and ragged tiles idle whole warps): at n = 98 the busiest scheduler drops from 52 to 44 of a matrix's 169 units.
+template <int NW, int NT, int ST>
+KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
+#ifdef KH_HOST_EMU
+    zgemm_body_t<NW, NT>(c, a);
+#else
+    static_assert(NW == NT, "staging strides assume a square CTA tile");
+    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, STAGE = BM * ZG_LDA + ZG_BK * LDB, NC = NW + 1;
+    constexpr int MAXU = (NW * NT + NC - 1) / NC;
+    const int tiles_n = (a.N + BN - 1) / BN, tiles = ((a.M + BM - 1) / BM) * tiles_n;
+    const int b = c.bx / tiles, tile = c.bx - b * tiles;
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    const cd* A = mat_ptr(a.A, b);
+    const cd* B = mat_ptr(a.B, b);
+    cd* sm = (cd*)KH_SMEM(c);
+    const int tid = c.tid, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int nk = (a.K + ZG_BK - 1) / ZG_BK;
+    const int nt = min(NT, (a.N - n0 + 7) >> 3), ns = min(NW, (a.M - m0 + 7) >> 3);
+    const int U = ns * nt, cnt = U / NC + (warp < U % NC ? 1 : 0), ustart = warp * (U / NC) + min(warp, U % NC);
+    int aoff[MAXU], boff[MAXU];
+#pragma unroll
+    for (int j = 0; j < MAXU; ++j) {
+        const int u = ustart + (j < cnt ? j : 0), strip = u / nt, tl = u - strip * nt;
+        aoff[j] = (strip * 8 + lr) * ZG_LDA + lk;
+        boff[j] = BM * ZG_LDA + lk * LDB + tl * 8 + lr;
+    }
+    const bool stager = warp < NW;
+    const int am = a.transA ? tid % BM : tid >> 4, ak = a.transA ? tid / BM : tid & 15;
+    const int bk = tid / BN, bn = tid - bk * BN;
+    const cd* asrc = a.transA ? A + (long long)ak * a.A.ld + m0 + am : A + (long long)(m0 + am) * a.A.ld + ak;
+    const cd* bsrc = B + (long long)bk * a.B.ld + n0 + bn;
+    const int adst = am * ZG_LDA + ak, bdst = BM * ZG_LDA + bk * LDB + bn;
+    const bool bn_ok = (n0 + bn) < a.N;
+    const long long a_pass = a.transA ? 4LL * a.A.ld : 2LL * NW * a.A.ld, b_pass = 4LL * a.B.ld;
+    const long long a_chunk = a.transA ? (long long)ZG_BK * a.A.ld : ZG_BK, b_chunk = (long long)ZG_BK * a.B.ld;
+    auto stage = [&](int buf, int kc) {
+        cd* s = sm + buf * STAGE;
+        const int k0 = kc * ZG_BK;
+        if (!a.transA) {
+            const bool kok = (k0 + ak) < a.K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = kok && (m0 + am + 2 * NW * i) < a.M;
+                kh_cp_async16(s + adst + 2 * NW * i * ZG_LDA, ok ? asrc + i * a_pass : A, ok);
+            }
+        } else {
+            const bool mok = (m0 + am) < a.M;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = mok && (k0 + ak + 4 * i) < a.K;
+                kh_cp_async16(s + adst + 4 * i, ok ? asrc + i * a_pass : A, ok);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = bn_ok && (k0 + bk + 4 * i) < a.K;
+            kh_cp_async16(s + bdst + 4 * i * LDB, ok ? bsrc + i * b_pass : B, ok);
+        }
+        asrc += a_chunk; bsrc += b_chunk;
+    };
+    double cr[MAXU][2], ci[MAXU][2];
+#pragma unroll
+    for (int t = 0; t < MAXU; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) { if (s < nk && stager) stage(s, s); kh_cp_async_commit(); }
+    int buf = 0, nbuf = ST - 1;
+    for (int kc = 0; kc < nk; ++kc) {
+        kh_cp_async_wait<ST - 2>();
+        __syncthreads();
+        if (kc + ST - 1 < nk && stager) stage(nbuf, kc + ST - 1);
+        kh_cp_async_commit();
+        const cd* sb = sm + buf * STAGE;
+        const int ks = min(ZG_BK / 4, (a.K - kc * ZG_BK + 3) >> 2);
+        if (cnt == MAXU) zgemm_mma_units<MAXU, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 1) zgemm_mma_units<MAXU - 1, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 2) zgemm_mma_units<MAXU - 2, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 3) zgemm_mma_units<(MAXU > 3 ? MAXU - 3 : 1), MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
+        else if (cnt > 0) {
+            for (int kk = 0; kk < ks; ++kk) {
+#pragma unroll
+                for (int j = 0; j < MAXU; ++j) {
+                    if (j < cnt) {
+                        const cd av = sb[aoff[j] + kk * 4], bv = sb[boff[j] + kk * 4 * LDB];
+                        kh_dmma(cr[j][0], cr[j][1], av.x, bv.x); kh_dmma(ci[j][0], ci[j][1], av.x, bv.y);
+                        kh_dmma(cr[j][0], cr[j][1], -av.y, bv.y); kh_dmma(ci[j][0], ci[j][1], av.y, bv.x);
+                    }
+                }
+            }
+        }
+        buf = (buf + 1 == ST) ? 0 : buf + 1;
+        nbuf = (nbuf + 1 == ST) ? 0 : nbuf + 1;
+    }
+    const cd* Cin = mat_ptr(a.Cin, b);
+    cd* Cout = mat_ptr(a.Cout, b);
+    const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
+    const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
+#pragma unroll
+    for (int j = 0; j < MAXU; ++j) {
+        if (j < cnt) {
+            const int u = ustart + j, strip = u / nt, tl = u - strip * nt;
+            const int row = m0 + strip * 8 + lr;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = n0 + tl * 8 + 2 * lk + h;
+                if (row < a.M && col < a.N)
+                    Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]));
+            }
+        }
+    }
+#endif
+}
+KH_DEV void zgemm56u3_body(const Cta& c, const zgemm_args& a) { zgemm_body_u<7, 7, 3>(c, a); }
 KH_DEV void zgemm56p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<7, 7, 3>(c, a); }
-KH_DEV void zgemm56p2_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<7, 7, 2>(c, a); }
 KH_DEV void zgemm64p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<8, 8, 3>(c, a); }
-KH_DEV void zgemm104p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<13, 13, 3>(c, a); }
 KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<8, 8>(c, a); }
 KH_DEV void zgemm56_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<7, 7>(c, a); }
 
@@ -315,22 +454,23 @@ static inline int zgemm_variant() {
     if (v < 0) { const char* e = getenv("KH_ZGEMM_VARIANT"); v = e ? atoi(e) : 0; }
     return v;
 }
+// Shapes that waste less padding on 56x56 tiles (n = 50: one tile, n = 98: 2x2 tiles) use the unit-balanced kernel, the rest
+// the 64x64 strip kernel.  KH_ZGEMM_VARIANT (developer switch, tests/zgemm_timing.py): 1 = strip-per-warp 56x56 pipeline,
+// 9 = the first-generation kernels (double buffer, two barriers per chunk).  Measured and dropped: a 104x104 one-CTA-per-matrix
+// tile (13 warps need > 128 registers for the 13 accumulator tiles), a 3-CTA/SM 2-stage variant (no gain), and a persistent
+// grid whose cp.async pipeline runs across tile boundaries (7 % slower: the per-tile cost is the epilogue, not the first load).
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     const double work = 8.0 * a.M * a.N * a.K * batch;
     const int var = zgemm_variant();
     const bool t56 = zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64);
     const unsigned g56 = (unsigned)batch * ((a.M + 55) / 56) * ((a.N + 55) / 56), g64 = (unsigned)batch * ((a.M + 63) / 64) * ((a.N + 63) / 64);
-    if (var == 9) {           // previous kernels (double buffer, two barriers per chunk)
+    if (var == 9) {
         if (t56) return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 2), st, a, "zgemm", work);
         return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 2), st, a, "zgemm", work);
     }
-    if (var == 2 && a.M > 56 && a.M <= 104 && a.N > 56 && a.N <= 104)
-        return kh_launch<zgemm_args, zgemm104p3_body, -1, 144>(dim3((unsigned)batch), 416, zgemm_smem(104, 3), st, a, "zgemm", work);
-    if (t56) {
-        if (var == 1) return kh_launch<zgemm_args, zgemm56p2_body, -1, 96>(dim3(g56), 224, zgemm_smem(56, 2), st, a, "zgemm", work);
-        return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, "zgemm", work);
-    }
+    if (t56 && var == 1) return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, "zgemm", work);
+    if (t56) return kh_launch<zgemm_args, zgemm56u3_body, 256, 2>(dim3(g56), 256, zgemm_smem(56, 3), st, a, "zgemm", work);
     return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, "zgemm", work);
 }
 

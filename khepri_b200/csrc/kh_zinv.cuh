@@ -283,11 +283,6 @@ __device__ __forceinline__ cd kh_crecip_fast(cd z) {
 }
 #define ZID_NB 16
 #define ZID_NMAX 104
-#ifdef ZID_PROFILE
-#define ZID_T(i) { long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; }
-#else
-#define ZID_T(i)
-#endif
 struct zid_slot { cd row[ZID_NB]; cd d; unsigned long long key; int idx; int pad; };
 __device__ __forceinline__ void zid_bar_panel() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // panel factorisation (warps 0-3, thread <-> row): block column k0 .. k0+nbk of As becomes the Gauss-Jordan block column P'
@@ -392,7 +387,7 @@ __device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr
         cp[0] = mk(cr0, ci0); cp[1] = mk(cr1, ci1);
     }
 }
-template <int NW, bool LA>
+template <int NW>
 __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& a) {
     const int n = a.n, b = c.bx, tid = c.tid, warp = tid >> 5, lane = tid & 31;
     const int np = (n + 7) & ~7, lda = np + 4, ldr = np + 2;
@@ -402,19 +397,17 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
     cd* R = As + np * lda;                        // [NB][ldr]
     zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][4 warp candidates + old row k]
     int* piv = (int*)(slots + 10);                // [np]
-#ifdef ZID_PROFILE
-    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
-#endif
-    for (int e = tid; e < np * np; e += c.nthr) {
-        const int i = e / np, j = e - i * np;
-        As[i * lda + j] = (i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(i == j ? 1.0 : 0.0, 0.0);
+    for (int i = warp; i < np; i += NW) {            // warp <-> row: coalesced, no index division, 4 loads in flight per lane
+        cd v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = lane + 32 * u; v[u] = (i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(i == j ? 1.0 : 0.0, 0.0); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = lane + 32 * u; if (j < np) As[i * lda + j] = v[u]; }
     }
     __syncthreads();
     int bad = 0;
-    ZID_T(0)
     if (warp < 4) zid_panel(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
     __syncthreads();
-    ZID_T(1)
     for (int k0 = 0; k0 < np; k0 += ZID_NB) {
         const int nbk = min(ZID_NB, np - k0);     // 16 or 8
         const int k1 = k0 + nbk, nbk1 = min(ZID_NB, np - k1);      // next panel (nbk1 <= 0: none)
@@ -430,25 +423,12 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
             }
         }
         __syncthreads();
-        ZID_T(2)
-        if (!LA) {
-            zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
-            __syncthreads();
-            ZID_T(3)
-            if (nbk1 > 0 && warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
-        } else if (nbk1 > 0) {
-            // ---------------- look-ahead: the next panel's columns first (all warps), then its factorisation by warps 0-3
-            //                  overlaps the rest of this update on the other warps
-            zid_update(As, R, lda, ldr, np, k0, nbk, k1 >> 3, (k1 + nbk1) >> 3, true, warp, NW, lane);
-            __syncthreads();
-            ZID_T(4)
-            if (warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
-            else zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, (k1 + nbk1) >> 3, false, warp - 4, NW - 4, lane);
-        } else {
-            zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
-        }
+        zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
         __syncthreads();
-        ZID_T(5)
+        // (a look-ahead schedule -- next panel factorised by warps 0-3 while the others finish this update -- was measured: no
+        //  gain, the panel's dependent DFMA chain queues behind the DMMAs on the shared FP64 pipe)
+        if (nbk1 > 0 && warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
+        __syncthreads();
     }
     // undo the row interchanges as column interchanges (reverse order): thread j follows stored column j to its final position
     int* dest = (int*)R;
@@ -458,21 +438,12 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         dest[tid] = pos;
     }
     __syncthreads();
-    ZID_T(6)
-    for (int e = tid; e < n * n; e += c.nthr) {
-        const int i = e / n, j = e - i * n;
-        Out[(long long)i * a.Ainv.ld + dest[j]] = As[i * lda + j];
-    }
-    ZID_T(7)
-#ifdef ZID_PROFILE
-    if ((tid == 0 || tid == 200) && b == 0) printf("zid n=%d LA=%d tid=%d: load %lld panel0 %lld rows %lld upd(noLA) %lld la-part1 %lld panel|rest %lld dest %lld store %lld\n", n, (int)LA, tid, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7]);
-#endif
+    for (int i = warp; i < n; i += NW)
+        for (int j = lane; j < n; j += 32) Out[(long long)i * a.Ainv.ld + dest[j]] = As[i * lda + j];
     if (a.info && tid == 0) a.info[b] = bad;
 }
-__device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, false>(c, a); }
-__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, false>(c, a); }
-__device__ __forceinline__ void zinv_dmma_la_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, true>(c, a); }
-__device__ __forceinline__ void zinv_dmma8_la_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, true>(c, a); }
+__device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16>(c, a); }
+__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8>(c, a); }
 static inline size_t zinv_dmma_smem(int n) {
     const int np = (n + 7) & ~7;
     return ((size_t)np * (np + 4) + (size_t)ZID_NB * (np + 2)) * sizeof(cd) + 10 * sizeof(zid_slot) + (size_t)np * 4 + 16;
@@ -661,10 +632,6 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
 #ifndef KH_HOST_EMU
     static int zvar = -1;
     if (zvar < 0) { const char* e = getenv("KH_ZINV_KERNEL"); zvar = e ? atoi(e) : 0; }   // 1: previous register-resident kernels
-    if (n <= 64 && n >= 16 && zvar == 2)
-        return kh_launch<zinv_args, zinv_dmma8_la_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
-    if (n <= ZID_NMAX && n >= 16 && zvar == 2)
-        return kh_launch<zinv_args, zinv_dmma_la_body, 512, 1>(dim3(batch), 512, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
     if (n <= 64 && n >= 16 && zvar != 1)
         return kh_launch<zinv_args, zinv_dmma8_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
     if (n <= ZID_NMAX && n >= 16 && zvar != 1)

@@ -46,6 +46,6 @@ if __name__ == "__main__":
         n = int(sys.argv[1]) if len(sys.argv) > 1 else 98
         batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4140
         peaks()
-        for v in os.environ.get("KH_ZG_VARIANTS", "9,0,1,2").split(","):
+        for v in os.environ.get("KH_ZG_VARIANTS", "9,1,0").split(","):
             env = dict(os.environ, KH_ZGEMM_VARIANT=v, KH_ZG_CHILD="1")
             subprocess.run([sys.executable, __file__, str(n), str(batch)], env=env)
