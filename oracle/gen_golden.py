@@ -231,12 +231,38 @@ def gen_bzi_beam():
     print("bzi beam done", np.abs(total).max())
 
 
+
+def gen_bands():
+    """Band post-processing: khepri.eigentricks on unit-cell S-matrices of the Crystal path."""
+    from khepri.eigentricks import scattering_eigenvalues as ref_eigs
+    out = {}
+    st5, srcs5 = cases.case_suh03()
+    st3 = cases.holey_pair(3, 128)
+    todo = [("p5a", st5, srcs5[10]), ("p5b", st5, dict(srcs5[120], theta=20.0, phi=30.0)),
+            ("p3a", st3, dict(wavelength=1 / 0.52, te=1.0, tm=0.0)), ("p3b", st3, dict(wavelength=1 / 0.58, te=1.0, tm=1.0, theta=35.0, phi=10.0))]
+    for tag, st, src in todo:
+        cl = ref_crystal(st)
+        cl.set_source(**src)
+        cl.solve()
+        S4 = np.asarray(cl.Stot)
+        S = np.block([[S4[0, 0], S4[0, 1]], [S4[1, 0], S4[1, 1]]])
+        w, v, det = ref_eigs(S, dos=True)
+        out[tag + "_S"] = S4
+        out[tag + "_w"] = w
+        out[tag + "_det"] = np.asarray(det)
+    np.savez_compressed(os.path.join(OUT, "bands.npz"), **out)
+    print("bands.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if "--bzi-beam" in sys.argv:
         gen_bzi_beam()
     elif "--analytical" in sys.argv:
         gen_analytical()
+    elif "--bands" in sys.argv:
+        gen_bands()
     else:
         main()
         gen_analytical()
         gen_bzi_beam()
+        gen_bands()

@@ -605,3 +605,36 @@ def rect_pixmap(shape, eps_bg, center, wh, eps, base=None):
     m = (xs >= x0) & (xs <= x0 + wh[0]) & (ys >= y0) & (ys <= y0 + wh[1])
     pm[m] = eps
     return pm
+
+
+# --------------------------------------------------------------------------- #
+# band post-processing (khepri/eigentricks.py)
+# --------------------------------------------------------------------------- #
+def scattering_splitlr(S):
+    """Pencil (Sl, Sr) of a flat 2n x 2n S-matrix.  eigentricks.py:5-21."""
+    h = S.shape[0] // 2
+    I = np.eye(h, dtype=S.dtype)
+    Z = np.zeros((h, h), dtype=S.dtype)
+    Sl = np.block([[S[:h, :h], Z], [S[h:, :h], -I]])
+    Sr = np.block([[I, -S[:h, h:]], [Z, -S[h:, h:]]])
+    return Sl, Sr
+
+
+def scattering_eigenvalues(S):
+    """Generalized eigenpairs of (Sl, Sr) with scipy's QZ, as the reference.  eigentricks.py:29-40."""
+    from scipy.linalg import eig as geig
+    Sl, Sr = scattering_splitlr(S)
+    if np.any(np.isnan(Sr)) or np.any(np.isnan(Sl)):
+        return None
+    return geig(Sl, Sr)
+
+
+def scattering_det(S):
+    """eigentricks.py:23-27."""
+    h = S.shape[0] // 2
+    return np.linalg.det(S[:h, :h] - S[:h, h:] @ inv(S[h:, h:]) @ S[h:, :h]) * np.linalg.det(S[h:, h:])
+
+
+def flat_smatrix(S4):
+    """(2,2,n,n) -> (2n,2n) block matrix."""
+    return np.block([[S4[0, 0], S4[0, 1]], [S4[1, 0], S4[1, 1]]])

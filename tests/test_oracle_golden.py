@@ -156,3 +156,25 @@ def test_bzi_beam_amplitudes_and_summed_fields():
         E, H = orc.fields_volume(st, sol, xo, yo, zo, None, None, incident_fields=A.reshape(-1))
         total = total + np.asarray((E, H))
     assert np.abs(total - g["fields"]).max() <= 1e-9 * np.abs(g["fields"]).max()
+
+
+def match_spectrum(got, want, tol):
+    """Every eigenvalue of `want` has a partner in `got` within tol relative (ordering is free, multiplicities respected)."""
+    got = list(np.asarray(got))
+    for w in np.asarray(want):
+        d = [abs(g - w) for g in got]
+        j = int(np.argmin(d))
+        assert d[j] <= tol * max(1.0, abs(w)), (w, got[j], d[j])
+        got.pop(j)
+
+
+@pytest.mark.parametrize("tag", ["p5a", "p5b", "p3a", "p3b"])
+def test_band_postprocessing(tag):
+    """eigentricks.scattering_eigenvalues / scattering_det of the reference on Crystal-path S-matrices."""
+    g = gold("bands")
+    S = orc.flat_smatrix(g[tag + "_S"])
+    w, v = orc.scattering_eigenvalues(S)
+    match_spectrum(w, g[tag + "_w"], 1e-10)
+    Sl, Sr = orc.scattering_splitlr(S)
+    assert np.abs(Sl @ v - (Sr @ v) * w[None, :]).max() <= 1e-9 * np.abs(w).max()
+    assert abs(orc.scattering_det(S) - g[tag + "_det"]) <= 1e-9 * abs(g[tag + "_det"])

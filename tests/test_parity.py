@@ -369,3 +369,31 @@ def test_convmat_512_and_batch_of_layers():
     for k, p in enumerate((pm, pm2)):
         ref = orc.convolution_matrix(p, (15, 15))
         assert np.abs(C[k] - ref).max() <= 1e-14 * np.abs(ref).max()
+
+
+# ----------------------------------------------------------------------------- band post-processing
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("tag", ["p5a", "p5b", "p3a", "p3b"])
+def test_scattering_eigenvalues(backend, tag):
+    """khepri.eigentricks.scattering_eigenvalues (eigentricks.py:29-40) as transfer matrix + batched eigensolver: spectrum
+    against the reference's QZ result, and the generalized residual Sl v = w Sr v of every returned pair."""
+    from khepri_b200 import eigentricks as et
+    from tests.test_oracle_golden import match_spectrum
+    eng = engine(backend)
+    g = gold("bands")
+    S4 = g[tag + "_S"]
+    w, v = et.scattering_eigenvalues(S4, engine=eng)
+    match_spectrum(w, g[tag + "_w"], 1e-8)
+    Sl, Sr = orc.scattering_splitlr(orc.flat_smatrix(S4))
+    assert np.abs(Sl @ v - (Sr @ v) * w[None, :]).max() <= 1e-8 * np.abs(w).max() * np.abs(v).max()
+    # flat layout + batch axis + determinant
+    Sflat = orc.flat_smatrix(S4)
+    wb, vb, det = et.scattering_eigenvalues(np.stack([Sflat, Sflat]), dos=True, engine=eng)
+    assert wb.shape == (2, w.size) and vb.shape == (2,) + v.shape and det.shape == (2,)
+    match_spectrum(wb[1], g[tag + "_w"], 1e-8)
+    assert abs(det[0] - g[tag + "_det"]) <= 1e-7 * abs(g[tag + "_det"])
+    Slh, Srh = et.scattering_splitlr(Sflat)
+    assert np.array_equal(Slh, Sl) and np.array_equal(Srh, Sr)
+    bad = S4.copy(); bad[0, 0, 0, 0] = np.nan
+    assert et.scattering_eigenvalues(bad, engine=eng) is None
+    assert et.band_structure(S4, engine=eng).ndim == 1
