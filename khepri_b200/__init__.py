@@ -7,6 +7,7 @@ without one -- there is no CPU fallback.
 """
 from .crystal import Crystal, Multilayer
 from . import beams
+from . import eigentricks
 from .draw import Drawing
 from .engine import Engine
 from .expansion import Expansion
@@ -14,4 +15,4 @@ from .extension import ExtendedLayer
 from .layer import Field, Formulation, Layer
 from ._lib import KhepriError
 
-__all__ = ["beams", "Crystal", "Multilayer", "Drawing", "Engine", "Expansion", "ExtendedLayer", "Field", "Formulation", "Layer", "KhepriError"]
+__all__ = ["beams", "eigentricks", "Crystal", "Multilayer", "Drawing", "Engine", "Expansion", "ExtendedLayer", "Field", "Formulation", "Layer", "KhepriError"]

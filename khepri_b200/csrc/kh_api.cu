@@ -593,11 +593,16 @@ extern "C" int kh_convmat(int L, int Nx, int Ny, int is_complex, const void* pix
     cd* G = b.get<cd>((size_t)L * Nx * (2 * Q - 1));
     cd* Ft = F ? (cd*)F : b.get<cd>((size_t)L * (2 * P - 1) * (2 * Q - 1));
     dft1_args a1{Nx, Ny, Q, is_complex, pix, G};
-    KH_TRY((kh_launch<dft1_args, dft1_body>(dim3(Nx, L), 256, (size_t)2 * Ny * sizeof(cd), st, a1)));
+    KH_TRY(dft1_launch(st, L, a1));
     dft2_args a2{Nx, Ny, P, Q, G, Ft};
-    KH_TRY((kh_launch<dft2_args, dft2_body>(dim3((2 * P - 1) * (2 * Q - 1), L), 128, 256 * sizeof(double), st, a2)));
+#ifndef KH_HOST_EMU
+    if (2 * Q - 1 <= 32 && (size_t)(Nx + 128) * sizeof(cd) <= (size_t)200 * 1024)
+        KH_TRY((kh_launch<dft2_args, dft2_rows_body>(dim3(2 * P - 1, L), 128, (size_t)(Nx + 128) * sizeof(cd), st, a2, "dft2")));
+    else
+#endif
+    KH_TRY((kh_launch<dft2_args, dft2_body>(dim3((2 * P - 1) * (2 * Q - 1), L), 128, 256 * sizeof(double), st, a2, "dft2")));
     gather_args a3{P, Q, Ft, (cd*)C};
-    KH_TRY((kh_launch<gather_args, gather_body>(dim3(64, L), 256, 0, st, a3)));
+    KH_TRY((kh_launch<gather_args, gather_body>(dim3(64, L), 256, 0, st, a3, "gather")));
     return 0;
 }
 extern "C" int kh_toeplitz_gather(const void* F, int Nx, int Ny, int P, int Q, void* C, int* err, void* stream) {
