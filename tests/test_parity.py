@@ -19,7 +19,7 @@ def rt_close(got, want, tol=RTOL):
 
 # ----------------------------------------------------------------------------- dense primitives
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 3), (50, 50, 50), (64, 64, 16), (65, 130, 33), (98, 98, 98)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 3), (50, 50, 50), (64, 64, 16), (65, 130, 33), (98, 98, 98), (98, 16, 98), (9, 98, 50), (104, 104, 8), (57, 57, 1), (112, 50, 19)])
 def test_zgemm(backend, shape):
     eng = engine(backend)
     rng = np.random.default_rng(1)
@@ -33,7 +33,7 @@ def test_zgemm(backend, shape):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("n", [1, 2, 18, 50, 98])
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 18, 24, 33, 50, 64, 65, 72, 98, 100, 104])
 def test_zinv(backend, n):
     eng = engine(backend)
     rng = np.random.default_rng(2)
