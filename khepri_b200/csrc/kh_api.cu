@@ -44,6 +44,11 @@ KH_DEV void copy4_body(const Cta& c, const copy4_args& a) {
     cd* d = a.dst + (long long)c.bx * a.dst_stride + (long long)c.by * a.n2;
     for (int e = c.tid; e < a.n2; e += c.nthr) d[e] = s[e];
 }
+struct zero_cd_args { long long count; cd* dst; };      // dst[b][0..count) = 0
+KH_DEV void zero_cd_body(const Cta& c, const zero_cd_args& a) {
+    cd* d = a.dst + (long long)c.bx * a.count;
+    for (long long e = c.tid; e < a.count; e += c.nthr) d[e] = mk(0.0, 0.0);
+}
 struct copyv_args { long long count; const cd* src; long long sstride; cd* dst; long long dstride; };   // strided vector copy
 KH_DEV void copyv_body(const Cta& c, const copyv_args& a) {
     const cd* s = a.src + (long long)c.bx * a.sstride;
@@ -142,7 +147,7 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     return 0;
 }
 // star product with a BD RIGHT operand: 4 GEMMs + 1 inverse + O(n^2) kernels
-static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info) {
+static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info, int flux_col = -1) {
     const int n = 2 * N;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -151,6 +156,31 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
     int e;
     if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
+    if (flux_col >= 0) {
+        // Last product of a flux-only solve: poynting_flux_end reads the two columns (g0, N + g0) of S11 and S21 that the
+        // incident order excites (crystal.py:372-381, one delta in `incident`), so only those columns of X = F^-1 A21 and of
+        // S11 = A11 + A12 B11 X are formed (matrix-vector products); S12 and S22 are not needed at all.
+        zero_cd_args zc{n2, X.p}; if ((e = kh_launch<zero_cd_args, zero_cd_body>(dim3(Bc), 256, 0, st, zc))) return e;
+        for (int k = 0; k < 2; ++k) {
+            const int col = flux_col + k * N;
+            MatRef b = A.blk[2]; b.p += col;
+            MatRef xo = X; xo.p += col;
+            zgemm_args g = zgemm_make(n, 1, n, Fi, b, xo);
+            if ((e = zgemm_launch(st, Bc, g))) return e;
+        }
+        if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                               // S21 = B21 X (other columns 0)
+        if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U))) return e;                                      // U = B11 X
+        for (int k = 0; k < 2; ++k) {
+            const int col = flux_col + k * N;
+            MatRef u = U; u.p += col;
+            MatRef so = O.blk[0]; so.p += col;
+            MatRef ci = A.blk[0]; ci.p += col;
+            zgemm_args g = zgemm_make(n, 1, n, A.blk[1], u, so);
+            g.Cin = ci; g.beta = 1.0;
+            if ((e = zgemm_launch(st, Bc, g))) return e;
+        }
+        return 0;
+    }
     if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                          // X = F^-1 A21
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                                   // S21 = B21 X
@@ -165,7 +195,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
 
 
 // S = A (*) B for any mix of dense / BD operands.  The result goes to out_bd when both are BD, else to out_dense.
-static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res) {
+static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res, int flux_col = -1) {
     const int n = 2 * N;
     if (A.bd && B.bd) {
         bd_star_args a{Bc, N, A.bdp, B.bdp, out_bd};
@@ -175,7 +205,7 @@ static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B,
     }
     int e;
     if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info);
-    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info);
+    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info, flux_col);
     else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info);
     res = sref_dense(out_dense, n);
     return e;
@@ -265,14 +295,14 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
     {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
         KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
     KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv, S(12), slab));                     // A^-1 -> 1
-    // [M1|M2|M3] = A^-1 [XB|XA|B]   (slabs 9..11 -> 12..14)
-    KH_TRY(gemm(st, 3 * Bc, n, mref(S(1), 0, n, Bc, n2), mref(S(9), slab, n, Bc, n2), mref(S(12), slab, n, Bc, n2)));
-    {   MatRef A = M(0), Bm = M(11);
-        KH_TRY(gemm(st, Bc, n, M(9), M(12), M(2), -1.0, &A, 1.0));               // T  = A - XB M1
-        KH_TRY(gemm(st, Bc, n, M(9), M(13), M(15), 1.0, &Bm, -1.0));             // R1 = XB M2 - B
-        zgemm_args g = zgemm_make(n, n, n, M(11), M(14), M(16), -1.0);           // R2 = X (A - B M3)
-        g.Cin = A; g.beta = 1.0; g.rowscale = v.xexp; g.rs_stride = n; g.rs_group = 1;
-        KH_TRY(zgemm_launch(st, Bc, g)); }
+    // E = XB A^-1 (-> 12) carries every appearance of A^-1 in alternative.py:186-193:
+    //   T = A - XB A^-1 XB = A - E XB,   X B A^-1 X A - B = E XA - B,   X (A - B A^-1 B) = XA - E B
+    // (4 products instead of the 6 of the literal schedule A^-1 [XB|XA|B] followed by XB M1, XB M2, B M3)
+    KH_TRY(gemm(st, Bc, n, M(9), M(1), M(12)));
+    {   MatRef A = M(0), Bm = M(11), XA = M(10);
+        KH_TRY(gemm(st, Bc, n, M(12), M(9), M(2), -1.0, &A, 1.0));               // T  = A - E XB
+        KH_TRY(gemm(st, Bc, n, M(12), M(10), M(15), 1.0, &Bm, -1.0));            // R1 = E XA - B
+        KH_TRY(gemm(st, Bc, n, M(12), M(11), M(16), -1.0, &XA, 1.0)); }          // R2 = XA - E B
     KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv, S(4), slab));                     // T^-1 -> 3
     // [S11|S12] = T^-1 [R1|R2]
     KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
@@ -451,8 +481,8 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             info_args ia{Bc, nullptr, sinfo, info_out};
             return kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia);
         };
-        auto combine = [&](const SRef& A, const SRef& Bm, SRef& res) -> int {
-            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res);
+        auto combine = [&](const SRef& A, const SRef& Bm, SRef& res, int flux_col = -1) -> int {
+            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res, flux_col);
             if (e) return e;
             if (res.bd) pb ^= 1;
             else { acc_full = cb.accD[pd]; pd ^= 1; e = note_info(); }
@@ -485,7 +515,11 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             }
             if (have_pend) {
                 if (!have_acc) { acc = pend; have_acc = true; }
-                else { SRef r2; KH_TRY(combine(acc, pend, r2)); acc = r2; }
+                else {
+                    // the chain ends here: without an S-matrix output only the flux columns of the total are needed
+                    const int fcol = (!out->Stot_dev && (flags & KH_WANT_FLUX)) ? (N - 1) / 2 : -1;
+                    SRef r2; KH_TRY(combine(acc, pend, r2, fcol)); acc = r2;
+                }
             }
         }
         if (!acc.bd && acc.blk[0].p != acc_full) acc_full = nullptr;      // acc still refers to a layer table

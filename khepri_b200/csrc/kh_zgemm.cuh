@@ -463,15 +463,18 @@ static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     const double work = 8.0 * a.M * a.N * a.K * batch;
     const int var = zgemm_variant();
+    // profiler name: products with a handful of columns (the flux columns of the last star product) are matrix-vector work,
+    // bound by reading A from HBM, and are reported apart from the tensor-bound GEMMs
+    const char* name = a.N <= 8 ? "zgemv" : "zgemm";
     const bool t56 = zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64);
     const unsigned g56 = (unsigned)batch * ((a.M + 55) / 56) * ((a.N + 55) / 56), g64 = (unsigned)batch * ((a.M + 63) / 64) * ((a.N + 63) / 64);
     if (var == 9) {
-        if (t56) return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 2), st, a, "zgemm", work);
-        return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 2), st, a, "zgemm", work);
+        if (t56) return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 2), st, a, name, work);
+        return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 2), st, a, name, work);
     }
-    if (t56 && var == 1) return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, "zgemm", work);
-    if (t56) return kh_launch<zgemm_args, zgemm56u3_body, 256, 2>(dim3(g56), 256, zgemm_smem(56, 3), st, a, "zgemm", work);
-    return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, "zgemm", work);
+    if (t56 && var == 1) return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, name, work);
+    if (t56) return kh_launch<zgemm_args, zgemm56u3_body, 256, 2>(dim3(g56), 256, zgemm_smem(56, 3), st, a, name, work);
+    return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, name, work);
 }
 
 // convenience builder: plain C = alpha*A*B (+ beta*Cin) on [batch, n, n] row-major stacks
