@@ -95,7 +95,29 @@ static int gemm(kh_stream_t st, int batch, int n, MatRef A, MatRef B, MatRef C, 
 
 // dense Redheffer star product (alternative.py:19-30) with the push-through identity
 // D^-1 B11 = B11 F^-1, F = I - A22 B11:  one inverse + ten GEMMs.  tmp: 7 slabs of [Bc][n][n].
-static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info) {
+// Flux-only forward chain: poynting_flux_end reads the two columns (g0, N + g0) of S11 and S21 of the total that the incident
+// order excites (crystal.py:372-381), and in  S = A (*) B  the columns of S11 / S21 depend on A11 and A21 through those same
+// columns only (S11 = A11 + A12 B11 F^-1 A21, S21 = B21 F^-1 A21; A12, A22 enter in full).  With fc >= 0 every product of the
+// chain therefore forms S11 / S21 in the two flux columns as matrix-vector products and S12 / S22 in full; the LAST product
+// needs no S12 / S22 at all.  cols2(): Cout[:, c] = Amat Bsrc[:, c] (+ Cin[:, c]) for c in {fc, fc + N}.
+static int cols2(kh_stream_t st, int Bc, int n, int fc, MatRef Amat, MatRef Bsrc, MatRef Cout, const MatRef* Cin = nullptr) {
+    for (int k = 0; k < 2; ++k) {
+        const int col = fc + k * (n / 2);
+        MatRef b = Bsrc; b.p += col;
+        MatRef c = Cout; c.p += col;
+        zgemm_args g = zgemm_make(n, 1, n, Amat, b, c);
+        if (Cin) { MatRef ci = *Cin; ci.p += col; g.Cin = ci; g.beta = 1.0; }
+        int e = zgemm_launch(st, Bc, g);
+        if (e) return e;
+    }
+    return 0;
+}
+static int zero_mat(kh_stream_t st, int Bc, long long n2, MatRef M) {
+    zero_cd_args zc{n2, M.p};
+    return kh_launch<zero_cd_args, zero_cd_body>(dim3(Bc), 256, 0, st, zc);
+}
+
+static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
     MatRef U = mref(tmp + 4 * slab, n2, n), Z = mref(tmp + 5 * slab, n2, n), Vt = mref(tmp + 6 * slab, n2, n);
@@ -103,11 +125,19 @@ static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& 
     int e;
     if ((e = gemm(st, Bc, n, A.blk[3], B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;     // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
-    if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                    // X = F^-1 A21
+    if (fc >= 0) {
+        if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                           // X = F^-1 A21      (flux columns)
+        if ((e = cols2(st, Bc, n, fc, B.blk[2], X, O.blk[2]))) return e;                     // S21 = B21 X
+        if ((e = cols2(st, Bc, n, fc, B.blk[0], X, U))) return e;                            // U = B11 X
+        if ((e = cols2(st, Bc, n, fc, A.blk[1], U, O.blk[0], &A.blk[0]))) return e;          // S11 = A11 + A12 U
+        if (last) return 0;
+    } else {
+        if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                // X = F^-1 A21
+        if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                          // S21 = B21 X
+        if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                 // U = B11 X
+        if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;     // S11 = A11 + A12 U
+    }
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                    // Y = F^-1 A22
-    if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                              // S21 = B21 X
-    if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                     // U = B11 X
-    if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;         // S11 = A11 + A12 U
     if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                     // Z = Y B12
     if ((e = gemm(st, Bc, n, B.blk[2], Z, O.blk[3], 1.0, &B.blk[3], 1.0))) return e;         // S22 = B22 + B21 Z
     if ((e = gemm(st, Bc, n, B.blk[0], Z, Vt, 1.0, &B.blk[1], 1.0))) return e;               // Vt = B12 + B11 Z
@@ -126,7 +156,7 @@ static int bdmul(kh_stream_t st, int Bc, int N, int side, const cd* bd, int blk,
 }
 
 // star product with a BD (uniform layer / half space) LEFT operand: 5 GEMMs + 1 inverse + O(n^2) kernels
-static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef& B, cd* out, cd* tmp, int* info) {
+static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
     const int n = 2 * N;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -136,10 +166,17 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     if ((e = bdmul(st, Bc, N, 0, A, 3, B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;           // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
     if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X))) return e;                                          // X = F^-1 A21
-    if ((e = bdmul(st, Bc, N, 1, A, 3, Fi, Y))) return e;                                          // Y = F^-1 A22
-    if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                                    // S21 = B21 X
-    if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                           // U = B11 X
+    if (fc >= 0) {
+        if ((e = cols2(st, Bc, n, fc, B.blk[2], X, O.blk[2]))) return e;                           // S21 = B21 X   (flux columns)
+        if ((e = zero_mat(st, Bc, n2, U))) return e;
+        if ((e = cols2(st, Bc, n, fc, B.blk[0], X, U))) return e;                                  // U = B11 X     (flux columns, 0 elsewhere)
+    } else {
+        if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                                // S21 = B21 X
+        if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                       // U = B11 X
+    }
     if ((e = bdmul(st, Bc, N, 0, A, 1, U, O.blk[0], 1.0, nullptr, 0.0, 0.0, A, 0))) return e;      // S11 = A11 + A12 U
+    if (fc >= 0 && last) return 0;
+    if ((e = bdmul(st, Bc, N, 1, A, 3, Fi, Y))) return e;                                          // Y = F^-1 A22
     if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                           // Z = Y B12
     if ((e = gemm(st, Bc, n, B.blk[2], Z, O.blk[3], 1.0, &B.blk[3], 1.0))) return e;               // S22 = B22 + B21 Z
     if ((e = gemm(st, Bc, n, B.blk[0], Z, Vt, 1.0, &B.blk[1], 1.0))) return e;                     // Vt = B12 + B11 Z
@@ -147,7 +184,7 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     return 0;
 }
 // star product with a BD RIGHT operand: 4 GEMMs + 1 inverse + O(n^2) kernels
-static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info, int flux_col = -1) {
+static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
     const int n = 2 * N;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -156,36 +193,21 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
     int e;
     if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
-    if (flux_col >= 0) {
-        // Last product of a flux-only solve: poynting_flux_end reads the two columns (g0, N + g0) of S11 and S21 that the
-        // incident order excites (crystal.py:372-381, one delta in `incident`), so only those columns of X = F^-1 A21 and of
-        // S11 = A11 + A12 B11 X are formed (matrix-vector products); S12 and S22 are not needed at all.
-        zero_cd_args zc{n2, X.p}; if ((e = kh_launch<zero_cd_args, zero_cd_body>(dim3(Bc), 256, 0, st, zc))) return e;
-        for (int k = 0; k < 2; ++k) {
-            const int col = flux_col + k * N;
-            MatRef b = A.blk[2]; b.p += col;
-            MatRef xo = X; xo.p += col;
-            zgemm_args g = zgemm_make(n, 1, n, Fi, b, xo);
-            if ((e = zgemm_launch(st, Bc, g))) return e;
-        }
-        if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                               // S21 = B21 X (other columns 0)
-        if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U))) return e;                                      // U = B11 X
-        for (int k = 0; k < 2; ++k) {
-            const int col = flux_col + k * N;
-            MatRef u = U; u.p += col;
-            MatRef so = O.blk[0]; so.p += col;
-            MatRef ci = A.blk[0]; ci.p += col;
-            zgemm_args g = zgemm_make(n, 1, n, A.blk[1], u, so);
-            g.Cin = ci; g.beta = 1.0;
-            if ((e = zgemm_launch(st, Bc, g))) return e;
-        }
-        return 0;
+    if (fc >= 0) {
+        if ((e = zero_mat(st, Bc, n2, X))) return e;
+        if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                                 // X = F^-1 A21  (flux columns, 0 elsewhere)
+    } else {
+        if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                      // X = F^-1 A21
     }
-    if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                          // X = F^-1 A21
-    if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                                   // S21 = B21 X
     if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U))) return e;                                          // U = B11 X
-    if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;               // S11 = A11 + A12 U
+    if (fc >= 0) {
+        if ((e = cols2(st, Bc, n, fc, A.blk[1], U, O.blk[0], &A.blk[0]))) return e;                // S11 = A11 + A12 U  (flux columns)
+        if (last) return 0;
+    } else {
+        if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;           // S11 = A11 + A12 U
+    }
+    if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
     if ((e = bdmul(st, Bc, N, 1, Bd, 1, Y, Z))) return e;                                          // Z = Y B12
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, Z, O.blk[3], 1.0, nullptr, 0.0, 0.0, Bd, 3))) return e;    // S22 = B22 + B21 Z
     if ((e = bdmul(st, Bc, N, 0, Bd, 0, Z, Vt, 1.0, nullptr, 0.0, 0.0, Bd, 1))) return e;          // Vt = B12 + B11 Z
@@ -195,7 +217,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
 
 
 // S = A (*) B for any mix of dense / BD operands.  The result goes to out_bd when both are BD, else to out_dense.
-static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res, int flux_col = -1) {
+static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res, int fc = -1, bool last = false) {
     const int n = 2 * N;
     if (A.bd && B.bd) {
         bd_star_args a{Bc, N, A.bdp, B.bdp, out_bd};
@@ -204,9 +226,9 @@ static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B,
         return e;
     }
     int e;
-    if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info);
-    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info, flux_col);
-    else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info);
+    if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info, fc, last);
+    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info, fc, last);
+    else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info, fc, last);
     res = sref_dense(out_dense, n);
     return e;
 }
@@ -481,8 +503,10 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             info_args ia{Bc, nullptr, sinfo, info_out};
             return kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia);
         };
-        auto combine = [&](const SRef& A, const SRef& Bm, SRef& res, int flux_col = -1) -> int {
-            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res, flux_col);
+        // without an S-matrix output only the flux columns of S11 / S21 are carried along the chain (see cols2)
+        const int fcol = (!want_fields && !out->Stot_dev && (flags & KH_WANT_FLUX)) ? (N - 1) / 2 : -1;
+        auto combine = [&](const SRef& A, const SRef& Bm, SRef& res, bool last = false) -> int {
+            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res, fcol, last);
             if (e) return e;
             if (res.bd) pb ^= 1;
             else { acc_full = cb.accD[pd]; pd ^= 1; e = note_info(); }
@@ -515,11 +539,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             }
             if (have_pend) {
                 if (!have_acc) { acc = pend; have_acc = true; }
-                else {
-                    // the chain ends here: without an S-matrix output only the flux columns of the total are needed
-                    const int fcol = (!out->Stot_dev && (flags & KH_WANT_FLUX)) ? (N - 1) / 2 : -1;
-                    SRef r2; KH_TRY(combine(acc, pend, r2, fcol)); acc = r2;
-                }
+                else { SRef r2; KH_TRY(combine(acc, pend, r2, true)); acc = r2; }      // the chain ends here
             }
         }
         if (!acc.bd && acc.blk[0].p != acc_full) acc_full = nullptr;      // acc still refers to a layer table
