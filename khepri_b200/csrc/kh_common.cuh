@@ -93,6 +93,35 @@ KH_HD double kh_rsqrt(double x) {
 #endif
 }
 
+#ifdef __CUDACC__
+// Division-free scalar helpers for latency-critical, redundantly computed scalars (Wilkinson shifts, Householder scalars):
+// on B200 a dependent FP64 op costs ~20 cycles and the library sqrt / division / hypot are 25-40 of them back to back.
+// 1/x for normal x: hardware seed (20 bits) + two Newton steps.
+__device__ __forceinline__ double kh_rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+// principal complex square root, ~2 ulp: exact power-of-four scaling, two reciprocal square roots, no division / hypot.
+__device__ __forceinline__ cd kh_csqrt_fast(cd z) {
+    const double m = fmax(fabs(z.x), fabs(z.y));
+    if (!(m > 0.0)) return mk(0.0, z.y);
+    const int e = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;          // m = f 2^e, f in [1, 2)
+    const int k = e & ~1;                                              // even: sqrt(2^k) is exact
+    const double sc = __hiloint2double((1023 - k) << 20, 0), bs = __hiloint2double((1023 + (k >> 1)) << 20, 0);
+    const double xs = z.x * sc, ys = z.y * sc;                         // max magnitude in [1, 4)
+    const double s2 = fma(xs, xs, ys * ys);
+    const double az = s2 * kh_rsqrt(s2);                               // |z| scaled
+    const double w = 0.5 * (fabs(xs) + az);                            // >= 0.5
+    const double rw = kh_rsqrt(w);
+    const double t = w * rw * bs, h = 0.5 * rw * bs;                   // sqrt(w), 1 / (2 sqrt(w)), scaled back
+    if (xs >= 0.0) return mk(t, ys * h);
+    return mk(fabs(ys) * h, copysign(t, ys));
+}
+#endif
+
 // ------------------------------------------------------------------ CTA context
 struct Cta {
     int tid, nthr;           // thread index / threads per CTA

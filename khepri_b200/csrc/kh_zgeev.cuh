@@ -318,10 +318,18 @@ KH_DEV void zhessz_body(const Cta& c, const zgeev_args& a) {
         const double xn2 = kh_warp_allsum(part);
         const cd alpha = HH(k + 1, k);
         if (xn2 == 0.0 && alpha.y == 0.0) continue;          // already reduced: H_k = I   (uniform across the CTA)
-        const double beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
-        const double rbeta = 1.0 / beta;
+        // sqrt, 1/beta and 1/(alpha - beta) sit on the critical path of every step (all threads wait for them): one reciprocal
+        // square root gives both |beta| and 1/beta, and the complex reciprocal is division free (kh_crecip_fast); the library
+        // sqrt + two divisions + Smith's complex division were ~2 k cycles of dependent FP64 work per Householder step
+        const double s2 = cabs2(alpha) + xn2, rs = kh_rsqrt(s2);
+        const double beta = -copysign(s2 * rs, alpha.x);
+        const double rbeta = -copysign(rs, alpha.x);
         const cd tau = mk((beta - alpha.x) * rbeta, -alpha.y * rbeta);
+#ifdef KH_HOST_EMU
         const cd sc = crecip(alpha - mk(beta, 0.0));
+#else
+        const cd sc = kh_crecip_fast(alpha - mk(beta, 0.0));
+#endif
         const cd ctau = cconj(tau);
         for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
             const cd vi = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
@@ -748,6 +756,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
         else if (its % 10 == 0) t = HQ(iact, iact) + mk(0.75 * cabs1(HQ(iact, iact - 1)), 0.0);
         else {
             t = HQ(iact, iact);
+#ifdef KH_HOST_EMU
             cd u = csqrt_(HQ(iact - 1, iact)) * csqrt_(HQ(iact, iact - 1));
             double s = cabs1(u);
             if (s != 0.0) {
@@ -762,6 +771,23 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 }
                 t = t - u * (u / (x + y));
             }
+#else
+            // Wilkinson shift with division-free scalar arithmetic: every thread of the CTA evaluates it before the sweep can
+            // start, and the three complex square roots + three divisions of the textbook form were several thousand cycles of
+            // dependent FP64 work per sweep.  (A shift only steers convergence: a few ulp in it do not touch the similarity.)
+            cd u = kh_csqrt_fast(HQ(iact - 1, iact)) * kh_csqrt_fast(HQ(iact, iact - 1));
+            double s = cabs1(u);
+            if (s != 0.0) {
+                cd x = 0.5 * (HQ(iact - 1, iact - 1) - t);
+                const double sx = cabs1(x);
+                s = fmax(s, sx);
+                const double rs = kh_rcp_fast(s);
+                cd xs = rs * x, us = rs * u;
+                cd y = s * kh_csqrt_fast(xs * xs + us * us);
+                if (sx > 0.0 && x.x * y.x + x.y * y.y < 0.0) y = -y;
+                t = t - u * (u * kh_crecip_fast(x + y));
+            }
+#endif
         }
         // ---- one implicit single-shift sweep over the window [l, iact], one barrier per rotation.
         // R(k): rows k,k+1 <- G_k (window columns);  C(k): columns k,k+1 <- . G_k^H (window rows <= k+2).
