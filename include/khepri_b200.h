@@ -146,6 +146,13 @@ int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl_dev, const
                          const double* z_host, int nz, const double* zpos_host, void* F_dev,
                          void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Fourier fields only (crystal.py:234-277 _fourier_fields; fields_coords_xy(..., return_fourier=True), :326-327):
+ * S_dev [B][nz][6][N] c128 = (sx, sy, sz, ux, uy, uz) per depth, the coefficient vectors the inverse transform of
+ * kh_fields_batch consumes.  Workspace: kh_fields_workspace_bytes(plan, B, 1, nz). */
+int kh_fields_fourier_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                            const kh_outputs* solved, const double* z_host, int nz, const double* zpos_host, void* S_dev,
+                            void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- Brillouin-zone-integration source (beams.py:164-191, amplitudes_from_fields) ---------------- */
 /* amp_dev [B][N][4] c128 = scale * sum_p fields_dev[p][c] exp(-i ((kp[b] + g) . r_p)), c = (Ex, Ey, Hx, Hy);
  * kp_dev [B][2] c128, g_dev [2][N] f64, x_dev / y_dev [npts] f64, fields_dev [npts][4] c128. */

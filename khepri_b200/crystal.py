@@ -335,6 +335,18 @@ class Crystal:
                                self.stack_positions, grid=grid)
         return F[0]
 
+    def _fields_fourier(self, zs, incident_fields):
+        """crystal.py:234-277 for a list of depths -> DEVICE [nz, 6, N]."""
+        assert self.solved, "Call solve first."
+        if self._solved is None or self._solved_src != (self.source.wavelength, tuple(self.kp)):
+            raise AssertionError("Layer at z did not store eigenspace.")     # crystal.py:245
+        for z in zs:
+            layer, _, _ = self.locate_layer(z)
+            assert layer.fields, f"Layer at {z} did not store eigenspace."
+        plan = self._get_plan(True)
+        inc = np.asarray(incident_fields, dtype=np.complex128).reshape(1, 2, plan.n)
+        return self.engine.fields_fourier(plan, self._solved, [self.source.wavelength], [self.kp], inc, zs, self.stack_positions)[0]
+
     def fields_batch_sum(self, wavelengths, kps, incident_fields, x, y, zs, chunk=64):
         """Sum over a batch of sources of the field maps (Ex,Ey,Ez,Hx,Hy,Hz)(z, y, x): the k-sum of the Brillouin-zone
         integration loop (examples/bzi/bzi_animation.py:59-80) -- solve with retained eigenspaces, reconstruct with each
@@ -369,12 +381,14 @@ class Crystal:
         x, y = ensure_array(x), ensure_array(y)
         assert x.shape == y.shape and (len(x.shape) == 2), "x and y must be 2D meshgrids"
         assert self.solved, "Call solve first."
-        if return_fourier or isinstance(z, str):
-            raise NotImplementedError("return_fourier / 'farfield' are not available on the GPU path")
+        if isinstance(z, str):
+            raise NotImplementedError("'farfield' is not available (the reference's own far-field path calls an undefined function, crystal.py:323)")
         if incident_fields is None:
             incident_fields = np.hstack(self.get_source_as_field_vectors())
         elif isinstance(incident_fields, tuple) and len(incident_fields) == 2:
             incident_fields = np.hstack(incident_fields)
+        if return_fourier:                                  # crystal.py:326-327 -> (sx, sy, sz, ux, uy, uz), each (N,)
+            return tuple(self._fields_fourier([float(z)], incident_fields).cpu().numpy()[0])
         F = self._fields_points(x, y, [float(z)], incident_fields).cpu().numpy()[0]
         F = F.reshape((6,) + x.shape)
         return np.split(F, 2, axis=0)

@@ -674,6 +674,10 @@ extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, 
                                const double*, int, const double*, void*, void*, size_t, void*) {
     return fail(KH_ESTATE, "kh_fields_batch: not built");
 }
+extern "C" int kh_fields_fourier_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, int,
+                                       const double*, void*, void*, size_t, void*) {
+    return fail(KH_ESTATE, "kh_fields_fourier_batch: not built");
+}
 #endif
 
 // ---------------------------------------------------------------------------- FP64 peak probe

@@ -270,11 +270,12 @@ extern "C" size_t kh_fields_grid_workspace_bytes(const kh_plan* plan, int B, int
 }
 
 // grid = 0: scattered points (x_dev[p], y_dev[p]), p < npts.  grid = 1: x_dev[nx], y_dev[ny] are the axes of a rectangular grid.
+// grid = 2: no inverse transform, F_dev receives the Fourier fields [B][nz][6][N] (x_dev, y_dev unused, npts = 1 for the layout).
 static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
                        const kh_outputs* solved, const double* x_dev, const double* y_dev, int npts, int grid, int nx, int ny,
                        const double* z_host, int nz, const double* zpos_host, void* F_dev,
                        void* ws_dev, size_t ws_bytes, void* stream) {
-    if (!plan || B < 0 || !wl_dev || !kp_dev || !inc_dev || !solved || !x_dev || !y_dev || npts < 1 || !z_host || nz < 1 || !zpos_host || !F_dev || !ws_dev)
+    if (!plan || B < 0 || !wl_dev || !kp_dev || !inc_dev || !solved || (grid != 2 && (!x_dev || !y_dev)) || npts < 1 || !z_host || nz < 1 || !zpos_host || !F_dev || !ws_dev)
         return fail(KH_EINVAL, "kh_fields_batch: bad arguments");
     if (!(solved->prefix_dev && solved->suffix_dev && solved->W_dev && solved->V_dev && solved->L_dev))
         return fail(KH_EINVAL, "kh_fields_batch: needs the KH_WANT_FIELDS outputs of kh_solve_batch");
@@ -282,15 +283,16 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
     const kh_plan* p = plan;
     if (p->has_ext) return fail(KH_EINVAL, "kh_fields_batch: extended layers are not supported");
     if (p->layers[p->stack[0]].kind != KH_LAYER_HALF_INC) return fail(KH_EINVAL, "kh_fields_batch: the stack must start with the incidence half space");
-    if (grid && p->Q > FLD_QMAX) return fail(KH_EINVAL, "kh_fields_grid_batch: more than 16 harmonics along y; use kh_fields_batch");
-    if (ws_bytes < (grid ? kh_fields_grid_workspace_bytes(p, B, nx, ny, nz) : kh_fields_workspace_bytes(p, B, npts, nz)))
+    if (grid == 1 && p->Q > FLD_QMAX) return fail(KH_EINVAL, "kh_fields_grid_batch: more than 16 harmonics along y; use kh_fields_batch");
+    if (ws_bytes < (grid == 1 ? kh_fields_grid_workspace_bytes(p, B, nx, ny, nz) : kh_fields_workspace_bytes(p, B, npts, nz)))
         return fail(KH_ENOMEM, "kh_fields_batch: workspace too small");
     kh_stream_t st = (kh_stream_t)stream;
     const int N = p->N, n = p->n, Ls = (int)p->stack.size(), nL = (int)p->layers.size();
     const long long n2 = (long long)n * n;
     Bump bump{(char*)ws_dev, ws_bytes, 0};
     FieldBufs f;
-    layout_fields(p, B, npts, nz, bump, f, grid ? nx : 0, grid ? ny : 0);
+    layout_fields(p, B, npts, nz, bump, f, grid == 1 ? nx : 0, grid == 1 ? ny : 0);
+    if (grid == 2) f.Sall = (cd*)F_dev;                      // fld_z writes the coefficients straight into the caller's buffer
 
     // host: locate every depth (crystal.py:208-232) -> stack position, layer, distance to the right face
     std::vector<int> zpos(nz), zlay(nz);
@@ -352,6 +354,7 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
     {   fld_z_args a{B, N, nz, f.zpos, f.zlayer, f.zdist, f.m12, (long long)Ls * 2 * n, 2LL * n,
                      Wd, Vd, (const cd*)solved->L_dev, (long long)nL * n2, nL, f.ICp, f.ICs, f.Kx, f.Ky, f.k0, f.Sall};
         KH_TRY((kh_launch<fld_z_args, fld_z_body>(dim3(B, nz), 256, (size_t)5 * n * sizeof(cd), st, a))); }
+    if (grid == 2) return 0;
     if (grid) {
         {   fld_gtab_args a{B, N, p->P, p->Q, nx, ny, (const cd*)kp_dev, p->g_dev, x_dev, y_dev, f.Xt, f.Yt};
             KH_TRY((kh_launch<fld_gtab_args, fld_gtab_body>(dim3(B, N + p->Q), 256, 0, st, a, "fld_grid"))); }
@@ -386,7 +389,11 @@ extern "C" int kh_fields_grid_batch(const kh_plan* plan, int B, const double* wl
     if (nx < 1 || ny < 1) return fail(KH_EINVAL, "kh_fields_grid_batch: bad grid");
     return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, xs_dev, ys_dev, nx * ny, 1, nx, ny, z_host, nz, zpos_host, F_dev, ws_dev, ws_bytes, stream);
 }
-
+extern "C" int kh_fields_fourier_batch(const kh_plan* plan, int B, const double* wl_dev, const void* kp_dev, const void* inc_dev,
+                                       const kh_outputs* solved, const double* z_host, int nz, const double* zpos_host, void* S_dev,
+                                       void* ws_dev, size_t ws_bytes, void* stream) {
+    return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, nullptr, nullptr, 1, 2, 0, 0, z_host, nz, zpos_host, S_dev, ws_dev, ws_bytes, stream);
+}
 
 // ---- Brillouin-zone-integration source (khepri/beams.py:164-191, amplitudes_from_fields): Fourier amplitudes of a
 // real-space beam for every k-point of the BZ grid,

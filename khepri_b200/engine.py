@@ -324,6 +324,29 @@ class Engine:
               "kh_fields_batch")
         return F
 
+    def fields_fourier(self, plan, solved, wl, kp, inc, z, stack_positions):
+        """Fourier fields (sx, sy, sz, ux, uy, uz) at depths z for every solve of a want_fields solve
+        (crystal.py:234-277) -> DEVICE tensor [B, nz, 6, N]."""
+        B = solved["prefix"].shape[0]
+        wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(B), _f64)
+        kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2), _c128)
+        inc_d = self.to_dev(np.asarray(inc, dtype=np.complex128).reshape(B, 2, plan.n), _c128)
+        z_h = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(-1))
+        zp_h = np.ascontiguousarray(np.asarray(stack_positions, dtype=np.float64).reshape(-1))
+        assert zp_h.size == plan.Ls + 1, "stack_positions must hold Ls+1 interface positions"
+        nz = z_h.size
+        S = torch.empty((B, nz, 6, plan.n // 2), dtype=_c128, device=self.device)
+        out = Outputs()
+        out.prefix_dev, out.suffix_dev = solved["prefix"].data_ptr(), solved["suffix"].data_ptr()
+        out.W_dev, out.V_dev, out.L_dev = solved["W"].data_ptr(), solved["V"].data_ptr(), solved["L"].data_ptr()
+        wb = self.lib.kh_fields_workspace_bytes(plan.handle, B, 1, nz)
+        ws = self.workspace(wb)
+        dp = C.POINTER(C.c_double)
+        check(self.lib, self.lib.kh_fields_fourier_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(inc_d), C.byref(out),
+                                                         z_h.ctypes.data_as(dp), nz, zp_h.ctypes.data_as(dp), _ptr(S), _ptr(ws), ws.numel(), self.stream()),
+              "kh_fields_fourier_batch")
+        return S
+
     def beam_amplitudes(self, kps, g, x, y, fields4, scale):
         """beams.amplitudes_from_fields for a batch of k-points -> DEVICE [B, N, 4] (Ex, Ey, Hx, Hy per harmonic)."""
         kp_d = self.to_dev(np.asarray(kps, dtype=np.complex128).reshape(-1, 2), _c128)

@@ -254,8 +254,26 @@ def gen_bands():
     print("bands.npz", {k: v.shape for k, v in out.items()})
 
 
+def gen_fields_fourier():
+    """fields_coords_xy(..., return_fourier=True) (crystal.py:326-327): the six Fourier vectors at every depth of the
+    fields55 case, plus one oblique two-polarisation source with explicit incident fields."""
+    st, src, (X, Y, z) = cases.case_fields(5)
+    cl = ref_crystal(st, fields=True)
+    cl.set_source(**src)
+    cl.solve()
+    FF = np.array([np.array(cl.fields_coords_xy(X, Y, zi, return_fourier=True)) for zi in z])
+    src2 = dict(wavelength=1.9, te=0.6, tm=0.8, theta=17.0, phi=25.0)
+    cl.set_source(**src2)
+    cl.solve()
+    FF2 = np.array([np.array(cl.fields_coords_xy(X, Y, zi, return_fourier=True)) for zi in z])
+    np.savez(os.path.join(OUT, "fields55_fourier.npz"), FF=FF, FF_oblique=FF2, z=np.asarray(z))
+    print("fields fourier done", FF.shape)
+
+
 if __name__ == "__main__":
-    if "--bzi-beam" in sys.argv:
+    if "--fields-fourier" in sys.argv:
+        gen_fields_fourier()
+    elif "--bzi-beam" in sys.argv:
         gen_bzi_beam()
     elif "--analytical" in sys.argv:
         gen_analytical()
@@ -266,3 +284,4 @@ if __name__ == "__main__":
         gen_analytical()
         gen_bzi_beam()
         gen_bands()
+        gen_fields_fourier()

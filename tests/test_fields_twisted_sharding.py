@@ -37,6 +37,31 @@ def test_fields_volume_golden(backend, pp, tag, tol):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_fields_return_fourier_golden(backend):
+    """fields_coords_xy(..., return_fourier=True) -> (sx, sy, sz, ux, uy, uz) vs the unmodified reference (crystal.py:326-327),
+    and consistency with the real-space maps through the oracle's idft (fourier.py:136-142)."""
+    eng = engine(backend)
+    g = gold("fields55_fourier")
+    st, src, (X, Y, z) = cases.case_fields(5)
+    cl = build_crystal(st, eng, fields=True)
+    for s, key in ((src, "FF"), (dict(wavelength=1.9, te=0.6, tm=0.8, theta=17.0, phi=25.0), "FF_oblique")):
+        cl.set_source(**s)
+        cl.solve()
+        for iz in (0, 4, len(z) - 1):
+            ff = cl.fields_coords_xy(X, Y, z[iz], return_fourier=True)
+            assert isinstance(ff, tuple) and len(ff) == 6 and ff[0].shape == (25,)
+            assert np.abs(np.array(ff) - g[key][iz]).max() <= 1e-9 * np.abs(g[key]).max()
+        E, _ = cl.fields_coords_xy(X, Y, z[4])
+        k0 = 2 * np.pi / s["wavelength"]
+        Kx, Ky, _ = cl.expansion.k_vectors(cl.kp, s["wavelength"])
+        ff = cl.fields_coords_xy(X, Y, z[4], return_fourier=True)
+        Ex = orc.idft(ff[0], k0 * Kx, k0 * Ky, X, Y)
+        assert np.abs(Ex - E[0]).max() <= 1e-10 * max(1.0, np.abs(E).max())
+    with pytest.raises(NotImplementedError):
+        cl.fields_coords_xy(X, Y, "farfield")
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_fields_need_retained_eigenspace(backend):
     eng = engine(backend)
     st, src, (X, Y, z) = cases.case_fields(5, slices=1)

@@ -107,6 +107,20 @@ def test_fields_volume(pp, tag, tol):
     np.testing.assert_allclose(orc.flux_end(st, sol, src["te"], src["tm"]), g["RT"], rtol=1e-10)
 
 
+def test_fields_fourier_golden():
+    """fields_coords_xy(..., return_fourier=True) (crystal.py:326-327) of the unmodified reference, normal and oblique source."""
+    g = gold("fields55_fourier")
+    st, src, (X, Y, z) = cases.case_fields(5)
+    for s, key in ((src, "FF"), (dict(wavelength=1.9, te=0.6, tm=0.8, theta=17.0, phi=25.0), "FF_oblique")):
+        kp = src_kp(st, s)
+        sol = orc.solve_structure(st, s["wavelength"], kp)
+        e = orc.incident_vector(st["pw"], s["te"], s["tm"], (kp[0], kp[1], orc.source_kzi(st, s["wavelength"], kp)))
+        inc = np.concatenate([e, np.zeros_like(e)])
+        FF = np.array([np.array(orc.fields_fourier_at(st, sol, zi, inc)) for zi in z])
+        assert FF.shape == g[key].shape == (len(z), 6, 25)
+        assert np.abs(FF - g[key]).max() <= 1e-9 * np.abs(g[key]).max()
+
+
 def test_twisted_bilayer_extended():
     g = gold("twisted33")
     tw = cases.twisted_case()
