@@ -8,6 +8,7 @@ without one -- there is no CPU fallback.
 from .crystal import Crystal, Multilayer
 from . import beams
 from . import eigentricks
+from . import factory
 from .draw import Drawing
 from .engine import Engine
 from .expansion import Expansion

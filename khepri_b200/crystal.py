@@ -347,6 +347,12 @@ class Crystal:
         inc = np.asarray(incident_fields, dtype=np.complex128).reshape(1, 2, plan.n)
         return self.engine.fields_fourier(plan, self._solved, [self.source.wavelength], [self.kp], inc, zs, self.stack_positions)[0]
 
+    def _fourier_fields(self, z, incident_fields):
+        """crystal.py:234-277 -> (sx, sy, sz, ux, uy, uz) Fourier vectors at depth z."""
+        if isinstance(incident_fields, tuple) and len(incident_fields) == 2:
+            incident_fields = np.hstack(incident_fields)
+        return tuple(self._fields_fourier([float(z)], incident_fields).cpu().numpy()[0])
+
     def fields_batch_sum(self, wavelengths, kps, incident_fields, x, y, zs, chunk=64):
         """Sum over a batch of sources of the field maps (Ex,Ey,Ez,Hx,Hy,Hz)(z, y, x): the k-sum of the Brillouin-zone
         integration loop (examples/bzi/bzi_animation.py:59-80) -- solve with retained eigenspaces, reconstruct with each
@@ -388,7 +394,7 @@ class Crystal:
         elif isinstance(incident_fields, tuple) and len(incident_fields) == 2:
             incident_fields = np.hstack(incident_fields)
         if return_fourier:                                  # crystal.py:326-327 -> (sx, sy, sz, ux, uy, uz), each (N,)
-            return tuple(self._fields_fourier([float(z)], incident_fields).cpu().numpy()[0])
+            return self._fourier_fields(z, incident_fields)
         F = self._fields_points(x, y, [float(z)], incident_fields).cpu().numpy()[0]
         F = F.reshape((6,) + x.shape)
         return np.split(F, 2, axis=0)

@@ -164,6 +164,14 @@ def test_woodpile_and_doubling(backend):
         rt_close(cl.poynting_flux_end(), g["RT"][i])
         cl.Stot = redheffer_product(cl.Stot, cl.Stot, engine=eng)
         rt_close(cl.poynting_flux_end(), g["RT_doubled"][i])
+    # the reference's builder (factory.py:3-24) with woodpile.py:36-39 parameters: same pixmaps bit for bit, same fluxes
+    from khepri_b200.factory import make_woodpile
+    wp = make_woodpile(0.28, 3.6 ** 2, 0.5, 1.414 / 4, (5, 5), (256, 256), engine=eng)
+    for name in "ABCD":
+        assert np.array_equal(np.asarray(wp.layers[name].epsilon), st["layers"][name][1])
+    wp.set_source(**srcs[4])
+    wp.solve()
+    rt_close(wp.poynting_flux_end(), g["RT"][4])
     if backend == "cuda":
         st, srcs = cases.case_woodpile((11, 11), 2, 2)
         cl = build_crystal(st, eng)
