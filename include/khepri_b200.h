@@ -153,6 +153,13 @@ int kh_fields_fourier_batch(const kh_plan* plan, int B, const double* wl_dev, co
                             const kh_outputs* solved, const double* z_host, int nz, const double* zpos_host, void* S_dev,
                             void* ws_dev, size_t ws_bytes, void* stream);
 
+/* fourier.idft (fourier.py:136-142) as a standalone operator on scattered points:
+ * out_dev [M][npts] c128 = sum_g s_dev[m][g] exp(i (kx[g] x[p] + ky[g] y[p])); kx_dev, ky_dev [N] c128 (callers pass k0 * Kx,
+ * k0 * Ky as crystal.py:329 does), x_dev, y_dev [npts] f64, s_dev [M][N] c128. */
+size_t kh_idft_work_bytes(int N, int npts);
+int kh_idft_batch(int M, int N, int npts, const void* kx_dev, const void* ky_dev, const double* x_dev, const double* y_dev,
+                  const void* s_dev, void* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- Brillouin-zone-integration source (beams.py:164-191, amplitudes_from_fields) ---------------- */
 /* amp_dev [B][N][4] c128 = scale * sum_p fields_dev[p][c] exp(-i ((kp[b] + g) . r_p)), c = (Ex, Ey, Hx, Hy);
  * kp_dev [B][2] c128, g_dev [2][N] f64, x_dev / y_dev [npts] f64, fields_dev [npts][4] c128. */

@@ -55,6 +55,8 @@ SIGNATURES = {
     "kh_fields_grid_batch": (i32, [vp, i32, vp, vp, vp, C.POINTER(Outputs), vp, i32, vp, i32, C.POINTER(f64), i32, C.POINTER(f64),
                                    vp, vp, sz, vp]),
     "kh_fields_fourier_batch": (i32, [vp, i32, vp, vp, vp, C.POINTER(Outputs), C.POINTER(f64), i32, C.POINTER(f64), vp, vp, sz, vp]),
+    "kh_idft_work_bytes": (sz, [i32, i32]),
+    "kh_idft_batch": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "kh_beam_amplitudes_work_bytes": (sz, [i32, i32, i32]),
     "kh_beam_amplitudes": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, f64, vp, vp, sz, vp]),
     "kh_fp64_peak": (i32, [i32, i32, i32, vp, C.POINTER(f64)]),

@@ -678,6 +678,10 @@ extern "C" int kh_fields_fourier_batch(const kh_plan*, int, const double*, const
                                        const double*, void*, void*, size_t, void*) {
     return fail(KH_ESTATE, "kh_fields_fourier_batch: not built");
 }
+extern "C" size_t kh_idft_work_bytes(int, int) { return 0; }
+extern "C" int kh_idft_batch(int, int, int, const void*, const void*, const double*, const double*, const void*, void*, void*, size_t, void*) {
+    return fail(KH_ESTATE, "kh_idft_batch: not built");
+}
 #endif
 
 // ---------------------------------------------------------------------------- FP64 peak probe

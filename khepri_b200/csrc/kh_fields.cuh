@@ -395,6 +395,36 @@ extern "C" int kh_fields_fourier_batch(const kh_plan* plan, int B, const double*
     return fields_impl(plan, B, wl_dev, kp_dev, inc_dev, solved, nullptr, nullptr, 1, 2, 0, 0, z_host, nz, zpos_host, S_dev, ws_dev, ws_bytes, stream);
 }
 
+// ---- fourier.idft (khepri/fourier.py:136-142) as a standalone operator: out[m][p] = sum_g s[m][g] exp(i (kx_g x_p + ky_g y_p)),
+// kx, ky complex per harmonic (callers pass k0 * Kx), points scattered.  Phase matrix, then ONE DMMA GEMM [M x N] . [N x npts].
+struct idft_phase_args { int N, npts, gy; const cd* kx; const cd* ky; const double* x; const double* y; cd* Ph; };
+KH_DEV void idft_phase_body(const Cta& c, const idft_phase_args& a) {
+    const int g = c.bx;
+    const cd kx = a.kx[g], ky = a.ky[g];
+    cd* o = a.Ph + (long long)g * a.npts;
+    for (int p = c.by * c.nthr + c.tid; p < a.npts; p += c.nthr * a.gy) {
+        cd arg = a.x[p] * kx + a.y[p] * ky;
+        o[p] = cexp_(mk(-arg.y, arg.x));
+    }
+}
+extern "C" size_t kh_idft_work_bytes(int N, int npts) { return (size_t)N * npts * sizeof(cd) + 512; }
+extern "C" int kh_idft_batch(int M, int N, int npts, const void* kx_dev, const void* ky_dev, const double* x_dev, const double* y_dev,
+                             const void* s_dev, void* out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+    if (M < 0 || N < 1 || npts < 1 || !kx_dev || !ky_dev || !x_dev || !y_dev || !s_dev || !out_dev || !ws_dev)
+        return fail(KH_EINVAL, "kh_idft_batch: bad arguments");
+    if (ws_bytes < kh_idft_work_bytes(N, npts)) return fail(KH_ENOMEM, "kh_idft_batch: workspace too small");
+    if (M == 0) return 0;
+    kh_stream_t st = (kh_stream_t)stream;
+    Bump bump{(char*)ws_dev, ws_bytes, 0};
+    cd* Ph = bump.get<cd>((size_t)N * npts);
+    int gy = (npts + 4095) / 4096; if (gy > 64) gy = 64;
+    {   idft_phase_args a{N, npts, gy, (const cd*)kx_dev, (const cd*)ky_dev, x_dev, y_dev, Ph};
+        KH_TRY((kh_launch<idft_phase_args, idft_phase_body>(dim3(N, gy), 256, 0, st, a, "idft_phase"))); }
+    zgemm_args g = zgemm_make(M, npts, N, mref((cd*)s_dev, 0, N), mref(Ph, 0, npts), mref(out_dev, 0, npts));
+    KH_TRY(zgemm_launch(st, 1, g));
+    return 0;
+}
+
 // ---- Brillouin-zone-integration source (khepri/beams.py:164-191, amplitudes_from_fields): Fourier amplitudes of a
 // real-space beam for every k-point of the BZ grid,
 //     amp[b][g][c] = scale * sum_p F[p][c] exp(-i ((kp_x[b] + g_x) x_p + (kp_y[b] + g_y) y_p)),   c = (Ex, Ey, Hx, Hy)

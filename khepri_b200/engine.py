@@ -347,6 +347,30 @@ class Engine:
               "kh_fields_fourier_batch")
         return S
 
+    def idft(self, s, kx, ky, x, y):
+        """fourier.idft (fourier.py:136-142) for a stack of coefficient vectors s [M, N] at scattered points -> DEVICE [M, npts]."""
+        s_d = self.to_dev(np.asarray(s, dtype=np.complex128), _c128) if not torch.is_tensor(s) else s.to(self.device, _c128)
+        s_d = s_d.reshape(-1, s_d.shape[-1]).contiguous()
+        M, N = s_d.shape
+        kx_d = self.to_dev(np.asarray(kx, dtype=np.complex128).reshape(-1), _c128)
+        ky_d = self.to_dev(np.asarray(ky, dtype=np.complex128).reshape(-1), _c128)
+        x_d = self.to_dev(np.asarray(x, dtype=np.float64).reshape(-1), _f64)
+        y_d = self.to_dev(np.asarray(y, dtype=np.float64).reshape(-1), _f64)
+        npts = x_d.numel()
+        assert kx_d.numel() == N and ky_d.numel() == N and y_d.numel() == npts
+        out = torch.empty((M, npts), dtype=_c128, device=self.device)
+        cap = max(1, int((2 << 30) // (N * 16)))                     # points per call: phase matrix <= 2 GB
+        for lo in range(0, npts, cap):
+            hi = min(npts, lo + cap)
+            part = out if (lo == 0 and hi == npts) else torch.empty((M, hi - lo), dtype=_c128, device=self.device)
+            wb = self.lib.kh_idft_work_bytes(N, hi - lo)
+            ws = self.workspace(wb)
+            check(self.lib, self.lib.kh_idft_batch(M, N, hi - lo, _ptr(kx_d), _ptr(ky_d), _ptr(x_d[lo:hi]), _ptr(y_d[lo:hi]), _ptr(s_d), _ptr(part),
+                                                   _ptr(ws), ws.numel(), self.stream()), "kh_idft_batch")
+            if part is not out:
+                out[:, lo:hi] = part
+        return out
+
     def beam_amplitudes(self, kps, g, x, y, fields4, scale):
         """beams.amplitudes_from_fields for a batch of k-points -> DEVICE [B, N, 4] (Ex, Ey, Hx, Hy per harmonic)."""
         kp_d = self.to_dev(np.asarray(kps, dtype=np.complex128).reshape(-1, 2), _c128)

@@ -65,3 +65,15 @@ def analytical_coefficients(expansion, islands, eps_host):
     Gx, Gy, epw = expansion.g_vectors_expanded(3)
     data = [(transform(isl["type"], isl["params"], Gx, Gy, expansion.sigma), isl["epsilon"]) for isl in islands]
     return combine_fourier_masks(data, eps_host, inverse=False).reshape(epw)
+
+
+def idft(ffield, kx, ky, x, y, engine=None):
+    """Fourier -> real space at the points (x, y) (fourier.py:136-142): f = sum_g ffield[g] exp(i (kx[g] x + ky[g] y)).
+    Same arguments and result as the reference (ffield (N,) -> array of x's shape); a stack ffield (M, N) gives (M,) + x.shape
+    in one launch pair (kh_idft_batch: phase matrix + one DMMA GEMM).  Runs on the engine's device; no CPU path."""
+    from .engine import Engine
+    eng = engine or Engine.default()
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    s = np.asarray(ffield, dtype=np.complex128)
+    out = eng.idft(s.reshape(-1, s.shape[-1]), kx, ky, x, y).cpu().numpy()
+    return out.reshape(s.shape[:-1] + x.shape)

@@ -267,6 +267,14 @@ def gen_fields_fourier():
     cl.solve()
     FF2 = np.array([np.array(cl.fields_coords_xy(X, Y, zi, return_fourier=True)) for zi in z])
     np.savez(os.path.join(OUT, "fields55_fourier.npz"), FF=FF, FF_oblique=FF2, z=np.asarray(z))
+    # fourier.idft itself on scattered points with complex k (deterministic inputs, no RNG state shared with the tests)
+    from khepri.fourier import idft
+    rng = np.random.default_rng(11)
+    sv = rng.standard_normal(25) + 1j * rng.standard_normal(25)
+    kx = rng.standard_normal(25) * 4 + 0.05j * rng.standard_normal(25)
+    ky = rng.standard_normal(25) * 4 + 0j
+    xx, yy = rng.random((6, 7)), rng.random((6, 7)) - 0.5
+    np.savez(os.path.join(OUT, "idft.npz"), s=sv, kx=kx, ky=ky, x=xx, y=yy, out=idft(sv, kx, ky, xx, yy))
     print("fields fourier done", FF.shape)
 
 

@@ -62,6 +62,27 @@ def test_fields_return_fourier_golden(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_idft_operator(backend):
+    """khepri_b200.fourier.idft == fourier.py:136-142 (oracle restatement) on scattered points, complex k, stacks and ragged sizes."""
+    from khepri_b200.fourier import idft
+    eng = engine(backend)
+    g = gold("idft")                                                     # output of the unmodified reference
+    assert np.abs(idft(g["s"], g["kx"], g["ky"], g["x"], g["y"], engine=eng) - g["out"]).max() <= 1e-12
+    rng = np.random.default_rng(7)
+    for N, shape, M in ((25, (6, 7), 1), (9, (1, 1), 3), (49, (5, 13), 6), (1, (3, 2), 2)):
+        s = rng.standard_normal((M, N)) + 1j * rng.standard_normal((M, N))
+        kx = rng.standard_normal(N) * 4 + 0.05j * rng.standard_normal(N)
+        ky = rng.standard_normal(N) * 4 + 0j
+        x, y = rng.random(shape), rng.random(shape) - 0.5
+        want = np.array([orc.idft(s[m], kx, ky, x, y) for m in range(M)])
+        got = idft(s, kx, ky, x, y, engine=eng)
+        assert got.shape == (M,) + shape
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+        one = idft(s[0], kx, ky, x, y, engine=eng)                       # the reference's call shape
+        assert one.shape == shape and np.abs(one - want[0]).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_fields_need_retained_eigenspace(backend):
     eng = engine(backend)
     st, src, (X, Y, z) = cases.case_fields(5, slices=1)

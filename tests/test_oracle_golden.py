@@ -121,6 +121,11 @@ def test_fields_fourier_golden():
         assert np.abs(FF - g[key]).max() <= 1e-9 * np.abs(g[key]).max()
 
 
+def test_idft_golden():
+    g = gold("idft")
+    np.testing.assert_allclose(orc.idft(g["s"], g["kx"], g["ky"], g["x"], g["y"]), g["out"], rtol=0, atol=1e-13)
+
+
 def test_twisted_bilayer_extended():
     g = gold("twisted33")
     tw = cases.twisted_case()
