@@ -20,7 +20,7 @@ def header_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = header_symbols()
     for must in ("kh_convmat", "kh_toeplitz_gather", "kh_zgemm_batched", "kh_zinv_batched", "kh_zgeev_batched", "kh_plan_create",
-                 "kh_solve_batch", "kh_star_batch", "kh_flux_batch", "kh_fields_batch"):
+                 "kh_solve_batch", "kh_star_batch", "kh_flux_batch", "kh_fields_batch", "kh_fields_fourier_batch", "kh_idft_batch"):
         assert must in syms
 
 
@@ -116,3 +116,31 @@ def test_set_device_adds_half_spaces_like_the_reference():
     assert cl.layers["Strans"].formulation == Formulation.HALF_SPACE_TRN and cl.layers["Strans"].epsilon == 3.0
     assert cl.layers["U"].fields and not cl.layers["P"].fields
     assert cl.depth == pytest.approx(0.4) and not cl.solved and not cl.source_defined
+
+
+@pytest.mark.gpu
+def test_integration_stub_idft_raw_ctypes():
+    """The reference-side stub of INTEGRATION.md 2b, verbatim in spirit: raw ctypes on the C ABI (no khepri_b200 host code),
+    checked against the unmodified reference's idft output (tests/golden/idft.npz)."""
+    import ctypes as C
+    import torch
+    lib = C.CDLL(os.path.join(ROOT, "khepri_b200", "lib", "libkhepri_b200.so"))
+    lib.kh_last_error.restype = C.c_char_p
+    lib.kh_idft_work_bytes.restype = C.c_size_t
+    lib.kh_idft_work_bytes.argtypes = [C.c_int, C.c_int]
+    lib.kh_idft_batch.argtypes = [C.c_int] * 3 + [C.c_void_p] * 7 + [C.c_size_t, C.c_void_p]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "idft.npz"))
+    dev = torch.device("cuda")
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=dev)
+    s, kxd, kyd = t(g["s"].reshape(1, -1), np.complex128), t(g["kx"], np.complex128), t(g["ky"], np.complex128)
+    xd, yd = t(g["x"].ravel(), np.float64), t(g["y"].ravel(), np.float64)
+    N, npts = s.shape[1], xd.numel()
+    out = torch.empty((1, npts), dtype=torch.complex128, device=dev)
+    ws = torch.empty(lib.kh_idft_work_bytes(N, npts), dtype=torch.uint8, device=dev)
+    rc = lib.kh_idft_batch(1, N, npts, kxd.data_ptr(), kyd.data_ptr(), xd.data_ptr(), yd.data_ptr(), s.data_ptr(),
+                           out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.kh_last_error()
+    assert np.abs(out.cpu().numpy().reshape(g["x"].shape) - g["out"]).max() <= 1e-12
+    # error behaviour: bad arguments and an undersized workspace are status codes, not crashes
+    assert lib.kh_idft_batch(1, N, npts, None, kyd.data_ptr(), xd.data_ptr(), yd.data_ptr(), s.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), None) != 0
+    assert lib.kh_idft_batch(1, N, npts, kxd.data_ptr(), kyd.data_ptr(), xd.data_ptr(), yd.data_ptr(), s.data_ptr(), out.data_ptr(), ws.data_ptr(), 16, None) != 0
