@@ -357,16 +357,14 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
     cb.layerS.assign(p->layers.size(), nullptr);
     cb.layerV.assign(p->layers.size(), nullptr);
     cb.layerL.assign(p->layers.size(), nullptr);
-    bool any_dense = false;
     for (size_t i = 0; i < p->layers.size(); ++i) {
         const kh_layer_desc& L = p->layers[i];
         if (layer_is_bd(p, (int)i)) {
             cb.layerS[i] = b.get<cd>((size_t)Bc * 16 * N);
             if (flags & KH_WANT_FIELDS) { cb.layerV[i] = b.get<cd>((size_t)Bc * 4 * N); cb.layerL[i] = b.get<cd>((size_t)Bc * N); }
-        } else if (L.kind == KH_LAYER_PIXMAP) { cb.layerS[i] = b.get<cd>((size_t)Bc * 2 * n2); any_dense = true; }
-        else { cb.layerS[i] = b.get<cd>((size_t)Bc * 4 * n2); any_dense = true; }
+        } else if (L.kind == KH_LAYER_PIXMAP) { cb.layerS[i] = b.get<cd>((size_t)Bc * 2 * n2); }
+        else { cb.layerS[i] = b.get<cd>((size_t)Bc * 4 * n2); }
     }
-    (void)any_dense;
     cb.pool = b.get<cd>((size_t)LAYER_TMP_SLABS * Bc * n2);
     cb.vec.w = b.get<cd>((size_t)Bc * n); cb.vec.lam = b.get<cd>((size_t)Bc * n);
     cb.vec.xexp = b.get<cd>((size_t)Bc * n); cb.vec.scale = b.get<cd>((size_t)Bc * n); cb.vec.tau = b.get<cd>((size_t)Bc * n);

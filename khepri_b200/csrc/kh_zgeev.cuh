@@ -109,7 +109,7 @@ KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
     const cd* A = mat_ptr(a.A, b);
     cd* Hg = mat_ptr(a.Hw, b);
     cd* Zt = mat_ptr(a.Zt, b);
-    const int ldz = a.Zt.ld;
+    const int ldz = a.Zt.ld; (void)ldz;
     cd* scout = a.scale + (long long)b * a.scale_stride;
     cd* tauout = a.tau + (long long)b * a.tau_stride;
     // shared: [vv n][uu n][scratch 192 dbl][dsc n dbl][H]
