@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KH_ABI_VERSION 1
+#define KH_ABI_VERSION 2
 #define KH_EINVAL (-1)
 #define KH_ENOMEM (-2)   /* workspace too small */
 #define KH_ESTATE (-3)
@@ -56,7 +56,7 @@ typedef struct {
     void* W_dev;                   /* [B][n_layers][n][n] layer eigenvectors, E part (Layer.W), per layer-table index */
     void* V_dev;                   /* [B][n_layers][n][n] layer eigenvectors, H part (Layer.V)                        */
     void* L_dev;                   /* [B][n_layers][n]    layer eigenvalues lambda (Layer.L)                          */
-    int* info_dev;                 /* [B] 0 = ok; bit0 eigensolver did not converge, bit1 singular pivot */
+    int* info_dev;                 /* [B] 0 = ok; bit0 eigensolver did not converge, bit1 singular pivot, bit2 doubling bound exceeded */
 } kh_outputs;
 
 int kh_abi_version(void);
@@ -103,6 +103,19 @@ int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev,
                    int n_layers, const kh_layer_desc* layers, int n_stack, const int* stack,
                    int Nb, const double* glhs_dev, const double* grhs_dev);
 void kh_plan_destroy(kh_plan* plan);
+
+/* How patterned layers get their S-matrix when no eigenspace has to be retained (flux / Stot outputs).
+ *   KH_METHOD_EIG       eigen-decomposition of Omega^2 = P Q (alternative.py:158-195, the Crystal path's algorithm).
+ *   KH_METHOD_DOUBLING  the reference's legacy algorithm (khepri/tmat/scattering.py:25-51): transfer matrix of a thin
+ *                       slice (power series of exp) -> S-matrix (matrix_s, tmat/matrices.py:167-176) -> self star
+ *                       products; GEMMs and inverses only.  kappa bounds k0 * sqrt(rho(Omega^2)) over the batch, i.e.
+ *                       kappa * depth bounds the largest |lambda k0 d| of a layer; the layer is cut into 2^s slices with
+ *                       kappa * depth / 2^s <= theta_slice.  If the bound turns out too small for a solve (checked on the
+ *                       device against ||Omega^2||_1), bit 2 of its info is set.
+ * Solves that retain eigenspaces (KH_WANT_FIELDS) always use KH_METHOD_EIG. */
+#define KH_METHOD_EIG 0
+#define KH_METHOD_DOUBLING 1
+int kh_plan_set_method(kh_plan* plan, int method, double kappa, double theta_slice);
 
 /* ---- batched solve = Crystal.solve + poynting_flux_end over B (wavelength, k-point) pairs --- */
 #define KH_WANT_STOT 1

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libkhepri_b200.so")
 KH_EINVAL, KH_ENOMEM, KH_ESTATE = -1, -2, -3
 LAYER_UNIFORM, LAYER_PIXMAP, LAYER_HALF_INC, LAYER_HALF_TRN, LAYER_EXTENDED = 0, 1, 3, 4, 5
 WANT_STOT, WANT_FLUX, WANT_FIELDS = 1, 2, 4
+METHOD_EIG, METHOD_DOUBLING = 0, 1
 
 
 class LayerDesc(C.Structure):
@@ -43,6 +44,7 @@ SIGNATURES = {
     "kh_plan_create": (i32, [C.POINTER(vp), i32, i32, vp, f64, f64, f64, f64, i32, C.POINTER(LayerDesc), i32,
                              C.POINTER(i32), i32, vp, vp]),
     "kh_plan_destroy": (None, [vp]),
+    "kh_plan_set_method": (i32, [vp, i32, f64, f64]),
     "kh_solve_workspace_bytes": (sz, [vp, i32, i32]),
     "kh_solve_batch": (i32, [vp, i32, vp, vp, vp, C.POINTER(Outputs), vp, sz, vp]),
     "kh_star_workspace_bytes": (sz, [i32, i32]),
@@ -82,7 +84,7 @@ def bind(path=None):
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.kh_abi_version() != 1:
+    if lib.kh_abi_version() != 2:
         raise KhepriError("khepri_b200: ABI version mismatch")
     return lib
 

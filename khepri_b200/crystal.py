@@ -182,7 +182,7 @@ class Crystal:
             return {"kind": _lib.LAYER_UNIFORM, "eps": layer.epsilon, "depth": layer.depth, "retain": retain}
         if f == Formulation.FFT or f == Formulation.ANALYTICAL:
             Cm, ICm = layer.convmat_device(eng)
-            return {"kind": _lib.LAYER_PIXMAP, "depth": layer.depth, "C": Cm, "IC": ICm, "retain": retain}
+            return {"kind": _lib.LAYER_PIXMAP, "depth": layer.depth, "C": Cm, "IC": ICm, "retain": retain, "eps_bound": layer.eps_bound()}
         if f == Formulation.HALF_SPACE_INC:
             return {"kind": _lib.LAYER_HALF_INC, "eps": layer.epsilon, "retain": retain}
         if f == Formulation.HALF_SPACE_TRN:
@@ -194,8 +194,7 @@ class Crystal:
         for name in self.global_stacking:
             layer = self.layers[name]
             base = layer.base if isinstance(layer, EL) else layer
-            eps = base.epsilon
-            key.append((name, id(layer), int(base.formulation), float(base.depth), id(eps) if isinstance(eps, (np.ndarray, list, tuple)) else complex(eps)))
+            key.append((name, id(layer), base.content_key()))
         key.append(self.expansion._g_vectors.tobytes())
         return tuple(key)
 
@@ -253,6 +252,8 @@ class Crystal:
         bad = int(info.max().item()) if info.numel() else 0
         if bad & 2:
             raise np.linalg.LinAlgError("Singular matrix")
+        if bad & 4:
+            raise np.linalg.LinAlgError("doubling method: spectral bound exceeded (use method='eig')")
         if bad & 1:
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 

@@ -242,6 +242,8 @@ struct kh_plan {
     std::vector<int> stack;
     int Nb; const double* glhs_dev; const double* grhs_dev;
     bool has_ext;
+    // how patterned layers get their S-matrix when no eigenspace has to be retained (kh_plan_set_method)
+    int method = KH_METHOD_EIG; double dbl_kappa = 0.0, dbl_theta = 0.0;
 };
 
 extern "C" int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev, double epsi_re, double epsi_im,
@@ -270,6 +272,13 @@ extern "C" int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev,
     return 0;
 }
 extern "C" void kh_plan_destroy(kh_plan* plan) { delete plan; }
+extern "C" int kh_plan_set_method(kh_plan* plan, int method, double kappa, double theta_slice) {
+    if (!plan || (method != KH_METHOD_EIG && method != KH_METHOD_DOUBLING)) return fail(KH_EINVAL, "kh_plan_set_method: bad arguments");
+    if (method == KH_METHOD_DOUBLING && !(kappa > 0.0 && theta_slice >= 0.25 && theta_slice <= 16.0))
+        return fail(KH_EINVAL, "kh_plan_set_method: doubling needs kappa > 0 and 0.25 <= theta_slice <= 16");
+    plan->method = method; plan->dbl_kappa = kappa; plan->dbl_theta = theta_slice;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------- patterned-layer solve
 #define LAYER_TMP_SLABS 17
@@ -328,6 +337,102 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
     KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv, S(4), slab));                     // T^-1 -> 3
     // [S11|S12] = T^-1 [R1|R2]
     KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- patterned layer without an eigensolver
+// Slice transfer matrix by a truncated power series + self star products (see kh_rcwa.cuh, "slab S-matrix without an
+// eigensolver"; reference: khepri/tmat/scattering.py:25-51).  theta = kappa * depth bounds x sqrt(rho(Omega^2)) for the
+// whole layer (kappa from the host, kh_plan_set_method); the layer is cut into 2^s slices with theta / 2^s <= theta_slice
+// and the series keeps t terms, theta_slice^(2t) / (2t)! < 1e-19.  Everything is a batched DMMA GEMM or the batched inverse.
+struct DblShape { int s, t, q; };
+static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
+    DblShape d; d.s = 0;
+    double th = kappa * depth;
+    while (th > theta_slice && d.s < 30) { th *= 0.5; d.s += 1; }
+    if (th < 1e-3) th = 1e-3;
+    double term = 1.0; int t = 0;                       // term = th^(2t) / (2t)!
+    while (term > 1e-19 && t < 60) { t += 1; term *= th * th / ((2.0 * t - 1.0) * (2.0 * t)); }
+    d.t = t + 1;
+    if (d.t < 3) d.t = 3;
+    int best = 2; long long bc = 1 << 30;
+    for (int q = 2; q <= KH_DBL_QMAX; ++q) { const long long c = (q - 1) + 2LL * ((d.t + q - 1) / q - 1); if (c < bc) { bc = c; best = q; } }
+    d.q = best;
+    return d;
+}
+static double dbl_factorial(int k) { double f = 1.0; for (int i = 2; i <= k; ++i) f *= i; return f; }
+
+static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const cd* IC, double depth, const DblShape& sh, double theta_slice,
+                               const cd* Kx, const cd* Ky, const double* k0, cd* pool, int* info_dbl, int* info_inv, cd* Sout) {
+    const int n = 2 * N, q = sh.q;
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    auto S = [&](int s) { return pool + (long long)s * slab; };
+    auto M = [&](int s) { return mref(S(s), n2, n); };
+    auto pair = [&](int s0, int s1) { return mref(S(s0), n2, n, 2, (long long)(s1 - s0) * slab); };      // batch index 2b + h -> slab s0 / s1
+    auto both = [&](int s0) { return mref(S(s0), n2, n, 2, 0); };                                        // both halves of a pair read slab s0
+    const double hx = depth / (double)(1LL << sh.s);
+    {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};
+        KH_TRY((kh_launch<pq_args, pq_body>(dim3(Bc), 256, 0, st, a))); }
+    KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q -> 2 ; Omega^(2i) -> slab i + 1
+    {   dbl_check_args a{Bc, n, S(2), k0, hx, 2.0 * theta_slice + 1.0, info_dbl};
+        KH_TRY((kh_launch<dbl_check_args, dbl_check_body>(dim3(Bc), 128, 256 * sizeof(double), st, a))); }
+    for (int i = 2; i <= q; ++i) KH_TRY(gemm(st, Bc, n, M(1 + i / 2), M(1 + (i - i / 2)), M(1 + i)));
+    // Horner over blocks of q coefficients, both series as one batch of 2 Bc products:  R <- R Om^q + B_j
+    const int J = (sh.t + q - 1) / q;
+    auto blocks = [&](int j, int dst0, int dst1) -> int {
+        dbl_lincomb_args a;
+        memset(&a, 0, sizeof(a));
+        a.B = Bc; a.n = n; a.q = q; a.k0 = k0; a.hx = hx;
+        for (int i = 1; i < q; ++i) a.pw[i] = S(1 + i);
+        for (int i = 0; i < q; ++i) {
+            const int k = j * q + i;                                             // series index
+            if (k < sh.t) { a.coef[0][i] = 1.0 / dbl_factorial(2 * k + 1); a.xpow[0][i] = 2 * k + 1; }          // Sc
+            if (k < sh.t - 1) { a.coef[1][i] = 1.0 / dbl_factorial(2 * k + 2); a.xpow[1][i] = 2 * k + 2; }      // Dc
+        }
+        a.out[0] = S(dst0); a.out[1] = S(dst1);
+        return kh_launch<dbl_lincomb_args, dbl_lincomb_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_lincomb");
+    };
+    int cur = 8, oth = 10;                                                       // (Sc, Dc) pair: slabs cur, cur + 1
+    KH_TRY(blocks(J - 1, cur, cur + 1));
+    for (int j = J - 2; j >= 0; --j) {
+        KH_TRY(blocks(j, 12, 13));
+        zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
+        g.Cin = pair(12, 13); g.beta = 1.0;
+        KH_TRY(zgemm_launch(st, 2 * Bc, g));
+        const int t = cur; cur = oth; oth = t;
+    }
+    const int sSc = cur, sDc = cur + 1, sM12 = oth, sDP = oth + 1;
+    {   zgemm_args g = zgemm_make(n, n, n, pair(sSc, sDc), both(0), pair(sM12, sDP));                      // M12 = Sc P ; DP = Dc P
+        KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
+    {   zgemm_args g = zgemm_make(n, n, n, both(1), pair(sSc, sDP), pair(12, 13));                         // M21 = Q Sc ; m22 = Q DP
+        KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
+    KH_TRY(gemm(st, Bc, n, M(2), M(sDc), M(3)));                                                           // m11 = Omega^2 Dc
+    {   dbl_tconv_args a{Bc, N, S(3), S(sM12), S(12), S(13), Kx, Ky, S(4), S(5)};                          // T22 -> 4, T21 -> 5
+        KH_TRY((kh_launch<dbl_tconv_args, dbl_tconv_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_tconv"))); }
+    MatRef O11 = mref(Sout, 2 * n2, n), O12 = mref(Sout + n2, 2 * n2, n);
+    MatRef s12 = sh.s == 0 ? O12 : M(6), s11 = sh.s == 0 ? O11 : M(7);
+    KH_TRY(zinv_launch(st, Bc, n, M(4), s12, info_inv, S(14), 3 * slab));                                   // S12 = T22^-1
+    KH_TRY(gemm(st, Bc, n, s12, M(5), s11, -1.0));                                                          // S11 = -S12 T21
+    // doublings  S <- S (*) S  of the mirror-symmetric slab (alternative.py:19-30 with A = B, A22 = A11, A21 = A12):
+    //   D = I - S11 S11,  Y = D^-1 S12,  S12' = S12 Y,  S11' = S11 + S12 (S11 Y)
+    for (int it = 0; it < sh.s; ++it) {
+        const int t0 = (it & 1) ? 8 : 0, t1 = t0 + 1, p0 = t0 + 2;               // scratch sets {0,1,2,3} / {8,9,10,11} alternate
+        const bool last = (it + 1 == sh.s);
+        KH_TRY(gemm(st, Bc, n, s11, s11, M(t0), -1.0, nullptr, 0.0, 1.0));                                  // D
+        KH_TRY(zinv_launch(st, Bc, n, M(t0), M(t1), info_inv, S(14), 3 * slab));                            // D^-1
+        KH_TRY(gemm(st, Bc, n, M(t1), s12, M(t0)));                                                         // Y
+        if (!last) {
+            MatRef Ap = s12; Ap.inner = 2; Ap.si = (long long)(s11.p - s12.p);                              // (S12, S11)
+            zgemm_args g = zgemm_make(n, n, n, Ap, both(t0), pair(p0, p0 + 1));                             // (S12', Z)
+            KH_TRY(zgemm_launch(st, 2 * Bc, g));
+            KH_TRY(gemm(st, Bc, n, s12, M(p0 + 1), M(t1), 1.0, &s11, 1.0));                                 // S11' = S11 + S12 Z
+            s11 = M(t1); s12 = M(p0);
+        } else {
+            KH_TRY(gemm(st, Bc, n, s11, M(t0), M(p0 + 1)));                                                 // Z
+            KH_TRY(gemm(st, Bc, n, s12, M(p0 + 1), O11, 1.0, &s11, 1.0));
+            KH_TRY(gemm(st, Bc, n, s12, M(t0), O12));
+        }
+    }
     return 0;
 }
 
@@ -435,9 +540,12 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
     size_t per1 = kh_solve_workspace_bytes(p, 1, flags), per2 = kh_solve_workspace_bytes(p, 2, flags);
     size_t slope = per2 > per1 ? per2 - per1 : 1;
     if (ws_bytes < per1) return fail(KH_ENOMEM, "kh_solve_batch: workspace smaller than one solve (" + std::to_string(per1) + " bytes)");
-    long long chunk = 1 + (long long)((ws_bytes - per1) / (slope + 1024));
-    if (chunk > B) chunk = B;
-    while (chunk > 1 && kh_solve_workspace_bytes(p, (int)chunk, flags) > ws_bytes) --chunk;
+    long long chunk = B;
+    if (kh_solve_workspace_bytes(p, B, flags) > ws_bytes) {          // the whole batch does not fit: estimate, then shrink until it does
+        chunk = 1 + (long long)((ws_bytes - per1) / (slope + 1024));
+        if (chunk > B) chunk = B;
+        while (chunk > 1 && kh_solve_workspace_bytes(p, (int)chunk, flags) > ws_bytes) --chunk;
+    }
     if (chunk < B) {                           // balance the chunks: a remainder of a few solves would pay the full latency of every kernel
         const long long nch = (B + chunk - 1) / chunk;
         chunk = (B + nch - 1) / nch;
@@ -475,9 +583,16 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
                 cd* Wk = want_fields ? (cd*)out->W_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
                 cd* Vk = want_fields ? (cd*)out->V_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
                 cd* Lk = want_fields ? (cd*)out->L_dev + ((long long)b0 * nL + (long long)i) * n : nullptr;
+                if (p->method == KH_METHOD_DOUBLING && !want_fields) {
+                    const DblShape sh = dbl_shape(p->dbl_kappa, L.depth, p->dbl_theta);
+                    KH_TRY(solve_patterned_dbl(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, sh, p->dbl_theta, cb.Kx, cb.Ky, cb.k0,
+                                               cb.pool, info_out ? info_out : cb.info, cb.vec.info_inv, cb.layerS[i]));
+                    if (info_out) { info_args ia{Bc, nullptr, cb.vec.info_inv, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                } else {
                 KH_TRY(solve_patterned(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, cb.Kx, cb.Ky, cb.k0, cb.pool,
                                        cb.vec, cb.layerS[i], Wk, Vk, Lk, (long long)nL * n2, (long long)nL * n));
                 if (info_out) { info_args ia{Bc, cb.vec.info_eig, cb.vec.info_inv, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                }
                 S[i] = sref_sym(cb.layerS[i], n);
             } else {
                 if (want_fields) return fail(KH_EINVAL, "kh_solve_batch: field outputs are not available for extended layers");

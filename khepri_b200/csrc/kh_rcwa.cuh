@@ -395,3 +395,87 @@ KH_DEV void flux_body(const Cta& c, const flux_args& a) {
     accT = cta_sum(c, accT, scratch);
     if (c.tid == 0) { a.RT[2 * b] = accR; a.RT[2 * b + 1] = accT; }
 }
+
+// ------------------------------------------------------------------ slab S-matrix without an eigensolver
+// The reference's legacy solver builds a layer's S-matrix as  T = expm(A dz) on a thin slice, S = matrix_s(T), then
+// `slicing_pow` self star products (khepri/tmat/scattering.py:25-51, tmat/matrices.py:167-176, 189-211).  The same idea in
+// the Crystal path's field basis (s, u), d/dz' [s; u] = [[0, P], [Q, 0]] [s; u] (alternative.py:158-171), z' = k0 z:
+//   exp(x [[0,P],[Q,0]]) = [[I + Om Dc, Sc P], [Q Sc, I + Q Dc P]],   Om = P Q,
+//   Sc = x sum_k (x^2 Om)^k / (2k+1)!,   Dc = x^2 sum_k (x^2 Om)^k / (2k+2)!
+// i.e. two matrix polynomials in the n x n matrix Om (Paterson-Stockmeyer: powers Om^2..Om^q once, then Horner in Om^q),
+// every flop a DMMA GEMM.  dbl_lincomb forms the Horner blocks  sum_i c_i(b) Om^i  with the per-solve slice thickness
+// x_b = k0[b] * hx folded into the coefficients.
+#define KH_DBL_QMAX 6
+struct dbl_lincomb_args {
+    int B, n, q;                      // powers I, Om, .., Om^(q-1)
+    const cd* pw[KH_DBL_QMAX];        // pw[i] = Om^i as [B][n][n] (pw[0] unused)
+    const double* k0; double hx;      // x_b = k0[b] * hx
+    double coef[2][KH_DBL_QMAX]; int xpow[2][KH_DBL_QMAX];     // out_o = sum_i coef[o][i] x_b^xpow[o][i] Om^i
+    cd* out[2];                       // [B][n][n] each
+};
+KH_DEV void dbl_lincomb_body(const Cta& c, const dbl_lincomb_args& a) {
+    const int n = a.n, b = c.bx, q = a.q;
+    const long long off = (long long)b * n * n;
+    const double x = a.k0[b] * a.hx;
+    double cf[2][KH_DBL_QMAX];
+    for (int o = 0; o < 2; ++o)
+        for (int i = 0; i < KH_DBL_QMAX; ++i) cf[o][i] = (i < q && a.coef[o][i] != 0.0) ? a.coef[o][i] * pow(x, (double)a.xpow[o][i]) : 0.0;
+    const int per = (n * n + 3) / 4, e0 = c.by * per, e1 = (e0 + per < n * n) ? e0 + per : n * n;
+    for (int e = e0 + c.tid; e < e1; e += c.nthr) {
+        const int i = e / n, j = e - i * n;
+        cd v0 = mk(i == j ? cf[0][0] : 0.0, 0.0), v1 = mk(i == j ? cf[1][0] : 0.0, 0.0);
+        for (int k = 1; k < q; ++k) { const cd p = a.pw[k][off + e]; v0 = v0 + cf[0][k] * p; v1 = v1 + cf[1][k] * p; }
+        a.out[0][off + e] = v0; a.out[1][off + e] = v1;
+    }
+}
+
+// Transfer matrix of the slice in the mode basis of the zero-thickness free-space gaps (W0 = I, V0; alternative.py:84-99,
+// fields.py:46-51 R0 = [[W0, W0], [-V0, V0]]):  only the second block row of T = R0^-1 M R0 is needed,
+//   T22 = (E1 + E2) / 2,  T21 = (E1 - E2) / 2,  E1 = M11 + V0^-1 M21,  E2 = (M12 + V0^-1 M22) V0,
+// because the slab is mirror symmetric (S22 = S11, S21 = S12; alternative.py:195):  S12 = T22^-1,  S11 = -T22^-1 T21
+// (matrix_s of tmat/matrices.py:167-176 for these two blocks).  V0, V0^-1 are 2x2 blocks of diagonals: O(n^2) work.
+// M11 and M22 arrive without their identity (M11 = I + m11, M22 = I + m22).
+struct dbl_tconv_args { int B, N; const cd* m11; const cd* M12; const cd* M21; const cd* m22; const cd* Kx; const cd* Ky; cd* T22; cd* T21; };
+KH_DEV void dbl_tconv_body(const Cta& c, const dbl_tconv_args& a) {
+    const int N = a.N, n = 2 * N, b = c.bx;
+    const long long off = (long long)b * n * n;
+    const cd* kx = a.Kx + (long long)b * N;
+    const cd* ky = a.Ky + (long long)b * N;
+    const int per = (n * N + 3) / 4, e0 = c.by * per, e1 = (e0 + per < n * N) ? e0 + per : n * N;
+    for (int e = e0 + c.tid; e < e1; e += c.nthr) {
+        const int i = e / N, gj = e - i * N, hi = i >= N, gi = i - hi * N;
+        const m22 Vi = m22_inv(v0_block(kx[gi], ky[gi]));
+        const m22 Vj = v0_block(kx[gj], ky[gj]);
+        const cd vi0 = hi ? Vi.c : Vi.a, vi1 = hi ? Vi.d : Vi.b;          // row hi of V0^-1 at harmonic gi
+        const long long r0 = off + (long long)gi * n, r1 = off + (long long)(N + gi) * n, ri = off + (long long)i * n;
+        const int j0 = gj, j1 = N + gj;
+        cd e1a = a.m11[ri + j0] + vi0 * a.M21[r0 + j0] + vi1 * a.M21[r1 + j0];
+        cd e1b = a.m11[ri + j1] + vi0 * a.M21[r0 + j1] + vi1 * a.M21[r1 + j1];
+        if (i == j0) e1a.x += 1.0;
+        if (i == j1) e1b.x += 1.0;
+        cd g0 = a.M12[ri + j0] + vi0 * a.m22[r0 + j0] + vi1 * a.m22[r1 + j0];
+        cd g1 = a.M12[ri + j1] + vi0 * a.m22[r0 + j1] + vi1 * a.m22[r1 + j1];
+        if (gi == gj) { g0 = g0 + vi0; g1 = g1 + vi1; }                    // the identity of M22: V0^-1 I picks column gj / N + gj
+        const cd e2a = g0 * Vj.a + g1 * Vj.c, e2b = g0 * Vj.b + g1 * Vj.d;
+        a.T22[ri + j0] = 0.5 * (e1a + e2a); a.T22[ri + j1] = 0.5 * (e1b + e2b);
+        a.T21[ri + j0] = 0.5 * (e1a - e2a); a.T21[ri + j1] = 0.5 * (e1b - e2b);
+    }
+}
+
+// safety net for the (slices, terms) the host chose from its bound on the spectrum: theta_b = x_b sqrt(||Om||_1) must stay
+// below theta_lim, otherwise bit 2 of info is raised for that solve (the truncated series may have lost accuracy).
+struct dbl_check_args { int B, n; const cd* Om; const double* k0; double hx, theta_lim; int* info; };
+KH_DEV void dbl_check_body(const Cta& c, const dbl_check_args& a) {
+    const int n = a.n, b = c.bx;
+    const cd* A = a.Om + (long long)b * n * n;
+    double* scratch = (double*)c.smem;
+    double m = 0.0;
+    for (int j = c.tid; j < n; j += c.nthr) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += cabsd(A[(long long)i * n + j]);
+        m = fmax(m, s);
+    }
+    m = cta_max(c, m, scratch);
+    const double th = a.k0[b] * a.hx * sqrt(m);
+    if (c.tid == 0 && !(th <= a.theta_lim)) KH_ATOMIC_OR(&a.info[b], 4);
+}

@@ -46,6 +46,10 @@ class Plan:
         self.glhs = torch.as_tensor(np.ascontiguousarray(glhs, dtype=np.float64), device=dev) if glhs is not None else None
         self.grhs = torch.as_tensor(np.ascontiguousarray(grhs, dtype=np.float64), device=dev) if grhs is not None else None
         self._keep = []
+        self.gmax = float(np.sqrt((g_host ** 2).sum(axis=0)).max())
+        self.eps_bound = max([float(L.get("eps_bound", 0.0)) for L in layers] + [0.0])
+        self.has_patterned = any(int(L["kind"]) == _lib.LAYER_PIXMAP for L in layers)
+        self._method_state = None
         descs = (LayerDesc * len(layers))()
         for i, L in enumerate(layers):
             d = descs[i]
@@ -95,6 +99,7 @@ class Engine:
         self._ws = None
         self.workspace_cap_bytes = workspace_cap_bytes
         self.launch_count = 0
+        self.doubling_theta = 8.0       # largest |lambda k0 d| of one slice of the doubling method (see _select_method)
 
     @classmethod
     def default(cls):
@@ -212,12 +217,51 @@ class Engine:
         return w, W, info
 
     # ------------------------------------------------------------------ the batched solve
-    def solve_batch(self, plan, wl, kp, pol=None, want_S=False, want_flux=True, want_orders=False, want_fields=False, chunk=None):
+    # ------------------------------------------------------------------ patterned-layer method
+    def _select_method(self, plan, wl, kp, want_fields, method):
+        """Picks how patterned layers get their S-matrix (kh_plan_set_method).  "eig": eigen-decomposition (the only
+        choice when eigenspaces are retained); "doubling": slice series + self star products, GEMMs only.  "auto" takes
+        doubling whenever no eigenspace is retained.  For doubling the host supplies kappa >= k0 sqrt(rho(Omega^2)):
+        rho is bounded from the largest in-plane wavevector of the basis and the largest permittivity (the device checks
+        the bound per solve and raises info bit 2)."""
+        import os
+        method = os.environ.get("KHEPRI_B200_METHOD", method or "auto")
+        if method == "auto":
+            method = "doubling" if (plan.has_patterned and not want_fields) else "eig"
+        if method not in ("eig", "doubling"):
+            raise ValueError(f"unknown method {method!r}")
+        if method == "doubling" and (want_fields or not plan.has_patterned):
+            method = "eig"
+        if method == "eig":
+            state = ("eig",)
+            if plan._method_state != state:
+                check(self.lib, self.lib.kh_plan_set_method(plan.handle, _lib.METHOD_EIG, 0.0, 0.0), "kh_plan_set_method")
+                plan._method_state = state
+            return method
+        if isinstance(wl, torch.Tensor):
+            wl_min = float(wl.min().item())
+            kp_max = float(kp.abs().pow(2).sum(dim=-1).max().sqrt().item())
+        else:
+            wl_min = float(np.min(wl))
+            kpa = np.abs(np.asarray(kp)).reshape(-1, 2)
+            kp_max = float(np.sqrt((kpa ** 2).sum(axis=1).max()))
+        k0 = 2.0 * np.pi / wl_min
+        kappa = float(np.sqrt(1.25 * (kp_max + plan.gmax) ** 2 + plan.eps_bound * k0 * k0))
+        theta = float(os.environ.get("KHEPRI_B200_THETA", self.doubling_theta))
+        state = ("doubling", kappa, theta)
+        if plan._method_state != state:
+            check(self.lib, self.lib.kh_plan_set_method(plan.handle, _lib.METHOD_DOUBLING, kappa, theta), "kh_plan_set_method")
+            plan._method_state = state
+        return method
+
+    def solve_batch(self, plan, wl, kp, pol=None, want_S=False, want_flux=True, want_orders=False, want_fields=False, chunk=None, method=None):
         """Crystal.solve (+ poynting_flux_end) for B sources.  wl [B], kp [B,2] complex, pol [B,2] = (te, tm).
 
         Returns a dict of DEVICE tensors: RT [B,2], orders [B,2,N], Stot [B,2,2,n,n], info [B] and, with
         want_fields, prefix/suffix [B,Ls,2,2,n,n], W/V [B,nL,n,n], L [B,nL,n].
         """
+        if (wl.numel() if isinstance(wl, torch.Tensor) else np.size(wl)) > 0:
+            self._select_method(plan, wl, kp, want_fields, method)
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(-1) if not isinstance(wl, torch.Tensor) else wl.reshape(-1), _f64)
         B = wl_d.numel()
         kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2) if not isinstance(kp, torch.Tensor) else kp.reshape(B, 2), _c128)

@@ -31,7 +31,31 @@ class Layer:
         self.S = None
         self.IC = None
         self.fields = False
-        self._cache = None           # device copies of (C, C^-1), keyed on the identity of the pixmap array
+        self._cache = None           # device copies of (C, C^-1), keyed on the CONTENT of the pixmap / island list
+
+    def content_key(self):
+        """Hashable token of everything the layer's S-matrix depends on besides the source.  Keyed on content, not on
+        object identity: the reference recomputes convolution_matrix(self.epsilon) on every solve (layer.py:157), so a
+        pixmap mutated in place must invalidate the cached convolution matrix and the plan."""
+        import hashlib
+        eps = self.epsilon
+        if self.formulation == Formulation.FFT:
+            arr = np.ascontiguousarray(eps)
+            tok = (arr.shape, str(arr.dtype), hashlib.blake2b(arr.view(np.uint8).reshape(-1).data, digest_size=16).hexdigest())
+        elif self.formulation == Formulation.ANALYTICAL:
+            tok = (repr(eps), complex(self.eps_host))
+        else:
+            tok = complex(eps)
+        return (int(self.formulation), float(self.depth), tok)
+
+    def eps_bound(self):
+        """max |epsilon| of a patterned layer (bounds the spectrum of Omega^2 for the doubling method)."""
+        if self.formulation == Formulation.FFT:
+            return float(np.max(np.abs(self.epsilon)))
+        if self.formulation == Formulation.ANALYTICAL:
+            vals = [abs(complex(self.eps_host))] + [abs(complex(isl["epsilon"])) for isl in self.epsilon]
+            return float(max(vals))
+        return float(abs(complex(self.epsilon)))
 
     @classmethod
     def pixmap_or_uniform(cls, expansion, pixmap, depth):
@@ -86,7 +110,7 @@ class Layer:
     # -- device-side convolution matrix (tools.convolution_matrix + np.linalg.inv, layer.py:157-158),
     #    computed once per pixmap instead of once per solve
     def convmat_device(self, engine):
-        key = (id(self.epsilon), tuple(self.expansion.pw), id(engine))
+        key = (self.content_key(), tuple(self.expansion.pw), id(engine))
         if self._cache is None or self._cache[0] != key:
             if self.formulation == Formulation.ANALYTICAL:         # layer.py:161-168: analytic coefficients -> Toeplitz gather
                 from .fourier import analytical_coefficients

@@ -35,7 +35,7 @@ def test_cuda_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/khepri_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(header_symbols())
     bound = _lib.bind()
-    assert bound.kh_abi_version() == 1
+    assert bound.kh_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_cuda():
