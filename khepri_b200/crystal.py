@@ -45,6 +45,8 @@ class Crystal:
         self.stacking_reverse_matrices = list()
         self.stack_positions = []
         self._engine = engine
+        # how patterned layers get their S-matrix: "auto" | "eig" | "doubling" (Engine._select_method); results agree to rounding
+        self.method = "auto"
         self._plan = None
         self._plan_key = None
         self._S_host = None
@@ -223,7 +225,7 @@ class Crystal:
         logging.debug("Solving each required layer")
         want_fields = self._wants_fields() and not any(isinstance(self.layers[n], EL) for n in self.global_stacking)
         plan = self._get_plan(want_fields)
-        res = self.engine.solve_batch(plan, [self.source.wavelength], [self.kp], want_S=True, want_flux=False, want_fields=want_fields)
+        res = self.engine.solve_batch(plan, [self.source.wavelength], [self.kp], want_S=True, want_flux=False, want_fields=want_fields, method=self.method)
         self._check_info(res["info"])
         layer_sizes = [self.layers[name].depth for name in self.global_stacking]
         self.stack_positions = list(np.cumsum(layer_sizes))
@@ -294,7 +296,7 @@ class Crystal:
         pol = np.stack([np.broadcast_to(np.asarray(te, dtype=np.complex128), (B,)),
                         np.broadcast_to(np.asarray(tm, dtype=np.complex128), (B,))], axis=1)
         plan = self._get_plan(False)
-        res = self.engine.solve_batch(plan, wl, kp, pol, want_S=return_S, want_flux=True, want_orders=not only_total, chunk=chunk)
+        res = self.engine.solve_batch(plan, wl, kp, pol, want_S=return_S, want_flux=True, want_orders=not only_total, chunk=chunk, method=self.method)
         self._check_info(res["info"])
         RT = res["RT"].cpu().numpy()
         out = [RT[:, 0], RT[:, 1]]

@@ -55,10 +55,10 @@ KH_DEV void copyv_body(const Cta& c, const copyv_args& a) {
     cd* d = a.dst + (long long)c.bx * a.dstride;
     for (long long e = c.tid; e < a.count; e += c.nthr) d[e] = s[e];
 }
-struct info_args { int B; const int* e1; const int* e2; int* out; };
+struct info_args { int B; const int* e1; const int* e2; int* out; int div; };      // out[b / div] |= 1 (e1[b] != 0) | 2 (e2[b] != 0)
 KH_DEV void info_body(const Cta& c, const info_args& a) {
     int b = c.bx * c.nthr + c.tid;
-    if (b < a.B) { int v = 0; if (a.e1 && a.e1[b]) v |= 1; if (a.e2 && a.e2[b]) v |= 2; if (v) KH_ATOMIC_OR(&a.out[b], v); }
+    if (b < a.B) { int v = 0; if (a.e1 && a.e1[b]) v |= 1; if (a.e2 && a.e2[b]) v |= 2; if (v) KH_ATOMIC_OR(&a.out[b / a.div], v); }
 }
 struct zero_int_args { int B; int* p; };
 KH_DEV void zero_int_body(const Cta& c, const zero_int_args& a) {
@@ -117,14 +117,14 @@ static int zero_mat(kh_stream_t st, int Bc, long long n2, MatRef M) {
     return kh_launch<zero_cd_args, zero_cd_body>(dim3(Bc), 256, 0, st, zc);
 }
 
-static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
+static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false, int imode = 0) {
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
     MatRef U = mref(tmp + 4 * slab, n2, n), Z = mref(tmp + 5 * slab, n2, n), Vt = mref(tmp + 6 * slab, n2, n);
     SRef O = sref_dense(out, n);
     int e;
     if ((e = gemm(st, Bc, n, A.blk[3], B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;     // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab, imode))) return e;   // (X..Vt are still free: work space)
     if (fc >= 0) {
         if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                           // X = F^-1 A21      (flux columns)
         if ((e = cols2(st, Bc, n, fc, B.blk[2], X, O.blk[2]))) return e;                     // S21 = B21 X
@@ -156,7 +156,7 @@ static int bdmul(kh_stream_t st, int Bc, int N, int side, const cd* bd, int blk,
 }
 
 // star product with a BD (uniform layer / half space) LEFT operand: 5 GEMMs + 1 inverse + O(n^2) kernels
-static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
+static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false, int imode = 0) {
     const int n = 2 * N;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -164,7 +164,7 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     SRef O = sref_dense(out, n);
     int e;
     if ((e = bdmul(st, Bc, N, 0, A, 3, B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;           // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab, imode))) return e;   // (X..Vt are still free: work space)
     if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X))) return e;                                          // X = F^-1 A21
     if (fc >= 0) {
         if ((e = cols2(st, Bc, n, fc, B.blk[2], X, O.blk[2]))) return e;                           // S21 = B21 X   (flux columns)
@@ -184,7 +184,7 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     return 0;
 }
 // star product with a BD RIGHT operand: 4 GEMMs + 1 inverse + O(n^2) kernels
-static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info, int fc = -1, bool last = false) {
+static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd* Bd, cd* out, cd* tmp, int* info, int fc = -1, bool last = false, int imode = 0) {
     const int n = 2 * N;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -192,7 +192,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
     SRef O = sref_dense(out, n);
     int e;
     if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
-    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab))) return e;   // (X..Vt are still free: work space)
+    if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab, imode))) return e;   // (X..Vt are still free: work space)
     if (fc >= 0) {
         if ((e = zero_mat(st, Bc, n2, X))) return e;
         if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                                 // X = F^-1 A21  (flux columns, 0 elsewhere)
@@ -217,7 +217,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
 
 
 // S = A (*) B for any mix of dense / BD operands.  The result goes to out_bd when both are BD, else to out_dense.
-static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res, int fc = -1, bool last = false) {
+static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B, cd* out_dense, cd* out_bd, cd* tmp, int* info, SRef& res, int fc = -1, bool last = false, int imode = 0) {
     const int n = 2 * N;
     if (A.bd && B.bd) {
         bd_star_args a{Bc, N, A.bdp, B.bdp, out_bd};
@@ -226,9 +226,9 @@ static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B,
         return e;
     }
     int e;
-    if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info, fc, last);
-    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info, fc, last);
-    else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info, fc, last);
+    if (A.bd) e = star_bd_dense(st, Bc, N, A.bdp, B, out_dense, tmp, info, fc, last, imode);
+    else if (B.bd) e = star_dense_bd(st, Bc, N, A, B.bdp, out_dense, tmp, info, fc, last, imode);
+    else e = dense_star(st, Bc, n, A, B, out_dense, tmp, info, fc, last, imode);
     res = sref_dense(out_dense, n);
     return e;
 }
@@ -282,7 +282,8 @@ extern "C" int kh_plan_set_method(kh_plan* plan, int method, double kappa, doubl
 
 // ---------------------------------------------------------------------------- patterned-layer solve
 #define LAYER_TMP_SLABS 17
-struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; cd* tau; int* info_eig; int* info_inv; };
+struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; cd* tau; int* info_eig; int* info_inv;
+                  int* info_acc; int info_div; };      // info_acc[b / info_div] |= 1 (eigensolver) | 2 (zero pivot): the solve's status word
 
 // Solves one patterned layer for Bc solves of dimension n = 2N (alternative.py:158-195):
 // P, Q -> Omega^2 -> eig -> W, lambda, V -> A, B, X -> S11, S12 (written to Sout [Bc][2][n][n]).
@@ -304,6 +305,8 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         a.rot_cap = (int)((a.rlog_stride - 2 - a.sw_cap) / 3);
         a.istate = v.info_inv + Bc;                                           // (middle third of the info block: unused elsewhere)
         KH_TRY(zgeev_launch(st, Bc, a)); }
+    {   info_args ia{Bc, v.info_eig, nullptr, v.info_acc, v.info_div};
+        KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
     {   zgemm_args g = zgemm_make(n, n, n, M(3), M(4), M(5));                    // W = diag(scale) Z X
         g.transA = 1; g.rowscale = v.scale; g.rs_stride = n; g.rs_group = 1;
         KH_TRY(zgemm_launch(st, Bc, g)); }
@@ -317,7 +320,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
         copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
     }
-    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_inv, S(8), slab));                     // W^-1 -> 7
+    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_acc, S(8), slab, v.info_div));                     // W^-1 -> 7
     {   pv0_args a{Bc, N, S(0), Kx, Ky, S(6)};                                   // P V0 -> 6
         KH_TRY((kh_launch<pv0_args, pv0_body>(dim3(Bc), 256, 0, st, a))); }
     {   zgemm_args g = zgemm_make(n, n, n, M(7), M(6), M(8));                    // V^-1 V0 = L^-1 (W^-1 (P V0)) -> 8
@@ -325,7 +328,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(zgemm_launch(st, Bc, g)); }
     {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
         KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
-    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_inv, S(12), slab));                     // A^-1 -> 1
+    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_acc, S(12), slab, v.info_div));                     // A^-1 -> 1
     // E = XB A^-1 (-> 12) carries every appearance of A^-1 in alternative.py:186-193:
     //   T = A - XB A^-1 XB = A - E XB,   X B A^-1 X A - B = E XA - B,   X (A - B A^-1 B) = XA - E B
     // (4 products instead of the 6 of the literal schedule A^-1 [XB|XA|B] followed by XB M1, XB M2, B M3)
@@ -334,7 +337,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(gemm(st, Bc, n, M(12), M(9), M(2), -1.0, &A, 1.0));               // T  = A - E XB
         KH_TRY(gemm(st, Bc, n, M(12), M(10), M(15), 1.0, &Bm, -1.0));            // R1 = E XA - B
         KH_TRY(gemm(st, Bc, n, M(12), M(11), M(16), -1.0, &XA, 1.0)); }          // R2 = XA - E B
-    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_inv, S(4), slab));                     // T^-1 -> 3
+    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_acc, S(4), slab, v.info_div));                     // T^-1 -> 3
     // [S11|S12] = T^-1 [R1|R2]
     KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
     return 0;
@@ -345,11 +348,12 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
 // eigensolver"; reference: khepri/tmat/scattering.py:25-51).  theta = kappa * depth bounds x sqrt(rho(Omega^2)) for the
 // whole layer (kappa from the host, kh_plan_set_method); the layer is cut into 2^s slices with theta / 2^s <= theta_slice
 // and the series keeps t terms, theta_slice^(2t) / (2t)! < 1e-19.  Everything is a batched DMMA GEMM or the batched inverse.
-struct DblShape { int s, t, q; };
+struct DblShape { int s, t, q; double theta; };      // theta: the bound on |lambda k0 d| of one slice that (t, q) were sized for
 static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
     DblShape d; d.s = 0;
     double th = kappa * depth;
     while (th > theta_slice && d.s < 30) { th *= 0.5; d.s += 1; }
+    d.theta = th;
     if (th < 1e-3) th = 1e-3;
     double term = 1.0; int t = 0;                       // term = th^(2t) / (2t)!
     while (term > 1e-19 && t < 60) { t += 1; term *= th * th / ((2.0 * t - 1.0) * (2.0 * t)); }
@@ -362,8 +366,8 @@ static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
 }
 static double dbl_factorial(int k) { double f = 1.0; for (int i = 2; i <= k; ++i) f *= i; return f; }
 
-static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const cd* IC, double depth, const DblShape& sh, double theta_slice,
-                               const cd* Kx, const cd* Ky, const double* k0, cd* pool, int* info_dbl, int* info_inv, cd* Sout) {
+static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const cd* IC, double depth, const DblShape& sh,
+                               const cd* Kx, const cd* Ky, const double* k0, cd* pool, int* info_acc, cd* Sout) {
     const int n = 2 * N, q = sh.q;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     auto S = [&](int s) { return pool + (long long)s * slab; };
@@ -374,7 +378,7 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};
         KH_TRY((kh_launch<pq_args, pq_body>(dim3(Bc), 256, 0, st, a))); }
     KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q -> 2 ; Omega^(2i) -> slab i + 1
-    {   dbl_check_args a{Bc, n, S(2), k0, hx, 2.0 * theta_slice + 1.0, info_dbl};
+    {   dbl_check_args a{Bc, n, S(2), k0, hx, 1.75 * sh.theta + 0.25, info_acc};      // ||.||_1 overestimates rho by up to ~2 (theta by ~1.4)
         KH_TRY((kh_launch<dbl_check_args, dbl_check_body>(dim3(Bc), 128, 256 * sizeof(double), st, a))); }
     for (int i = 2; i <= q; ++i) KH_TRY(gemm(st, Bc, n, M(1 + i / 2), M(1 + (i - i / 2)), M(1 + i)));
     // Horner over blocks of q coefficients, both series as one batch of 2 Bc products:  R <- R Om^q + B_j
@@ -411,7 +415,7 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
         KH_TRY((kh_launch<dbl_tconv_args, dbl_tconv_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_tconv"))); }
     MatRef O11 = mref(Sout, 2 * n2, n), O12 = mref(Sout + n2, 2 * n2, n);
     MatRef s12 = sh.s == 0 ? O12 : M(6), s11 = sh.s == 0 ? O11 : M(7);
-    KH_TRY(zinv_launch(st, Bc, n, M(4), s12, info_inv, S(14), 3 * slab));                                   // S12 = T22^-1
+    KH_TRY(zinv_launch(st, Bc, n, M(4), s12, info_acc, S(14), 3 * slab, 1));                                   // S12 = T22^-1
     KH_TRY(gemm(st, Bc, n, s12, M(5), s11, -1.0));                                                          // S11 = -S12 T21
     // doublings  S <- S (*) S  of the mirror-symmetric slab (alternative.py:19-30 with A = B, A22 = A11, A21 = A12):
     //   D = I - S11 S11,  Y = D^-1 S12,  S12' = S12 Y,  S11' = S11 + S12 (S11 Y)
@@ -419,7 +423,7 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
         const int t0 = (it & 1) ? 8 : 0, t1 = t0 + 1, p0 = t0 + 2;               // scratch sets {0,1,2,3} / {8,9,10,11} alternate
         const bool last = (it + 1 == sh.s);
         KH_TRY(gemm(st, Bc, n, s11, s11, M(t0), -1.0, nullptr, 0.0, 1.0));                                  // D
-        KH_TRY(zinv_launch(st, Bc, n, M(t0), M(t1), info_inv, S(14), 3 * slab));                            // D^-1
+        KH_TRY(zinv_launch(st, Bc, n, M(t0), M(t1), info_acc, S(14), 3 * slab, 1));                            // D^-1
         KH_TRY(gemm(st, Bc, n, M(t1), s12, M(t0)));                                                         // Y
         if (!last) {
             MatRef Ap = s12; Ap.inner = 2; Ap.si = (long long)(s11.p - s12.p);                              // (S12, S11)
@@ -583,15 +587,15 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
                 cd* Wk = want_fields ? (cd*)out->W_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
                 cd* Vk = want_fields ? (cd*)out->V_dev + ((long long)b0 * nL + (long long)i) * n2 : nullptr;
                 cd* Lk = want_fields ? (cd*)out->L_dev + ((long long)b0 * nL + (long long)i) * n : nullptr;
+                int* acc = info_out ? info_out : cb.info;                  // status word of each solve (scratch when the caller wants none)
                 if (p->method == KH_METHOD_DOUBLING && !want_fields) {
                     const DblShape sh = dbl_shape(p->dbl_kappa, L.depth, p->dbl_theta);
-                    KH_TRY(solve_patterned_dbl(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, sh, p->dbl_theta, cb.Kx, cb.Ky, cb.k0,
-                                               cb.pool, info_out ? info_out : cb.info, cb.vec.info_inv, cb.layerS[i]));
-                    if (info_out) { info_args ia{Bc, nullptr, cb.vec.info_inv, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                    KH_TRY(solve_patterned_dbl(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, sh, cb.Kx, cb.Ky, cb.k0,
+                                               cb.pool, acc, cb.layerS[i]));
                 } else {
-                KH_TRY(solve_patterned(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, cb.Kx, cb.Ky, cb.k0, cb.pool,
-                                       cb.vec, cb.layerS[i], Wk, Vk, Lk, (long long)nL * n2, (long long)nL * n));
-                if (info_out) { info_args ia{Bc, cb.vec.info_eig, cb.vec.info_inv, info_out}; KH_TRY((kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia))); }
+                    LayerVec v = cb.vec; v.info_acc = acc; v.info_div = 1;
+                    KH_TRY(solve_patterned(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, cb.Kx, cb.Ky, cb.k0, cb.pool,
+                                           v, cb.layerS[i], Wk, Vk, Lk, (long long)nL * n2, (long long)nL * n));
                 }
                 S[i] = sref_sym(cb.layerS[i], n);
             } else {
@@ -610,19 +614,14 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         bool have_acc = false;
         cd* acc_full = nullptr;                 // set when acc is a contiguous dense [Bc][4][n][n] stack
         int pd = 0, pb = 0;
-        int* sinfo = cb.vec.info_inv + 2 * Bc;
-        auto note_info = [&]() -> int {
-            if (!info_out) return 0;
-            info_args ia{Bc, nullptr, sinfo, info_out};
-            return kh_launch<info_args, info_body>(dim3((Bc + 255) / 256), 256, 0, st, ia);
-        };
+        int* sinfo = info_out ? info_out : cb.info;      // the star products' inverses flag zero pivots straight into the solve's status word
         // without an S-matrix output only the flux columns of S11 / S21 are carried along the chain (see cols2)
         const int fcol = (!want_fields && !out->Stot_dev && (flags & KH_WANT_FLUX)) ? (N - 1) / 2 : -1;
         auto combine = [&](const SRef& A, const SRef& Bm, SRef& res, bool last = false) -> int {
-            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res, fcol, last);
+            int e = star_any(st, Bc, N, A, Bm, cb.accD[pd], cb.accB[pb], cb.pool, sinfo, res, fcol, last, 1);
             if (e) return e;
             if (res.bd) pb ^= 1;
-            else { acc_full = cb.accD[pd]; pd ^= 1; e = note_info(); }
+            else { acc_full = cb.accD[pd]; pd ^= 1; }
             return e;
         };
         if (want_fields) {
@@ -664,7 +663,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         }
 
         // ---- reverse chain (layer.py:49-59), only when fields are wanted
-        if (want_fields) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0));
+        if (want_fields) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0, info_out ? info_out : cb.info));
 
         if (flags & KH_WANT_FLUX) {
             flux_args a{Bc, N, final_dst, wl, kp, pol, p->g_dev, p->epsi, p->epse,
@@ -781,22 +780,6 @@ extern "C" int kh_toeplitz_gather(const void* F, int Nx, int Ny, int P, int Q, v
 
 // ---------------------------------------------------------------------------- fields (implemented in kh_fields.cuh)
 #include "kh_fields.cuh"
-#ifndef KH_FIELDS_IMPL
-extern "C" size_t kh_fields_workspace_bytes(const kh_plan*, int, int, int) { return 0; }
-extern "C" int kh_fields_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, const double*, int,
-                               const double*, int, const double*, void*, void*, size_t, void*) {
-    return fail(KH_ESTATE, "kh_fields_batch: not built");
-}
-extern "C" int kh_fields_fourier_batch(const kh_plan*, int, const double*, const void*, const void*, const kh_outputs*, const double*, int,
-                                       const double*, void*, void*, size_t, void*) {
-    return fail(KH_ESTATE, "kh_fields_fourier_batch: not built");
-}
-extern "C" size_t kh_idft_work_bytes(int, int) { return 0; }
-extern "C" int kh_idft_batch(int, int, int, const void*, const void*, const double*, const double*, const void*, void*, void*, size_t, void*) {
-    return fail(KH_ESTATE, "kh_idft_batch: not built");
-}
-#endif
-
 // ---------------------------------------------------------------------------- FP64 peak probe
 extern "C" int kh_fp64_peak(int mode, int iters, int blocks, double* scratch_dev, double* tflops_out) {
 #ifdef KH_HOST_EMU

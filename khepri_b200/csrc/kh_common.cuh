@@ -198,11 +198,15 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
     if constexpr (MAXT == 0) kern = kh_entry<Args, Body>;           // no launch bounds
     else if constexpr (MAXT < 0) kern = kh_entry_mr<Args, Body, MINB>;   // MAXT < 0: MINB is a register cap
     else kern = kh_entry_lb<Args, Body, MAXT, MINB>;
-    static size_t configured = 0;            // per-instantiation opt-in to > 48 KB dynamic smem
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
+    if (smem > 48 * 1024) {                   // opt-in to > 48 KB dynamic smem: a per-DEVICE attribute of this instantiation
+        static size_t configured[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) configured[dev] = smem;
+        }
     }
     g_prof.launches++;
     if (g_prof.on) {

@@ -66,9 +66,9 @@ static int solve_extended(kh_stream_t st, const kh_plan* p, int Bc, int li, cons
         KH_TRY((kh_launch<bd_layer_args, bd_layer_body>(dim3(Be), 64, 0, st, a)));
         src_kind = 0; src = cb.ebd;
     } else if (base.kind == KH_LAYER_PIXMAP) {
+        LayerVec v = cb.evec; v.info_acc = info_out ? info_out : cb.info; v.info_div = Nb;     // sub-solve b * Nb + s reports into solve b
         KH_TRY(solve_patterned(st, Be, Nb, (const cd*)base.C_dev, (const cd*)base.IC_dev, base.depth, cb.eKx, cb.eKy, cb.ek0,
-                               cb.epool, cb.evec, cb.eS, nullptr, nullptr, nullptr, 0, 0));
-        (void)info_out;
+                               cb.epool, v, cb.eS, nullptr, nullptr, nullptr, 0, 0));
         src_kind = 1; src = cb.eS;
     } else return fail(KH_EINVAL, "extended layer: base must be uniform or pixmap");
     ext_scatter_args a{Bc, Nb, L.ext_mode, src_kind, src, cb.layerS[li]};
@@ -109,7 +109,7 @@ static int keep_eigenspace_bd(kh_stream_t st, const kh_plan* p, int Bc, ChunkBuf
 }
 
 // reverse partial products (layer.py:49-59): suffix[Ls-1] = identity, suffix[i] = S_{i+1} (*) suffix[i+1]
-static int reverse_chain(kh_stream_t st, const kh_plan* p, int Bc, const std::vector<SRef>& S, ChunkBufs& cb, const kh_outputs* out, int b0) {
+static int reverse_chain(kh_stream_t st, const kh_plan* p, int Bc, const std::vector<SRef>& S, ChunkBufs& cb, const kh_outputs* out, int b0, int* info_acc) {
     const int N = p->N, n = p->n, Ls = (int)p->stack.size();
     const long long n2 = (long long)n * n;
     {   bd_identity_args a{Bc, N, cb.accB[0]};
@@ -121,7 +121,7 @@ static int reverse_chain(kh_stream_t st, const kh_plan* p, int Bc, const std::ve
         if (i == 0) break;
         const SRef& L = S[p->stack[i]];
         SRef r2;
-        KH_TRY(star_any(st, Bc, N, L, acc, cb.accR[pd], cb.accB[pb], cb.pool, cb.vec.info_inv + 2 * Bc, r2));
+        KH_TRY(star_any(st, Bc, N, L, acc, cb.accR[pd], cb.accB[pb], cb.pool, info_acc, r2, -1, false, 1));
         if (r2.bd) pb ^= 1; else pd ^= 1;
         acc = r2;
     }

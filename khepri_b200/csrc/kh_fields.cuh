@@ -361,10 +361,12 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
         // enough CTAs for a few waves: split the y range when the batch of maps is small
         int ysplit = 1;
         while ((long long)B * nz * 6 * ysplit < 4 * 148 && ysplit * 2 <= ny && ysplit < 16) ysplit *= 2;
-        const int nyl = (ny + ysplit - 1) / ysplit + 1;
+        // ... and until the y phase table of one CTA fits in shared memory (tall grids: ny = 2048 with Q = 9 needs 295 KB unsplit)
+        auto table_bytes = [&](int ys) { return ((size_t)N + (size_t)p->Q * ((ny + ys - 1) / ys + 1)) * sizeof(cd); };
+        while (table_bytes(ysplit) > (size_t)KH_SMEM_MAX && ysplit < ny) ysplit *= 2;
         fld_grid_args a{B, N, p->P, p->Q, nx, ny, 6 * nz, ysplit, f.Sall, f.Xt, f.Yt, (cd*)F_dev};
-        const size_t sm = ((size_t)N + (size_t)p->Q * nyl) * sizeof(cd);
-        if (sm > (size_t)KH_SMEM_MAX) return fail(KH_EINVAL, "kh_fields_grid_batch: grid too tall for the phase table in shared memory");
+        const size_t sm = table_bytes(ysplit);
+        if (sm > (size_t)KH_SMEM_MAX) return fail(KH_EINVAL, "kh_fields_grid_batch: basis too large for the phase table in shared memory");
         const double work = 8.0 * ((double)N * nx + (double)p->Q * nx * ny) * 6.0 * nz * B;
         return kh_launch<fld_grid_args, fld_grid_body>(dim3(B, 6 * nz * ysplit), nx >= 256 ? 256 : (nx >= 128 ? 128 : 64), sm, st, a, "fld_grid", work);
     }

@@ -2,7 +2,7 @@
 // LAPACK zgeev at khepri/alternative.py:172 for the Omega^2 = P Q problem of every patterned layer).
 //
 // Three kernels per batch (each phase gets its own launch shape and shows up separately in ncu):
-//   zhess : diagonal balancing with powers of two (exact similarity, as zgebal 'S') and Householder
+//   zhessz: diagonal balancing with powers of two (exact similarity, as zgebal 'S') and Householder
 //           reduction to upper Hessenberg form with the Schur vectors accumulated.  Z is kept
 //           TRANSPOSED in HBM/L2 (Zt) so every column operation on Z is a coalesced row operation.
 //   zqr   : single-shift QR iteration (Wilkinson / exceptional shifts, LAPACK zlahqr deflation test).
@@ -42,6 +42,7 @@ struct zgeev_args {
     int na = 0, iact_stop = 0, phase = 0; int* istate = nullptr;
 };
 
+#define KH_ENOMEM_ZGEEV (-2)
 #define ZGEEV_EPS 2.220446049250313e-16   /* LAPACK ulp = eps*base */
 #define ZGEEV_SAFMIN 2.2250738585072014e-308
 
@@ -103,143 +104,6 @@ __device__ long long kh_qr_dbg[16];
 #define QT_MARK()
 #define QT_ADD(v)
 #endif
-// ============================================================================ 1. balance + Hessenberg
-KH_DEV void zhess_body(const Cta& c, const zgeev_args& a) {
-    const int n = a.n, b = c.bx;
-    const cd* A = mat_ptr(a.A, b);
-    cd* Hg = mat_ptr(a.Hw, b);
-    cd* Zt = mat_ptr(a.Zt, b);
-    const int ldz = a.Zt.ld; (void)ldz;
-    cd* scout = a.scale + (long long)b * a.scale_stride;
-    cd* tauout = a.tau + (long long)b * a.tau_stride;
-    // shared: [vv n][uu n][scratch 192 dbl][dsc n dbl][H]
-    cd* vv = (cd*)KH_SMEM(c);
-    cd* uu = vv + n;
-    double* scratch = (double*)(uu + n);
-    double* dsc = scratch + 192;       // [n] balancing factors; the region is 4n doubles and is reused as q / zu afterwards
-    cd* H; int ld;
-    if (a.use_smem) { H = (cd*)(KH_SMEM(c) + (((2 * n * 16 + 192 * 8 + 4 * n * 8) + 15) & ~15)); ld = a.ld_s; }   // offset arithmetic keeps the shared address space
-    else { H = Hg; ld = a.Hw.ld; }
-#define HH(i, j) H[(long long)(i) * ld + (j)]
-#define ZT(i, j) Zt[(long long)(i) * ldz + (j)]
-    if (a.use_smem || H != A)
-        for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; HH(i, j) = A[(long long)i * a.A.ld + j]; }
-    for (int i = c.tid; i < n; i += c.nthr) { dsc[i] = 1.0; tauout[i] = mk(0.0, 0.0); }
-    c.sync();
-
-    // ---- balancing (Jacobi-style sweeps of the EISPACK balanc criterion; powers of two, so exact)
-    for (int sweep = 0; sweep < 12; ++sweep) {
-        double changed = 0.0;
-        for (int i = c.tid; i < n; i += c.nthr) {
-            double cn = 0.0, rn = 0.0;
-            for (int j = 0; j < n; ++j) if (j != i) { cn += cabs1(HH(j, i)); rn += cabs1(HH(i, j)); }
-            double f = 1.0;
-            if (cn != 0.0 && rn != 0.0 && cn <= 1e300 && rn <= 1e300) {      // (NaN/inf rows are left alone)
-                double g = rn * 0.5, s = cn + rn, cc = cn;
-                for (int q = 0; q < 1100 && cc < g; ++q) { f *= 2.0; cc *= 4.0; }
-                g = rn * 2.0;
-                for (int q = 0; q < 1100 && cc >= g; ++q) { f *= 0.5; cc *= 0.25; }
-                if ((cc + rn) / f >= 0.95 * s) f = 1.0;
-            }
-            uu[i].x = f;
-            if (f != 1.0) changed = 1.0;
-        }
-        changed = cta_max(c, changed, scratch);
-        c.sync();
-        if (changed == 0.0) break;
-        for (int e = c.tid; e < n * n; e += c.nthr) {
-            int i = e / n, j = e - i * n;
-            double f = uu[j].x / uu[i].x;
-            if (f != 1.0) HH(i, j) = f * HH(i, j);
-        }
-        for (int i = c.tid; i < n; i += c.nthr) dsc[i] *= uu[i].x;
-        c.sync();
-    }
-    for (int i = c.tid; i < n; i += c.nthr) scout[i] = mk(dsc[i], 0.0);
-
-    // ---- Householder reduction (zgehd2 / zlarfg conventions: H_k = I - tau v v^H, A <- H_k^H A H_k), written
-    // as ONE rank-2 update per step:  A -= pt conj(v)^T + (conj(tau) v) q^T  with p = A v, q^T = v^H A, s = v^H p,
-    // pt = tau p - |tau|^2 s v.  Three barriers per step, everything in shared memory.  The reflectors stay below
-    // the sub-diagonal (LAPACK layout); Z = H_0 H_1 ... is formed afterwards by zunghr, also in shared memory.
-    cd* pp_ = uu;                      // p  [n]
-    cd* qq_ = (cd*)dsc;                // q  [n]   (dsc is dead after balancing)
-    const int lane = c.tid % KH_WARP;
-#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
-    long long ht = clock64(), h_norm = 0, h_v = 0, h_mv = 0, h_upd = 0, h_n;
-#define HT_ADD(v) do { h_n = clock64(); (v) += h_n - ht; ht = h_n; } while (0)
-#else
-#define HT_ADD(v)
-#endif
-    for (int k = 0; k + 2 < n; ++k) {
-        double part = 0.0;                                   // every warp computes the column norm redundantly
-        for (int i = k + 2 + lane; i < n; i += KH_WARP) part += cabs2(HH(i, k));
-        const double xn2 = kh_warp_allsum(part);
-        const cd alpha = HH(k + 1, k);
-        if (xn2 == 0.0 && alpha.y == 0.0) continue;          // already reduced: H_k = I   (uniform across the CTA)
-        const double beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
-        const cd tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
-        const cd sc = crecip(alpha - mk(beta, 0.0));
-        c.sync();                                              // all warps have read column k
-        HT_ADD(h_norm);
-        for (int i = k + 1 + c.tid; i < n; i += c.nthr) {
-            const cd vi = (i == k + 1) ? mk(1.0, 0.0) : HH(i, k) * sc;
-            vv[i] = vi;
-            HH(i, k) = (i == k + 1) ? mk(beta, 0.0) : vi;     // reflector kept in place
-        }
-        if (c.tid == 0) tauout[k] = tau;
-        c.sync();
-        HT_ADD(h_v);
-        // p = A v (one thread per row), q = v^H A (one thread per column)
-        for (int t = c.tid; t < 2 * n; t += c.nthr) {
-            cd a0 = mk(0, 0), a1 = mk(0, 0);
-            if (t < n) {
-                const int r = t;
-                int j = k + 1;
-                for (; j + 1 < n; j += 2) { cfma(a0, HH(r, j), vv[j]); cfma(a1, HH(r, j + 1), vv[j + 1]); }
-                if (j < n) cfma(a0, HH(r, j), vv[j]);
-                pp_[r] = a0 + a1;
-            } else {
-                const int j = t - n;
-                if (j > k) {
-                    int i = k + 1;
-                    for (; i + 1 < n; i += 2) { cfma(a0, cconj(vv[i]), HH(i, j)); cfma(a1, cconj(vv[i + 1]), HH(i + 1, j)); }
-                    if (i < n) cfma(a0, cconj(vv[i]), HH(i, j));
-                }
-                qq_[j] = a0 + a1;
-            }
-        }
-        c.sync();
-        HT_ADD(h_mv);
-        double sr = 0.0, si = 0.0;                           // s = v^H p, redundantly per warp
-        for (int i = k + 1 + lane; i < n; i += KH_WARP) { const cd w = cconj(vv[i]) * pp_[i]; sr += w.x; si += w.y; }
-        const cd sv = mk(kh_warp_allsum(sr), kh_warp_allsum(si));
-        const cd t2s = cabs2(tau) * sv;
-        const cd ctau = cconj(tau);
-        const int ncol = n - k - 1;
-        const int nseg = (ncol + 3) / 4;
-        for (int e = c.tid; e < n * nseg; e += c.nthr) {      // rank-2 update: thread = (row, residue class of columns)
-            const int i = e / nseg, sg = e - i * nseg;
-            cd pt = tau * pp_[i], tv = mk(0, 0);
-            if (i > k) { tv = ctau * vv[i]; pt = pt - t2s * vv[i]; }
-            for (int j = k + 1 + sg; j < n; j += nseg) {
-                cd h = HH(i, j);
-                cfms(h, pt, cconj(vv[j]));
-                cfms(h, tv, qq_[j]);
-                HH(i, j) = h;
-            }
-        }
-        c.sync();
-        HT_ADD(h_upd);
-    }
-#if defined(KH_QR_TIMING) && !defined(KH_HOST_EMU)
-    if (c.tid == 0 && b == 0) { kh_qr_dbg[8] += h_norm; kh_qr_dbg[9] += h_v; kh_qr_dbg[10] += h_mv; kh_qr_dbg[11] += h_upd; }
-#endif
-    if (a.use_smem)
-        for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; Hg[(long long)i * a.Hw.ld + j] = HH(i, j); }
-#undef HH
-#undef ZT
-}
-
 // ============================================================================ 1a. fused shared-memory variant
 // Balance + Hessenberg reduction + formation of Z in ONE kernel with the matrix resident in shared memory (n <= ~117).
 // Per reduction step three barriers: [norm, v] | [p = A v, q = v^H A with several threads per dot product, s = v^H p] |
@@ -465,50 +329,6 @@ KH_DEV void zhessz_body(const Cta& c, const zgeev_args& a) {
 #endif
     for (int e = c.tid; e < n * n; e += c.nthr) { int j = e / n, i = e - j * n; Ztg[(long long)j * ldz + i] = HH(i, j); }
 #undef HH
-}
-
-// ============================================================================ 1b. Z = H_0 H_1 ... H_{n-3} (zunghr), backward accumulation
-KH_DEV void zunghr_body(const Cta& c, const zgeev_args& a) {
-    const int n = a.n, b = c.bx;
-    const cd* Hg = mat_ptr(a.Hw, b);
-    cd* Ztg = mat_ptr(a.Zt, b);
-    const int ldg = a.Hw.ld, ldz = a.Zt.ld;
-    const cd* taus = a.tau + (long long)b * a.tau_stride;
-    // shared: [vv n][ww n][Z n x ld]   (Z stays in global memory, transposed, when it does not fit)
-    cd* vv = (cd*)KH_SMEM(c);
-    cd* ww = vv + n;
-    cd* Z; int ld; bool tr;            // tr: Z is addressed transposed (global Zt)
-    if (a.use_smem) { Z = ww + n; ld = a.ld_s; tr = false; }
-    else { Z = Ztg; ld = ldz; tr = true; }
-#define ZZ(i, j) Z[tr ? ((long long)(j) * ld + (i)) : ((long long)(i) * ld + (j))]
-    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; ZZ(i, j) = mk(i == j ? 1.0 : 0.0, 0.0); }
-    c.sync();
-    for (int k = n - 3; k >= 0; --k) {
-        const cd tau = taus[k];
-        if (tau.x == 0.0 && tau.y == 0.0) continue;                       // uniform
-        for (int i = k + 1 + c.tid; i < n; i += c.nthr) vv[i] = (i == k + 1) ? mk(1.0, 0.0) : Hg[(long long)i * ldg + k];
-        c.sync();
-        // w = v^H Z[k+1:, k+1:]  (one thread per column), then Z[k+1:, k+1:] -= tau v w
-        for (int j = k + 1 + c.tid; j < n; j += c.nthr) {
-            cd a0 = mk(0, 0), a1 = mk(0, 0);
-            int i = k + 1;
-            for (; i + 1 < n; i += 2) { cfma(a0, cconj(vv[i]), ZZ(i, j)); cfma(a1, cconj(vv[i + 1]), ZZ(i + 1, j)); }
-            if (i < n) cfma(a0, cconj(vv[i]), ZZ(i, j));
-            ww[j] = tau * (a0 + a1);
-        }
-        c.sync();
-        const int m = n - k - 1;
-        for (int e = c.tid; e < m * m; e += c.nthr) {
-            const int i = k + 1 + e / m, j = k + 1 + (e - (e / m) * m);
-            cd z = ZZ(i, j);
-            cfms(z, vv[i], ww[j]);
-            ZZ(i, j) = z;
-        }
-        c.sync();
-    }
-    if (a.use_smem)
-        for (int e = c.tid; e < n * n; e += c.nthr) { int j = e / n, i = e - j * n; Ztg[(long long)j * ldz + i] = ZZ(i, j); }
-#undef ZZ
 }
 
 // ============================================================================ 2. shifted QR on the packed Hessenberg matrix
@@ -1296,13 +1116,8 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     const bool tiled_hess = !a.use_smem && a.rlog && a.rlog_stride / 2 >= zhb_work_cd(n);
     if (tiled_hess) e = zhess_blocked_launch(st, batch, n, a.A, a.Hw, a.Zt, a.X, (cd*)a.rlog, a.rlog_stride / 2, a.scale, a.scale_stride, a.tau, a.tau_stride, 0.25 * work);
     else if (a.use_smem) e = kh_launch<zgeev_args, zhessz_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, 1), st, a, "zgeev_hess", 0.25 * work);
-    else e = kh_launch<zgeev_args, zhess_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), zhess_smem_bytes(n, a.ld_s, a.use_smem), st, a, "zgeev_hess", 0.25 * work);
+    else return KH_ENOMEM_ZGEEV;            // beyond shared memory the blocked reduction needs the log work space (kh_zgeev_work_bytes provides it)
     if (e) return e;
-    if (!a.use_smem && !tiled_hess) {   zgeev_args u = a;
-        const size_t usm = (size_t)2 * n * sizeof(cd) + (size_t)n * u.ld_s * sizeof(cd) + 16;
-        u.use_smem = usm <= (size_t)KH_SMEM_MAX;
-        e = kh_launch<zgeev_args, zunghr_body>(dim3(batch), n <= 42 ? 128 : (n <= 85 ? 256 : 384), u.use_smem ? usm : (size_t)2 * n * sizeof(cd) + 16, st, u, "zgeev_hess", 0.0);
-        if (e) return e; }
     zgeev_args q = a;
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
     const int zcw = (q.rlog && q.sw_cap >= 1) ? zrot_strip(n, q.sw_cap) : 0;

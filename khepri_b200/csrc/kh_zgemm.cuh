@@ -51,13 +51,10 @@ __device__ __forceinline__ void kh_cp_async_commit() { asm volatile("cp.async.co
 template <int N> __device__ __forceinline__ void kh_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
-// NW warps x NT column tiles: CTA tile (8 NW) x (8 NT).  (8,8) = 64x64 for general shapes; (7,7) = 56x56
-// wastes less padding at n = 50 (one tile) and n = 98 (2x2 tiles).
+// Host-emulation stand-in for the DMMA kernels below (tests/hostemu): the same tiling of the output, plain loops.
 template <int NW, int NT>
 KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
-    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, THREADS = 32 * NW;
-    // 1-D grid, tile index fastest: the CTAs that share a matrix's A / B panels are launched next to each other, so the
-    // second reader of a panel finds it in L2 (with the batch index fastest every panel was fetched from HBM once per tile)
+    constexpr int BM = 8 * NW, BN = 8 * NT;
     const int tiles_n = (a.N + BN - 1) / BN, tiles = ((a.M + BM - 1) / BM) * tiles_n;
     const int b = c.bx / tiles, tile = c.bx - b * tiles;
     const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -67,7 +64,6 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
     cd* Cout = mat_ptr(a.Cout, b);
     const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
     const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
-#ifdef KH_HOST_EMU
     for (int i = m0; i < m0 + BM && i < a.M; ++i)
         for (int j = n0; j < n0 + BN && j < a.N; ++j) {
             cd acc = mk(0, 0);
@@ -77,88 +73,6 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
             }
             Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc);
         }
-#else
-    cd* As = (cd*)KH_SMEM(c);                           // [2][BM][LDA]
-    cd* Bs = As + 2 * BM * ZG_LDA;                      // [2][BK][LDB]
-    const int warp = c.tid >> 5, lane = c.tid & 31;
-    const int lr = lane >> 2, lk = lane & 3;
-    double cr[NT][2], ci[NT][2];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
-    const int nk = (a.K + ZG_BK - 1) / ZG_BK;
-    const int nt = min(NT, (a.N - n0 + 7) >> 3);
-    const bool warp_active = (m0 + warp * 8) < a.M;
-
-    auto stage = [&](int buf, int kc) {
-        const int k0 = kc * ZG_BK;
-        cd* as = As + buf * BM * ZG_LDA;
-        cd* bs = Bs + buf * ZG_BK * LDB;
-        if (!a.transA) {
-            for (int e = c.tid; e < BM * ZG_BK; e += THREADS) {
-                int m = e >> 4, k = e & 15;
-                bool ok = (m0 + m) < a.M && (k0 + k) < a.K;
-                kh_cp_async16(as + m * ZG_LDA + k, ok ? A + (long long)(m0 + m) * a.A.ld + k0 + k : A, ok);
-            }
-        } else {
-            for (int e = c.tid; e < BM * ZG_BK; e += THREADS) {
-                int k = e / BM, m = e - k * BM;
-                bool ok = (m0 + m) < a.M && (k0 + k) < a.K;
-                kh_cp_async16(as + m * ZG_LDA + k, ok ? A + (long long)(k0 + k) * a.A.ld + m0 + m : A, ok);
-            }
-        }
-        for (int e = c.tid; e < ZG_BK * BN; e += THREADS) {
-            int k = e / BN, n = e - k * BN;
-            bool ok = (k0 + k) < a.K && (n0 + n) < a.N;
-            kh_cp_async16(bs + k * LDB + n, ok ? B + (long long)(k0 + k) * a.B.ld + n0 + n : B, ok);
-        }
-        kh_cp_async_commit();
-    };
-
-    if (nk > 0) stage(0, 0);
-    for (int kc = 0; kc < nk; ++kc) {
-        const int buf = kc & 1;
-        if (kc + 1 < nk) { stage(buf ^ 1, kc + 1); kh_cp_async_wait<1>(); }
-        else kh_cp_async_wait<0>();
-        __syncthreads();
-        if (warp_active) {
-            const cd* as = As + buf * BM * ZG_LDA + (warp * 8 + lr) * ZG_LDA + lk;
-            const cd* bs = Bs + buf * ZG_BK * LDB + lk * LDB + lr;
-#pragma unroll
-            for (int kk = 0; kk < ZG_BK / 4; ++kk) {
-                if (kc * ZG_BK + kk * 4 >= a.K) break;           // ragged K: skip the all-zero MMA steps
-                cd av = as[kk * 4];
-                double nai = -av.y;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    if (t < nt) {
-                        cd bv = bs[kk * 4 * LDB + t * 8];
-                        kh_dmma(cr[t][0], cr[t][1], av.x, bv.x);
-                        kh_dmma(ci[t][0], ci[t][1], av.x, bv.y);
-                        kh_dmma(cr[t][0], cr[t][1], nai, bv.y);
-                        kh_dmma(ci[t][0], ci[t][1], av.y, bv.x);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (warp_active) {
-        const int row = m0 + warp * 8 + lr;
-        if (row < a.M) {
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                if (t < nt) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int col = n0 + t * 8 + 2 * lk + h;
-                        if (col < a.N)
-                            Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]));
-                    }
-                }
-            }
-        }
-    }
-#endif
 }
 
 #ifndef KH_HOST_EMU
@@ -442,37 +356,22 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
 #endif
 }
 KH_DEV void zgemm56u3_body(const Cta& c, const zgemm_args& a) { zgemm_body_u<7, 7, 3>(c, a); }
-KH_DEV void zgemm56p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<7, 7, 3>(c, a); }
 KH_DEV void zgemm64p3_body(const Cta& c, const zgemm_args& a) { zgemm_body_p<8, 8, 3>(c, a); }
-KH_DEV void zgemm_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<8, 8>(c, a); }
-KH_DEV void zgemm56_body(const Cta& c, const zgemm_args& a) { zgemm_body_t<7, 7>(c, a); }
 
 static inline long long zgemm_padded(int M, int N, int T) { return (long long)((M + T - 1) / T) * T * ((N + T - 1) / T) * T; }
 static inline size_t zgemm_smem(int T, int ST) { return (size_t)ST * (T * ZG_LDA + ZG_BK * (T + 2)) * sizeof(cd); }
-static inline int zgemm_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("KH_ZGEMM_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
 // Shapes that waste less padding on 56x56 tiles (n = 50: one tile, n = 98: 2x2 tiles) use the unit-balanced kernel, the rest
-// the 64x64 strip kernel.  KH_ZGEMM_VARIANT (developer switch, tests/zgemm_timing.py): 1 = strip-per-warp 56x56 pipeline,
-// 9 = the first-generation kernels (double buffer, two barriers per chunk).  Measured and dropped: a 104x104 one-CTA-per-matrix
-// tile (13 warps need > 128 registers for the 13 accumulator tiles), a 3-CTA/SM 2-stage variant (no gain), and a persistent
-// grid whose cp.async pipeline runs across tile boundaries (7 % slower: the per-tile cost is the epilogue, not the first load).
+// the 64x64 strip kernel.  Measured and dropped in round 1: a strip-per-warp 56x56 pipeline, the first-generation double-buffer
+// kernels, a 104x104 one-CTA-per-matrix tile (13 warps need > 128 registers for the 13 accumulator tiles), a 3-CTA/SM 2-stage
+// variant (no gain), and a persistent grid whose cp.async pipeline runs across tile boundaries (7 % slower).
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     const double work = 8.0 * a.M * a.N * a.K * batch;
-    const int var = zgemm_variant();
     // profiler name: products with a handful of columns (the flux columns of the last star product) are matrix-vector work,
     // bound by reading A from HBM, and are reported apart from the tensor-bound GEMMs
     const char* name = a.N <= 8 ? "zgemv" : "zgemm";
     const bool t56 = zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64);
     const unsigned g56 = (unsigned)batch * ((a.M + 55) / 56) * ((a.N + 55) / 56), g64 = (unsigned)batch * ((a.M + 63) / 64) * ((a.N + 63) / 64);
-    if (var == 9) {
-        if (t56) return kh_launch<zgemm_args, zgemm56_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 2), st, a, name, work);
-        return kh_launch<zgemm_args, zgemm_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 2), st, a, name, work);
-    }
-    if (t56 && var == 1) return kh_launch<zgemm_args, zgemm56p3_body, 224, 2>(dim3(g56), 224, zgemm_smem(56, 3), st, a, name, work);
     if (t56) return kh_launch<zgemm_args, zgemm56u3_body, 256, 2>(dim3(g56), 256, zgemm_smem(56, 3), st, a, name, work);
     return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, name, work);
 }

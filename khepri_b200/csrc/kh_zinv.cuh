@@ -9,10 +9,18 @@
 #include "kh_common.cuh"
 #include "kh_zgemm.cuh"
 
+// status bookkeeping shared by the inverse kernels (see zinv_args::info_mode)
+KH_DEV void zinv_note(int* info, int mode, int b, int bad) {
+    if (!info) return;
+    if (mode == 0) info[b] = bad;
+    else if (bad) KH_ATOMIC_OR(&info[b / mode], 2);
+}
+
 struct zinv_args {
     int n;
     MatRef A, Ainv;      // Ainv may alias A
     int* info;           // per-matrix status (0 ok, k+1 = zero pivot at step k); may be null
+    int info_mode = 0;   // 0: info[b] = status.  m > 0: accumulate, info[b / m] |= 2 on a zero pivot (pipeline use: the solve's info word)
     int use_smem;
     int ld_s;            // shared-memory leading dimension (odd)
 };
@@ -99,159 +107,10 @@ KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
             Out[(long long)i * a.Ainv.ld + j] = W[(long long)i * ld + j];
         }
     }
-    if (a.info && c.tid == 0) a.info[b] = bad;
+    if (c.tid == 0) zinv_note(a.info, a.info_mode, b, bad);
 }
 
 
-#ifndef KH_HOST_EMU
-// ---------------------------------------------------------------------------------------------
-// Register-resident variant for n <= 100 (the 5x5 and 7x7 harmonic bases): the whole matrix lives
-// in the register file, each thread owning a TR x 5 tile (the matrix is padded with identity rows /
-// columns up to the tile grid, so the elimination loop has no bounds checks).  Per step only the
-// pivot column and the two rows of the interchange travel through shared memory (double buffered:
-// two barriers per step); the rank-1 update is pure register DFMA work.  Because tiles are aligned,
-// the pivot column / row of step k sit in register slot (k mod 5, k mod TR) of their owners, so the
-// step loop is unrolled by lcm(TR, 5) and every register index is a compile-time constant.
-#define ZIR_TC 5
-template <int TR, int KQ, int KP>
-__device__ __forceinline__ void zir_step(int k, int n, int NP, int tid, int lane, bool live, int i0, int j0, int tx, int ty,
-                                         cd (&r)[TR][ZIR_TC], cd* colk, cd* rowK, cd* rowP, int* piv, int& bad) {
-    cd* ck = colk + (k & 1) * NP; cd* rK = rowK + (k & 1) * NP; cd* rP = rowP + (k & 1) * NP;
-    const bool own_col = live && (j0 + KQ == k), own_row = live && (i0 + KP == k);
-    // A: publish column k and row k
-    if (own_col) {
-#pragma unroll
-        for (int p = 0; p < TR; ++p) ck[i0 + p] = r[p][KQ];
-    }
-    if (own_row) {
-#pragma unroll
-        for (int q = 0; q < ZIR_TC; ++q) rK[j0 + q] = r[KP][q];
-    }
-    __syncthreads();
-    // B: every warp finds the pivot row (izamax over rows k..n-1, ties -> smallest index)
-    double best = -1.0; int pr = k;
-    for (int i = k + lane; i < n; i += 32) { const double v = cabs1(ck[i]); if (v > best) { best = v; pr = i; } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, pr, o);
-        if (ov > best || (ov == best && oi < pr)) { best = ov; pr = oi; }
-    }
-    const int pp = pr - i0;
-    const bool own_prow = live && pr != k && (unsigned)pp < (unsigned)TR;
-    if (__any_sync(0xffffffffu, own_prow)) {                 // rare per warp: a real branch
-        if (own_prow) {
-#pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) {
-                cd v = r[0][q];
-#pragma unroll
-                for (int p2 = 1; p2 < TR; ++p2) if (pp == p2) v = r[p2][q];
-                rP[j0 + q] = v;
-            }
-        }
-    }
-    if (tid == 0) piv[k] = pr;
-    __syncthreads();
-    // C: interchange + eliminate.  Row k becomes the scaled pivot row; row pr receives the old row k.
-    const cd* prow = (pr == k) ? rK : rP;
-    const cd pv = ck[pr];
-    if (pv.x == 0.0 && pv.y == 0.0 && !bad) bad = k + 1;
-    const cd d = crecip(pv);
-    cd f[TR];
-#pragma unroll
-    for (int p = 0; p < TR; ++p) f[p] = ck[i0 + p];
-    if (__any_sync(0xffffffffu, own_prow)) {
-        if (own_prow) {
-#pragma unroll
-            for (int p = 0; p < TR; ++p) if (p == pp) {
-                f[p] = ck[k];
-#pragma unroll
-                for (int q = 0; q < ZIR_TC; ++q) r[p][q] = rK[j0 + q];
-            }
-        }
-    }
-    if (own_col) {
-#pragma unroll
-        for (int p = 0; p < TR; ++p) r[p][KQ] = mk(0.0, 0.0);
-    }
-#pragma unroll
-    for (int q = 0; q < ZIR_TC; ++q) {
-        cd pj = prow[j0 + q] * d;
-        if (q == KQ && own_col) pj = d;
-#pragma unroll
-        for (int p = 0; p < TR; ++p) cfms(r[p][q], f[p], pj);
-        if (own_row) r[KP][q] = pj;
-    }
-    // (no barrier here: the next step writes the other buffer set)
-}
-
-template <int TR, int U, int L>
-struct zir_unroll {
-    static __device__ __forceinline__ void run(int kb, int n, int NP, int tid, int lane, bool live, int i0, int j0, int tx, int ty,
-                                               cd (&r)[TR][ZIR_TC], cd* colk, cd* rowK, cd* rowP, int* piv, int& bad) {
-        if (kb + U < n) {
-            zir_step<TR, U % ZIR_TC, U % TR>(kb + U, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
-            zir_unroll<TR, U + 1, L>::run(kb, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
-        }
-    }
-};
-template <int TR, int L>
-struct zir_unroll<TR, L, L> {
-    static __device__ __forceinline__ void run(int, int, int, int, int, bool, int, int, int, int, cd (&)[TR][ZIR_TC], cd*, cd*, cd*, int*, int&) {}
-};
-
-template <int TR>
-__device__ __forceinline__ void zinv_reg_body(const Cta& c, const zinv_args& a) {
-    constexpr int L = (TR == 2) ? 10 : ((TR == 3) ? 15 : 20);             // lcm(TR, 5)
-    const int n = a.n, b = c.bx, tid = c.tid, lane = tid & 31;
-    const cd* A = mat_ptr(a.A, b);
-    cd* Out = mat_ptr(a.Ainv, b);
-    const int TXN = (n + ZIR_TC - 1) / ZIR_TC, TYN = (n + TR - 1) / TR;
-    const int NP = max(TXN * ZIR_TC, TYN * TR);
-    const bool live = tid < TXN * TYN;
-    const int ty = live ? tid / TXN : 0, tx = live ? tid - ty * TXN : 0;
-    const int i0 = ty * TR, j0 = tx * ZIR_TC;
-    cd* colk = (cd*)KH_SMEM(c);               // [2][NP]
-    cd* rowK = colk + 2 * NP;                 // [2][NP]
-    cd* rowP = rowK + 2 * NP;                 // [2][NP]
-    int* piv = (int*)(rowP + 2 * NP);         // [n]
-    int* dest = piv + n;                      // [n]
-    cd r[TR][ZIR_TC];
-#pragma unroll
-    for (int p = 0; p < TR; ++p)
-#pragma unroll
-        for (int q = 0; q < ZIR_TC; ++q) {
-            const int i = i0 + p, j = j0 + q;
-            r[p][q] = (live && i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk((i == j) ? 1.0 : 0.0, 0.0);
-        }
-    int bad = 0;
-    for (int kb = 0; kb < n; kb += L)
-        zir_unroll<TR, 0, L>::run(kb, n, NP, tid, lane, live, i0, j0, tx, ty, r, colk, rowK, rowP, piv, bad);
-    __syncthreads();
-    // undo the row interchanges as column interchanges (reverse order) -> destination column of every stored column
-    if (tid == 0) {
-        for (int j = 0; j < n; ++j) dest[j] = j;                  // dest[pos] = stored column sitting at pos
-        for (int k = n - 1; k >= 0; --k) { const int p = piv[k]; const int t = dest[k]; dest[k] = dest[p]; dest[p] = t; }
-        for (int pos = 0; pos < n; ++pos) piv[dest[pos]] = pos;   // invert (piv is free now)
-        for (int j = 0; j < n; ++j) dest[j] = piv[j];
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll
-        for (int p = 0; p < TR; ++p)
-#pragma unroll
-            for (int q = 0; q < ZIR_TC; ++q) {
-                const int i = i0 + p, j = j0 + q;
-                if (i < n && j < n) Out[(long long)i * a.Ainv.ld + dest[j]] = r[p][q];
-            }
-    }
-    if (a.info && tid == 0) a.info[b] = bad;
-}
-__device__ __forceinline__ void zinv_reg_small_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
-__device__ __forceinline__ void zinv_reg_mid_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
-__device__ __forceinline__ void zinv_reg_large_body(const Cta& c, const zinv_args& a) { zinv_reg_body<4>(c, a); }
-__device__ __forceinline__ void zinv_reg_t3_body(const Cta& c, const zinv_args& a) { zinv_reg_body<3>(c, a); }
-__device__ __forceinline__ void zinv_reg_t2x_body(const Cta& c, const zinv_args& a) { zinv_reg_body<2>(c, a); }
-#endif
 
 #ifndef KH_HOST_EMU
 // ---------------------------------------------------------------------------------------------
@@ -440,7 +299,7 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
     __syncthreads();
     for (int i = warp; i < n; i += NW)
         for (int j = lane; j < n; j += 32) Out[(long long)i * a.Ainv.ld + dest[j]] = As[i * lda + j];
-    if (a.info && tid == 0) a.info[b] = bad;
+    if (tid == 0) zinv_note(a.info, a.info_mode, b, bad);
 }
 __device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16>(c, a); }
 __device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8>(c, a); }
@@ -469,6 +328,7 @@ struct zinvb_args {
     int* piv; long long piv_stride;   // [batch][n] pivot rows (absolute)
     int* info;
     int lds;
+    int info_mode = 0;
 };
 
 KH_DEV void zinvb_panel_body(const Cta& c, const zinvb_args& a) {
@@ -535,7 +395,10 @@ KH_DEV void zinvb_panel_body(const Cta& c, const zinvb_args& a) {
         A[(long long)(k0 + s) * ld + j] = mk(0.0, 0.0);
     }
     for (int s = c.tid; s < nb; s += c.nthr) pivg[k0 + s] = pivs[s];
-    if (a.info && c.tid == 0) { if (k0 == 0) a.info[b] = bad; else if (bad && a.info[b] == 0) a.info[b] = bad; }
+    if (a.info && c.tid == 0) {
+        if (a.info_mode > 0) { if (bad) KH_ATOMIC_OR(&a.info[b / a.info_mode], 2); }
+        else if (k0 == 0) a.info[b] = bad; else if (bad && a.info[b] == 0) a.info[b] = bad;
+    }
 }
 
 // undo the row interchanges: out[:, j] = in[:, src[j]] with src = the column swaps (k <-> piv[k]) applied for k = n-1 .. 0
@@ -582,7 +445,7 @@ static inline long long zinv_work_cd(int n) { return (long long)zinvb_nb(n) * n 
 #define KH_ZINV_BLOCKED_MIN 101
 #endif
 
-static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work) {
+static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work, int info_mode = 0) {
     int e;
     if (A.p != Ainv.p) {
         zcopym_args cp{n, A, Ainv};
@@ -591,7 +454,7 @@ static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A
     const int nb = zinvb_nb(n);
     const long long wstride = zinv_work_cd(n);
     zinvb_args a;
-    a.n = n; a.nb = nb; a.A = Ainv; a.R = work; a.r_stride = wstride; a.info = info; a.lds = nb + 1;
+    a.n = n; a.nb = nb; a.A = Ainv; a.R = work; a.r_stride = wstride; a.info = info; a.lds = nb + 1; a.info_mode = info_mode;
     a.piv = (int*)(work + (long long)nb * n); a.piv_stride = wstride * 4;
     const size_t sm = (size_t)n * 16 + 32 * 16 + 128 * 8 + 32 * 4 + 16 + (size_t)n * a.lds * sizeof(cd);
     for (int k0 = 0; k0 < n; k0 += nb) {
@@ -624,34 +487,16 @@ static inline size_t zinv_smem_bytes(int n, int ld_s, int use_smem) {
     return s;
 }
 
-static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work = nullptr, long long work_cd = 0) {
+static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work = nullptr, long long work_cd = 0, int info_mode = 0) {
     if (batch <= 0 || n <= 0) return 0;
-    if (n >= KH_ZINV_BLOCKED_MIN && work && work_cd >= (long long)batch * zinv_work_cd(n)) return zinv_blocked_launch(st, batch, n, A, Ainv, info, work);
+    if (n >= KH_ZINV_BLOCKED_MIN && work && work_cd >= (long long)batch * zinv_work_cd(n)) return zinv_blocked_launch(st, batch, n, A, Ainv, info, work, info_mode);
     zinv_args a;
-    a.n = n; a.A = A; a.Ainv = Ainv; a.info = info;
+    a.n = n; a.A = A; a.Ainv = Ainv; a.info = info; a.info_mode = info_mode;
 #ifndef KH_HOST_EMU
-    static int zvar = -1;
-    if (zvar < 0) { const char* e = getenv("KH_ZINV_KERNEL"); zvar = e ? atoi(e) : 0; }   // 1: previous register-resident kernels
-    if (n <= 64 && n >= 16 && zvar != 1)
+    if (n <= 64 && n >= 16)
         return kh_launch<zinv_args, zinv_dmma8_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
-    if (n <= ZID_NMAX && n >= 16 && zvar != 1)
+    if (n <= ZID_NMAX && n >= 16)
         return kh_launch<zinv_args, zinv_dmma_body, 512, 1>(dim3(batch), 512, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
-    if (n <= 100) {
-        a.use_smem = 0; a.ld_s = 0;
-        const int txn = (n + ZIR_TC - 1) / ZIR_TC;
-        const int tiles2 = txn * ((n + 1) / 2), tiles4 = txn * ((n + 3) / 4);
-        const size_t sm = (size_t)6 * (n + 8) * sizeof(cd) + (size_t)2 * n * sizeof(int) + 16;
-        const double work = 8.0 * n * n * n * batch;
-        if (tiles2 <= 256) return kh_launch<zinv_args, zinv_reg_small_body, 256, 2>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
-        if (tiles2 <= 512) return kh_launch<zinv_args, zinv_reg_mid_body, 512, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
-#ifndef KH_ZINV_VARIANT
-#define KH_ZINV_VARIANT 0
-#endif
-        const int tiles3 = txn * ((n + 2) / 3);
-        if (KH_ZINV_VARIANT == 1 && tiles3 <= 704) return kh_launch<zinv_args, zinv_reg_t3_body, 704, 1>(dim3(batch), ((tiles3 + 31) / 32) * 32, sm, st, a, "zinv", work);
-        if (KH_ZINV_VARIANT == 2 && tiles2 <= 1024) return kh_launch<zinv_args, zinv_reg_t2x_body, 1024, 1>(dim3(batch), ((tiles2 + 31) / 32) * 32, sm, st, a, "zinv", work);
-        return kh_launch<zinv_args, zinv_reg_large_body, 512, 1>(dim3(batch), ((tiles4 + 31) / 32) * 32, sm, st, a, "zinv", work);
-    }
 #endif
     a.ld_s = n | 1;
     a.use_smem = zinv_smem_bytes(n, a.ld_s, 1) <= (size_t)KH_SMEM_MAX;

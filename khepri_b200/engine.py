@@ -225,7 +225,8 @@ class Engine:
         rho is bounded from the largest in-plane wavevector of the basis and the largest permittivity (the device checks
         the bound per solve and raises info bit 2)."""
         import os
-        method = os.environ.get("KHEPRI_B200_METHOD", method or "auto")
+        if method in (None, "auto"):
+            method = os.environ.get("KHEPRI_B200_METHOD", "auto")          # developer switch for A/B runs of bench.py
         if method == "auto":
             method = "doubling" if (plan.has_patterned and not want_fields) else "eig"
         if method not in ("eig", "doubling"):

@@ -278,8 +278,42 @@ def gen_fields_fourier():
     print("fields fourier done", FF.shape)
 
 
+def gen_round2():
+    """Round 2: the two BASELINE configs that had no golden at their own size.
+    C5 at 9x9 (n = 162: blocked inverse / tiled Hessenberg inside the field pipeline), volume on a small grid plus one
+    256 x 256 plane kept on a strided subset; C4 large set: direct 13x13 / 15x15 bases (n = 338 / 450), R, T and a strided
+    subset of Stot[0,0] / Stot[1,0] for two sources each."""
+    import time
+    st, src, (X, Y, z), (XP, YP, zp, stride) = cases.case_fields_plane(9)
+    cl = ref_crystal(st, fields=True)
+    cl.set_source(**src)
+    t0 = time.time()
+    cl.solve()
+    E, H = cl.fields_volume(X, Y, z)
+    Ep, Hp = cl.fields_coords_xy(XP, YP, zp)
+    np.savez(os.path.join(OUT, "fields99.npz"), E=E, H=H, RT=np.array(cl.poynting_flux_end()),
+             Eplane=np.asarray(Ep)[:, ::stride, ::stride], Hplane=np.asarray(Hp)[:, ::stride, ::stride], zplane=zp, stride=stride)
+    print("fields99 done", time.time() - t0, np.abs(E).max())
+    for pp in (13, 15):
+        st, srcs = cases.case_supercell(pp)
+        cl = ref_crystal(st)
+        rt, s11, s21 = [], [], []
+        for sc in srcs:
+            t0 = time.time()
+            cl.set_source(**sc)
+            cl.solve()
+            rt.append(cl.poynting_flux_end())
+            S = np.asarray(cl.Stot)
+            s11.append(S[0, 0][::9, ::7].copy())
+            s21.append(S[1, 0][::9, ::7].copy())
+            print(pp, "solve", time.time() - t0, rt[-1])
+        np.savez(os.path.join(OUT, f"supercell{pp}.npz"), RT=np.array(rt), S11=np.array(s11), S21=np.array(s21))
+
+
 if __name__ == "__main__":
-    if "--fields-fourier" in sys.argv:
+    if "--round2" in sys.argv:
+        gen_round2()
+    elif "--fields-fourier" in sys.argv:
         gen_fields_fourier()
     elif "--bzi-beam" in sys.argv:
         gen_bzi_beam()
@@ -293,3 +327,4 @@ if __name__ == "__main__":
         gen_bzi_beam()
         gen_bands()
         gen_fields_fourier()
+        gen_round2()

@@ -136,6 +136,30 @@ def case_fields(pp=5, slices=4, res=128, grid=(12, 10, 9)):
     return st, src, (X, Y, z)
 
 
+def two_layer_structure(pp, res=256):
+    """Direct supercell basis with two different pixmap layers around a uniform spacer (the large end of C4:
+    notebooks/Twisted.ipynb cells 6-8 solve a (15, 15) Crystal with two 512^2 pixmap layers of depth 0.2)."""
+    pm = disc_pixmap((res, res), 4.0, (0.0, 0.0), 0.25, 1.0)
+    pm2 = pm.T.copy() + 0.5 * rect_pixmap((res, res), 0.0, (0.1, 0.0), (0.3, 0.5), 1.0)
+    layers = {"A": ("pixmap", pm, 0.2), "B": ("pixmap", pm2, 0.2), "U": ("uniform", 1.0, 0.3)}
+    return _st((pp, pp), layers, ["A", "U", "B"])
+
+
+def case_supercell(pp):
+    """Two sources on the direct pp x pp basis (n = 2 pp^2: 338 at 13x13, 450 at 15x15): normal and oblique incidence."""
+    st = two_layer_structure(pp)
+    srcs = [dict(wavelength=1 / 0.74, te=1.0, tm=0.0, theta=0.0, phi=0.0), dict(wavelength=1 / 0.81, te=0.6, tm=0.8, theta=14.0, phi=25.0)]
+    return st, srcs
+
+
+def case_fields_plane(pp=9, npl=256, stride=8):
+    """C5 at its own basis size: 9x9 harmonics, sliced holey pair, plus one npl x npl plane (compared on a strided subset)."""
+    st, src, (X, Y, z) = case_fields(pp, slices=4, res=128)
+    xp = np.linspace(0, 1, npl)
+    XP, YP = np.meshgrid(xp, xp, indexing="xy")
+    return st, src, (X, Y, z), (XP, YP, 0.8, stride)
+
+
 def twisted_case(pw=(3, 3), nf=3, nt=3):
     """notebooks/PRL_2021_BL.ipynb cells 2-8 (C4 parity set), sub-sampled."""
     pm = disc_pixmap((128, 128), 4, (0, 0), 0.25, 1.0)

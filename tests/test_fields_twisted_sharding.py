@@ -36,6 +36,27 @@ def test_fields_volume_golden(backend, pp, tag, tol):
     assert np.abs(cl.stacking_reverse_matrices[0][0, 0] - orc.star(orc.identity_smatrix(2 * pp * pp), cl.stacking_reverse_matrices[0])[0, 0]).max() < 1e-12
 
 
+@pytest.mark.gpu
+def test_fields_volume_9x9_golden():
+    """C5 at its own basis size (9x9 harmonics, n = 162: blocked inverse and tiled Hessenberg inside the field pipeline):
+    volume on a small grid and one 256 x 256 plane (separable grid kernel), compared with the unmodified reference on a
+    strided subset of the plane.  Sliced stack, so the reference itself is reproducible to ~1e-9."""
+    eng = engine("cuda")
+    g = gold("fields99")
+    st, src, (X, Y, z), (XP, YP, zp, stride) = cases.case_fields_plane(9)
+    cl = build_crystal(st, eng, fields=True)
+    cl.set_source(**src)
+    cl.solve()
+    E, H = cl.fields_volume(X, Y, z)
+    assert np.abs(E - g["E"]).max() <= 1e-9 * np.abs(g["E"]).max()
+    assert np.abs(H - g["H"]).max() <= 1e-9 * np.abs(g["H"]).max()
+    Ep, Hp = cl.fields_coords_xy(XP, YP, zp)
+    assert Ep.shape == (3, 256, 256)
+    assert np.abs(Ep[:, ::stride, ::stride] - g["Eplane"]).max() <= 1e-9 * np.abs(g["Eplane"]).max()
+    assert np.abs(Hp[:, ::stride, ::stride] - g["Hplane"]).max() <= 1e-9 * np.abs(g["Hplane"]).max()
+    np.testing.assert_allclose(cl.poynting_flux_end(), g["RT"], rtol=1e-9)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_fields_return_fourier_golden(backend):
     """fields_coords_xy(..., return_fourier=True) -> (sx, sy, sz, ux, uy, uz) vs the unmodified reference (crystal.py:326-327),

@@ -197,3 +197,30 @@ def test_band_postprocessing(tag):
     Sl, Sr = orc.scattering_splitlr(S)
     assert np.abs(Sl @ v - (Sr @ v) * w[None, :]).max() <= 1e-9 * np.abs(w).max()
     assert abs(orc.scattering_det(S) - g[tag + "_det"]) <= 1e-9 * abs(g[tag + "_det"])
+
+
+def test_fields99_golden():
+    """C5 at its own basis size (9x9, n = 162), volume on a small grid + one 256x256 plane on a strided subset."""
+    g = gold("fields99")
+    st, src, (X, Y, z), (XP, YP, zp, stride) = cases.case_fields_plane(9)
+    sol = orc.solve_structure(st, src["wavelength"], src_kp(st, src))
+    E, H = orc.fields_volume(st, sol, X, Y, z, src["te"], src["tm"])
+    assert np.abs(E - g["E"]).max() <= 1e-8 * np.abs(g["E"]).max()
+    assert np.abs(H - g["H"]).max() <= 1e-8 * np.abs(g["H"]).max()
+    Ep, Hp = orc.fields_volume(st, sol, XP[::stride, ::stride], YP[::stride, ::stride], [zp], src["te"], src["tm"])
+    assert np.abs(Ep[0] - g["Eplane"]).max() <= 1e-8 * np.abs(g["Eplane"]).max()
+    assert np.abs(Hp[0] - g["Hplane"]).max() <= 1e-8 * np.abs(g["Hplane"]).max()
+    np.testing.assert_allclose(orc.flux_end(st, sol, src["te"], src["tm"]), g["RT"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("pp", [13, 15])
+def test_supercell_large_bases(pp):
+    """C4 large set: direct 13x13 / 15x15 bases (n = 338 / 450), R, T and strided subsets of Stot[0,0], Stot[1,0]."""
+    g = gold(f"supercell{pp}")
+    st, srcs = cases.case_supercell(pp)
+    for i, s in enumerate(srcs[:1 if pp == 15 else 2]):
+        kp = src_kp(st, s)
+        sol = orc.solve_structure(st, s["wavelength"], kp, want_reverse=False)
+        np.testing.assert_allclose(orc.flux_end(st, sol, s["te"], s["tm"]), g["RT"][i], rtol=1e-9, atol=1e-12)
+        assert np.abs(sol["Stot"][0, 0][::9, ::7] - g["S11"][i]).max() <= 1e-9 * np.abs(g["S11"][i]).max()
+        assert np.abs(sol["Stot"][1, 0][::9, ::7] - g["S21"][i]).max() <= 1e-9 * np.abs(g["S21"][i]).max()

@@ -6,7 +6,7 @@ import pytest
 
 from oracle import rcwa_oracle as orc
 from tests import cases
-from tests.util import BACKENDS, build_crystal, engine, gold, sweep_sources
+from tests.util import BACKENDS, METHODS, build_crystal, engine, gold, sweep_sources
 
 RTOL = 1e-9
 
@@ -99,14 +99,15 @@ def test_convmat_vs_reference(backend):
 
 
 # ----------------------------------------------------------------------------- spectra
+@pytest.mark.parametrize("method", METHODS)
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_suh03_spectrum_golden(backend):
+def test_suh03_spectrum_golden(backend, method):
     """README suh03 (configs[0]): 5x5 harmonics, [Scyl, S1, Scyl], 151 frequencies."""
     eng = engine(backend)
     g = gold("suh03")
     st, srcs = cases.case_suh03()
     idx = list(range(151)) if backend == "cuda" else list(range(0, 151, 10)) + [150]
-    cl = build_crystal(st, eng)
+    cl = build_crystal(st, eng, method=method)
     R, T = sweep_sources(cl, [srcs[i] for i in idx])
     rt_close(np.stack([R, T], 1), g["RT"][idx])
     (Rs, Ro), (Ts, To), S = sweep_sources(cl, [srcs[i] for i in g["Sidx"]], only_total=False, return_S=True)
@@ -136,27 +137,29 @@ def test_scalar_api_matches_reference_loop(backend):
     assert cl.stack_positions[0] == -np.inf and cl.stack_positions[-1] == np.inf
 
 
+@pytest.mark.parametrize("method", METHODS)
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("pw,nk,nwl,tag", [((3, 3), 4, 5, "bzi33"), ((7, 7), 3, 3, "bzi77")])
-def test_bzi_stack(backend, pw, nk, nwl, tag):
+def test_bzi_stack(backend, pw, nk, nwl, tag, method):
     """configs[1]: 16-layer grating stack, epse=4, explicit k-points of the Brillouin-zone grid."""
     if backend == "emu" and pw == (7, 7):
         pytest.skip("covered on the GPU; too slow in emulation")
     eng = engine(backend)
     st, srcs = cases.case_bzi(pw, nk, nwl)
-    cl = build_crystal(st, eng)
+    cl = build_crystal(st, eng, method=method)
     R, T = sweep_sources(cl, srcs)
     rt_close(np.stack([R, T], 1), gold(tag)["RT"])
 
 
+@pytest.mark.parametrize("method", METHODS)
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_woodpile_and_doubling(backend):
+def test_woodpile_and_doubling(backend, method):
     """configs[2] geometry at 5x5 (+ 11x11 on the GPU) incl. Stot (*) Stot (woodpile.py:85)."""
     from khepri_b200.alternative import redheffer_product
     eng = engine(backend)
     g = gold("woodpile55")
     st, srcs = cases.case_woodpile((5, 5), 3, 3)
-    cl = build_crystal(st, eng)
+    cl = build_crystal(st, eng, method=method)
     sel = range(9) if backend == "cuda" else (0, 4)
     for i in sel:
         cl.set_source(**srcs[i])
@@ -174,17 +177,18 @@ def test_woodpile_and_doubling(backend):
     rt_close(wp.poynting_flux_end(), g["RT"][4])
     if backend == "cuda":
         st, srcs = cases.case_woodpile((11, 11), 2, 2)
-        cl = build_crystal(st, eng)
+        cl = build_crystal(st, eng, method=method)
         R, T = sweep_sources(cl, srcs)
         rt_close(np.stack([R, T], 1), gold("woodpile1111")["RT"])
 
 
+@pytest.mark.parametrize("method", METHODS)
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_oblique_hexagonal_lossy(backend):
+def test_oblique_hexagonal_lossy(backend, method):
     eng = engine(backend)
     g = gold("oblique")
     st, srcs = cases.case_oblique()
-    cl = build_crystal(st, eng)
+    cl = build_crystal(st, eng, method=method)
     (Rs, Ro), (Ts, To) = sweep_sources(cl, srcs, only_total=False)
     rt_close(np.stack([Rs, Ts], 1), g["RT"])
     rt_close(np.stack([Ro, To], 1), g["orders"])
@@ -193,15 +197,16 @@ def test_oblique_hexagonal_lossy(backend):
     rt_close(cl.poynting_flux_end(), g["RT"][2])
 
 
+@pytest.mark.parametrize("method", METHODS)
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("which", ["tidy", "mixed", "rect"])
-def test_analytical_layers(backend, which):
+def test_analytical_layers(backend, which, method):
     """Crystal.add_layer_analytical -- host-side analytic island transforms, device Toeplitz gather + inverse,
     then the same batched layer solve as a pixmap layer.  Golden vectors from the unmodified reference."""
     eng = engine(backend)
     g = gold("analytical")
     st, srcs = cases.case_analytical(which)
-    cl = build_crystal(st, eng)
+    cl = build_crystal(st, eng, method=method)
     R, T = sweep_sources(cl, srcs)
     rt_close(np.stack([R, T], 1), g["RT_" + which])
     name = [k for k, v in st["layers"].items() if v[0] == "analytical"][0]
@@ -288,7 +293,7 @@ def test_zinv_blocked(backend, n):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("n", [120, 131, 170, 242, 300])
+@pytest.mark.parametrize("n", [120, 131, 170, 242, 300, 450])
 def test_zgeev_tiled(backend, n):
     """Tiled eigensolver (blocked Hessenberg panels + DMMA GEMM updates, tiled QR sweeps) for n beyond shared memory."""
     if backend != "cuda" and n > 170:
@@ -405,3 +410,95 @@ def test_scattering_eigenvalues(backend, tag):
     bad = S4.copy(); bad[0, 0, 0, 0] = np.nan
     assert et.scattering_eigenvalues(bad, engine=eng) is None
     assert et.band_structure(S4, engine=eng).ndim == 1
+
+
+# ----------------------------------------------------------------------------- round 2: methods, chunking, cache keys, large bases
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_doubling_matches_eig_on_deep_and_lossy_layers(backend):
+    """The doubling method (slice series + self star products; reference legacy path tmat/scattering.py:25-51) against the
+    eigen-decomposition method and the oracle on layers that need several doublings (depth 2.5), lossy pixmaps, oblique
+    incidence and a thin layer that needs none."""
+    eng = engine(backend)
+    pm = cases.disc_pixmap((64, 64), 2.0, (0.1, 0.0), 0.3, 9.0)
+    pml = pm * (1 - 0.02j)
+    layers = {"deep": ("pixmap", pm, 2.5), "thin": ("pixmap", pml, 0.03), "U": ("uniform", 2.1 - 0.1j, 0.4)}
+    st = cases._st((5, 5), layers, ["thin", "U", "deep", "thin"], epsi=1.0, epse=2.25)
+    srcs = [dict(wavelength=1.7, te=1.0, tm=0.3, theta=0.0, phi=0.0), dict(wavelength=1.1, te=0.2, tm=1.0, theta=33.0, phi=40.0),
+            dict(wavelength=2.9, te=1.0, tm=1.0, theta=70.0, phi=-15.0)]
+    ref = np.array([orc.solve_rt(st, s["wavelength"], s["te"], s["tm"], s["theta"], s["phi"]) for s in srcs])
+    out = {}
+    for method in METHODS:
+        cl = build_crystal(st, eng, method=method)
+        R, T, S = sweep_sources(cl, srcs, return_S=True)
+        rt_close(np.stack([R, T], 1), ref)
+        out[method] = S
+    rt_close(out["doubling"], out["eig"], 1e-9)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_doubling_flags_an_underestimated_spectrum(backend):
+    """The host's bound on the spectrum of Omega^2 is checked on the device: a bound that is far too small raises info bit 2
+    (surfaced as LinAlgError) instead of returning a truncated series."""
+    eng = engine(backend)
+    st, srcs = cases.case_suh03()
+    cl = build_crystal(st, eng, method="doubling")
+    plan = cl._get_plan(False)
+    keep = (plan.gmax, plan.eps_bound)
+    plan.gmax, plan.eps_bound = 1e-3, 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        sweep_sources(cl, srcs[:2])
+    plan.gmax, plan.eps_bound = keep
+    R, T = sweep_sources(cl, srcs[:2])
+    rt_close(np.stack([R, T], 1), gold("suh03")["RT"][:2])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("method", METHODS)
+def test_whole_batch_is_one_chunk_when_the_workspace_fits(backend, method):
+    """kh_solve_batch must not split a batch that fits its workspace (round-1 bug: every batch ran as two half chunks)."""
+    eng = engine(backend)
+    st, srcs = cases.case_suh03()
+    cl = build_crystal(st, eng, method=method)
+    lib = eng.lib
+    sweep_sources(cl, srcs[:1])                                            # plan + convolution matrices built
+    l0 = lib.kh_launch_count(); sweep_sources(cl, srcs[:1]); one = lib.kh_launch_count() - l0
+    l0 = lib.kh_launch_count(); sweep_sources(cl, srcs[:12]); twelve = lib.kh_launch_count() - l0
+    assert twelve == one, (one, twelve)
+    l0 = lib.kh_launch_count(); sweep_sources(cl, srcs[:12], chunk=6); halves = lib.kh_launch_count() - l0
+    assert halves > twelve
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_pixmap_mutated_in_place_is_seen(backend):
+    """The reference recomputes convolution_matrix(layer.epsilon) on every solve (layer.py:157): editing a pixmap in place
+    and solving again must give the new structure's result, not a cached one."""
+    eng = engine(backend)
+    st, srcs = cases.case_suh03()
+    cl = build_crystal(st, eng)
+    cl.set_source(**srcs[40])
+    cl.solve()
+    r0, _ = cl.poynting_flux_end()
+    eps = cl.layers["Scyl"].epsilon
+    eps[10:50, 10:50] = 9.0
+    cl.solve()
+    r1, t1 = cl.poynting_flux_end()
+    st2 = dict(st); st2["layers"] = dict(st["layers"]); st2["layers"]["Scyl"] = ("pixmap", eps.copy(), st["layers"]["Scyl"][2])
+    ref = orc.solve_rt(st2, srcs[40]["wavelength"], 1.0, 0.0)
+    rt_close([r1, t1], ref)
+    assert abs(r1 - r0) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("pp", [13, 15])
+def test_supercell_large_bases_golden(pp, method):
+    """C4 large set: direct 13x13 / 15x15 bases (n = 338 / 450; tiled Hessenberg / QR / blocked inverse, or the doubling
+    method) against the unmodified reference: R, T and strided subsets of Stot[0,0], Stot[1,0]."""
+    eng = engine("cuda")
+    g = gold(f"supercell{pp}")
+    st, srcs = cases.case_supercell(pp)
+    cl = build_crystal(st, eng, method=method)
+    R, T, S = sweep_sources(cl, srcs, return_S=True)
+    rt_close(np.stack([R, T], 1), g["RT"])
+    rt_close(S[:, 0, 0, ::9, ::7], g["S11"])
+    rt_close(S[:, 1, 0, ::9, ::7], g["S21"])

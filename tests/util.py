@@ -39,9 +39,13 @@ def gold(name):
     return np.load(os.path.join(GOLD, name + ".npz"))
 
 
-def build_crystal(st, eng, fields=False):
+METHODS = ["eig", "doubling"]       # both ways a patterned layer gets its S-matrix (Engine._select_method)
+
+
+def build_crystal(st, eng, fields=False, method="auto"):
     from khepri_b200 import Crystal
     cl = Crystal(st["pw"], lattice=st["lattice"], epsi=st["epsi"], epse=st["epse"], engine=eng)
+    cl.method = method
     for name, spec in st["layers"].items():
         if spec[0] == "uniform":
             cl.add_layer_uniform(name, spec[1], spec[2])
