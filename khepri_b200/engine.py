@@ -218,7 +218,7 @@ class Engine:
 
     # ------------------------------------------------------------------ the batched solve
     # ------------------------------------------------------------------ patterned-layer method
-    def _select_method(self, plan, wl, kp, want_fields, method):
+    def _select_method(self, plan, wl, kp, want_fields, method, bounds=None):
         """Picks how patterned layers get their S-matrix (kh_plan_set_method).  "eig": eigen-decomposition (the only
         choice when eigenspaces are retained); "doubling": slice series + self star products, GEMMs only.  "auto" takes
         doubling whenever no eigenspace is retained.  For doubling the host supplies kappa >= k0 sqrt(rho(Omega^2)):
@@ -239,7 +239,9 @@ class Engine:
                 check(self.lib, self.lib.kh_plan_set_method(plan.handle, _lib.METHOD_EIG, 0.0, 0.0), "kh_plan_set_method")
                 plan._method_state = state
             return method
-        if isinstance(wl, torch.Tensor):
+        if bounds is not None:                  # (min wavelength, max |kp|) supplied by the caller: no device round trip
+            wl_min, kp_max = float(bounds[0]), float(bounds[1])
+        elif isinstance(wl, torch.Tensor):
             wl_min = float(wl.min().item())
             kp_max = float(kp.abs().pow(2).sum(dim=-1).max().sqrt().item())
         else:
@@ -255,14 +257,16 @@ class Engine:
             plan._method_state = state
         return method
 
-    def solve_batch(self, plan, wl, kp, pol=None, want_S=False, want_flux=True, want_orders=False, want_fields=False, chunk=None, method=None):
+    def solve_batch(self, plan, wl, kp, pol=None, want_S=False, want_flux=True, want_orders=False, want_fields=False, chunk=None, method=None, bounds=None):
         """Crystal.solve (+ poynting_flux_end) for B sources.  wl [B], kp [B,2] complex, pol [B,2] = (te, tm).
 
         Returns a dict of DEVICE tensors: RT [B,2], orders [B,2,N], Stot [B,2,2,n,n], info [B] and, with
         want_fields, prefix/suffix [B,Ls,2,2,n,n], W/V [B,nL,n,n], L [B,nL,n].
+        method: "auto" | "eig" | "doubling" (see _select_method).  bounds = (min wavelength, max |kp|) of the batch, optional:
+        with DEVICE inputs it saves the reduction + host read the doubling method otherwise needs to size its series.
         """
         if (wl.numel() if isinstance(wl, torch.Tensor) else np.size(wl)) > 0:
-            self._select_method(plan, wl, kp, want_fields, method)
+            self._select_method(plan, wl, kp, want_fields, method, bounds)
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(-1) if not isinstance(wl, torch.Tensor) else wl.reshape(-1), _f64)
         B = wl_d.numel()
         kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2) if not isinstance(kp, torch.Tensor) else kp.reshape(B, 2), _c128)

@@ -43,18 +43,8 @@ METHODS = ["eig", "doubling"]       # both ways a patterned layer gets its S-mat
 
 
 def build_crystal(st, eng, fields=False, method="auto"):
-    from khepri_b200 import Crystal
-    cl = Crystal(st["pw"], lattice=st["lattice"], epsi=st["epsi"], epse=st["epse"], engine=eng)
-    cl.method = method
-    for name, spec in st["layers"].items():
-        if spec[0] == "uniform":
-            cl.add_layer_uniform(name, spec[1], spec[2])
-        elif spec[0] == "analytical":
-            cl.add_layer_analytical(name, spec[1], spec[3], spec[2])
-        else:
-            cl.add_layer_pixmap(name, spec[1], spec[2])
-    cl.set_device(st["stack"], [fields] * len(st["stack"]))
-    return cl
+    import workloads
+    return workloads.build_crystal(st, eng, fields=fields, method=method)
 
 
 def sweep_sources(cl, srcs, **kw):
