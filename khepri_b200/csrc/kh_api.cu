@@ -101,16 +101,8 @@ static int gemm(kh_stream_t st, int batch, int n, MatRef A, MatRef B, MatRef C, 
 // chain therefore forms S11 / S21 in the two flux columns as matrix-vector products and S12 / S22 in full; the LAST product
 // needs no S12 / S22 at all.  cols2(): Cout[:, c] = Amat Bsrc[:, c] (+ Cin[:, c]) for c in {fc, fc + N}.
 static int cols2(kh_stream_t st, int Bc, int n, int fc, MatRef Amat, MatRef Bsrc, MatRef Cout, const MatRef* Cin = nullptr) {
-    for (int k = 0; k < 2; ++k) {
-        const int col = fc + k * (n / 2);
-        MatRef b = Bsrc; b.p += col;
-        MatRef c = Cout; c.p += col;
-        zgemm_args g = zgemm_make(n, 1, n, Amat, b, c);
-        if (Cin) { MatRef ci = *Cin; ci.p += col; g.Cin = ci; g.beta = 1.0; }
-        int e = zgemm_launch(st, Bc, g);
-        if (e) return e;
-    }
-    return 0;
+    zgemv2_args a{n, fc, fc + n / 2, Amat, Bsrc, Cin ? *Cin : mref(nullptr, 0, 0), Cout};
+    return kh_launch<zgemv2_args, zgemv2_body>(dim3(Bc), 256, (size_t)2 * n * sizeof(cd), st, a, "zgemv", 16.0 * n * n * Bc);
 }
 static int zero_mat(kh_stream_t st, int Bc, long long n2, MatRef M) {
     zero_cd_args zc{n2, M.p};
@@ -244,7 +236,14 @@ struct kh_plan {
     bool has_ext;
     // how patterned layers get their S-matrix when no eigenspace has to be retained (kh_plan_set_method)
     int method = KH_METHOD_EIG; double dbl_kappa = 0.0, dbl_theta = 0.0;
+    // The same structure with every run of m consecutive identical layers replaced by ONE layer of m times the depth (exact:
+    // a uniform or patterned slab of depth m d is m slabs of depth d in a row; the BZI stack's 14 identical spacer layers become
+    // one closed-form table).  Used whenever no per-position output (prefix / suffix products, eigenspaces) is requested.
+    // Layer indices of the original table stay valid (ext_base); merged layers are appended.
+    kh_plan* collapsed = nullptr;
+    ~kh_plan() { delete collapsed; }
 };
+static const kh_plan* plan_view(const kh_plan* p, bool want_fields) { return (!want_fields && p->collapsed) ? p->collapsed : p; }
 
 extern "C" int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev, double epsi_re, double epsi_im,
                               double epse_re, double epse_im, int n_layers, const kh_layer_desc* layers, int n_stack,
@@ -268,6 +267,34 @@ extern "C" int kh_plan_create(kh_plan** plan, int P, int Q, const double* g_dev,
     }
     for (int i = 0; i < n_stack; ++i)
         if (stack[i] < 0 || stack[i] >= n_layers) { delete p; return fail(KH_EINVAL, "kh_plan_create: bad stack index"); }
+    {   // collapsed view: runs of the same uniform / pixmap layer
+        kh_plan* c = new kh_plan(*p);
+        c->collapsed = nullptr;
+        c->stack.clear();
+        bool any = false;
+        for (int i = 0; i < n_stack;) {
+            int j = i + 1;
+            const int k = layers[stack[i]].kind;
+            if (k == KH_LAYER_UNIFORM || k == KH_LAYER_PIXMAP) while (j < n_stack && stack[j] == stack[i]) ++j;
+            const int m = j - i;
+            if (m == 1) c->stack.push_back(stack[i]);
+            else {
+                int found = -1;
+                for (size_t e = (size_t)n_layers; e < c->layers.size(); ++e)
+                    if (c->layers[e].retain == -(stack[i] + 1) && c->layers[e].depth == layers[stack[i]].depth * m) found = (int)e;
+                if (found < 0) {
+                    kh_layer_desc d = layers[stack[i]];
+                    d.depth *= m; d.retain = -(stack[i] + 1);          // (retain is meaningless here: tags the base layer of a merged entry)
+                    c->layers.push_back(d);
+                    found = (int)c->layers.size() - 1;
+                }
+                c->stack.push_back(found);
+                any = true;
+            }
+            i = j;
+        }
+        if (any) p->collapsed = c; else delete c;
+    }
     *plan = p;
     return 0;
 }
@@ -277,6 +304,7 @@ extern "C" int kh_plan_set_method(kh_plan* plan, int method, double kappa, doubl
     if (method == KH_METHOD_DOUBLING && !(kappa > 0.0 && theta_slice >= 0.25 && theta_slice <= 16.0))
         return fail(KH_EINVAL, "kh_plan_set_method: doubling needs kappa > 0 and 0.25 <= theta_slice <= 16");
     plan->method = method; plan->dbl_kappa = kappa; plan->dbl_theta = theta_slice;
+    if (plan->collapsed) { plan->collapsed->method = method; plan->collapsed->dbl_kappa = kappa; plan->collapsed->dbl_theta = theta_slice; }
     return 0;
 }
 
@@ -344,14 +372,15 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
 }
 
 // ---------------------------------------------------------------------------- patterned layer without an eigensolver
-// Slice transfer matrix by a truncated power series + self star products (see kh_rcwa.cuh, "slab S-matrix without an
-// eigensolver"; reference: khepri/tmat/scattering.py:25-51).  theta = kappa * depth bounds x sqrt(rho(Omega^2)) for the
-// whole layer (kappa from the host, kh_plan_set_method); the layer is cut into 2^s slices with theta / 2^s <= theta_slice
-// and the series keeps t terms, theta_slice^(2t) / (2t)! < 1e-19.  Everything is a batched DMMA GEMM or the batched inverse.
+// Transfer matrix of half a slice by a truncated power series, S-matrix of the slice from its even / odd reflection operators,
+// then self star products (see kh_rcwa.cuh, "slab S-matrix without an eigensolver"; reference: khepri/tmat/scattering.py:25-51).
+// theta = kappa * depth bounds x sqrt(rho(Omega^2)) for the whole layer (kappa from the host, kh_plan_set_method); the layer is
+// cut into 2^s slices with theta / 2^(s+1) <= theta_slice and the series keeps t terms, theta_half^(2t) / (2t)! < 1e-19.
+// Everything is a batched DMMA GEMM or the batched inverse.
 struct DblShape { int s, t, q; double theta; };      // theta: the bound on |lambda k0 d| of one slice that (t, q) were sized for
 static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
     DblShape d; d.s = 0;
-    double th = kappa * depth;
+    double th = 0.5 * kappa * depth;                    // the series covers HALF a slice (even/odd split, see dbl_eo): depth / 2^(s+1)
     while (th > theta_slice && d.s < 30) { th *= 0.5; d.s += 1; }
     d.theta = th;
     if (th < 1e-3) th = 1e-3;
@@ -374,7 +403,7 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     auto M = [&](int s) { return mref(S(s), n2, n); };
     auto pair = [&](int s0, int s1) { return mref(S(s0), n2, n, 2, (long long)(s1 - s0) * slab); };      // batch index 2b + h -> slab s0 / s1
     auto both = [&](int s0) { return mref(S(s0), n2, n, 2, 0); };                                        // both halves of a pair read slab s0
-    const double hx = depth / (double)(1LL << sh.s);
+    const double hx = 0.5 * depth / (double)(1LL << sh.s);      // half a slice
     {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};
         KH_TRY((kh_launch<pq_args, pq_body>(dim3(Bc), 256, 0, st, a))); }
     KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q -> 2 ; Omega^(2i) -> slab i + 1
@@ -396,12 +425,21 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
         a.out[0] = S(dst0); a.out[1] = S(dst1);
         return kh_launch<dbl_lincomb_args, dbl_lincomb_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_lincomb");
     };
+    // the block polynomial of step j is added in the GEMM's epilogue (zgemm_args::poly_*): no separate pass over the powers
+    auto poly = [&](zgemm_args& g, int j) {
+        g.poly_q = q; g.poly_k0 = k0; g.poly_hx = hx;
+        for (int i = 1; i < q; ++i) g.poly_pw[i] = S(1 + i);
+        for (int i = 0; i < q; ++i) {
+            const int k = j * q + i;
+            if (k < sh.t) { g.poly_coef[0][i] = 1.0 / dbl_factorial(2 * k + 1); g.poly_xpow[0][i] = 2 * k + 1; }
+            if (k < sh.t - 1) { g.poly_coef[1][i] = 1.0 / dbl_factorial(2 * k + 2); g.poly_xpow[1][i] = 2 * k + 2; }
+        }
+    };
     int cur = 8, oth = 10;                                                       // (Sc, Dc) pair: slabs cur, cur + 1
     KH_TRY(blocks(J - 1, cur, cur + 1));
     for (int j = J - 2; j >= 0; --j) {
-        KH_TRY(blocks(j, 12, 13));
         zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
-        g.Cin = pair(12, 13); g.beta = 1.0;
+        poly(g, j);
         KH_TRY(zgemm_launch(st, 2 * Bc, g));
         const int t = cur; cur = oth; oth = t;
     }
@@ -411,12 +449,15 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     {   zgemm_args g = zgemm_make(n, n, n, both(1), pair(sSc, sDP), pair(12, 13));                         // M21 = Q Sc ; m22 = Q DP
         KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
     KH_TRY(gemm(st, Bc, n, M(2), M(sDc), M(3)));                                                           // m11 = Omega^2 Dc
-    {   dbl_tconv_args a{Bc, N, S(3), S(sM12), S(12), S(13), Kx, Ky, S(4), S(5)};                          // T22 -> 4, T21 -> 5
-        KH_TRY((kh_launch<dbl_tconv_args, dbl_tconv_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_tconv"))); }
+    {   dbl_eo_args a{Bc, N, S(3), S(sM12), S(12), S(13), Kx, Ky, S(4), S(5), S(6), S(7)};                    // Ee+ -> 4, Eo+ -> 5, Ee- -> 6, Eo- -> 7
+        KH_TRY((kh_launch<dbl_eo_args, dbl_eo_body>(dim3(Bc, 4), 256, (size_t)N * sizeof(m22), st, a, "dbl_eo"))); }
+    KH_TRY(zinv_launch(st, 2 * Bc, n, pair(4, 5), pair(8, 9), info_acc, S(14), 3 * slab, 2));                   // (Ee+)^-1 -> 8, (Eo+)^-1 -> 9
+    {   zgemm_args g = zgemm_make(n, n, n, pair(6, 7), pair(8, 9), pair(10, 11));                              // r_e -> 10, r_o -> 11
+        KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
     MatRef O11 = mref(Sout, 2 * n2, n), O12 = mref(Sout + n2, 2 * n2, n);
-    MatRef s12 = sh.s == 0 ? O12 : M(6), s11 = sh.s == 0 ? O11 : M(7);
-    KH_TRY(zinv_launch(st, Bc, n, M(4), s12, info_acc, S(14), 3 * slab, 1));                                   // S12 = T22^-1
-    KH_TRY(gemm(st, Bc, n, s12, M(5), s11, -1.0));                                                          // S11 = -S12 T21
+    MatRef s12 = sh.s == 0 ? O12 : M(13), s11 = sh.s == 0 ? O11 : M(12);
+    {   dbl_combine_args a{Bc, n, S(10), S(11), s11, s12};                                                     // S of two half slices
+        KH_TRY((kh_launch<dbl_combine_args, dbl_combine_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_eo"))); }
     // doublings  S <- S (*) S  of the mirror-symmetric slab (alternative.py:19-30 with A = B, A22 = A11, A21 = A12):
     //   D = I - S11 S11,  Y = D^-1 S12,  S12' = S12 Y,  S11' = S11 + S12 (S11 Y)
     for (int it = 0; it < sh.s; ++it) {
@@ -500,7 +541,7 @@ extern "C" size_t kh_solve_workspace_bytes(const kh_plan* plan, int chunk, int f
     if (!plan || chunk < 1) return 0;
     Bump b{nullptr, 0, 0};
     ChunkBufs cb;
-    layout_chunk(plan, chunk, flags, b, cb);
+    layout_chunk(plan_view(plan, (flags & KH_WANT_FIELDS) != 0), chunk, flags, b, cb);
     return b.off + 256;
 }
 
@@ -527,7 +568,8 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
     if (!plan || B < 0 || !wl_dev || !kp_dev || !out || !ws_dev) return fail(KH_EINVAL, "kh_solve_batch: bad arguments");
     if (B == 0) return 0;
     kh_stream_t st = (kh_stream_t)stream;
-    const kh_plan* p = plan;
+    const bool fields_req = out->prefix_dev || out->suffix_dev || out->W_dev || out->V_dev || out->L_dev;
+    const kh_plan* p = plan_view(plan, fields_req);
     const int N = p->N, n = p->n, Ls = (int)p->stack.size();
     const long long n2 = (long long)n * n;
     int flags = 0;
@@ -541,14 +583,14 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
     }
     if ((flags & KH_WANT_FLUX) && (!out->RT_dev || !pol_dev)) return fail(KH_EINVAL, "kh_solve_batch: flux needs RT_dev and pol_dev");
     // chunk size: largest that fits the workspace
-    size_t per1 = kh_solve_workspace_bytes(p, 1, flags), per2 = kh_solve_workspace_bytes(p, 2, flags);
+    size_t per1 = kh_solve_workspace_bytes(plan, 1, flags), per2 = kh_solve_workspace_bytes(plan, 2, flags);
     size_t slope = per2 > per1 ? per2 - per1 : 1;
     if (ws_bytes < per1) return fail(KH_ENOMEM, "kh_solve_batch: workspace smaller than one solve (" + std::to_string(per1) + " bytes)");
     long long chunk = B;
-    if (kh_solve_workspace_bytes(p, B, flags) > ws_bytes) {          // the whole batch does not fit: estimate, then shrink until it does
+    if (kh_solve_workspace_bytes(plan, B, flags) > ws_bytes) {          // the whole batch does not fit: estimate, then shrink until it does
         chunk = 1 + (long long)((ws_bytes - per1) / (slope + 1024));
         if (chunk > B) chunk = B;
-        while (chunk > 1 && kh_solve_workspace_bytes(p, (int)chunk, flags) > ws_bytes) --chunk;
+        while (chunk > 1 && kh_solve_workspace_bytes(plan, (int)chunk, flags) > ws_bytes) --chunk;
     }
     if (chunk < B) {                           // balance the chunks: a remainder of a few solves would pay the full latency of every kernel
         const long long nch = (B + chunk - 1) / chunk;

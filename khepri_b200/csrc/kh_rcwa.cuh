@@ -429,36 +429,56 @@ KH_DEV void dbl_lincomb_body(const Cta& c, const dbl_lincomb_args& a) {
     }
 }
 
-// Transfer matrix of the slice in the mode basis of the zero-thickness free-space gaps (W0 = I, V0; alternative.py:84-99,
-// fields.py:46-51 R0 = [[W0, W0], [-V0, V0]]):  only the second block row of T = R0^-1 M R0 is needed,
-//   T22 = (E1 + E2) / 2,  T21 = (E1 - E2) / 2,  E1 = M11 + V0^-1 M21,  E2 = (M12 + V0^-1 M22) V0,
-// because the slab is mirror symmetric (S22 = S11, S21 = S12; alternative.py:195):  S12 = T22^-1,  S11 = -T22^-1 T21
-// (matrix_s of tmat/matrices.py:167-176 for these two blocks).  V0, V0^-1 are 2x2 blocks of diagonals: O(n^2) work.
-// M11 and M22 arrive without their identity (M11 = I + m11, M22 = I + m22).
-struct dbl_tconv_args { int B, N; const cd* m11; const cd* M12; const cd* M21; const cd* m22; const cd* Kx; const cd* Ky; cd* T22; cd* T21; };
-KH_DEV void dbl_tconv_body(const Cta& c, const dbl_tconv_args& a) {
+// S-matrix of TWO slices from the transfer matrix M of ONE (thickness h): the slab of thickness 2h is mirror symmetric about its
+// mid-plane, so its response splits into an even (u = 0 on the mid-plane) and an odd (s = 0) problem.  With the mode basis of
+// the zero-thickness free-space gaps (W0 = I, V0; alternative.py:84-99, fields.py:46-51: s = c+ + c-, u = V0 (c- - c+) at the
+// right face), the even fields at the face are [M11; M21] s_mid and the odd ones [M12; M22] u_mid, hence the reflection operators
+//   r_e = (M11 - V0^-1 M21) (M11 + V0^-1 M21)^-1,      r_o = (M12 - V0^-1 M22) (M12 + V0^-1 M22)^-1
+// and  S11 = S22 = (r_e + r_o) / 2,  S12 = S21 = (r_e - r_o) / 2  (the symmetric form alternative.py:195 returns).  This is
+// matrix_s (tmat/matrices.py:167-176) followed by the first multS doubling (tmat/scattering.py:46-49), at the price of two
+// inverses and two products instead of one inverse, one product and a full star product.
+// dbl_eo forms the four operands  Ee+- = M11 +- V0^-1 M21,  Eo+- = M12 +- V0^-1 M22  (V0^-1: 2x2 blocks of diagonals, O(n^2));
+// M11 and M22 arrive without their identity (M11 = I + m11, M22 = I + m22).  Thread <-> (harmonic g, column j): rows g and N + g.
+struct dbl_eo_args { int B, N; const cd* m11; const cd* M12; const cd* M21; const cd* m22; const cd* Kx; const cd* Ky;
+                     cd* Eep; cd* Eop; cd* Eem; cd* Eom; };
+KH_DEV void dbl_eo_body(const Cta& c, const dbl_eo_args& a) {
     const int N = a.N, n = 2 * N, b = c.bx;
     const long long off = (long long)b * n * n;
-    const cd* kx = a.Kx + (long long)b * N;
-    const cd* ky = a.Ky + (long long)b * N;
-    const int per = (n * N + 3) / 4, e0 = c.by * per, e1 = (e0 + per < n * N) ? e0 + per : n * N;
+    m22* Vi = (m22*)KH_SMEM(c);                                 // [N]: V0^-1 per harmonic (complex divisions: once per CTA, not per element)
+    for (int g = c.tid; g < N; g += c.nthr) Vi[g] = m22_inv(v0_block(a.Kx[(long long)b * N + g], a.Ky[(long long)b * N + g]));
+    c.sync();
+    const int per = (N * n + 3) / 4, e0 = c.by * per, e1 = (e0 + per < N * n) ? e0 + per : N * n;
     for (int e = e0 + c.tid; e < e1; e += c.nthr) {
-        const int i = e / N, gj = e - i * N, hi = i >= N, gi = i - hi * N;
-        const m22 Vi = m22_inv(v0_block(kx[gi], ky[gi]));
-        const m22 Vj = v0_block(kx[gj], ky[gj]);
-        const cd vi0 = hi ? Vi.c : Vi.a, vi1 = hi ? Vi.d : Vi.b;          // row hi of V0^-1 at harmonic gi
-        const long long r0 = off + (long long)gi * n, r1 = off + (long long)(N + gi) * n, ri = off + (long long)i * n;
-        const int j0 = gj, j1 = N + gj;
-        cd e1a = a.m11[ri + j0] + vi0 * a.M21[r0 + j0] + vi1 * a.M21[r1 + j0];
-        cd e1b = a.m11[ri + j1] + vi0 * a.M21[r0 + j1] + vi1 * a.M21[r1 + j1];
-        if (i == j0) e1a.x += 1.0;
-        if (i == j1) e1b.x += 1.0;
-        cd g0 = a.M12[ri + j0] + vi0 * a.m22[r0 + j0] + vi1 * a.m22[r1 + j0];
-        cd g1 = a.M12[ri + j1] + vi0 * a.m22[r0 + j1] + vi1 * a.m22[r1 + j1];
-        if (gi == gj) { g0 = g0 + vi0; g1 = g1 + vi1; }                    // the identity of M22: V0^-1 I picks column gj / N + gj
-        const cd e2a = g0 * Vj.a + g1 * Vj.c, e2b = g0 * Vj.b + g1 * Vj.d;
-        a.T22[ri + j0] = 0.5 * (e1a + e2a); a.T22[ri + j1] = 0.5 * (e1b + e2b);
-        a.T21[ri + j0] = 0.5 * (e1a - e2a); a.T21[ri + j1] = 0.5 * (e1b - e2b);
+        const int g = e / n, j = e - g * n;
+        const m22 v = Vi[g];
+        const long long r0 = off + (long long)g * n + j, r1 = off + (long long)(N + g) * n + j;
+        const cd a0 = a.M21[r0], a1 = a.M21[r1];
+        cd b0 = a.m22[r0], b1 = a.m22[r1];
+        if (j == g) b0.x += 1.0;
+        if (j == N + g) b1.x += 1.0;
+        const cd t0 = v.a * a0 + v.b * a1, t1 = v.c * a0 + v.d * a1;          // rows g, N + g of V0^-1 M21
+        const cd u0 = v.a * b0 + v.b * b1, u1 = v.c * b0 + v.d * b1;          // rows g, N + g of V0^-1 M22
+        cd p0 = a.m11[r0], p1 = a.m11[r1];
+        if (j == g) p0.x += 1.0;
+        if (j == N + g) p1.x += 1.0;
+        const cd q0 = a.M12[r0], q1 = a.M12[r1];
+        a.Eep[r0] = p0 + t0; a.Eep[r1] = p1 + t1; a.Eem[r0] = p0 - t0; a.Eem[r1] = p1 - t1;
+        a.Eop[r0] = q0 + u0; a.Eop[r1] = q1 + u1; a.Eom[r0] = q0 - u0; a.Eom[r1] = q1 - u1;
+    }
+}
+// S11 = (r_e + r_o) / 2, S12 = (r_e - r_o) / 2
+struct dbl_combine_args { int B, n; const cd* re; const cd* ro; MatRef S11, S12; };
+KH_DEV void dbl_combine_body(const Cta& c, const dbl_combine_args& a) {
+    const int n = a.n, b = c.bx;
+    const long long off = (long long)b * n * n;
+    cd* o11 = mat_ptr(a.S11, b);
+    cd* o12 = mat_ptr(a.S12, b);
+    const int per = (n * n + 3) / 4, e0 = c.by * per, e1 = (e0 + per < n * n) ? e0 + per : n * n;
+    for (int e = e0 + c.tid; e < e1; e += c.nthr) {
+        const int i = e / n, j = e - i * n;
+        const cd x = a.re[off + e], y = a.ro[off + e];
+        o11[(long long)i * a.S11.ld + j] = 0.5 * (x + y);
+        o12[(long long)i * a.S12.ld + j] = 0.5 * (x - y);
     }
 }
 
@@ -478,4 +498,31 @@ KH_DEV void dbl_check_body(const Cta& c, const dbl_check_args& a) {
     m = cta_max(c, m, scratch);
     const double th = a.k0[b] * a.hx * sqrt(m);
     if (c.tid == 0 && !(th <= a.theta_lim)) KH_ATOMIC_OR(&a.info[b], 4);
+}
+
+// ------------------------------------------------------------------ two columns of a product (flux columns of the star chain)
+// Cout[:, c] = A B[:, c] (+ Cin[:, c]) for c in {c0, c1}: matrix-vector work, bound by reading A once (n^2 16 B per solve).
+// One CTA per solve; the two B columns are staged in shared memory, warp <-> row, lanes stride over k, shuffle reduction.
+struct zgemv2_args { int n, c0, c1; MatRef A, B, Cin, Cout; };
+KH_DEV void zgemv2_body(const Cta& c, const zgemv2_args& a) {
+    const int n = a.n, b = c.bx;
+    const cd* A = mat_ptr(a.A, b);
+    const cd* Bm = mat_ptr(a.B, b);
+    const cd* Cin = mat_ptr(a.Cin, b);
+    cd* Co = mat_ptr(a.Cout, b);
+    cd* x0 = (cd*)KH_SMEM(c);
+    cd* x1 = x0 + n;
+    for (int k = c.tid; k < n; k += c.nthr) { x0[k] = Bm[(long long)k * a.B.ld + a.c0]; x1[k] = Bm[(long long)k * a.B.ld + a.c1]; }
+    c.sync();
+    const int lane = c.tid % KH_WARP, warp = c.tid / KH_WARP, nw = (c.nthr + KH_WARP - 1) / KH_WARP;
+    for (int i = warp; i < n; i += nw) {
+        const cd* ar = A + (long long)i * a.A.ld;
+        cd s0 = mk(0, 0), s1 = mk(0, 0);
+        for (int k = lane; k < n; k += KH_WARP) { const cd v = ar[k]; cfma(s0, v, x0[k]); cfma(s1, v, x1[k]); }
+        s0.x = kh_warp_allsum(s0.x); s0.y = kh_warp_allsum(s0.y); s1.x = kh_warp_allsum(s1.x); s1.y = kh_warp_allsum(s1.y);
+        if (lane == 0) {
+            if (Cin) { s0 = s0 + Cin[(long long)i * a.Cin.ld + a.c0]; s1 = s1 + Cin[(long long)i * a.Cin.ld + a.c1]; }
+            Co[(long long)i * a.Cout.ld + a.c0] = s0; Co[(long long)i * a.Cout.ld + a.c1] = s1;
+        }
+    }
 }

@@ -22,15 +22,38 @@ struct zgemm_args {
     const cd* colscale;         // optional, length N per batch group
     long long cs_stride; int cs_group;
     int cs_divide;              // 1: divide by colscale instead of multiplying
+    // Optional polynomial addend (Horner steps of the doubling method, kh_api.cu solve_patterned_dbl):  the product gets
+    //   + sum_{i < poly_q} poly_coef[h][i] x^poly_xpow[h][i] Om^i,   x = poly_k0[b / 2] * poly_hx,  h = b % 2
+    // added in the epilogue, Om^i = poly_pw[i] + (b / 2) M N (Om^0 = I): the batch is a PAIR batch, both series share the powers.
+    int poly_q;
+    const cd* poly_pw[6];
+    const double* poly_k0; double poly_hx;
+    double poly_coef[2][6]; int poly_xpow[2][6];
 };
+struct zgemm_poly { double cf[6]; long long off; };
+KH_DEV void zgemm_poly_prepare(const zgemm_args& a, int b, zgemm_poly& pl) {
+    if (a.poly_q <= 0) return;
+    const int h = b & 1;
+    const double x = a.poly_k0[b >> 1] * a.poly_hx;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const double cc = h ? a.poly_coef[1][i] : a.poly_coef[0][i]; const int xp = h ? a.poly_xpow[1][i] : a.poly_xpow[0][i];
+        pl.cf[i] = (i < a.poly_q && cc != 0.0) ? cc * pow(x, (double)xp) : 0.0; }
+    pl.off = (long long)(b >> 1) * a.M * a.N;
+}
 
 #define ZG_BK 16
 #define ZG_LDA 20
 #define ZG_EMU_TILE 64
 
-KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc) {
+KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc, const zgemm_poly& pl) {
     cd v = a.alpha * acc;
     if (cin) v = v + a.beta * cin[(long long)row * a.Cin.ld + col];
+    if (a.poly_q > 0) {
+        const long long e = pl.off + (long long)row * a.N + col;
+        if (row == col) v.x += pl.cf[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) if (i < a.poly_q) v = v + pl.cf[i] * a.poly_pw[i][e];
+    }
     if (a.diag != 0.0 && row == col) v.x += a.diag;
     if (rs) v = rs[row] * v;
     if (cs) v = a.cs_divide ? v / cs[col] : v * cs[col];
@@ -64,6 +87,7 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
     cd* Cout = mat_ptr(a.Cout, b);
     const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
     const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
+    zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
     for (int i = m0; i < m0 + BM && i < a.M; ++i)
         for (int j = n0; j < n0 + BN && j < a.N; ++j) {
             cd acc = mk(0, 0);
@@ -71,7 +95,7 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
                 cd av = a.transA ? A[(long long)k * a.A.ld + i] : A[(long long)i * a.A.ld + k];
                 cfma(acc, av, B[(long long)k * a.B.ld + j]);
             }
-            Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc);
+            Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc, pl);
         }
 }
 
@@ -201,6 +225,7 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
             cd* Cout = mat_ptr(a.Cout, b);
             const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
             const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
+            zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 if (t < nt) {
@@ -208,7 +233,7 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
                     for (int h = 0; h < 2; ++h) {
                         int col = n0 + t * 8 + 2 * lk + h;
                         if (col < a.N)
-                            Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]));
+                            Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]), pl);
                     }
                 }
             }
@@ -340,6 +365,7 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
     cd* Cout = mat_ptr(a.Cout, b);
     const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
     const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
+    zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
 #pragma unroll
     for (int j = 0; j < MAXU; ++j) {
         if (j < cnt) {
@@ -349,7 +375,7 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
             for (int h = 0; h < 2; ++h) {
                 const int col = n0 + tl * 8 + 2 * lk + h;
                 if (row < a.M && col < a.N)
-                    Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]));
+                    Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]), pl);
             }
         }
     }

@@ -99,7 +99,7 @@ class Engine:
         self._ws = None
         self.workspace_cap_bytes = workspace_cap_bytes
         self.launch_count = 0
-        self.doubling_theta = 8.0       # largest |lambda k0 d| of one slice of the doubling method (see _select_method)
+        self.doubling_theta = 10.0      # largest |lambda k0 d| of one slice of the doubling method (see _select_method)
 
     @classmethod
     def default(cls):
