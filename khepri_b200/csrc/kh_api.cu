@@ -104,11 +104,6 @@ static int cols2(kh_stream_t st, int Bc, int n, int fc, MatRef Amat, MatRef Bsrc
     zgemv2_args a{n, fc, fc + n / 2, Amat, Bsrc, Cin ? *Cin : mref(nullptr, 0, 0), Cout};
     return kh_launch<zgemv2_args, zgemv2_body>(dim3(Bc), 256, (size_t)2 * n * sizeof(cd), st, a, "zgemv", 16.0 * n * n * Bc);
 }
-static int zero_mat(kh_stream_t st, int Bc, long long n2, MatRef M) {
-    zero_cd_args zc{n2, M.p};
-    return kh_launch<zero_cd_args, zero_cd_body>(dim3(Bc), 256, 0, st, zc);
-}
-
 static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false, int imode = 0) {
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -139,12 +134,13 @@ static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& 
 #define STAR_TMP_SLABS 7
 
 static int bdmul(kh_stream_t st, int Bc, int N, int side, const cd* bd, int blk, MatRef M, MatRef out, double alpha = 1.0,
-                 const MatRef* Cin = nullptr, double beta = 0.0, double diag = 0.0, const cd* addbd = nullptr, int addblk = 0) {
+                 const MatRef* Cin = nullptr, double beta = 0.0, double diag = 0.0, const cd* addbd = nullptr, int addblk = 0, int fc = -1) {
     bdmul_args a;
     a.B = Bc; a.N = N; a.side = side; a.bd = bd; a.blk = blk; a.M = M; a.out = out;
     a.Cin = Cin ? *Cin : mref(nullptr, 0, 0);
     a.addbd = addbd; a.addblk = addblk; a.alpha = alpha; a.beta = beta; a.diag = diag;
-    return kh_launch<bdmul_args, bdmul_body>(dim3(Bc, 4), 256, 0, st, a, "bdmul");
+    a.csel = fc >= 0; a.c0 = fc; a.c1 = fc + N;                      // fc >= 0: the two flux columns only
+    return kh_launch<bdmul_args, bdmul_body>(dim3(Bc, a.csel ? 1 : 4), a.csel ? 128 : 256, 0, st, a, "bdmul");
 }
 
 // star product with a BD (uniform layer / half space) LEFT operand: 5 GEMMs + 1 inverse + O(n^2) kernels
@@ -157,16 +153,15 @@ static int star_bd_dense(kh_stream_t st, int Bc, int N, const cd* A, const SRef&
     int e;
     if ((e = bdmul(st, Bc, N, 0, A, 3, B.blk[0], F, -1.0, nullptr, 0.0, 1.0))) return e;           // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab, imode))) return e;   // (X..Vt are still free: work space)
-    if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X))) return e;                                          // X = F^-1 A21
+    if ((e = bdmul(st, Bc, N, 1, A, 2, Fi, X, 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e;  // X = F^-1 A21   (flux columns only when fc >= 0)
     if (fc >= 0) {
         if ((e = cols2(st, Bc, n, fc, B.blk[2], X, O.blk[2]))) return e;                           // S21 = B21 X   (flux columns)
-        if ((e = zero_mat(st, Bc, n2, U))) return e;
-        if ((e = cols2(st, Bc, n, fc, B.blk[0], X, U))) return e;                                  // U = B11 X     (flux columns, 0 elsewhere)
+        if ((e = cols2(st, Bc, n, fc, B.blk[0], X, U))) return e;                                  // U = B11 X     (flux columns)
     } else {
         if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                                // S21 = B21 X
         if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                       // U = B11 X
     }
-    if ((e = bdmul(st, Bc, N, 0, A, 1, U, O.blk[0], 1.0, nullptr, 0.0, 0.0, A, 0))) return e;      // S11 = A11 + A12 U
+    if ((e = bdmul(st, Bc, N, 0, A, 1, U, O.blk[0], 1.0, nullptr, 0.0, 0.0, A, 0, fc))) return e;  // S11 = A11 + A12 U
     if (fc >= 0 && last) return 0;
     if ((e = bdmul(st, Bc, N, 1, A, 3, Fi, Y))) return e;                                          // Y = F^-1 A22
     if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                           // Z = Y B12
@@ -186,13 +181,12 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
     if ((e = bdmul(st, Bc, N, 1, Bd, 0, A.blk[3], F, -1.0, nullptr, 0.0, 1.0))) return e;          // F = I - A22 B11
     if ((e = zinv_launch(st, Bc, n, F, Fi, info, tmp + 2 * slab, 5 * slab, imode))) return e;   // (X..Vt are still free: work space)
     if (fc >= 0) {
-        if ((e = zero_mat(st, Bc, n2, X))) return e;
-        if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                                 // X = F^-1 A21  (flux columns, 0 elsewhere)
+        if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                                 // X = F^-1 A21  (flux columns)
     } else {
         if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                      // X = F^-1 A21
     }
-    if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2]))) return e;                                   // S21 = B21 X
-    if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U))) return e;                                          // U = B11 X
+    if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2], 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e;      // S21 = B21 X
+    if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U, 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e;             // U = B11 X
     if (fc >= 0) {
         if ((e = cols2(st, Bc, n, fc, A.blk[1], U, O.blk[0], &A.blk[0]))) return e;                // S11 = A11 + A12 U  (flux columns)
         if (last) return 0;
@@ -384,9 +378,12 @@ static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
     while (th > theta_slice && d.s < 30) { th *= 0.5; d.s += 1; }
     d.theta = th;
     if (th < 1e-3) th = 1e-3;
+    // series length: the first neglected term th^(2t) / (2t)! below 1e-17 of cosh(th), the size of the block entries it is added
+    // to (an order of magnitude of margin; measured floors: t = 16 at th = 5.8, t = 19 at th = 8.7, against 20 and 24 from this rule)
+    const double tol = 1e-17 * cosh(th);
     double term = 1.0; int t = 0;                       // term = th^(2t) / (2t)!
-    while (term > 1e-19 && t < 60) { t += 1; term *= th * th / ((2.0 * t - 1.0) * (2.0 * t)); }
-    d.t = t + 1;
+    while (term > tol && t < 80) { t += 1; term *= th * th / ((2.0 * t - 1.0) * (2.0 * t)); }
+    d.t = t;
     if (d.t < 3) d.t = 3;
     int best = 2; long long bc = 1 << 30;
     for (int q = 2; q <= KH_DBL_QMAX; ++q) { const long long c = (q - 1) + 2LL * ((d.t + q - 1) / q - 1); if (c < bc) { bc = c; best = q; } }
@@ -435,7 +432,8 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
             if (k < sh.t - 1) { g.poly_coef[1][i] = 1.0 / dbl_factorial(2 * k + 2); g.poly_xpow[1][i] = 2 * k + 2; }
         }
     };
-    int cur = 8, oth = 10;                                                       // (Sc, Dc) pair: slabs cur, cur + 1
+    // slabs: 0 P, 1 Q, 1 + i Omega^(2i) (i <= q <= 8), (10, 11) / (12, 13) ping-pong pairs, 14..16 work space of the inverse
+    int cur = 10, oth = 12;                                                      // (Sc, Dc) pair: slabs cur, cur + 1
     KH_TRY(blocks(J - 1, cur, cur + 1));
     for (int j = J - 2; j >= 0; --j) {
         zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
@@ -446,17 +444,17 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     const int sSc = cur, sDc = cur + 1, sM12 = oth, sDP = oth + 1;
     {   zgemm_args g = zgemm_make(n, n, n, pair(sSc, sDc), both(0), pair(sM12, sDP));                      // M12 = Sc P ; DP = Dc P
         KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
-    {   zgemm_args g = zgemm_make(n, n, n, both(1), pair(sSc, sDP), pair(12, 13));                         // M21 = Q Sc ; m22 = Q DP
+    {   zgemm_args g = zgemm_make(n, n, n, both(1), pair(sSc, sDP), pair(3, 4));                           // M21 = Q Sc -> 3 ; m22 = Q DP -> 4
         KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
-    KH_TRY(gemm(st, Bc, n, M(2), M(sDc), M(3)));                                                           // m11 = Omega^2 Dc
-    {   dbl_eo_args a{Bc, N, S(3), S(sM12), S(12), S(13), Kx, Ky, S(4), S(5), S(6), S(7)};                    // Ee+ -> 4, Eo+ -> 5, Ee- -> 6, Eo- -> 7
+    KH_TRY(gemm(st, Bc, n, M(2), M(sDc), M(5)));                                                           // m11 = Omega^2 Dc -> 5
+    {   dbl_eo_args a{Bc, N, S(5), S(sM12), S(3), S(4), Kx, Ky, S(6), S(7), S(8), S(9)};                   // Ee+ -> 6, Eo+ -> 7, Ee- -> 8, Eo- -> 9
         KH_TRY((kh_launch<dbl_eo_args, dbl_eo_body>(dim3(Bc, 4), 256, (size_t)N * sizeof(m22), st, a, "dbl_eo"))); }
-    KH_TRY(zinv_launch(st, 2 * Bc, n, pair(4, 5), pair(8, 9), info_acc, S(14), 3 * slab, 2));                   // (Ee+)^-1 -> 8, (Eo+)^-1 -> 9
-    {   zgemm_args g = zgemm_make(n, n, n, pair(6, 7), pair(8, 9), pair(10, 11));                              // r_e -> 10, r_o -> 11
+    KH_TRY(zinv_launch(st, 2 * Bc, n, pair(6, 7), pair(cur, cur + 1), info_acc, S(14), 3 * slab, 2));           // (Ee+)^-1, (Eo+)^-1
+    {   zgemm_args g = zgemm_make(n, n, n, pair(8, 9), pair(cur, cur + 1), pair(oth, oth + 1));                // r_e, r_o
         KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
     MatRef O11 = mref(Sout, 2 * n2, n), O12 = mref(Sout + n2, 2 * n2, n);
-    MatRef s12 = sh.s == 0 ? O12 : M(13), s11 = sh.s == 0 ? O11 : M(12);
-    {   dbl_combine_args a{Bc, n, S(10), S(11), s11, s12};                                                     // S of two half slices
+    MatRef s12 = sh.s == 0 ? O12 : M(6), s11 = sh.s == 0 ? O11 : M(5);
+    {   dbl_combine_args a{Bc, n, S(oth), S(oth + 1), s11, s12};                                               // S of two half slices
         KH_TRY((kh_launch<dbl_combine_args, dbl_combine_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_eo"))); }
     // doublings  S <- S (*) S  of the mirror-symmetric slab (alternative.py:19-30 with A = B, A22 = A11, A21 = A12):
     //   D = I - S11 S11,  Y = D^-1 S12,  S12' = S12 Y,  S11' = S11 + S12 (S11 Y)

@@ -210,6 +210,7 @@ struct bdmul_args {
     MatRef M, Cin, out;             // Cin.p may be null
     const cd* addbd; int addblk;    // optional BD block added to the result
     double alpha, beta, diag;
+    int csel, c0, c1;               // csel: only the output columns c0, c1 are formed (flux columns of the star chain), O(n) work
 };
 KH_DEV void bdmul_body(const Cta& c, const bdmul_args& a) {
     const int N = a.N, n = 2 * N, b = c.bx;
@@ -218,9 +219,10 @@ KH_DEV void bdmul_body(const Cta& c, const bdmul_args& a) {
     const cd* M = mat_ptr(a.M, b);
     const cd* Cin = mat_ptr(a.Cin, b);
     cd* out = mat_ptr(a.out, b);
-    const int rows_per = (n + 3) / 4, r0 = c.by * rows_per, r1 = (r0 + rows_per < n) ? r0 + rows_per : n;
-    for (int e = r0 * n + c.tid; e < r1 * n; e += c.nthr) {
-        const int i = e / n, j = e - i * n;
+    const int rows_per = a.csel ? n : (n + 3) / 4, r0 = c.by * rows_per, r1 = (r0 + rows_per < n) ? r0 + rows_per : n;      // csel: one CTA per solve
+    const int width = a.csel ? 2 : n;
+    for (int e = r0 * width + c.tid; e < r1 * width; e += c.nthr) {
+        const int i = e / width, jj = e - i * width, j = a.csel ? (jj ? a.c1 : a.c0) : jj;
         const int hi = i >= N, gi = i - hi * N, hj = j >= N, gj = j - hj * N;
         cd v;
         if (a.side == 0) v = bd[(hi * 2 + 0) * N + gi] * M[(long long)gi * a.M.ld + j] + bd[(hi * 2 + 1) * N + gi] * M[(long long)(N + gi) * a.M.ld + j];
@@ -405,7 +407,7 @@ KH_DEV void flux_body(const Cta& c, const flux_args& a) {
 // i.e. two matrix polynomials in the n x n matrix Om (Paterson-Stockmeyer: powers Om^2..Om^q once, then Horner in Om^q),
 // every flop a DMMA GEMM.  dbl_lincomb forms the Horner blocks  sum_i c_i(b) Om^i  with the per-solve slice thickness
 // x_b = k0[b] * hx folded into the coefficients.
-#define KH_DBL_QMAX 6
+#define KH_DBL_QMAX 8
 struct dbl_lincomb_args {
     int B, n, q;                      // powers I, Om, .., Om^(q-1)
     const cd* pw[KH_DBL_QMAX];        // pw[i] = Om^i as [B][n][n] (pw[0] unused)
