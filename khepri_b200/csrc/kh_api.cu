@@ -304,6 +304,7 @@ extern "C" int kh_plan_set_method(kh_plan* plan, int method, double kappa, doubl
 
 // ---------------------------------------------------------------------------- patterned-layer solve
 #define LAYER_TMP_SLABS 17
+#define DBL_BLOCK_SLABS (2 * (KH_DBL_JMAX - 1))          /* extra slabs of the doubling method: the Horner blocks below the top one */
 struct LayerVec { cd* w; cd* lam; cd* xexp; cd* scale; cd* tau; int* info_eig; int* info_inv;
                   int* info_acc; int info_div; };      // info_acc[b / info_div] |= 1 (eigensolver) | 2 (zero pivot): the solve's status word
 
@@ -393,7 +394,7 @@ static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
 static double dbl_factorial(int k) { double f = 1.0; for (int i = 2; i <= k; ++i) f *= i; return f; }
 
 static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const cd* IC, double depth, const DblShape& sh,
-                               const cd* Kx, const cd* Ky, const double* k0, cd* pool, int* info_acc, cd* Sout) {
+                               const cd* Kx, const cd* Ky, const double* k0, cd* pool, cd* xtra, int* info_acc, cd* Sout) {
     const int n = 2 * N, q = sh.q;
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     auto S = [&](int s) { return pool + (long long)s * slab; };
@@ -434,12 +435,29 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     };
     // slabs: 0 P, 1 Q, 1 + i Omega^(2i) (i <= q <= 8), (10, 11) / (12, 13) ping-pong pairs, 14..16 work space of the inverse
     int cur = 10, oth = 12;                                                      // (Sc, Dc) pair: slabs cur, cur + 1
-    KH_TRY(blocks(J - 1, cur, cur + 1));
-    for (int j = J - 2; j >= 0; --j) {
-        zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
-        poly(g, j);
-        KH_TRY(zgemm_launch(st, 2 * Bc, g));
-        const int t = cur; cur = oth; oth = t;
+    if (J <= KH_DBL_JMAX && xtra) {
+        // every block polynomial in one pass over the powers (top block -> the Horner start, block j < J - 1 -> extra slabs 2j, 2j + 1)
+        dbl_blocks_args a;
+        memset(&a, 0, sizeof(a));
+        a.B = Bc; a.n = n; a.q = q; a.J = J; a.t = sh.t; a.k0 = k0; a.hx = hx;
+        for (int i = 1; i < q; ++i) a.pw[i] = S(1 + i);
+        for (int j = 0; j < J - 1; ++j) { a.out[j][0] = xtra + (long long)(2 * j) * slab; a.out[j][1] = xtra + (long long)(2 * j + 1) * slab; }
+        a.out[J - 1][0] = S(cur); a.out[J - 1][1] = S(cur + 1);
+        KH_TRY((kh_launch<dbl_blocks_args, dbl_blocks_body>(dim3(Bc, 4), 256, (size_t)2 * J * q * sizeof(double), st, a, "dbl_lincomb")));
+        for (int j = J - 2; j >= 0; --j) {
+            zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
+            g.Cin = mref(xtra + (long long)(2 * j) * slab, n2, n, 2, slab); g.beta = 1.0;
+            KH_TRY(zgemm_launch(st, 2 * Bc, g));
+            const int t = cur; cur = oth; oth = t;
+        }
+    } else {                                                                     // very long series: block by block
+        KH_TRY(blocks(J - 1, cur, cur + 1));
+        for (int j = J - 2; j >= 0; --j) {
+            zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
+            poly(g, j);
+            KH_TRY(zgemm_launch(st, 2 * Bc, g));
+            const int t = cur; cur = oth; oth = t;
+        }
     }
     const int sSc = cur, sDc = cur + 1, sM12 = oth, sDP = oth + 1;
     {   zgemm_args g = zgemm_make(n, n, n, pair(sSc, sDc), both(0), pair(sM12, sDP));                      // M12 = Sc P ; DP = Dc P
@@ -486,6 +504,7 @@ struct ChunkBufs {
     std::vector<cd*> layerV;        // per BD layer (retain): [Bc][4][N]
     std::vector<cd*> layerL;        // per BD layer (retain): [Bc][N]
     cd* pool;                       // LAYER_TMP_SLABS x [Bc][n][n]
+    cd* dblx;                       // DBL_BLOCK_SLABS x [Bc][n][n] (doubling method only)
     LayerVec vec;
     cd* accD[2]; cd* accB[2]; cd* expA; cd* expB; cd* accR[2];
     int* info;
@@ -514,6 +533,7 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
         else { cb.layerS[i] = b.get<cd>((size_t)Bc * 4 * n2); }
     }
     cb.pool = b.get<cd>((size_t)LAYER_TMP_SLABS * Bc * n2);
+    cb.dblx = (p->method == KH_METHOD_DOUBLING && !(flags & KH_WANT_FIELDS)) ? b.get<cd>((size_t)DBL_BLOCK_SLABS * Bc * n2) : nullptr;
     cb.vec.w = b.get<cd>((size_t)Bc * n); cb.vec.lam = b.get<cd>((size_t)Bc * n);
     cb.vec.xexp = b.get<cd>((size_t)Bc * n); cb.vec.scale = b.get<cd>((size_t)Bc * n); cb.vec.tau = b.get<cd>((size_t)Bc * n);
     cb.vec.info_eig = b.get<int>(Bc); cb.vec.info_inv = b.get<int>((size_t)3 * Bc);
@@ -631,7 +651,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
                 if (p->method == KH_METHOD_DOUBLING && !want_fields) {
                     const DblShape sh = dbl_shape(p->dbl_kappa, L.depth, p->dbl_theta);
                     KH_TRY(solve_patterned_dbl(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, sh, cb.Kx, cb.Ky, cb.k0,
-                                               cb.pool, acc, cb.layerS[i]));
+                                               cb.pool, cb.dblx, acc, cb.layerS[i]));
                 } else {
                     LayerVec v = cb.vec; v.info_acc = acc; v.info_div = 1;
                     KH_TRY(solve_patterned(st, Bc, N, (const cd*)L.C_dev, (const cd*)L.IC_dev, L.depth, cb.Kx, cb.Ky, cb.k0, cb.pool,

@@ -484,6 +484,46 @@ KH_DEV void dbl_combine_body(const Cta& c, const dbl_combine_args& a) {
     }
 }
 
+// All Horner blocks of both series in ONE pass over the powers:  out[j][o] = sum_{i<q} c_o[j q + i](b) Om^i  for j < J.
+// (Per Horner step the powers would be read again: q - 1 slabs each time; here they are read once and 2 J slabs are written.)
+#define KH_DBL_JMAX 6
+struct dbl_blocks_args {
+    int B, n, q, J, t;
+    const cd* pw[KH_DBL_QMAX];
+    const double* k0; double hx;
+    cd* out[KH_DBL_JMAX][2];
+};
+KH_DEV void dbl_blocks_body(const Cta& c, const dbl_blocks_args& a) {
+    const int n = a.n, b = c.bx, q = a.q, J = a.J;
+    const long long off = (long long)b * n * n;
+    double* cf = (double*)KH_SMEM(c);                   // [2][J q]: Sc coefficients x^(2k+1) / (2k+1)!, Dc coefficients x^(2k+2) / (2k+2)!
+    if (c.tid == 0) {
+        const double x = a.k0[b] * a.hx;
+        double ps = x, pd = 0.5 * x * x;                // k = 0
+        for (int k = 0; k < J * q; ++k) {
+            cf[k] = (k < a.t) ? ps : 0.0;
+            cf[J * q + k] = (k < a.t - 1) ? pd : 0.0;
+            ps *= x * x / ((2.0 * k + 2.0) * (2.0 * k + 3.0));
+            pd *= x * x / ((2.0 * k + 3.0) * (2.0 * k + 4.0));
+        }
+    }
+    c.sync();
+    const int per = (n * n + 3) / 4, e0 = c.by * per, e1 = (e0 + per < n * n) ? e0 + per : n * n;
+    for (int e = e0 + c.tid; e < e1; e += c.nthr) {
+        const int i = e / n, j2 = e - i * n;
+        cd p[KH_DBL_QMAX];
+        p[0] = mk(i == j2 ? 1.0 : 0.0, 0.0);
+#pragma unroll
+        for (int k = 1; k < KH_DBL_QMAX; ++k) p[k] = (k < q) ? a.pw[k][off + e] : mk(0.0, 0.0);
+        for (int j = 0; j < J; ++j) {
+            cd v0 = mk(0, 0), v1 = mk(0, 0);
+#pragma unroll
+            for (int k = 0; k < KH_DBL_QMAX; ++k) if (k < q) { v0 = v0 + cf[j * q + k] * p[k]; v1 = v1 + cf[J * q + j * q + k] * p[k]; }
+            a.out[j][0][off + e] = v0; a.out[j][1][off + e] = v1;
+        }
+    }
+}
+
 // safety net for the (slices, terms) the host chose from its bound on the spectrum: theta_b = x_b sqrt(||Om||_1) must stay
 // below theta_lim, otherwise bit 2 of info is raised for that solve (the truncated series may have lost accuracy).
 struct dbl_check_args { int B, n; const cd* Om; const double* k0; double hx, theta_lim; int* info; };
