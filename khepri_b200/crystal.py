@@ -99,7 +99,9 @@ class Crystal:
         self.stack_retain_mask = [True]
         self.stack_retain_mask.extend(fields_mask)
         self.stack_retain_mask.append(True)
-        for name, enabled in zip(self.global_stacking, self.stack_retain_mask):
+        # (void stacks have no half spaces: align the mask with the stack -- the reference zips the padded mask, crystal.py:157-159)
+        aligned = self.stack_retain_mask if not self.void else self.stack_retain_mask[1:-1]
+        for name, enabled in zip(self.global_stacking, aligned):
             self.layers[name].fields |= enabled
             if hasattr(self.layers[name], "base"):
                 self.layers[name].base.fields |= enabled
@@ -238,7 +240,7 @@ class Crystal:
         self._solved_src = (self.source.wavelength, tuple(self.kp))
         if want_fields:
             pre, suf = res["prefix"][0].cpu().numpy(), res["suffix"][0].cpu().numpy()
-            mask = self.stack_retain_mask
+            mask = self.stack_retain_mask if not self.void else self.stack_retain_mask[1:-1]
             self.stacking_matrices = [pre[i] if mask[i] else None for i in range(len(mask))]
             self.stacking_reverse_matrices = [suf[i] if (i == 0 or mask[i]) else None for i in range(len(mask))]
             W, V, L = res["W"][0].cpu().numpy(), res["V"][0].cpu().numpy(), res["L"][0].cpu().numpy()

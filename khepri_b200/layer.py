@@ -122,3 +122,44 @@ class Layer:
                 raise np.linalg.LinAlgError("Singular matrix")     # what np.linalg.inv raises in the reference
             self._cache = (key, Cm, ICm)
         return self._cache[1], self._cache[2]
+
+    # -- Layer.solve of the reference (layer.py:145-194): S, and with `fields` also W, V, L, IC, for ONE source.
+    #    A one-layer, half-space-free Crystal through the same batched kernels (the star product with the identity is exact).
+    def solve(self, k_parallel, wavelength, engine=None):
+        from .crystal import Crystal
+        cl = Crystal(self.expansion.pw, void=True, engine=engine)
+        cl.expansion = self.expansion
+        keep = self.fields
+        cl.layers["L"] = self
+        cl.set_device(["L"], [keep])
+        cl.set_source(wavelength, kp=tuple(k_parallel))
+        cl.solve()
+        self.S = np.asarray(cl.Stot)
+        self.fields = keep
+        if self.formulation in (Formulation.FFT, Formulation.ANALYTICAL):
+            Cm, ICm = self.convmat_device(cl.engine)
+            self.C = Cm.cpu().numpy()
+            self.IC = ICm.cpu().numpy() if keep else None
+        else:
+            self.IC = 1 / self.epsilon if keep else None
+        if not keep:
+            self.W = self.V = self.L = None
+        return self
+
+
+def stack_layers(pw, layers, mask, engine=None):
+    """layer.py:35-60: forward partial products (kept where mask), reverse partial products, total, from solved layers."""
+    from .alternative import redheffer_product, scattering_identity
+    Stot = scattering_identity(pw, block=True)
+    Sls = []
+    for i, layer in enumerate(layers):
+        Stot = redheffer_product(Stot, layer.S, engine=engine)
+        Sls.append(Stot.copy() if mask[i] else None)
+    Srev = scattering_identity(pw, block=True)
+    rmask = list(reversed(mask[1:]))
+    Srs = []
+    for i, layer in enumerate(reversed(layers[1:])):
+        Srs.append(Srev.copy() if rmask[i] else None)
+        Srev = redheffer_product(np.asarray(layer.S).copy(), Srev, engine=engine)
+    Srs.append(Srev.copy())
+    return Sls, list(reversed(Srs)), Stot

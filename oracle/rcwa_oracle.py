@@ -195,8 +195,8 @@ def uniform_layer_modes(Kx, Ky, eps):
     return np.identity(2 * N), Qm / lam, lam
 
 
-def structured_layer_modes(Kx, Ky, C):
-    """alternative.py:158-178: Omega^2 = P Q, eig, lambda = sqrt, V = Q W / lambda."""
+def pq_matrices(Kx, Ky, C):
+    """alternative.py:160-171: the coupled first-order system d/dz' [s; u] = [[0, P], [Q, 0]] [s; u] (Laurent rule)."""
     N = len(Kx)
     dKx, dKy = np.diag(Kx), np.diag(Ky)
     one = np.eye(N)
@@ -205,9 +205,36 @@ def structured_layer_modes(Kx, Ky, C):
                    [dKy @ iCKy - one, -dKy @ iCKx]]).astype(complex)
     Qm = np.block([[dKx @ dKy, C - dKx @ dKx],
                    [dKy @ dKy - C, -dKy @ dKx]]).astype(complex)
+    return Pm, Qm
+
+
+def structured_layer_modes(Kx, Ky, C):
+    """alternative.py:158-178: Omega^2 = P Q, eig, lambda = sqrt, V = Q W / lambda."""
+    Pm, Qm = pq_matrices(Kx, Ky, C)
     lam2, W = eig(Pm @ Qm)
     lam = np.sqrt(lam2 + 0j)
     return W, Qm @ W / lam, lam
+
+
+def layer_smatrix_doubling(Pm, Qm, W0, V0, depth, k0, slicing_pow=3):
+    """The reference's LEGACY layer algorithm (khepri/tmat/scattering.py:25-51) restated in the Crystal path's field basis:
+    transfer matrix of a thin slice by scipy's expm (scattering.py:42-43), change to the mode basis of the free-space gaps
+    (its U ... Vi, here R0 = [[W0, W0], [-V0, V0]], fields.py:46-51), matrix_s (tmat/matrices.py:167-176), then `slicing_pow`
+    self star products (scattering.py:46-49, multS = redheffer_product).  No eigen-decomposition: an independent check of
+    structured_layer_modes + layer_smatrix, and the oracle of the CUDA path's "doubling" method."""
+    from scipy.linalg import expm
+    n = Pm.shape[0]
+    zero = np.zeros((n, n))
+    gen = np.block([[zero, Pm], [Qm, zero]])
+    M = expm(gen * (k0 * depth / 2 ** slicing_pow))
+    R0 = np.block([[W0, W0], [-V0, V0]])
+    T = solve(R0, M @ R0)                               # [c+; c-] at the right face = T [c+; c-] at the left face
+    T11, T12, T21, T22 = T[:n, :n], T[:n, n:], T[n:, :n], T[n:, n:]
+    S12 = inv(T22)
+    S = np.array([[-S12 @ T21, S12], [T11 - T12 @ S12 @ T21, T12 @ S12]])
+    for _ in range(slicing_pow):
+        S = star(S, S)
+    return S
 
 
 def layer_smatrix(W, V, W0, V0, lam, depth, k0):
@@ -323,12 +350,20 @@ def _structure_g(st):
     return g_vectors(st["pw"], st["lattice"])
 
 
+PATTERNED_BY_DOUBLING = None      # set to a slicing_pow to route patterned layers through layer_smatrix_doubling (tests only)
+
+
 def solve_layer(spec, g, pw, kp, wl):
     """layer.py:145-194 -> dict(S, W, V, L, IC)."""
     Kx, Ky, _ = k_vectors(g, kp, wl)
     W0, V0 = free_space_modes(Kx, Ky)
     k0 = TWO_PI / wl
     kind = spec[0]
+    if kind == "pixmap" and PATTERNED_BY_DOUBLING is not None:
+        C = convolution_matrix(spec[1], pw)
+        Pm, Qm = pq_matrices(Kx, Ky, C)
+        return {"S": layer_smatrix_doubling(Pm, Qm, W0, V0, spec[2], k0, PATTERNED_BY_DOUBLING), "W": None, "V": None, "L": None,
+                "IC": inv(C), "depth": spec[2]}
     if kind == "pixmap":
         C = convolution_matrix(spec[1], pw)          # recomputed per solve, as the reference does
         IC = inv(C)

@@ -144,3 +144,34 @@ def test_integration_stub_idft_raw_ctypes():
     # error behaviour: bad arguments and an undersized workspace are status codes, not crashes
     assert lib.kh_idft_batch(1, N, npts, None, kyd.data_ptr(), xd.data_ptr(), yd.data_ptr(), s.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), None) != 0
     assert lib.kh_idft_batch(1, N, npts, kxd.data_ptr(), kyd.data_ptr(), xd.data_ptr(), yd.data_ptr(), s.data_ptr(), out.data_ptr(), ws.data_ptr(), 16, None) != 0
+
+
+def test_layer_api_solve_and_stack_layers():
+    """The reference's Layer-level API (layer.py:35-60, 145-194; examples/layer_api): Layer.solve leaves S (and W, V, L, IC with
+    `fields`) on the layer, stack_layers chains solved layers."""
+    from khepri_b200 import Expansion, Layer
+    from khepri_b200.layer import stack_layers
+    from oracle import rcwa_oracle as orc
+    from tests import cases
+    from tests.util import engine
+    eng = engine("emu")
+    e = Expansion((3, 3))
+    pm = cases.disc_pixmap((64, 64), 4.0, (0.0, 0.0), 0.25, 1.0)
+    kp, wl = (0.3, -0.1), 1.3
+    lp = Layer.pixmap(e, pm, 0.3)
+    lp.fields = True
+    lu = Layer.uniform(e, 2.2, 0.4)
+    lp.solve(kp, wl, engine=eng)
+    lu.solve(kp, wl, engine=eng)
+    g = orc.g_vectors((3, 3), np.eye(2))
+    rp = orc.solve_layer(("pixmap", pm, 0.3), g, (3, 3), kp, wl)
+    ru = orc.solve_layer(("uniform", 2.2, 0.4), g, (3, 3), kp, wl)
+    assert np.abs(lp.S - rp["S"]).max() < 1e-10 and np.abs(lu.S - ru["S"]).max() < 1e-12
+    assert np.abs(lp.IC - rp["IC"]).max() < 1e-11 and lp.W.shape == (18, 18) and lp.L.shape == (18,)
+    assert lu.W is None and lu.IC is None                                  # dropped without `fields` (layer.py:190-194)
+    from tests.test_oracle_golden import match_spectrum
+    match_spectrum(lp.L ** 2, rp["L"] ** 2, 1e-9)
+    Sls, Srs, Stot = stack_layers((3, 3), [lp, lu, lp], [True, False, True], engine=eng)
+    pre, suf, tot = orc.stack_chain(18, [rp["S"], ru["S"], rp["S"]])
+    assert np.abs(Stot - tot).max() < 1e-10 and Sls[1] is None and np.abs(Sls[2] - pre[2]).max() < 1e-10
+    assert np.abs(Srs[0] - suf[0]).max() < 1e-10

@@ -224,3 +224,21 @@ def test_supercell_large_bases(pp):
         np.testing.assert_allclose(orc.flux_end(st, sol, s["te"], s["tm"]), g["RT"][i], rtol=1e-9, atol=1e-12)
         assert np.abs(sol["Stot"][0, 0][::9, ::7] - g["S11"][i]).max() <= 1e-9 * np.abs(g["S11"][i]).max()
         assert np.abs(sol["Stot"][1, 0][::9, ::7] - g["S21"][i]).max() <= 1e-9 * np.abs(g["S21"][i]).max()
+
+
+def test_legacy_expm_doubling_reproduces_the_crystal_path():
+    """the reference's legacy layer algorithm (tmat/scattering.py:25-51: expm of a thin slice, matrix_s, self
+    star products) restated in the Crystal basis reproduces the Crystal path's golden spectra without any eigensolver --
+    the two algorithms of the reference agree, and either can check the CUDA path."""
+    g = gold("suh03")
+    st, srcs = cases.case_suh03()
+    idx = [0, 37, 75, 112, 150]
+    orc.PATTERNED_BY_DOUBLING = 4
+    try:
+        rt = oracle_sweep(st, [srcs[i] for i in idx])
+        st2, srcs2 = cases.case_bzi((3, 3), 4, 5)
+        rt2 = oracle_sweep(st2, srcs2[:6])
+    finally:
+        orc.PATTERNED_BY_DOUBLING = None
+    np.testing.assert_allclose(rt, g["RT"][idx], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(rt2, gold("bzi33")["RT"][:6], rtol=1e-9, atol=1e-11)
