@@ -402,44 +402,9 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
     auto pair = [&](int s0, int s1) { return mref(S(s0), n2, n, 2, (long long)(s1 - s0) * slab); };      // batch index 2b + h -> slab s0 / s1
     auto both = [&](int s0) { return mref(S(s0), n2, n, 2, 0); };                                        // both halves of a pair read slab s0
     const double hx = 0.5 * depth / (double)(1LL << sh.s);      // half a slice
-    // Products with P and Q never touch the dense n x n matrices: P = Kc IC Kr + J and Q = Dq + [[0, C], [-C, 0]] (Kc = [Kx; Ky],
-    // Kr = [Ky, -Kx], J = [[0, I], [-I, 0]], Dq: 2 x 2 blocks of diagonals), so each costs one N x N x n GEMM (a quarter, for Q two
-    // quarters) with the diagonal parts folded into the GEMM's addend / store (zgemm_args::st_mode).  X, Y: batched n x n, nb items.
-    const MatRef Cs = mref(C, 0, N), ICs = mref(IC, 0, N);                       // shared by the batch (stride 0)
-    auto rows_from = [&](MatRef m, int r0) { m.p += (long long)r0 * m.ld; return m; };
-    auto st_common = [&](zgemm_args& g, int mode, int nb, MatRef X) {
-        g.st_mode = mode; g.st_N = N; g.st_group = nb / Bc; g.st_Kx = Kx; g.st_Ky = Ky; g.st_X = X;
-    };
-    auto q_left = [&](int nb, MatRef X, MatRef Y) -> int {                       // Y = Q X
-        zgemm_args g = zgemm_make(N, n, N, Cs, rows_from(X, N), Y);
-        st_common(g, 1, nb, X);
-        int e = zgemm_launch(st, nb, g);
-        if (e) return e;
-        zgemm_args h = zgemm_make(N, n, N, Cs, X, rows_from(Y, N), -1.0);
-        st_common(h, 2, nb, X);
-        return zgemm_launch(st, nb, h);
-    };
-    auto thin = [&](int nb, int mode, MatRef X, MatRef T) -> int {
-        dbl_thin_args a{nb, N, mode, nb / Bc, Kx, Ky, X, T};
-        return kh_launch<dbl_thin_args, dbl_thin_body>(dim3(nb, 2), 256, 0, st, a, "dbl_thin");
-    };
-    auto p_left = [&](int nb, MatRef X, MatRef T, MatRef Y) -> int {             // Y = P X   (T: N x n scratch, ld n)
-        int e = thin(nb, 0, X, T);
-        if (e) return e;
-        zgemm_args g = zgemm_make(N, n, N, ICs, T, Y);
-        st_common(g, 3, nb, X);
-        return zgemm_launch(st, nb, g);
-    };
-    auto p_right = [&](int nb, MatRef X, MatRef T, MatRef Y) -> int {            // Y = X P   (T: n x N scratch, ld N)
-        int e = thin(nb, 1, X, T);
-        if (e) return e;
-        zgemm_args g = zgemm_make(n, N, N, T, ICs, Y);
-        st_common(g, 4, nb, X);
-        return zgemm_launch(st, nb, g);
-    };
-    {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};                             // (only Q is used: the operand of Omega^2 = P Q)
+    {   pq_args a{Bc, N, C, IC, Kx, Ky, S(0), S(1)};
         KH_TRY((kh_launch<pq_args, pq_body>(dim3(Bc), 256, 0, st, a))); }
-    KH_TRY(p_left(Bc, M(1), mref(S(0), n2, n), M(2)));                           // Omega^2 = P Q -> 2 ; Omega^(2i) -> slab i + 1   (P's slab is the scratch)
+    KH_TRY(gemm(st, Bc, n, M(0), M(1), M(2)));                                   // Omega^2 = P Q -> 2 ; Omega^(2i) -> slab i + 1
     {   dbl_check_args a{Bc, n, S(2), k0, hx, 1.75 * sh.theta + 0.25, info_acc};      // ||.||_1 overestimates rho by up to ~2 (theta by ~1.4)
         KH_TRY((kh_launch<dbl_check_args, dbl_check_body>(dim3(Bc), 128, 256 * sizeof(double), st, a))); }
     for (int i = 2; i <= q; ++i) KH_TRY(gemm(st, Bc, n, M(1 + i / 2), M(1 + (i - i / 2)), M(1 + i)));
@@ -494,12 +459,13 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
             const int t = cur; cur = oth; oth = t;
         }
     }
-    const int sSc = cur, sDc = cur + 1, sM12 = oth;
-    // M21 = Q Sc -> 3, X2 = Q Dc -> 4;  m11 = P X2 -> 5;  M12 = Sc P -> sM12, m22 = X2 P -> sM12 + 1   (M11 = I + m11, M22 = I + m22)
-    KH_TRY(q_left(2 * Bc, pair(sSc, sDc), pair(3, 4)));
-    KH_TRY(p_left(Bc, M(4), mref(S(6), n2, n), M(5)));
-    KH_TRY(p_right(2 * Bc, pair(sSc, 4), mref(S(6), n2, N, 2, slab), pair(sM12, sM12 + 1)));
-    {   dbl_eo_args a{Bc, N, S(5), S(sM12), S(3), S(sM12 + 1), Kx, Ky, S(6), S(7), S(8), S(9)};                   // Ee+ -> 6, Eo+ -> 7, Ee- -> 8, Eo- -> 9
+    const int sSc = cur, sDc = cur + 1, sM12 = oth, sDP = oth + 1;
+    {   zgemm_args g = zgemm_make(n, n, n, pair(sSc, sDc), both(0), pair(sM12, sDP));                      // M12 = Sc P ; DP = Dc P
+        KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
+    {   zgemm_args g = zgemm_make(n, n, n, both(1), pair(sSc, sDP), pair(3, 4));                           // M21 = Q Sc -> 3 ; m22 = Q DP -> 4
+        KH_TRY(zgemm_launch(st, 2 * Bc, g)); }
+    KH_TRY(gemm(st, Bc, n, M(2), M(sDc), M(5)));                                                           // m11 = Omega^2 Dc -> 5
+    {   dbl_eo_args a{Bc, N, S(5), S(sM12), S(3), S(4), Kx, Ky, S(6), S(7), S(8), S(9)};                   // Ee+ -> 6, Eo+ -> 7, Ee- -> 8, Eo- -> 9
         KH_TRY((kh_launch<dbl_eo_args, dbl_eo_body>(dim3(Bc, 4), 256, (size_t)N * sizeof(m22), st, a, "dbl_eo"))); }
     KH_TRY(zinv_launch(st, 2 * Bc, n, pair(6, 7), pair(cur, cur + 1), info_acc, S(14), 3 * slab, 2));           // (Ee+)^-1, (Eo+)^-1
     {   zgemm_args g = zgemm_make(n, n, n, pair(8, 9), pair(cur, cur + 1), pair(oth, oth + 1));                // r_e, r_o

@@ -431,22 +431,6 @@ KH_DEV void dbl_lincomb_body(const Cta& c, const dbl_lincomb_args& a) {
     }
 }
 
-// Thin operands of the structured products (see zgemm_args::st_mode):  mode 0:  T[g][j] = Ky[g] X[g][j] - Kx[g] X[N+g][j]  (Kr X,
-// N x n);  mode 1:  T[i][g] = X[i][g] Kx[g] + X[i][N+g] Ky[g]  (X Kc, n x N).  X is a (possibly pair-) batched n x n operand.
-struct dbl_thin_args { int B, N, mode, group; const cd* Kx; const cd* Ky; MatRef X, T; };
-KH_DEV void dbl_thin_body(const Cta& c, const dbl_thin_args& a) {
-    const int N = a.N, n = 2 * N, b = c.bx;
-    const cd* kx = a.Kx + (long long)(b / a.group) * N;
-    const cd* ky = a.Ky + (long long)(b / a.group) * N;
-    const cd* X = mat_ptr(a.X, b);
-    cd* T = mat_ptr(a.T, b);
-    const int per = (N * n + 1) / 2, e0 = c.by * per, e1 = (e0 + per < N * n) ? e0 + per : N * n;
-    for (int e = e0 + c.tid; e < e1; e += c.nthr) {
-        if (a.mode == 0) { const int g = e / n, j = e - g * n; T[(long long)g * a.T.ld + j] = ky[g] * X[(long long)g * a.X.ld + j] - kx[g] * X[(long long)(N + g) * a.X.ld + j]; }
-        else { const int i = e / N, g = e - i * N; T[(long long)i * a.T.ld + g] = X[(long long)i * a.X.ld + g] * kx[g] + X[(long long)i * a.X.ld + N + g] * ky[g]; }
-    }
-}
-
 // S-matrix of TWO slices from the transfer matrix M of ONE (thickness h): the slab of thickness 2h is mirror symmetric about its
 // mid-plane, so its response splits into an even (u = 0 on the mid-plane) and an odd (s = 0) problem.  With the mode basis of
 // the zero-thickness free-space gaps (W0 = I, V0; alternative.py:84-99, fields.py:46-51: s = c+ + c-, u = V0 (c- - c+) at the

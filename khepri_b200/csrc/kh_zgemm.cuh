@@ -29,16 +29,6 @@ struct zgemm_args {
     const cd* poly_pw[8];
     const double* poly_k0; double poly_hx;
     double poly_coef[2][8]; int poly_xpow[2][8];
-    // Structured products with the RCWA system matrices (kh_api.cu solve_patterned_dbl; P = Kc IC Kr + J, Q = Dq + [[0, C], [-C, 0]]
-    // with Kc = [Kx; Ky], Kr = [Ky, -Kx] diagonal blocks, alternative.py:160-171): the dense factor is only N x N (N = n / 2), the
-    // diagonal parts ride along.  st_Kx / st_Ky: [batch / st_group][st_N]; st_X: the n x n operand the structure is applied to.
-    //   st_mode 1 (Q X, top half):    out[g][j]     =  (C X_bottom)[g][j] + KxKy[g] X[g][j] - Kx[g]^2 X[N+g][j]          (addend, preloaded)
-    //   st_mode 2 (Q X, bottom half): out[N+g][j]   = -(C X_top)[g][j]    + Ky[g]^2 X[g][j] - KxKy[g] X[N+g][j]          (alpha = -1)
-    //   st_mode 3 (P X):  acc = IC (Kr X);   out[g][j] = Kx[g] acc + X[N+g][j],   out[N+g][j] = Ky[g] acc - X[g][j]      (two stores)
-    //   st_mode 4 (X P):  acc = (X Kc) IC;   out[i][g] = acc Ky[g] - X[i][N+g],   out[i][N+g] = -acc Kx[g] + X[i][g]     (two stores)
-    int st_mode, st_N, st_group;
-    const cd* st_Kx; const cd* st_Ky;
-    MatRef st_X;
 };
 struct zgemm_poly { double cf[8]; long long off; };
 KH_DEV void zgemm_poly_prepare(const zgemm_args& a, int b, zgemm_poly& pl) {
@@ -59,18 +49,11 @@ KH_DEV void zgemm_poly_prepare(const zgemm_args& a, int b, zgemm_poly& pl) {
 // into the accumulators BEFORE the K loop (C += A B on top of it): the loads overlap the pipeline prologue instead of stalling
 // the epilogue, where every warp waited on them with nothing else to issue (a Cin epilogue cost 10 %, a polynomial one 50 %).
 KH_DEV bool zgemm_preload(const zgemm_args& a) {
-    return (a.alpha == 1.0 || a.alpha == -1.0) && !a.rowscale && !a.colscale && (a.Cin.p != nullptr || a.poly_q > 0 || a.st_mode == 1 || a.st_mode == 2);      // alpha = -1: start from -addend, negate at the end
+    return (a.alpha == 1.0 || a.alpha == -1.0) && !a.rowscale && !a.colscale && (a.Cin.p != nullptr || a.poly_q > 0);      // alpha = -1: start from -addend, negate at the end
 }
-KH_DEV cd zgemm_addend(const zgemm_args& a, int b, const cd* cin, int row, int col, const zgemm_poly& pl) {
+KH_DEV cd zgemm_addend(const zgemm_args& a, const cd* cin, int row, int col, const zgemm_poly& pl) {
     cd v = mk(0.0, 0.0);
     if (cin) v = a.beta * cin[(long long)row * a.Cin.ld + col];
-    if (a.st_mode == 1 || a.st_mode == 2) {             // the diagonal part of Q applied to X
-        const long long ko = (long long)(b / a.st_group) * a.st_N + row;
-        const cd kx = a.st_Kx[ko], ky = a.st_Ky[ko];
-        const cd* X = mat_ptr(a.st_X, b);
-        const cd x0 = X[(long long)row * a.st_X.ld + col], x1 = X[(long long)(a.st_N + row) * a.st_X.ld + col];
-        v = v + (a.st_mode == 1 ? (kx * ky) * x0 - (kx * kx) * x1 : (ky * ky) * x0 - (kx * ky) * x1);
-    }
     if (a.poly_q > 0) {
         const long long e = pl.off + (long long)row * a.N + col;
         if (row == col) v.x += pl.cf[0];
@@ -79,26 +62,6 @@ KH_DEV cd zgemm_addend(const zgemm_args& a, int b, const cd* cin, int row, int c
     }
     if (a.diag != 0.0 && row == col) v.x += a.diag;
     return v;
-}
-// store of one output element (all epilogue variants)
-struct zgemm_out { const cd* Cin; cd* Cout; const cd* rs; const cd* cs; bool pre; };
-KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc, const zgemm_poly& pl);
-KH_DEV void zgemm_store(const zgemm_args& a, int b, const zgemm_out& o, int row, int col, cd acc, const zgemm_poly& pl) {
-    if (a.st_mode == 3 || a.st_mode == 4) {
-        const int N = a.st_N;
-        const cd* X = mat_ptr(a.st_X, b);
-        const long long ko = (long long)(b / a.st_group) * N + (a.st_mode == 3 ? row : col);
-        const cd kx = a.st_Kx[ko], ky = a.st_Ky[ko];
-        if (a.st_mode == 3) {
-            o.Cout[(long long)row * a.Cout.ld + col] = kx * acc + X[(long long)(N + row) * a.st_X.ld + col];
-            o.Cout[(long long)(N + row) * a.Cout.ld + col] = ky * acc - X[(long long)row * a.st_X.ld + col];
-        } else {
-            o.Cout[(long long)row * a.Cout.ld + col] = acc * ky - X[(long long)row * a.st_X.ld + N + col];
-            o.Cout[(long long)row * a.Cout.ld + N + col] = X[(long long)row * a.st_X.ld + col] - acc * kx;
-        }
-        return;
-    }
-    o.Cout[(long long)row * a.Cout.ld + col] = o.pre ? a.alpha * acc : zgemm_epilogue(a, o.Cin, o.rs, o.cs, row, col, acc, pl);
 }
 KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc, const zgemm_poly& pl) {
     cd v = a.alpha * acc;
@@ -150,8 +113,7 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
                 cd av = a.transA ? A[(long long)k * a.A.ld + i] : A[(long long)i * a.A.ld + k];
                 cfma(acc, av, B[(long long)k * a.B.ld + j]);
             }
-            if (zgemm_preload(a)) acc = acc + a.alpha * zgemm_addend(a, b, Cin, i, j, pl);      // same arithmetic as the preloaded accumulators
-            zgemm_store(a, b, zgemm_out{Cin, Cout, rs, cs, zgemm_preload(a)}, i, j, acc, pl);
+            Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc, pl);
         }
 }
 
@@ -253,7 +215,7 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int col = n0 + t * 8 + 2 * lk + h;
-                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, b, Cin0, row, col, pl); cr[t][h] = v.x; ci[t][h] = v.y; }
+                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, Cin0, row, col, pl); cr[t][h] = v.x; ci[t][h] = v.y; }
                 }
             }
         }
@@ -304,7 +266,7 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
                     for (int h = 0; h < 2; ++h) {
                         int col = n0 + t * 8 + 2 * lk + h;
                         if (col < a.N)
-                            zgemm_store(a, b, zgemm_out{Cin, Cout, rs, cs, pre}, row, col, mk(cr[t][h], ci[t][h]), pl);
+                            Cout[(long long)row * a.Cout.ld + col] = pre ? a.alpha * mk(cr[t][h], ci[t][h]) : zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]), pl);
                     }
                 }
             }
@@ -417,7 +379,7 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int col = n0 + tl * 8 + 2 * lk + h;
-                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, b, Cin0, row, col, pl); cr[j][h] = v.x; ci[j][h] = v.y; }
+                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, Cin0, row, col, pl); cr[j][h] = v.x; ci[j][h] = v.y; }
                 }
             }
         }
@@ -462,7 +424,7 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
             for (int h = 0; h < 2; ++h) {
                 const int col = n0 + tl * 8 + 2 * lk + h;
                 if (row < a.M && col < a.N)
-                    zgemm_store(a, b, zgemm_out{Cin, Cout, rs, cs, pre}, row, col, mk(cr[j][h], ci[j][h]), pl);
+                    Cout[(long long)row * a.Cout.ld + col] = pre ? a.alpha * mk(cr[j][h], ci[j][h]) : zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]), pl);
             }
         }
     }
