@@ -387,7 +387,12 @@ static DblShape dbl_shape(double kappa, double depth, double theta_slice) {
     d.t = t;
     if (d.t < 3) d.t = 3;
     int best = 2; long long bc = 1 << 30;
-    for (int q = 2; q <= KH_DBL_QMAX; ++q) { const long long c = (q - 1) + 2LL * ((d.t + q - 1) / q - 1); if (c < bc) { bc = c; best = q; } }
+    for (int q = 2; q <= KH_DBL_QMAX; ++q) {
+        const int J = (d.t + q - 1) / q;
+        if (J > KH_DBL_JMAX && q > 6) continue;          // the block-by-block fallback keeps slabs 8, 9 for the current block
+        const long long c = (q - 1) + 2LL * (J - 1);
+        if (c < bc) { bc = c; best = q; }
+    }
     d.q = best;
     return d;
 }
@@ -423,19 +428,10 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
         a.out[0] = S(dst0); a.out[1] = S(dst1);
         return kh_launch<dbl_lincomb_args, dbl_lincomb_body>(dim3(Bc, 4), 256, 0, st, a, "dbl_lincomb");
     };
-    // the block polynomial of step j is added in the GEMM's epilogue (zgemm_args::poly_*): no separate pass over the powers
-    auto poly = [&](zgemm_args& g, int j) {
-        g.poly_q = q; g.poly_k0 = k0; g.poly_hx = hx;
-        for (int i = 1; i < q; ++i) g.poly_pw[i] = S(1 + i);
-        for (int i = 0; i < q; ++i) {
-            const int k = j * q + i;
-            if (k < sh.t) { g.poly_coef[0][i] = 1.0 / dbl_factorial(2 * k + 1); g.poly_xpow[0][i] = 2 * k + 1; }
-            if (k < sh.t - 1) { g.poly_coef[1][i] = 1.0 / dbl_factorial(2 * k + 2); g.poly_xpow[1][i] = 2 * k + 2; }
-        }
-    };
     // slabs: 0 P, 1 Q, 1 + i Omega^(2i) (i <= q <= 8), (10, 11) / (12, 13) ping-pong pairs, 14..16 work space of the inverse
     int cur = 10, oth = 12;                                                      // (Sc, Dc) pair: slabs cur, cur + 1
-    if (J <= KH_DBL_JMAX && xtra) {
+    const char* stepwise = getenv("KH_DBL_STEPWISE");               // test switch: exercise the block-by-block path on short series too
+    if (J <= KH_DBL_JMAX && xtra && !(stepwise && stepwise[0] == '1' && q <= 6)) {
         // every block polynomial in one pass over the powers (top block -> the Horner start, block j < J - 1 -> extra slabs 2j, 2j + 1)
         dbl_blocks_args a;
         memset(&a, 0, sizeof(a));
@@ -450,11 +446,12 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
             KH_TRY(zgemm_launch(st, 2 * Bc, g));
             const int t = cur; cur = oth; oth = t;
         }
-    } else {                                                                     // very long series: block by block
+    } else {                                                                     // very long series: one block per Horner step (slabs 8, 9 hold it: q <= 6 here)
         KH_TRY(blocks(J - 1, cur, cur + 1));
         for (int j = J - 2; j >= 0; --j) {
+            KH_TRY(blocks(j, 8, 9));
             zgemm_args g = zgemm_make(n, n, n, pair(cur, cur + 1), both(1 + q), pair(oth, oth + 1));
-            poly(g, j);
+            g.Cin = pair(8, 9); g.beta = 1.0;
             KH_TRY(zgemm_launch(st, 2 * Bc, g));
             const int t = cur; cur = oth; oth = t;
         }

@@ -22,56 +22,15 @@ struct zgemm_args {
     const cd* colscale;         // optional, length N per batch group
     long long cs_stride; int cs_group;
     int cs_divide;              // 1: divide by colscale instead of multiplying
-    // Optional polynomial addend (Horner steps of the doubling method, kh_api.cu solve_patterned_dbl):  the product gets
-    //   + sum_{i < poly_q} poly_coef[h][i] x^poly_xpow[h][i] Om^i,   x = poly_k0[b / 2] * poly_hx,  h = b % 2
-    // added in the epilogue, Om^i = poly_pw[i] + (b / 2) M N (Om^0 = I): the batch is a PAIR batch, both series share the powers.
-    int poly_q;
-    const cd* poly_pw[8];
-    const double* poly_k0; double poly_hx;
-    double poly_coef[2][8]; int poly_xpow[2][8];
 };
-struct zgemm_poly { double cf[8]; long long off; };
-KH_DEV void zgemm_poly_prepare(const zgemm_args& a, int b, zgemm_poly& pl) {
-    if (a.poly_q <= 0) return;
-    const int h = b & 1;
-    const double x = a.poly_k0[b >> 1] * a.poly_hx;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const double cc = h ? a.poly_coef[1][i] : a.poly_coef[0][i]; const int xp = h ? a.poly_xpow[1][i] : a.poly_xpow[0][i];
-        pl.cf[i] = (i < a.poly_q && cc != 0.0) ? cc * pow(x, (double)xp) : 0.0; }
-    pl.off = (long long)(b >> 1) * a.M * a.N;
-}
 
 #define ZG_BK 16
 #define ZG_LDA 20
 #define ZG_EMU_TILE 64
 
-// The additive part  beta Cin + poly + diag I  of the output.  With alpha == 1 and no row / column scaling the kernels load it
-// into the accumulators BEFORE the K loop (C += A B on top of it): the loads overlap the pipeline prologue instead of stalling
-// the epilogue, where every warp waited on them with nothing else to issue (a Cin epilogue cost 10 %, a polynomial one 50 %).
-KH_DEV bool zgemm_preload(const zgemm_args& a) {
-    return (a.alpha == 1.0 || a.alpha == -1.0) && !a.rowscale && !a.colscale && (a.Cin.p != nullptr || a.poly_q > 0);      // alpha = -1: start from -addend, negate at the end
-}
-KH_DEV cd zgemm_addend(const zgemm_args& a, const cd* cin, int row, int col, const zgemm_poly& pl) {
-    cd v = mk(0.0, 0.0);
-    if (cin) v = a.beta * cin[(long long)row * a.Cin.ld + col];
-    if (a.poly_q > 0) {
-        const long long e = pl.off + (long long)row * a.N + col;
-        if (row == col) v.x += pl.cf[0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) if (i < a.poly_q) v = v + pl.cf[i] * a.poly_pw[i][e];
-    }
-    if (a.diag != 0.0 && row == col) v.x += a.diag;
-    return v;
-}
-KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc, const zgemm_poly& pl) {
+KH_DEV cd zgemm_epilogue(const zgemm_args& a, const cd* cin, const cd* rs, const cd* cs, int row, int col, cd acc) {
     cd v = a.alpha * acc;
     if (cin) v = v + a.beta * cin[(long long)row * a.Cin.ld + col];
-    if (a.poly_q > 0) {
-        const long long e = pl.off + (long long)row * a.N + col;
-        if (row == col) v.x += pl.cf[0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) if (i < a.poly_q) v = v + pl.cf[i] * a.poly_pw[i][e];
-    }
     if (a.diag != 0.0 && row == col) v.x += a.diag;
     if (rs) v = rs[row] * v;
     if (cs) v = a.cs_divide ? v / cs[col] : v * cs[col];
@@ -105,7 +64,6 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
     cd* Cout = mat_ptr(a.Cout, b);
     const cd* rs = a.rowscale ? a.rowscale + (long long)(b / a.rs_group) * a.rs_stride : (const cd*)0;
     const cd* cs = a.colscale ? a.colscale + (long long)(b / a.cs_group) * a.cs_stride : (const cd*)0;
-    zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
     for (int i = m0; i < m0 + BM && i < a.M; ++i)
         for (int j = n0; j < n0 + BN && j < a.N; ++j) {
             cd acc = mk(0, 0);
@@ -113,7 +71,7 @@ KH_DEV void zgemm_body_t(const Cta& c, const zgemm_args& a) {
                 cd av = a.transA ? A[(long long)k * a.A.ld + i] : A[(long long)i * a.A.ld + k];
                 cfma(acc, av, B[(long long)k * a.B.ld + j]);
             }
-            Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc, pl);
+            Cout[(long long)i * a.Cout.ld + j] = zgemm_epilogue(a, Cin, rs, cs, i, j, acc);
         }
 }
 
@@ -204,22 +162,6 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
 
 #pragma unroll
     for (int s = 0; s < ST - 1; ++s) { if (s < nk) stage(s, s); kh_cp_async_commit(); }
-    const bool pre = zgemm_preload(a);
-    zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
-    if (pre && warp_active) {                    // accumulators start from the additive part (see zgemm_preload)
-        const cd* Cin0 = mat_ptr(a.Cin, b);
-        const int row = m0 + warp * 8 + lr;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            if (t < nt) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col = n0 + t * 8 + 2 * lk + h;
-                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, Cin0, row, col, pl); cr[t][h] = v.x; ci[t][h] = v.y; }
-                }
-            }
-        }
-    }
     int buf = 0, nbuf = ST - 1;
     for (int kc = 0; kc < nk; ++kc) {
         kh_cp_async_wait<ST - 2>();
@@ -266,7 +208,7 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
                     for (int h = 0; h < 2; ++h) {
                         int col = n0 + t * 8 + 2 * lk + h;
                         if (col < a.N)
-                            Cout[(long long)row * a.Cout.ld + col] = pre ? a.alpha * mk(cr[t][h], ci[t][h]) : zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]), pl);
+                            Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[t][h], ci[t][h]));
                     }
                 }
             }
@@ -367,23 +309,6 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
     for (int t = 0; t < MAXU; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
 #pragma unroll
     for (int s = 0; s < ST - 1; ++s) { if (s < nk && stager) stage(s, s); kh_cp_async_commit(); }
-    const bool pre = zgemm_preload(a);
-    zgemm_poly pl; zgemm_poly_prepare(a, b, pl);
-    if (pre) {                                   // accumulators start from the additive part (loads in flight during the prologue)
-        const cd* Cin0 = mat_ptr(a.Cin, b);
-#pragma unroll
-        for (int j = 0; j < MAXU; ++j) {
-            if (j < cnt) {
-                const int u = ustart + j, strip = u / nt, tl = u - strip * nt;
-                const int row = m0 + strip * 8 + lr;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col = n0 + tl * 8 + 2 * lk + h;
-                    if (row < a.M && col < a.N) { const cd v = a.alpha * zgemm_addend(a, Cin0, row, col, pl); cr[j][h] = v.x; ci[j][h] = v.y; }
-                }
-            }
-        }
-    }
     int buf = 0, nbuf = ST - 1;
     for (int kc = 0; kc < nk; ++kc) {
         kh_cp_async_wait<ST - 2>();
@@ -424,7 +349,7 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
             for (int h = 0; h < 2; ++h) {
                 const int col = n0 + tl * 8 + 2 * lk + h;
                 if (row < a.M && col < a.N)
-                    Cout[(long long)row * a.Cout.ld + col] = pre ? a.alpha * mk(cr[j][h], ci[j][h]) : zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]), pl);
+                    Cout[(long long)row * a.Cout.ld + col] = zgemm_epilogue(a, Cin, rs, cs, row, col, mk(cr[j][h], ci[j][h]));
             }
         }
     }

@@ -433,6 +433,20 @@ def test_doubling_matches_eig_on_deep_and_lossy_layers(backend):
         rt_close(np.stack([R, T], 1), ref)
         out[method] = S
     rt_close(out["doubling"], out["eig"], 1e-9)
+    # other slice angles (more / fewer self star products) and the block-by-block Horner path of very long series
+    import os
+    keep = eng.doubling_theta
+    try:
+        for theta, stepwise in ((2.0, "0"), (5.0, "1"), (12.0, "0")):
+            eng.doubling_theta = theta
+            os.environ["KH_DBL_STEPWISE"] = stepwise
+            cl = build_crystal(st, eng, method="doubling")
+            R, T, S = sweep_sources(cl, srcs, return_S=True)
+            rt_close(np.stack([R, T], 1), ref)
+            rt_close(S, out["eig"], 1e-9)
+    finally:
+        eng.doubling_theta = keep
+        os.environ.pop("KH_DBL_STEPWISE", None)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
