@@ -224,6 +224,49 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
 #define KH_ATOMIC_OR(ptr, v) atomicOr((ptr), (v))
 #endif
 
+// ------------------------------------------------------------------ TMA bulk copies (global -> shared, 1-D)
+// Matrices that a CTA keeps resident in shared memory are staged row by row with cp.async.bulk (the TMA engine moves each row,
+// completion is counted in bytes on an mbarrier) instead of per-thread loads + stores: no registers, no address arithmetic, and
+// the threads are free for the padding / setup work that overlaps the copy.  Rows are 16-byte aligned multiples of 16 bytes
+// (complex128), which is all the 1-D form needs -- no tensor map.
+#ifndef KH_HOST_EMU
+__device__ __forceinline__ unsigned kh_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kh_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kh_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void kh_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(kh_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void kh_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(kh_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(kh_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void kh_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(kh_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+#endif
+// Stages nrows rows of row_cd complex numbers (global, leading dimension ld_src) into shared memory (leading dimension ld_dst).
+// Collective over the CTA; `bar` is 8 bytes of shared memory reserved for this call, used once (phase 0).  Ends with a barrier.
+KH_DEV void kh_stage_rows(const Cta& c, cd* dst, int ld_dst, const cd* src, long long ld_src, int nrows, int row_cd, unsigned long long* bar) {
+#ifdef KH_HOST_EMU
+    (void)bar;
+    for (int i = c.tid; i < nrows; i += c.nthr)
+        for (int j = 0; j < row_cd; ++j) dst[(long long)i * ld_dst + j] = src[(long long)i * ld_src + j];
+#else
+    if (c.tid == 0) kh_mbar_init(bar, 1);
+    __syncthreads();
+    if (c.tid == 0) kh_mbar_expect_tx(bar, (unsigned)nrows * (unsigned)row_cd * 16u);
+    for (int i = c.tid; i < nrows; i += c.nthr) kh_bulk_g2s(dst + (long long)i * ld_dst, src + (long long)i * ld_src, (unsigned)row_cd * 16u, bar);
+    kh_mbar_wait(bar, 0);
+    __syncthreads();
+#endif
+}
+
 // Largest dynamic shared memory a CTA may opt in to on sm_100 (227 KB).
 #define KH_SMEM_MAX (227 * 1024)
 

@@ -40,6 +40,9 @@ struct zgeev_args {
     // kernel only needs the leading na x na block: later phases run with a smaller shared-memory footprint and more
     // CTAs per SM.  A phase starts from istate[b] (phase > 0) and stops once iact < iact_stop.
     int na = 0, iact_stop = 0, phase = 0; int* istate = nullptr;
+    // flag protocol of the relay sweep: a consumer that polls a progress counter more than spin_cap times gives up and the
+    // matrix is reported as failed (info = n + 1).  stress (tests only): random pauses after every publication / before every poll.
+    int spin_cap = 1 << 26, stress = 0;
 };
 
 #define KH_ENOMEM_ZGEEV (-2)
@@ -60,6 +63,10 @@ __device__ __forceinline__ double kh_lds_d(unsigned a) { double v; asm volatile(
 __device__ __forceinline__ void kh_sts_cd(unsigned a, cd v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v.x), "d"(v.y) : "memory"); }
 __device__ __forceinline__ void kh_sts_d(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void kh_st_release_saddr(unsigned a, int v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// acquire load of a progress counter: everything the producer wrote before its release store is visible to the loads that follow
+__device__ __forceinline__ int kh_ld_acquire_saddr(unsigned a) { int v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+// test switch (KH_QR_STRESS): pseudo-random pauses that shake the relative timing of producers and consumers
+__device__ __forceinline__ void kh_stress_pause(int on, int salt) { if (on) __nanosleep((((unsigned)salt * 2654435761u) >> 23) & 0x1ff); }
 #endif
 // one entry of the rotation queue of a sweep (shared memory): G(t) = (c, s), and the corner entries after R(t)
 struct alignas(16) kh_qrot { double c, pad; cd s, r, diag, nsub; };     // r = H[t][t-1], diag = H[t][t], nsub = H[t+1][t]
@@ -127,9 +134,8 @@ KH_DEV void zhessz_body(const Cta& c, const zgeev_args& a) {
     cd* spart = (cd*)scratch;           // [<= 32] per-warp partial sums of s = v^H p
     cd* tauout = a.tau + (long long)b * a.tau_stride;
 #define HH(i, j) Hs[(i) * ld + (j)]
-    for (int e = c.tid; e < n * n; e += c.nthr) { int i = e / n, j = e - i * n; HH(i, j) = A[(long long)i * a.A.ld + j]; }
     for (int i = c.tid; i < n; i += c.nthr) { dsc[i] = 1.0; tauout[i] = mk(0.0, 0.0); }
-    c.sync();
+    kh_stage_rows(c, Hs, ld, A, a.A.ld, n, n, (unsigned long long*)(scratch + 190));     // the matrix comes in by TMA bulk copies, one row each
     // ---- balancing (Jacobi-style sweeps of the EISPACK balanc criterion; powers of two, so exact)
     for (int sweep = 0; sweep < 12; ++sweep) {
         double changed = 0.0;
@@ -660,9 +666,9 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     // ---- follower mode: rotations generated by the warps to the left
                     while (t < tgen && t <= tlast) {
                         const int wg = (t - l) >> 5;
-                        int avail = prg[wg];
-                        if (avail <= t) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } continue; }
-                        __threadfence_block();
+                        kh_stress_pause(a.stress, t + 7 * w + b);
+                        const int avail = kh_ld_acquire_saddr(kh_saddr(ctl + 4 + wg));
+                        if (avail <= t) { if (++spins > a.spin_cap) { ctl[2] = 1; break; } continue; }
                         int tend = l + 32 * (wg + 1);                   // generation range of warp wg ends here
                         if (tend > avail) tend = avail;
                         if (tend > tgen) tend = tgen;
@@ -712,6 +718,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                             }
                             __syncwarp();
                             if (lane == 0) kh_st_release_saddr(sP, t + 1);
+                            kh_stress_pause(a.stress, 3 * t + b);
                             G = Gn; sub = nextsub; hd = hdn; h1 = h1n; a_t = a_t1; rs -= 1;
                             aq += (unsigned)sizeof(kh_qrot); lc = (lc + 1) & 31;
                         }
@@ -736,9 +743,9 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                     int t = rmin, spins = 0;
                     while (t < iact) {
                         const int wq = (t + 1 - l) >> 5;               // owner of column t+1 must have applied R(<= t) to it
-                        int avail = prg[wq];
-                        if (avail <= t) { if (++spins > (1 << 26)) { ctl[2] = 1; break; } continue; }
-                        __threadfence_block();
+                        kh_stress_pause(a.stress, t + 13 * warp + b);
+                        const int avail = kh_ld_acquire_saddr(kh_saddr(ctl + 4 + wq));
+                        if (avail <= t) { if (++spins > a.spin_cap) { ctl[2] = 1; break; } continue; }
                         int tend = l + 32 * (wq + 1) - 1;
                         if (tend > avail) tend = avail;
                         if (tend > iact) tend = iact;
@@ -945,9 +952,8 @@ KH_DEV void zrot_apply_body(const Cta& c, const zrot_args& a) {
     double* rb = (double*)(KH_SMEM(c) + (size_t)n * cw * sizeof(cd));
     int* sws = (int*)(KH_SMEM(c) + (size_t)n * cw * sizeof(cd) + (size_t)8 * CH * sizeof(double));
     if (nsw == 0 || cols <= 0) return;                               // uniform
-    for (int e = c.tid; e < n * cols; e += c.nthr) { const int k = e / cols, i = e - k * cols; Ms[k * cw + i] = Mg[(long long)k * ldm + i]; }
     for (int e = c.tid; e < 2 * nsw; e += c.nthr) sws[e] = swg[e];
-    c.sync();
+    kh_stage_rows(c, Ms, cw, Mg, ldm, n, cols, (unsigned long long*)(sws + 2 * a.sw_cap));      // strip rows by TMA bulk copies
     const int nrot = sws[2 * nsw - 1] + ((sws[2 * nsw - 2] >> 16) - (sws[2 * nsw - 2] & 0xffff));
     // chunk [s0, s1): whole sweeps, at most CH rotations (every sweep has fewer than n <= CH rotations)
     auto chunk_end = [&](int s0) {
@@ -1045,7 +1051,7 @@ static inline int zrot_chunk(int n, int sw_cap, int cw) {             // rotatio
     long long ch = room / (2 * 4 * (long long)sizeof(double));
     return ch > 4096 ? 4096 : (int)ch;
 }
-static inline size_t zrot_smem_bytes(int n, int sw_cap, int chunk, int cw) { return (size_t)n * cw * sizeof(cd) + (size_t)8 * chunk * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }
+static inline size_t zrot_smem_bytes(int n, int sw_cap, int chunk, int cw) { return (size_t)n * cw * sizeof(cd) + (size_t)8 * chunk * sizeof(double) + (size_t)2 * sw_cap * sizeof(int) + 16; }      // (+16: mbarrier of the staging copy)
 // work space (doubles per matrix) the log needs for the given capacities
 static inline long long zgeev_rlog_doubles(int rot_cap, int sw_cap) { return 2LL + sw_cap + 3LL * rot_cap; }
 
@@ -1119,6 +1125,11 @@ static inline int zgeev_launch(kh_stream_t st, int batch, zgeev_args a) {
     else return KH_ENOMEM_ZGEEV;            // beyond shared memory the blocked reduction needs the log work space (kh_zgeev_work_bytes provides it)
     if (e) return e;
     zgeev_args q = a;
+    {   // test switches of the relay sweep's flag protocol (tests/test_parity.py::test_qr_flag_protocol_*)
+        const char* e1 = getenv("KH_QR_SPIN_CAP"); const char* e2 = getenv("KH_QR_STRESS");
+        if (e1 && atoi(e1) > 0) q.spin_cap = atoi(e1);
+        if (e2) q.stress = atoi(e2);
+    }
     q.use_smem = zqr_smem_bytes(n, 1) <= (size_t)KH_SMEM_MAX;
     const int zcw = (q.rlog && q.sw_cap >= 1) ? zrot_strip(n, q.sw_cap) : 0;
     if (!(q.rlog && q.rot_cap >= n && q.sw_cap >= 1 && q.sw_cap < 65536 && n < 65536 && zcw > 0 &&

@@ -256,14 +256,15 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
     cd* R = As + np * lda;                        // [NB][ldr]
     zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][4 warp candidates + old row k]
     int* piv = (int*)(slots + 10);                // [np]
-    for (int i = warp; i < np; i += NW) {            // warp <-> row: coalesced, no index division, 4 loads in flight per lane
-        cd v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int j = lane + 32 * u; v[u] = (i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(i == j ? 1.0 : 0.0, 0.0); }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int j = lane + 32 * u; if (j < np) As[i * lda + j] = v[u]; }
+    unsigned long long* bar = (unsigned long long*)(piv + ((np + 1) & ~1));     // mbarrier of the staging copy
+    // identity padding by the threads while the TMA engine stages the n rows (cp.async.bulk, one row each, kh_stage_rows)
+    {   const int padc = np - n, nbot = padc * np;          // bottom rows n..np-1 in full, then columns n..np-1 of the rows above
+        for (int e = tid; e < nbot + n * padc; e += 32 * NW) {
+            const int i = e < nbot ? n + e / np : (e - nbot) / padc, j = e < nbot ? e % np : n + (e - nbot) % padc;
+            As[i * lda + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        }
     }
-    __syncthreads();
+    kh_stage_rows(c, As, lda, A, a.A.ld, n, n, bar);
     int bad = 0;
     if (warp < 4) zid_panel(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
     __syncthreads();
@@ -305,7 +306,7 @@ __device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a)
 __device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8>(c, a); }
 static inline size_t zinv_dmma_smem(int n) {
     const int np = (n + 7) & ~7;
-    return ((size_t)np * (np + 4) + (size_t)ZID_NB * (np + 2)) * sizeof(cd) + 10 * sizeof(zid_slot) + (size_t)np * 4 + 16;
+    return ((size_t)np * (np + 4) + (size_t)ZID_NB * (np + 2)) * sizeof(cd) + 10 * sizeof(zid_slot) + (size_t)np * 4 + 32;
 }
 #endif
 

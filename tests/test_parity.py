@@ -516,3 +516,55 @@ def test_supercell_large_bases_golden(pp, method):
     rt_close(np.stack([R, T], 1), g["RT"])
     rt_close(S[:, 0, 0, ::9, ::7], g["S11"])
     rt_close(S[:, 1, 0, ::9, ::7], g["S21"])
+
+
+# ----------------------------------------------------------------------------- flag protocol of the QR relay sweep (GPU only)
+@pytest.mark.gpu
+def test_qr_flag_protocol_under_timing_stress():
+    """The packed QR sweep hands rotations from warp to warp through release-stored / acquire-loaded progress counters in
+    shared memory (kh_zgeev.cuh, relay sweep) -- a pattern racecheck cannot model.  Litmus-style check: random pauses after
+    every publication and before every poll (KH_QR_STRESS) must not change ANY bit of the eigenvalues or eigenvectors of
+    20 000 matrices (every sweep of every matrix exercises the hand-over ~n times), at the sizes that run 2, 4 and 8 CTAs
+    per SM, and the residuals stay at rounding level."""
+    import os
+    eng = engine("cuda")
+    rng = np.random.default_rng(21)
+    for n, batch in ((98, 20000), (50, 20000), (18, 4000)):
+        A = rng.standard_normal((batch, n, n)) + 1j * rng.standard_normal((batch, n, n))
+        A[::3] *= np.logspace(-2, 2, n)[None, None, :]
+        w0, W0, info0 = eng.zgeev(A)
+        w0, W0 = w0.cpu().numpy(), W0.cpu().numpy()
+        assert int(info0.max().item()) == 0
+        os.environ["KH_QR_STRESS"] = "1"
+        try:
+            w1, W1, info1 = eng.zgeev(A)
+            w1, W1 = w1.cpu().numpy(), W1.cpu().numpy()
+        finally:
+            os.environ.pop("KH_QR_STRESS", None)
+        assert int(info1.max().item()) == 0
+        assert np.array_equal(w0, w1) and np.array_equal(W0, W1), n
+        for b in (0, batch // 2, batch - 1):
+            res = np.abs(A[b] @ W0[b] - W0[b] * w0[b][None, :]).max()
+            assert res <= 1e-11 * np.abs(A[b]).max() * np.abs(W0[b]).max(), res
+
+
+@pytest.mark.gpu
+def test_qr_flag_protocol_bail_out_is_reported():
+    """A consumer that polls a progress counter more than spin_cap times gives up: with an absurdly small cap (and pauses that
+    make producers late) the kernel must terminate and flag the matrices (info = n + 1) instead of hanging or returning garbage
+    silently; with the default cap the same input converges."""
+    import os
+    eng = engine("cuda")
+    rng = np.random.default_rng(22)
+    A = rng.standard_normal((512, 98, 98)) + 1j * rng.standard_normal((512, 98, 98))
+    os.environ["KH_QR_SPIN_CAP"] = "1"
+    os.environ["KH_QR_STRESS"] = "1"
+    try:
+        _, _, info = eng.zgeev(A)
+    finally:
+        os.environ.pop("KH_QR_SPIN_CAP", None)
+        os.environ.pop("KH_QR_STRESS", None)
+    info = info.cpu().numpy()
+    assert (info == 99).any() and set(np.unique(info)) <= {0, 99}
+    _, _, info = eng.zgeev(A)
+    assert int(info.max().item()) == 0
