@@ -767,6 +767,7 @@ KH_DEV void zqr_body_t(const Cta& c, const zgeev_args& a) {
                 }
             }
             __syncthreads();
+            if (ctl[2] != 0) { fail = nfull + 1; break; }      // a consumer gave up waiting (spin_cap): the sweep is incomplete, stop here (uniform: read after the barrier)
         } else
 #endif
         if (!PACKED) {
