@@ -195,7 +195,7 @@ class Crystal:
 
     def _geometry_key(self, want_fields):
         key = [want_fields, id(self.expansion), complex(self.epsi), complex(self.epse), tuple(self.global_stacking)]
-        for name in self.global_stacking:
+        for name in dict.fromkeys(self.global_stacking):            # each distinct layer once
             layer = self.layers[name]
             base = layer.base if isinstance(layer, EL) else layer
             key.append((name, id(layer), base.content_key()))
@@ -268,7 +268,7 @@ class Crystal:
 
     def poynting_flux_end(self, only_total=True):
         assert self.solved, "Call solve first"
-        plan = self._get_plan(self._plan_key[0] if self._plan_key else False)
+        plan = self._plan if self._plan is not None else self._get_plan(False)      # the plan the last solve() used
         pol = [(self.source.te, self.source.tm)]
         out = self.engine.flux(plan, self._S_device(), [self.source.wavelength], [self.kp], pol, want_orders=not only_total)
         if only_total:

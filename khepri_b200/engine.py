@@ -135,7 +135,8 @@ class Engine:
         arr = np.ascontiguousarray(a)
         t = torch.from_numpy(arr)
         if self.device.type == "cuda":
-            t = t.pin_memory().to(self.device, non_blocking=True)
+            # large inputs go through pinned memory (asynchronous DMA); for a few KB the page-locking costs more than the copy
+            t = t.pin_memory().to(self.device, non_blocking=True) if arr.nbytes >= (1 << 16) else t.to(self.device)
         return t.to(dtype).contiguous()
 
     # ------------------------------------------------------------------ convolution matrix
@@ -305,11 +306,14 @@ class Engine:
         lib = self.lib
         want = int(chunk) if chunk else B
         need = lib.kh_solve_workspace_bytes(plan.handle, want, flags)
-        cap = self._cap()
-        one = lib.kh_solve_workspace_bytes(plan.handle, 1, flags)
-        if one > cap:
-            raise KhepriError(f"one solve needs {one} bytes of workspace, cap is {cap}")
-        ws = self.workspace(min(need, cap) if not chunk else need)
+        if self._ws is not None and self._ws.numel() >= need:
+            ws = self._ws                          # (no cudaMemGetInfo on the hot path: 1.5 ms per call, most of a scalar solve)
+        else:
+            cap = self._cap()
+            one = lib.kh_solve_workspace_bytes(plan.handle, 1, flags)
+            if one > cap:
+                raise KhepriError(f"one solve needs {one} bytes of workspace, cap is {cap}")
+            ws = self.workspace(min(need, cap) if not chunk else need)
         ws_bytes = min(ws.numel(), need) if chunk else ws.numel()
         check(lib, lib.kh_solve_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(pol_d), C.byref(out), _ptr(ws), ws_bytes, self.stream()),
               "kh_solve_batch")
