@@ -225,7 +225,7 @@ class Crystal:
     def solve(self):
         assert self.source_defined, "Call set_source before solving."
         logging.debug("Solving each required layer")
-        want_fields = self._wants_fields() and not any(isinstance(self.layers[n], EL) for n in self.global_stacking)
+        want_fields = self._wants_fields()
         plan = self._get_plan(want_fields)
         res = self.engine.solve_batch(plan, [self.source.wavelength], [self.kp], want_S=True, want_flux=False, want_fields=want_fields, method=self.method)
         self._check_info(res["info"])
@@ -246,7 +246,7 @@ class Crystal:
             W, V, L = res["W"][0].cpu().numpy(), res["V"][0].cpu().numpy(), res["L"][0].cpu().numpy()
             for idx, name in enumerate(plan.names):
                 layer = self.layers.get(name) if isinstance(name, str) else None
-                if layer is not None and layer.fields and not isinstance(layer, EL):
+                if layer is not None and layer.fields:
                     layer.W, layer.V, layer.L = W[idx], V[idx], L[idx]
         else:
             self.stacking_matrices, self.stacking_reverse_matrices = [], []

@@ -507,6 +507,7 @@ struct ChunkBufs {
     int* info;
     // extended-layer scratch (small base problems at Nb harmonics, Bc*Nb sub-solves)
     cd *eKx, *eKy; double* ek0; cd* epool; LayerVec evec; cd* eS; cd* ebd; double* ewl; cd* ekp;
+    cd *eW, *eV, *eL, *eVbd, *eLbd;      // retained eigenspaces of the shifted base solves (fields only)
 };
 
 static bool layer_is_bd(const kh_plan* p, int i) {
@@ -549,6 +550,8 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
         cb.evec.info_eig = b.get<int>(Be); cb.evec.info_inv = b.get<int>(3 * Be);
         cb.eS = b.get<cd>(Be * 2 * nb2); cb.ebd = b.get<cd>(Be * 16 * Nb);
         cb.ewl = b.get<double>(Be); cb.ekp = b.get<cd>(Be * 2);
+        cb.eW = cb.eV = cb.eL = cb.eVbd = cb.eLbd = nullptr;
+        if (flags & KH_WANT_FIELDS) { cb.eW = b.get<cd>(Be * nb2); cb.eV = b.get<cd>(Be * nb2); cb.eL = b.get<cd>(Be * nb); cb.eVbd = b.get<cd>(Be * 4 * Nb); cb.eLbd = b.get<cd>(Be * Nb); }
     }
 }
 
@@ -656,8 +659,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
                 }
                 S[i] = sref_sym(cb.layerS[i], n);
             } else {
-                if (want_fields) return fail(KH_EINVAL, "kh_solve_batch: field outputs are not available for extended layers");
-                KH_TRY(solve_extended(st, p, Bc, (int)i, wl, kp, cb, info_out));
+                KH_TRY(solve_extended(st, p, Bc, (int)i, wl, kp, cb, info_out, want_fields ? out : nullptr, b0));
                 S[i] = sref_dense(cb.layerS[i], n);
             }
         }

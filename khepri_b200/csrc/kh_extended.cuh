@@ -46,7 +46,42 @@ KH_DEV void ext_scatter_body(const Cta& c, const ext_scatter_args& a) {
     }
 }
 
-static int solve_extended(kh_stream_t st, const kh_plan* p, int Bc, int li, const double* wl, const cd* kp, ChunkBufs& cb, int* info_out) {
+// Retained eigenspace of an extended layer (extension.py:100-110): W, V and lambda of the N_b shifted base solves scattered into
+// the joint basis with the same index map as the S-matrix blocks (_joint_subspace, extension.py:10-38); zero between shifts.
+// src_kind 0: uniform base (W = I, V as BD table [Be][4][Nb], lambda [Be][Nb]); 1: pixmap base (dense [Be][nb][nb], lambda [Be][nb]).
+struct ext_keep_args { int Bc, Nb, mode, src_kind, nL, li; const cd* Wsub; const cd* Vsub; const cd* Lsub; cd* Wout; cd* Vout; cd* Lout; };
+KH_DEV void ext_keep_body(const Cta& c, const ext_keep_args& a) {
+    const int Nb = a.Nb, nb = 2 * Nb, NN = Nb * Nb, n = 2 * NN, b = c.bx, which = c.by;      // which: 0 -> W, 1 -> V
+    const long long o = (long long)b * a.nL + a.li;
+    cd* d = (which ? a.Vout : a.Wout) + o * n * n;
+    for (int e = c.tid; e < n * n; e += c.nthr) {
+        int row = e / n, col = e - row * n;
+        int ha = row >= NN, hb = col >= NN;
+        int jr = row - ha * NN, jc = col - hb * NN;
+        int sr, r1, sc, r2;
+        if (a.mode == 0) { sr = jr / Nb; r1 = jr % Nb; sc = jc / Nb; r2 = jc % Nb; }
+        else { r1 = jr / Nb; sr = jr % Nb; r2 = jc / Nb; sc = jc % Nb; }
+        cd v = mk(0, 0);
+        if (sr == sc) {
+            const long long sub = (long long)b * Nb + sr;
+            if (a.src_kind == 1) v = (which ? a.Vsub : a.Wsub)[sub * nb * nb + (long long)(ha * Nb + r1) * nb + hb * Nb + r2];
+            else if (r1 == r2) v = which ? a.Vsub[sub * 4 * Nb + (ha * 2 + hb) * Nb + r1] : mk(ha == hb ? 1.0 : 0.0, 0.0);
+        }
+        d[e] = v;
+    }
+    if (which == 0) {
+        cd* Lo = a.Lout + o * n;
+        for (int i = c.tid; i < n; i += c.nthr) {
+            const int ha = i >= NN, jr = i - ha * NN;
+            const int sr = a.mode == 0 ? jr / Nb : jr % Nb, r1 = a.mode == 0 ? jr % Nb : jr / Nb;
+            const long long sub = (long long)b * Nb + sr;
+            Lo[i] = a.src_kind == 1 ? a.Lsub[sub * nb + ha * Nb + r1] : a.Lsub[sub * Nb + r1];
+        }
+    }
+}
+
+static int solve_extended(kh_stream_t st, const kh_plan* p, int Bc, int li, const double* wl, const cd* kp, ChunkBufs& cb, int* info_out,
+                          const kh_outputs* keep = nullptr, int b0 = 0) {
     const kh_layer_desc& L = p->layers[li];
     const kh_layer_desc& base = p->layers[L.ext_base];
     const int Nb = p->Nb, Be = Bc * Nb;
@@ -62,17 +97,24 @@ static int solve_extended(kh_stream_t st, const kh_plan* p, int Bc, int li, cons
     int src_kind;
     const cd* src;
     if (base.kind == KH_LAYER_UNIFORM) {
-        bd_layer_args a{Be, Nb, KH_LAYER_UNIFORM, mk(base.eps_re, base.eps_im), base.depth, cb.eKx, cb.eKy, cb.ek0, cb.ebd, nullptr, nullptr};
+        bd_layer_args a{Be, Nb, KH_LAYER_UNIFORM, mk(base.eps_re, base.eps_im), base.depth, cb.eKx, cb.eKy, cb.ek0, cb.ebd, keep ? cb.eVbd : nullptr, keep ? cb.eLbd : nullptr};
         KH_TRY((kh_launch<bd_layer_args, bd_layer_body>(dim3(Be), 64, 0, st, a)));
         src_kind = 0; src = cb.ebd;
     } else if (base.kind == KH_LAYER_PIXMAP) {
         LayerVec v = cb.evec; v.info_acc = info_out ? info_out : cb.info; v.info_div = Nb;     // sub-solve b * Nb + s reports into solve b
         KH_TRY(solve_patterned(st, Be, Nb, (const cd*)base.C_dev, (const cd*)base.IC_dev, base.depth, cb.eKx, cb.eKy, cb.ek0,
-                               cb.epool, v, cb.eS, nullptr, nullptr, nullptr, 0, 0));
+                               cb.epool, v, cb.eS, keep ? cb.eW : nullptr, keep ? cb.eV : nullptr, keep ? cb.eL : nullptr, (long long)(2 * Nb) * (2 * Nb), 2LL * Nb));
         src_kind = 1; src = cb.eS;
     } else return fail(KH_EINVAL, "extended layer: base must be uniform or pixmap");
     ext_scatter_args a{Bc, Nb, L.ext_mode, src_kind, src, cb.layerS[li]};
     KH_TRY((kh_launch<ext_scatter_args, ext_scatter_body>(dim3(Bc, 4), 256, 0, st, a)));
+    if (keep) {
+        const int nL = (int)p->layers.size();
+        const long long n2 = (long long)p->n * p->n;
+        ext_keep_args k{Bc, Nb, L.ext_mode, src_kind, nL, li, src_kind ? cb.eW : nullptr, src_kind ? cb.eV : cb.eVbd, src_kind ? cb.eL : cb.eLbd,
+                        (cd*)keep->W_dev + (long long)b0 * nL * n2, (cd*)keep->V_dev + (long long)b0 * nL * n2, (cd*)keep->L_dev + (long long)b0 * nL * p->n};
+        KH_TRY((kh_launch<ext_keep_args, ext_keep_body>(dim3(Bc, 2), 256, 0, st, k)));
+    }
     return 0;
 }
 

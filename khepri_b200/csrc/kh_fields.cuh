@@ -281,7 +281,6 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
         return fail(KH_EINVAL, "kh_fields_batch: needs the KH_WANT_FIELDS outputs of kh_solve_batch");
     if (B == 0) return 0;
     const kh_plan* p = plan;
-    if (p->has_ext) return fail(KH_EINVAL, "kh_fields_batch: extended layers are not supported");
     if (p->layers[p->stack[0]].kind != KH_LAYER_HALF_INC) return fail(KH_EINVAL, "kh_fields_batch: the stack must start with the incidence half space");
     if (grid == 1 && p->Q > FLD_QMAX) return fail(KH_EINVAL, "kh_fields_grid_batch: more than 16 harmonics along y; use kh_fields_batch");
     if (ws_bytes < (grid == 1 ? kh_fields_grid_workspace_bytes(p, B, nx, ny, nz) : kh_fields_workspace_bytes(p, B, npts, nz)))
@@ -315,6 +314,7 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
     for (int i = 0; i < nL; ++i) {
         const kh_layer_desc& L = p->layers[i];
         if (L.kind == KH_LAYER_PIXMAP) icp[i] = (const cd*)L.IC_dev;
+        else if (L.kind == KH_LAYER_EXTENDED) ics[i] = mk(1.0, 0.0);            // ExtendedLayer.IC = 1.0 (extension.py:112)
         else ics[i] = crecip(mk(L.eps_re, L.eps_im));
     }
     KH_TRY(kh_h2d(f.zpos, zpos.data(), nz * sizeof(int), st));

@@ -310,8 +310,33 @@ def gen_round2():
         np.savez(os.path.join(OUT, f"supercell{pp}.npz"), RT=np.array(rt), S11=np.array(s11), S21=np.array(s21))
 
 
+def gen_twisted_fields():
+    """Field maps of a twisted bilayer (extended layers with retained eigenspaces, extension.py:100-112; crystal.py:250-253)."""
+    tw = cases.twisted_case()
+    out = {}
+    for tag, it, jf, src in (("a", 1, 1, dict(te=1, tm=0)), ("b", 2, 0, dict(te=0.5, tm=1.0, theta=12.0, phi=20.0))):
+        e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
+        ta = tw["twists"][it]
+        e1.rotate(ta / 2)
+        e2.rotate(-ta / 2)
+        cl = Crystal.from_expansion(e1 + e2)
+        cl.add_layer("upper_layer", Layer.pixmap(e1, tw["pixmap"], tw["depths"][0]), extended=True)
+        cl.add_layer("lower_layer", Layer.pixmap(e2, tw["pixmap"], tw["depths"][2]), extended=True)
+        cl.add_layer("interlayer", Layer.uniform(e1, 1, tw["depths"][1]), extended=True)
+        cl.set_device(["upper_layer", "interlayer", "lower_layer"], [True] * 3)
+        cl.set_source(wavelength=1 / tw["freqs"][jf], **src)
+        cl.solve()
+        X, Y, z = cases.twisted_field_grid()
+        E, H = cl.fields_volume(X, Y, z)
+        out["E_" + tag], out["H_" + tag], out["RT_" + tag] = E, H, np.array(cl.poynting_flux_end())
+    np.savez(os.path.join(OUT, "twisted33_fields.npz"), **out)
+    print("twisted fields done", np.abs(out["E_a"]).max())
+
+
 if __name__ == "__main__":
-    if "--round2" in sys.argv:
+    if "--twisted-fields" in sys.argv:
+        gen_twisted_fields()
+    elif "--round2" in sys.argv:
         gen_round2()
     elif "--fields-fourier" in sys.argv:
         gen_fields_fourier()
@@ -328,3 +353,4 @@ if __name__ == "__main__":
         gen_bands()
         gen_fields_fourier()
         gen_round2()
+        gen_twisted_fields()

@@ -187,7 +187,7 @@ def test_bzi_beam_source_and_k_summed_fields(backend):
     assert np.abs(got - g["fields"]).max() <= 1e-9 * np.abs(g["fields"]).max()
 
 
-def _twisted(eng, tw, ta):
+def _twisted(eng, tw, ta, fields=False):
     from khepri_b200 import Crystal, Expansion, Layer
     e1, e2 = Expansion(tw["pw"]), Expansion(tw["pw"])
     e1.rotate(ta / 2)
@@ -196,7 +196,7 @@ def _twisted(eng, tw, ta):
     cl.add_layer("upper_layer", Layer.pixmap(e1, tw["pixmap"], tw["depths"][0]), extended=True)
     cl.add_layer("lower_layer", Layer.pixmap(e2, tw["pixmap"], tw["depths"][2]), extended=True)
     cl.add_layer("interlayer", Layer.uniform(e1, 1, tw["depths"][1]), extended=True)
-    cl.set_device(["upper_layer", "interlayer", "lower_layer"])
+    cl.set_device(["upper_layer", "interlayer", "lower_layer"], [fields] * 3)
     return cl
 
 
@@ -217,6 +217,26 @@ def test_twisted_bilayer_extended(backend):
     with pytest.raises(NotImplementedError):
         from khepri_b200 import Expansion, ExtendedLayer, Layer
         ExtendedLayer(cl.expansion, Layer.uniform(Expansion((3, 3)), 1, 0.1))     # base not part of the moire expansion
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_twisted_bilayer_field_maps(backend):
+    """Field maps of extended layers (extension.py:100-112: W, V, lambda of the shifted base solves scattered into the joint
+    basis; crystal.py:250-253) against the unmodified reference: pixmap bases and the uniform spacer, normal and oblique source."""
+    eng = engine(backend)
+    g = gold("twisted33_fields")
+    tw = cases.twisted_case()
+    X, Y, z = cases.twisted_field_grid()
+    todo = (("a", 1, 1, dict(te=1, tm=0)), ("b", 2, 0, dict(te=0.5, tm=1.0, theta=12.0, phi=20.0)))
+    for tag, it, jf, src in (todo if backend == "cuda" else todo[:1]):
+        cl = _twisted(eng, tw, tw["twists"][it], fields=True)
+        cl.set_source(wavelength=1 / tw["freqs"][jf], **src)
+        cl.solve()
+        np.testing.assert_allclose(cl.poynting_flux_end(), g["RT_" + tag], rtol=1e-9)
+        E, H = cl.fields_volume(X, Y, z)
+        assert np.abs(E - g["E_" + tag]).max() <= 1e-9 * np.abs(g["E_" + tag]).max()
+        assert np.abs(H - g["H_" + tag]).max() <= 1e-9 * np.abs(g["H_" + tag]).max()
+        assert cl.layers["upper_layer"].W.shape == (162, 162) and cl.layers["interlayer"].L.shape == (162,)
 
 
 # ----------------------------------------------------------------------------- sharding (gloo, world_size 2, CPU)

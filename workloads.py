@@ -169,6 +169,12 @@ def twisted_case(pw=(3, 3), nf=3, nt=3):
     return {"pw": pw, "pixmap": pm, "depths": (0.2, 0.3, 0.2), "freqs": freqs, "twists": twists}
 
 
+def twisted_field_grid():
+    """Small xyz grid through the three layers of the twisted bilayer (depths 0.2 / 0.3 / 0.2)."""
+    X, Y = np.meshgrid(np.linspace(0, 1, 6), np.linspace(0, 1, 5), indexing="xy")
+    return X, Y, np.linspace(0.01, 0.69, 7)
+
+
 def rect_island(center, wh, eps):
     """khepri/draw.py:46-55 (Drawing.rectangle's geometric description)."""
     x, y = center[0] - wh[0] / 2, center[1] - wh[1] / 2
