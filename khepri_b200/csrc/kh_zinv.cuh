@@ -189,25 +189,19 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         }
         const cd pv = win->row[0];
         if (pv.x == 0.0 && pv.y == 0.0 && !bad && k < n) bad = k + 1;
-        cd q[ZID_NB];                                  // the row after this step, already rotated
-        if (tid == k) {
+        // The row after this step, rotated in place (p[j-1] <- column j).  Row k itself (it becomes the scaled pivot row,
+        // row[j] d, and the new last column d) runs through the SAME update as every other row with p = 0 and g = -d:
+        // 0 - (-d) row[j] = d row[j], -g = d.  No divergent branch on the warp that owns row k, no copy of the rotated row.
+        const bool isk = (tid == k);
+        const cd g = isk ? mk(-d.x, -d.y) : p[0] * d;
+        cd nx = isk ? mk(0.0, 0.0) : p[1];
+        cfms(nx, g, win->row[1]);                      // next pivot column first, its reciprocal overlaps the rest of the update
+        dmine = kh_crecip_fast(nx);
+        key = (rowok && tid > k) ? (unsigned long long)__double_as_longlong(cabs1(nx)) + 1ull : 0ull;
+        p[0] = nx;
 #pragma unroll
-            for (int j = 1; j < ZID_NB; ++j) q[j - 1] = win->row[j] * d;
-            q[ZID_NB - 1] = d;
-            key = 0ull;
-        } else {
-            const cd g = p[0] * d;
-            cd nx = p[1];
-            cfms(nx, g, win->row[1]);                  // next pivot column first, its reciprocal overlaps the rest of the update
-            q[0] = nx;
-            dmine = kh_crecip_fast(nx);
-            key = (rowok && tid > k) ? (unsigned long long)__double_as_longlong(cabs1(nx)) + 1ull : 0ull;
-#pragma unroll
-            for (int j = 2; j < ZID_NB; ++j) { cd v = p[j]; cfms(v, g, win->row[j]); q[j - 1] = v; }
-            q[ZID_NB - 1] = -g;
-        }
-#pragma unroll
-        for (int j = 0; j < ZID_NB; ++j) p[j] = q[j];
+        for (int j = 2; j < ZID_NB; ++j) { cd v = isk ? mk(0.0, 0.0) : p[j]; cfms(v, g, win->row[j]); p[j - 1] = v; }
+        p[ZID_NB - 1] = mk(-g.x, -g.y);
     }
     if (rowok) {                                       // p[j] holds panel column (j + nbk) mod NB
 #pragma unroll

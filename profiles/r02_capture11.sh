@@ -1,0 +1,4 @@
+# Round 2, capture 11: GPU tests (extended-layer fields), bench
+set -x
+python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu_c11.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu_c11.log
+python bench.py --no-cpu > gpurun_out/r02_bench_c11_bzi77.json 2> gpurun_out/bench_c11.err; head -c 300 gpurun_out/r02_bench_c11_bzi77.json; echo
