@@ -343,7 +343,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
         copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
     }
-    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_acc, S(8), slab, v.info_div));                     // W^-1 -> 7
+    KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_acc, S(8), 2 * slab, v.info_div));                     // W^-1 -> 7
     {   pv0_args a{Bc, N, S(0), Kx, Ky, S(6)};                                   // P V0 -> 6
         KH_TRY((kh_launch<pv0_args, pv0_body>(dim3(Bc), 256, 0, st, a))); }
     {   zgemm_args g = zgemm_make(n, n, n, M(7), M(6), M(8));                    // V^-1 V0 = L^-1 (W^-1 (P V0)) -> 8
@@ -351,7 +351,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(zgemm_launch(st, Bc, g)); }
     {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
         KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
-    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_acc, S(12), slab, v.info_div));                     // A^-1 -> 1
+    KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_acc, S(12), 2 * slab, v.info_div));                     // A^-1 -> 1
     // E = XB A^-1 (-> 12) carries every appearance of A^-1 in alternative.py:186-193:
     //   T = A - XB A^-1 XB = A - E XB,   X B A^-1 X A - B = E XA - B,   X (A - B A^-1 B) = XA - E B
     // (4 products instead of the 6 of the literal schedule A^-1 [XB|XA|B] followed by XB M1, XB M2, B M3)
@@ -360,7 +360,7 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(gemm(st, Bc, n, M(12), M(9), M(2), -1.0, &A, 1.0));               // T  = A - E XB
         KH_TRY(gemm(st, Bc, n, M(12), M(10), M(15), 1.0, &Bm, -1.0));            // R1 = E XA - B
         KH_TRY(gemm(st, Bc, n, M(12), M(11), M(16), -1.0, &XA, 1.0)); }          // R2 = XA - E B
-    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_acc, S(4), slab, v.info_div));                     // T^-1 -> 3
+    KH_TRY(zinv_launch(st, Bc, n, M(2), M(3), v.info_acc, S(4), 2 * slab, v.info_div));                     // T^-1 -> 3
     // [S11|S12] = T^-1 [R1|R2]
     KH_TRY(gemm(st, 2 * Bc, n, mref(S(3), 0, n, Bc, n2), mref(S(15), slab, n, Bc, n2), mref(Sout, n2, n, Bc, 2 * n2)));
     return 0;
@@ -767,7 +767,12 @@ extern "C" int kh_zgemm_batched(int batch, int M, int N, int K, int transA, cons
     return 0;
 }
 extern "C" size_t kh_zinv_work_bytes(int batch, int n) {
-    return n >= KH_ZINV_BLOCKED_MIN ? (size_t)batch * (size_t)zinv_work_cd(n) * sizeof(cd) : 0;
+    if (n < KH_ZINV_BLOCKED_MIN) return 0;
+    long long w = zinv_work_cd(n);
+#ifndef KH_HOST_EMU
+    if (n <= ZIL_NMAX && zinv_l2_work_cd(n) > w) w = zinv_l2_work_cd(n);      // (enough for the single-launch small-batch variant too)
+#endif
+    return (size_t)batch * (size_t)w * sizeof(cd);
 }
 extern "C" int kh_zinv_batched(int batch, int n, const void* A, void* Ainv, int* info, void* work, size_t work_bytes, void* stream) {
     if (batch < 0 || n < 1 || !A || !Ainv) return fail(KH_EINVAL, "kh_zinv_batched: bad arguments");

@@ -240,6 +240,9 @@ static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, Fi
     f.zpos = b.get<int>(nz); f.zlayer = b.get<int>(nz); f.zdist = b.get<double>(nz);
     f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * B);
     f.zwork_cd = (int)n >= KH_ZINV_BLOCKED_MIN ? (long long)B * zinv_work_cd((int)n) : 0;
+#ifndef KH_HOST_EMU
+    if ((int)n >= KH_ZINV_BLOCKED_MIN && (int)n <= ZIL_NMAX && (long long)B * zinv_l2_work_cd((int)n) > f.zwork_cd) f.zwork_cd = (long long)B * zinv_l2_work_cd((int)n);
+#endif
     f.zwork = b.get<cd>((size_t)f.zwork_cd);
 }
 

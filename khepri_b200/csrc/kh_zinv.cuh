@@ -23,6 +23,7 @@ struct zinv_args {
     int info_mode = 0;   // 0: info[b] = status.  m > 0: accumulate, info[b / m] |= 2 on a zero pivot (pipeline use: the solve's info word)
     int use_smem;
     int ld_s;            // shared-memory leading dimension (odd)
+    cd* gwork = nullptr; // zinv_l2: [batch][np][np] working copies in global memory
 };
 
 KH_DEV void zinv_body(const Cta& c, const zinv_args& a) {
@@ -143,8 +144,9 @@ __device__ __forceinline__ cd kh_crecip_fast(cd z) {
 #define ZID_NB 16
 #define ZID_NMAX 104
 struct zid_slot { cd row[ZID_NB]; cd d; unsigned long long key; int idx; int pad; };
-__device__ __forceinline__ void zid_bar_panel() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-// panel factorisation (warps 0-3, thread <-> row): block column k0 .. k0+nbk of As becomes the Gauss-Jordan block column P'
+template <int PW> __device__ __forceinline__ void zid_bar_panel() { asm volatile("bar.sync 1, %0;" :: "n"(32 * PW) : "memory"); }
+// panel factorisation (warps 0 .. PW-1, thread <-> row): block column k0 .. k0+nbk of As becomes the Gauss-Jordan block column P'
+template <int PW>
 __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0, int nbk, zid_slot* slots, int* piv, int& bad, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const bool rowok = tid < np;
@@ -161,7 +163,7 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
 #pragma unroll 1
     for (int s = 0; s < nbk; ++s) {
         const int k = k0 + s;
-        zid_slot* sl = slots + (s & 1) * 5;            // 4 warp candidates + the old row k
+        zid_slot* sl = slots + (s & 1) * (PW + 1);     // PW warp candidates + the old row k
         // warp-level argmax (two 32-bit reductions + ballot, ties -> smallest row); the warp's winner publishes its row
         const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
         const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
@@ -169,21 +171,21 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         const unsigned who = __ballot_sync(0xffffffffu, khi == mhi && klo == mlo);
         const bool iswin = lane == __ffs(who) - 1;
         if (iswin || tid == k) {                       // one divergent block for both publishers (row k's copy is only read when pr != k)
-            zid_slot* dst = iswin ? sl + warp : sl + 4;
+            zid_slot* dst = iswin ? sl + warp : sl + PW;
 #pragma unroll
             for (int j = 0; j < ZID_NB; ++j) dst->row[j] = p[j];
             dst->d = dmine; dst->key = key; dst->idx = tid;
         }
-        zid_bar_panel();
+        zid_bar_panel<PW>();
         unsigned long long bk = sl[0].key; int wbest = 0;
 #pragma unroll
-        for (int w = 1; w < 4; ++w) { const unsigned long long ok = sl[w].key; if (ok > bk) { bk = ok; wbest = w; } }
+        for (int w = 1; w < PW; ++w) { const unsigned long long ok = sl[w].key; if (ok > bk) { bk = ok; wbest = w; } }
         const zid_slot* win = sl + wbest;
         const int pr = win->idx;
         const cd d = win->d;
         if (tid == 0) piv[k] = pr;
         if (tid == pr && pr != k) {                    // row k's old values: in its warp's slot if it won there, else in slot 4
-            const zid_slot* rk = (sl[k >> 5].idx == k) ? sl + (k >> 5) : sl + 4;
+            const zid_slot* rk = (sl[k >> 5].idx == k) ? sl + (k >> 5) : sl + PW;
 #pragma unroll
             for (int j = 0; j < ZID_NB; ++j) p[j] = rk->row[j];
         }
@@ -240,34 +242,42 @@ __device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr
         cp[0] = mk(cr0, ci0); cp[1] = mk(cr1, ci1);
     }
 }
-template <int NW>
+// GLOBAL = false: the matrix lives in shared memory (n <= 104).  GLOBAL = true: the same single-launch algorithm with the working
+// copy in a global-memory scratch (L2 resident: a batch below one wave is a few tens of MB), n <= 256, 8 panel warps -- for SMALL
+// batches of the 9x9 ... 11x11 bases (field maps, scalar solves), where the blocked multi-launch variant pays 19 launch latencies
+// of ~0.1 ms per inverse with the GPU almost empty.
+template <int NW, int PW, bool GLOBAL>
 __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& a) {
     const int n = a.n, b = c.bx, tid = c.tid, warp = tid >> 5, lane = tid & 31;
-    const int np = (n + 7) & ~7, lda = np + 4, ldr = np + 2;
+    const int np = (n + 7) & ~7, lda = GLOBAL ? np : np + 4, ldr = np + 2;
     const cd* A = mat_ptr(a.A, b);
     cd* Out = mat_ptr(a.Ainv, b);
-    cd* As = (cd*)KH_SMEM(c);                     // [np][lda]
-    cd* R = As + np * lda;                        // [NB][ldr]
-    zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][4 warp candidates + old row k]
-    int* piv = (int*)(slots + 10);                // [np]
+    cd* As = GLOBAL ? a.gwork + (long long)b * np * np : (cd*)KH_SMEM(c);      // [np][lda]
+    cd* R = GLOBAL ? (cd*)KH_SMEM(c) : As + np * lda;                          // [NB][ldr]
+    zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][PW warp candidates + old row k]
+    int* piv = (int*)(slots + 2 * (PW + 1));      // [np]
     unsigned long long* bar = (unsigned long long*)(piv + ((np + 1) & ~1));     // mbarrier of the staging copy
-    // identity padding by the threads while the TMA engine stages the n rows (cp.async.bulk, one row each, kh_stage_rows)
-    {   const int padc = np - n, nbot = padc * np;          // bottom rows n..np-1 in full, then columns n..np-1 of the rows above
+    if (GLOBAL) {
+        for (int e = tid; e < np * np; e += 32 * NW) { const int i = e / np, j = e - i * np; As[e] = (i < n && j < n) ? A[(long long)i * a.A.ld + j] : mk(i == j ? 1.0 : 0.0, 0.0); }
+        __syncthreads();
+    } else {
+        // identity padding by the threads while the TMA engine stages the n rows (cp.async.bulk, one row each, kh_stage_rows)
+        const int padc = np - n, nbot = padc * np;          // bottom rows n..np-1 in full, then columns n..np-1 of the rows above
         for (int e = tid; e < nbot + n * padc; e += 32 * NW) {
             const int i = e < nbot ? n + e / np : (e - nbot) / padc, j = e < nbot ? e % np : n + (e - nbot) % padc;
             As[i * lda + j] = mk(i == j ? 1.0 : 0.0, 0.0);
         }
+        kh_stage_rows(c, As, lda, A, a.A.ld, n, n, bar);
     }
-    kh_stage_rows(c, As, lda, A, a.A.ld, n, n, bar);
     int bad = 0;
-    if (warp < 4) zid_panel(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
+    if (warp < PW) zid_panel<PW>(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
     __syncthreads();
     for (int k0 = 0; k0 < np; k0 += ZID_NB) {
         const int nbk = min(ZID_NB, np - k0);     // 16 or 8
         const int k1 = k0 + nbk, nbk1 = min(ZID_NB, np - k1);      // next panel (nbk1 <= 0: none)
         // ---------------- interchanges of panel k0 on the other columns, pivot rows -> R (zeroed in place): thread <-> column
         {
-            const int j = tid - 128;
+            const int j = tid - 32 * PW;
             if (j >= 0 && j < np && (j < k0 || j >= k1)) {
                 for (int s = 0; s < nbk; ++s) {
                     const int k = k0 + s, pr = piv[k];
@@ -279,9 +289,9 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         __syncthreads();
         zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
         __syncthreads();
-        // (a look-ahead schedule -- next panel factorised by warps 0-3 while the others finish this update -- was measured: no
-        //  gain, the panel's dependent DFMA chain queues behind the DMMAs on the shared FP64 pipe)
-        if (nbk1 > 0 && warp < 4) zid_panel(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
+        // (a look-ahead schedule -- next panel factorised by the panel warps while the others finish this update -- was measured:
+        //  no gain, the panel's dependent DFMA chain queues behind the DMMAs on the shared FP64 pipe)
+        if (nbk1 > 0 && warp < PW) zid_panel<PW>(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
         __syncthreads();
     }
     // undo the row interchanges as column interchanges (reverse order): thread j follows stored column j to its final position
@@ -296,8 +306,15 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         for (int j = lane; j < n; j += 32) Out[(long long)i * a.Ainv.ld + dest[j]] = As[i * lda + j];
     if (tid == 0) zinv_note(a.info, a.info_mode, b, bad);
 }
-__device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16>(c, a); }
-__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8>(c, a); }
+__device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, 4, false>(c, a); }
+__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, 4, false>(c, a); }
+__device__ __forceinline__ void zinv_l2_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, 8, true>(c, a); }
+#define ZIL_NMAX 256
+static inline long long zinv_l2_work_cd(int n) { const long long np = (n + 7) & ~7; return np * np; }
+static inline size_t zinv_l2_smem(int n) {
+    const int np = (n + 7) & ~7;
+    return (size_t)ZID_NB * (np + 2) * sizeof(cd) + 18 * sizeof(zid_slot) + (size_t)np * 4 + 32;
+}
 static inline size_t zinv_dmma_smem(int n) {
     const int np = (n + 7) & ~7;
     return ((size_t)np * (np + 4) + (size_t)ZID_NB * (np + 2)) * sizeof(cd) + 10 * sizeof(zid_slot) + (size_t)np * 4 + 32;
@@ -484,6 +501,17 @@ static inline size_t zinv_smem_bytes(int n, int ld_s, int use_smem) {
 
 static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work = nullptr, long long work_cd = 0, int info_mode = 0) {
     if (batch <= 0 || n <= 0) return 0;
+#ifndef KH_HOST_EMU
+    {   // small batches of mid-size matrices: ONE launch, working copy in L2 (see zinv_dmma_body_t<.., true>)
+        const char* e = getenv("KH_ZINV_L2_MAXBATCH");       // (test / tuning switch; default: two waves of one CTA per SM)
+        const int l2max = e ? atoi(e) : 296;
+        if (n > ZID_NMAX && n <= ZIL_NMAX && batch <= l2max && work && work_cd >= (long long)batch * zinv_l2_work_cd(n)) {
+            zinv_args g;
+            g.n = n; g.A = A; g.Ainv = Ainv; g.info = info; g.info_mode = info_mode; g.use_smem = 0; g.ld_s = 0; g.gwork = work;
+            return kh_launch<zinv_args, zinv_l2_body, 512, 1>(dim3(batch), 512, zinv_l2_smem(n), st, g, "zinv", 8.0 * n * n * n * batch);
+        }
+    }
+#endif
     if (n >= KH_ZINV_BLOCKED_MIN && work && work_cd >= (long long)batch * zinv_work_cd(n)) return zinv_blocked_launch(st, batch, n, A, Ainv, info, work, info_mode);
     zinv_args a;
     a.n = n; a.A = A; a.Ainv = Ainv; a.info = info; a.info_mode = info_mode;

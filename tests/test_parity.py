@@ -274,10 +274,14 @@ def test_energy_conservation_and_batch_invariance(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("n", [101, 119, 150, 242, 450])
-def test_zinv_blocked(backend, n):
-    """Tiled inverse (blocked Gauss-Jordan panels + DMMA GEMM updates) for matrices beyond shared memory."""
-    if backend != "cuda" and n > 150:
-        pytest.skip("host emulation: small sizes only")
+@pytest.mark.parametrize("variant", ["auto", "blocked"])
+def test_zinv_blocked(backend, n, variant, monkeypatch):
+    """Inverse of matrices beyond shared memory: the blocked multi-launch variant (Gauss-Jordan panels + DMMA GEMM updates) and,
+    for small batches up to n = 256, the single-launch variant with the working copy in L2 ("auto" picks it for this batch)."""
+    if backend != "cuda" and (n > 150 or variant == "blocked"):
+        pytest.skip("host emulation: small sizes only, one variant")
+    if variant == "blocked":
+        monkeypatch.setenv("KH_ZINV_L2_MAXBATCH", "0")
     eng = engine(backend)
     rng = np.random.default_rng(12)
     A = rng.standard_normal((3, n, n)) + 1j * rng.standard_normal((3, n, n))
