@@ -572,3 +572,37 @@ def test_qr_flag_protocol_bail_out_is_reported():
     assert (info == 99).any() and set(np.unique(info)) <= {0, 99}
     _, _, info = eng.zgeev(A)
     assert int(info.max().item()) == 0
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_random_structures_both_methods_against_the_oracle(backend):
+    """Differential test on random structures: pixmaps (smooth, binary, lossy), P != Q and 1-D bases, oblique lattice, thin /
+    deep / repeated layers (collapsed runs), random oblique sources -- both layer methods against the oracle (R, T) and
+    against each other (full Stot)."""
+    eng = engine(backend)
+    rng = np.random.default_rng(5)
+    ntrial = 24 if backend == "cuda" else 9
+    for trial in range(ntrial):
+        pw = [(3, 3), (5, 3), (3, 5), (7, 1), (1, 5), (5, 5)][trial % 6]
+        res = (int(rng.integers(24, 64)), int(rng.integers(24, 64)))
+        pm = rng.uniform(1, 6, size=res)
+        if trial % 3 == 0:
+            pm = np.where(rng.random(res) > 0.5, 12.0, 1.0)
+        if trial % 4 == 1:
+            pm = pm * (1 - 0.05j)
+        d1, d2 = float(rng.choice([0.02, 0.3, 1.0, 2.7])), float(rng.uniform(0.05, 1.5))
+        layers = {"A": ("pixmap", pm, d1), "U": ("uniform", complex(rng.uniform(1, 4), -rng.uniform(0, 0.2)), d2),
+                  "B": ("pixmap", pm[::-1].copy(), float(rng.uniform(0.05, 0.8)))}
+        lat = np.eye(2) if trial % 5 else 0.8 * np.array([[1, 0], [0.5, np.sqrt(3) / 2]])
+        st = cases._st(pw, layers, [["A", "U", "B"], ["A", "A", "U", "B", "B"], ["B", "A"]][trial % 3], lattice=lat,
+                       epsi=float(rng.uniform(1, 2)), epse=float(rng.uniform(1, 3)))
+        srcs = [dict(wavelength=float(rng.uniform(0.7, 2.5)), te=float(rng.uniform(0, 1)), tm=float(rng.uniform(0.1, 1)),
+                     theta=float(rng.uniform(0, 70)), phi=float(rng.uniform(0, 360))) for _ in range(3)]
+        ref = np.array([orc.solve_rt(st, s["wavelength"], s["te"], s["tm"], s["theta"], s["phi"]) for s in srcs])
+        out = {}
+        for method in METHODS:
+            cl = build_crystal(st, eng, method=method)
+            R, T, S = sweep_sources(cl, srcs, return_S=True)
+            rt_close(np.stack([R, T], 1), ref)
+            out[method] = S
+        rt_close(out["doubling"], out["eig"], 1e-9)
