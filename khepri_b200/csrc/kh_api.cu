@@ -219,6 +219,38 @@ static int star_any(kh_stream_t st, int Bc, int N, const SRef& A, const SRef& B,
     return e;
 }
 
+// The END of a flux-only chain,  L (*) D (*) C  with D the last dense layer and C the block-diagonal rest (uniform layers +
+// emergence half space), associated from the right:  N = D (*) C  is needed only through N11 (n x n) and through N21 applied to
+// two vectors,
+//     G = (I - D22 C11)^-1,  H = G D21,  N11 = D11 + D12 C11 H,  N21 = C21 H,
+// and the last product then needs no GEMM beyond  F = I - L22 N11 :  x = F^-1 L21[:, cols],  S11 = L11 + L12 N11 x,  S21 = C21 H x
+// (alternative.py:19-30 twice, restricted to what poynting_flux_end reads, crystal.py:372-381).  Two inverses and two (L block
+// diagonal) or three (L dense) GEMMs instead of two inverses and three / six GEMMs of the left-to-right order.  tmp: 10 slabs.
+static int star_last3(kh_stream_t st, int Bc, int N, const SRef& L, const SRef& D, const cd* C, cd* out, cd* tmp, int* info, int fc, int imode) {
+    const int n = 2 * N;
+    const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
+    auto T = [&](int i) { return mref(tmp + (long long)i * slab, n2, n); };
+    MatRef F1 = T(0), G = T(1), H = T(2), K = T(3), N11 = T(4), F2 = T(5), Fi2 = T(6), X = T(7), U = T(8), W = T(9);
+    SRef O = sref_dense(out, n);
+    int e;
+    if ((e = bdmul(st, Bc, N, 1, C, 0, D.blk[3], F1, -1.0, nullptr, 0.0, 1.0))) return e;            // F1 = I - D22 C11
+    if ((e = zinv_launch(st, Bc, n, F1, G, info, tmp + 2 * slab, 8 * slab, imode))) return e;      // (slabs 2.. are still free: work space)
+    if ((e = gemm(st, Bc, n, G, D.blk[2], H))) return e;                                            // H = G D21
+    if ((e = bdmul(st, Bc, N, 0, C, 0, H, K))) return e;                                            // K = C11 H
+    if ((e = gemm(st, Bc, n, D.blk[1], K, N11, 1.0, &D.blk[0], 1.0))) return e;                     // N11 = D11 + D12 K
+    if (L.bd) { if ((e = bdmul(st, Bc, N, 0, L.bdp, 3, N11, F2, -1.0, nullptr, 0.0, 1.0))) return e; }       // F2 = I - L22 N11
+    else if ((e = gemm(st, Bc, n, L.blk[3], N11, F2, -1.0, nullptr, 0.0, 1.0))) return e;
+    if ((e = zinv_launch(st, Bc, n, F2, Fi2, info, tmp + 7 * slab, 3 * slab, imode))) return e;
+    if (L.bd) { if ((e = bdmul(st, Bc, N, 1, L.bdp, 2, Fi2, X, 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e; }   // x = F2^-1 L21   (flux columns)
+    else if ((e = cols2(st, Bc, n, fc, Fi2, L.blk[2], X))) return e;
+    if ((e = cols2(st, Bc, n, fc, N11, X, U))) return e;                                            // u = N11 x
+    if (L.bd) { if ((e = bdmul(st, Bc, N, 0, L.bdp, 1, U, O.blk[0], 1.0, nullptr, 0.0, 0.0, L.bdp, 0, fc))) return e; }   // S11 = L11 + L12 u
+    else if ((e = cols2(st, Bc, n, fc, L.blk[1], U, O.blk[0], &L.blk[0]))) return e;
+    if ((e = cols2(st, Bc, n, fc, H, X, W))) return e;                                              // w = H x
+    return bdmul(st, Bc, N, 0, C, 2, W, O.blk[2], 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc);         // S21 = C21 w
+}
+#define STAR_LAST3_SLABS 10
+
 // ---------------------------------------------------------------------------- plan
 struct kh_plan {
     int P, Q, N, n;
@@ -693,7 +725,13 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         } else {
             SRef pend; pend.bd = true; pend.bdp = nullptr;
             bool have_pend = false;
-            for (int i = 0; i < Ls; ++i) {
+            // flux-only chains that end  ... D (dense) C (block diagonal)  with something to the left of D: the last two products
+            // are associated from the right (star_last3)
+            int ilast = -1;
+            for (int i = 0; i < Ls; ++i) if (!S[p->stack[i]].bd) ilast = i;
+            const bool tail3 = fcol >= 0 && ilast > 0 && ilast < Ls - 1;
+            const int iend = tail3 ? ilast : Ls;
+            for (int i = 0; i < iend; ++i) {
                 const SRef& R = S[p->stack[i]];
                 if (R.bd) {
                     if (!have_pend) { pend = R; have_pend = true; }
@@ -710,7 +748,14 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             }
             if (have_pend) {
                 if (!have_acc) { acc = pend; have_acc = true; }
-                else { SRef r2; KH_TRY(combine(acc, pend, r2, true)); acc = r2; }      // the chain ends here
+                else { SRef r2; KH_TRY(combine(acc, pend, r2, !tail3)); acc = r2; }      // (without a tail the chain ends here)
+                have_pend = false;
+            }
+            if (tail3) {
+                SRef cbd = S[p->stack[ilast + 1]];
+                for (int i = ilast + 2; i < Ls; ++i) { SRef r2; KH_TRY(combine(cbd, S[p->stack[i]], r2)); cbd = r2; }
+                KH_TRY(star_last3(st, Bc, N, acc, S[p->stack[ilast]], cbd.bdp, cb.accD[pd], cb.pool, sinfo, fcol, 1));
+                acc = sref_dense(cb.accD[pd], n); acc_full = cb.accD[pd]; pd ^= 1;
             }
         }
         if (!acc.bd && acc.blk[0].p != acc_full) acc_full = nullptr;      // acc still refers to a layer table
