@@ -160,8 +160,12 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
     // The register panel is ROTATED by one column per pivot (the pivot column is always p[0], the next one p[1]) so that the
     // step is a real loop of ~600 instructions instead of 16 unrolled copies: the unrolled form ran out of the instruction
     // cache with a single warp per scheduler and nothing to hide the fetches.
+    // pivots k >= n sit in the identity padding (row k = e_k, column k zero elsewhere): their Gauss-Jordan step is the identity,
+    // so the loop stops at n and only records them
+    const int nsteps = (n - k0 < nbk) ? ((n - k0 > 0) ? n - k0 : 0) : nbk;
+    if (tid < nbk - nsteps) piv[k0 + nsteps + tid] = k0 + nsteps + tid;
 #pragma unroll 1
-    for (int s = 0; s < nbk; ++s) {
+    for (int s = 0; s < nsteps; ++s) {
         const int k = k0 + s;
         zid_slot* sl = slots + (s & 1) * (PW + 1);     // PW warp candidates + the old row k
         // warp-level argmax (two 32-bit reductions + ballot, ties -> smallest row); the warp's winner publishes its row
@@ -205,9 +209,9 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         for (int j = 2; j < ZID_NB; ++j) { cd v = isk ? mk(0.0, 0.0) : p[j]; cfms(v, g, win->row[j]); p[j - 1] = v; }
         p[ZID_NB - 1] = mk(-g.x, -g.y);
     }
-    if (rowok) {                                       // p[j] holds panel column (j + nbk) mod NB
+    if (rowok) {                                       // p[j] holds panel column (j + nsteps) mod NB
 #pragma unroll
-        for (int j = 0; j < ZID_NB; ++j) { const int col = (j + nbk) & (ZID_NB - 1); if (col < nbk) As[tid * lda + k0 + col] = p[j]; }
+        for (int j = 0; j < ZID_NB; ++j) { const int col = (j + nsteps) & (ZID_NB - 1); if (col < nbk) As[tid * lda + k0 + col] = p[j]; }
     }
 }
 // A[:, tile columns outside [skip0, skip1) or inside [only0, only1)] += P' R on 8x8 DMMA tiles; worker w of nwork takes tiles w, w + nwork, ...
