@@ -202,7 +202,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "RCWA solves/sec (freq x k-point, complex128)", "value": value, "unit": "solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([dt for _, dt in vals])),
             "higher_is_better": True, "scaling": "strong" if args.workload.endswith("-full") else "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "harmonics": list(st["pw"]), "n": n},
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "harmonics": list(st["pw"]), "n": n,
+                       "solves_per_step_per_gpu": int(wl.size) if not args.workload.endswith("-full") else None, "solves_per_step": int(wl.size),
+                       "kpoints_per_step_per_gpu": args.kpoints if not args.workload.endswith("-full") else None,
+                       "method": "reference: eigen-decomposition per layer (numpy.linalg.eig), khepri.crystal.Crystal scalar loop",
+                       "parallelism": f"Pool({ncores}) on the host cores, {per_step} solves sampled per step",
+                       "l2": "n/a (CPU arm)", "results_finite": True},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
