@@ -393,6 +393,10 @@ def run_gpu(args):
     rt = step_resident(nsteps - 1)
     rt = rt.cpu().numpy()
     finite = bool(np.isfinite(rt).all())
+    # status words of one more step (0 = every solve clean: no zero pivot, no eigensolver failure, doubling bound respected)
+    chk = eng.solve_batch(plan, dev_in[nsteps - 1][0], dev_in[nsteps - 1][1], dev_in[nsteps - 1][2], want_flux=True, method=cl.method, bounds=bounds[nsteps - 1])
+    info_max = int(chk["info"].max().item())
+    energy = float(np.abs(chk["RT"].cpu().numpy().sum(1) - 1).max())
 
     if rank == 0:
         solves = B_total * args.steps
@@ -464,7 +468,7 @@ def run_gpu(args):
                            "method": method + (" (slice power series + self star products; eigensolver only when eigenspaces are retained)" if method == "doubling" else ""),
                            "parallelism": f"dp{world} (independent (freq,k) solves sharded, NCCL all_gather of R,T only)",
                            "l2": "per-step working set (workspace of several GB) exceeds the 126 MB L2, no explicit flush",
-                           "results_finite": finite},
+                           "results_finite": finite, "results_info_max": info_max, "results_max_abs_R_plus_T_minus_1": energy},
                 "clocks": sampler.summary(),
                 "e2e": {"value": solves / (ms_e2e * 1e-3), "unit": "solves/s",
                         "h2d_bytes_per_step": int((B_total if full else B) * (8 + 32 + 32)) // (world if full else 1),
