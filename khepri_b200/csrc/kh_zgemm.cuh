@@ -244,13 +244,13 @@ __device__ __forceinline__ void zgemm_mma_units(double (&cr)[MAXU][2], double (&
 // (strip, tile) units of the tile are dealt out evenly over them instead of one 8-row strip per warp.  With NW = 7 a CTA has
 // 8 compute warps = 2 per scheduler, whereas 7 strip-warps leave the 4th scheduler of an SM with half the DMMA work of the
 // others (and ragged tiles idle whole warps): at n = 98 the busiest scheduler drops from 52 to 44 of a matrix's 169 units.
-template <int NW, int NT, int ST>
+template <int NW, int NT, int ST, int NC = NW + 1>
 KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
 #ifdef KH_HOST_EMU
     zgemm_body_t<NW, NT>(c, a);
 #else
     static_assert(NW == NT, "staging strides assume a square CTA tile");
-    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, STAGE = BM * ZG_LDA + ZG_BK * LDB, NC = NW + 1;
+    constexpr int BM = 8 * NW, BN = 8 * NT, LDB = BN + 2, STAGE = BM * ZG_LDA + ZG_BK * LDB;
     constexpr int MAXU = (NW * NT + NC - 1) / NC;
     const int tiles_n = (a.N + BN - 1) / BN, tiles = ((a.M + BM - 1) / BM) * tiles_n;
     const int b = c.bx / tiles, tile = c.bx - b * tiles;
