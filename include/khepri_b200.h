@@ -112,7 +112,9 @@ void kh_plan_destroy(kh_plan* plan);
  *                       kappa * depth bounds the largest |lambda k0 d| of a layer; the layer is cut into 2^s slices with
  *                       kappa * depth / 2^s <= theta_slice.  If the bound turns out too small for a solve (checked on the
  *                       device against ||Omega^2||_1), bit 2 of its info is set.
- * Solves that retain eigenspaces (KH_WANT_FIELDS) always use KH_METHOD_EIG. */
+ * Solves that retain eigenspaces (KH_WANT_FIELDS) always use KH_METHOD_EIG.
+ * The setting is part of the plan's state: call it before kh_solve_workspace_bytes / kh_solve_batch of the batch it applies to (a plan
+ * is thread-compatible, not thread-safe: one thread at a time per handle). */
 #define KH_METHOD_EIG 0
 #define KH_METHOD_DOUBLING 1
 int kh_plan_set_method(kh_plan* plan, int method, double kappa, double theta_slice);

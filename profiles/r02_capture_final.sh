@@ -3,6 +3,8 @@
 set -x
 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu_final.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_final.log 2>&1; tail -2 gpurun_out/r02_smoke_final.log
+python profiles/accuracy_probe.py > gpurun_out/r02_accuracy_final.jsonl 2> gpurun_out/acc_final.err; cut -c 1-160 gpurun_out/r02_accuracy_final.jsonl
+python profiles/fields_bench.py 51 > gpurun_out/r02_fields_final_51.jsonl 2> gpurun_out/fields_final.err; cut -c 1-300 gpurun_out/r02_fields_final_51.jsonl
 python bench.py > gpurun_out/r02_bench_final_bzi77.json 2> gpurun_out/bench_final.err; head -c 300 gpurun_out/r02_bench_final_bzi77.json; echo
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_final_reference_arm.json 2> gpurun_out/ref_final.err; head -c 300 gpurun_out/r02_bench_final_reference_arm.json; echo
 python bench.py --workload bzi77-full --no-cpu > gpurun_out/r02_bench_final_bzi77_full.json 2> gpurun_out/full_final.err; head -c 300 gpurun_out/r02_bench_final_bzi77_full.json; echo
