@@ -367,20 +367,21 @@ static int solve_patterned(kh_stream_t st, int Bc, int N, const cd* C, const cd*
         KH_TRY(zgemm_launch(st, Bc, g)); }
     {   lam_args a{Bc, n, depth, v.w, k0, v.lam, v.xexp, v.tau};                // v.tau is free after the eigensolver: 1/lambda
         KH_TRY((kh_launch<lam_args, lam_body>(dim3(Bc), 128, 0, st, a))); }
-    if (Wkeep) {                                                                 // V = Q W / lambda is only needed for field maps
-        zgemm_args g = zgemm_make(n, n, n, M(1), M(5), M(6));
+    {   zgemm_args g = zgemm_make(n, n, n, M(1), M(5), M(6));                    // V = Q W / lambda -> 6   (alternative.py:176)
         g.colscale = v.lam; g.cs_stride = n; g.cs_group = 1; g.cs_divide = 1;
-        KH_TRY(zgemm_launch(st, Bc, g));
+        KH_TRY(zgemm_launch(st, Bc, g)); }
+    if (Wkeep) {
         copyv_args cw{n2, S(5), n2, Wkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cw)));
         copyv_args cv{n2, S(6), n2, Vkeep, keep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cv)));
         copyv_args cl{n, v.lam, n, Lkeep, lkeep_stride}; KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 128, 0, st, cl)));
     }
     KH_TRY(zinv_launch(st, Bc, n, M(5), M(7), v.info_acc, S(8), 2 * slab, v.info_div));                     // W^-1 -> 7
-    {   pv0_args a{Bc, N, S(0), Kx, Ky, S(6)};                                   // P V0 -> 6
+    // V^-1 V0 through the inverse of V itself, as the reference does (alternative.py:183).  Round 1 used V^-1 = L^-1 W^-1 P (a GEMM
+    // instead of an inverse): exact algebra, but the 1 / lambda amplifies the eigen-residual of modes near cut-off (lambda -> 0, next
+    // to a Rayleigh anomaly) -- 3e-8 in S at the worst point of the configs[1] k-grid against 4e-13 for this form.
+    KH_TRY(zinv_launch(st, Bc, n, M(6), M(13), v.info_acc, S(8), 2 * slab, v.info_div));                    // V^-1 -> 13
+    {   pv0_args a{Bc, N, S(13), Kx, Ky, S(8)};                                  // V^-1 V0 -> 8   (V0: 2x2 blocks of diagonals, O(n^2))
         KH_TRY((kh_launch<pv0_args, pv0_body>(dim3(Bc), 256, 0, st, a))); }
-    {   zgemm_args g = zgemm_make(n, n, n, M(7), M(6), M(8));                    // V^-1 V0 = L^-1 (W^-1 (P V0)) -> 8
-        g.rowscale = v.tau; g.rs_stride = n; g.rs_group = 1;
-        KH_TRY(zgemm_launch(st, Bc, g)); }
     {   ab2_args a{Bc, n, S(7), S(8), v.xexp, S(0), S(11), S(9), S(10)};         // A->0, B->11, XB->9, XA->10
         KH_TRY((kh_launch<ab2_args, ab2_body>(dim3(Bc), 256, 0, st, a))); }
     KH_TRY(zinv_launch(st, Bc, n, M(0), M(1), v.info_acc, S(12), 2 * slab, v.info_div));                     // A^-1 -> 1
