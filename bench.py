@@ -280,6 +280,41 @@ def extras(eng, dev, fp64_peak, quick):
     dt = time.perf_counter() - t0
     out.append({"config": "C1 suh03 5x5 drop-in SCALAR loop: 151 x (set_source; solve; poynting_flux_end), host API, wall clock",
                 "harmonics": [5, 5], "n": 50, "solves": len(srcs), "ms": dt * 1e3, "solves_per_s": len(srcs) / dt, "finite": bool(np.isfinite(acc))})
+    if not quick:
+        # C5: field maps 9x9 on a 256 x 256 x 128 grid, 17 frequencies per batch (solve with retained eigenspaces + reconstruction;
+        # the 13.7 GB of (E, H) stay on the device).  HBM-bound output: 6 nz nx ny 16 B per frequency.
+        nf = 17
+        st5, src5, _ = wk.case_fields(9, slices=4, res=128)
+        xs = np.linspace(0, 1, 256); ys = np.linspace(0, 1, 256); zs = np.linspace(0.0001, 2.2, 128)
+        X, Y = np.meshgrid(xs, ys, indexing="xy")
+        cl5 = wk.build_crystal(st5, eng, fields=True)
+        plan5 = cl5._get_plan(True)
+        wl5 = 1 / np.linspace(0.49, 0.6, 51)[:nf]
+        kp5 = np.zeros((nf, 2), dtype=complex); pol5 = np.tile([[1.0, 0.0]], (nf, 1)).astype(complex)
+        inc = []
+        for w in wl5:
+            cl5.set_source(wavelength=float(w), te=1.0, tm=0.0)
+            inc.append(np.hstack(cl5.get_source_as_field_vectors()))
+        inc = np.asarray(inc)
+        cl5.solve()
+        F = None
+        for rep in range(2):
+            del F
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            solved = eng.solve_batch(plan5, wl5, kp5, pol5, want_flux=True, want_fields=True)
+            e1.record()
+            F = eng.fields(plan5, solved, wl5, kp5, inc, X.ravel(), Y.ravel(), zs, cl5.stack_positions, grid=(xs, ys))
+            e2.record()
+            torch.cuda.synchronize()
+        ms_s, ms_f = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        gb = F.numel() * 16 / 1e9
+        out.append({"config": f"C5 field maps 9x9, 256x256x128 grid, {nf} frequencies batched (device-resident output)", "harmonics": [9, 9], "n": 162,
+                    "ms_solve_retained_eigenspaces": ms_s, "ms_field_kernels": ms_f, "ms_field_kernels_per_volume": ms_f / nf,
+                    "volumes_per_s_incl_solve": nf / ((ms_s + ms_f) * 1e-3), "output_GB": gb, "field_kernels_GBps": gb / (ms_f * 1e-3),
+                    "finite": bool(torch.isfinite(torch.view_as_real(F[0])).all().item())})
+        del F
     return out
 
 
