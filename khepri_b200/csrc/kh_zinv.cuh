@@ -146,13 +146,13 @@ __device__ __forceinline__ cd kh_crecip_fast(cd z) {
 struct zid_slot { cd row[ZID_NB]; cd d; unsigned long long key; int idx; int pad; };
 template <int PW> __device__ __forceinline__ void zid_bar_panel() { asm volatile("bar.sync 1, %0;" :: "n"(32 * PW) : "memory"); }
 // panel factorisation (warps 0 .. PW-1, thread <-> row): block column k0 .. k0+nbk of As becomes the Gauss-Jordan block column P'
-template <int PW>
+template <int PW, int NB>
 __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0, int nbk, zid_slot* slots, int* piv, int& bad, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const bool rowok = tid < np;
-    cd p[ZID_NB];
+    cd p[NB];
 #pragma unroll
-    for (int j = 0; j < ZID_NB; ++j) p[j] = (rowok && j < nbk) ? As[tid * lda + k0 + j] : mk(0.0, 0.0);
+    for (int j = 0; j < NB; ++j) p[j] = (rowok && j < nbk) ? As[tid * lda + k0 + j] : mk(0.0, 0.0);
     // speculative per-row quantities of the NEXT pivot column: 1 / entry and the ordering key of |re| + |im|
     // (bits of a non-negative double order like an unsigned integer; +1 so an eligible zero beats an ineligible row)
     cd dmine = kh_crecip_fast(p[0]);
@@ -177,7 +177,7 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         if (iswin || tid == k) {                       // one divergent block for both publishers (row k's copy is only read when pr != k)
             zid_slot* dst = iswin ? sl + warp : sl + PW;
 #pragma unroll
-            for (int j = 0; j < ZID_NB; ++j) dst->row[j] = p[j];
+            for (int j = 0; j < NB; ++j) dst->row[j] = p[j];
             dst->d = dmine; dst->key = key; dst->idx = tid;
         }
         zid_bar_panel<PW>();
@@ -191,7 +191,7 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         if (tid == pr && pr != k) {                    // row k's old values: in its warp's slot if it won there, else in slot 4
             const zid_slot* rk = (sl[k >> 5].idx == k) ? sl + (k >> 5) : sl + PW;
 #pragma unroll
-            for (int j = 0; j < ZID_NB; ++j) p[j] = rk->row[j];
+            for (int j = 0; j < NB; ++j) p[j] = rk->row[j];
         }
         const cd pv = win->row[0];
         if (pv.x == 0.0 && pv.y == 0.0 && !bad && k < n) bad = k + 1;
@@ -206,12 +206,12 @@ __device__ __forceinline__ void zid_panel(cd* As, int lda, int np, int n, int k0
         key = (rowok && tid > k) ? (unsigned long long)__double_as_longlong(cabs1(nx)) + 1ull : 0ull;
         p[0] = nx;
 #pragma unroll
-        for (int j = 2; j < ZID_NB; ++j) { cd v = isk ? mk(0.0, 0.0) : p[j]; cfms(v, g, win->row[j]); p[j - 1] = v; }
-        p[ZID_NB - 1] = mk(-g.x, -g.y);
+        for (int j = 2; j < NB; ++j) { cd v = isk ? mk(0.0, 0.0) : p[j]; cfms(v, g, win->row[j]); p[j - 1] = v; }
+        p[NB - 1] = mk(-g.x, -g.y);
     }
     if (rowok) {                                       // p[j] holds panel column (j + nsteps) mod NB
 #pragma unroll
-        for (int j = 0; j < ZID_NB; ++j) { const int col = (j + nsteps) & (ZID_NB - 1); if (col < nbk) As[tid * lda + k0 + col] = p[j]; }
+        for (int j = 0; j < NB; ++j) { const int col = (j + nsteps) & (NB - 1); if (col < nbk) As[tid * lda + k0 + col] = p[j]; }
     }
 }
 // A[:, tile columns outside [skip0, skip1) or inside [only0, only1)] += P' R on 8x8 DMMA tiles; worker w of nwork takes tiles w, w + nwork, ...
@@ -250,7 +250,7 @@ __device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr
 // copy in a global-memory scratch (L2 resident: a batch below one wave is a few tens of MB), n <= 256, 8 panel warps -- for SMALL
 // batches of the 9x9 ... 11x11 bases (field maps, scalar solves), where the blocked multi-launch variant pays 19 launch latencies
 // of ~0.1 ms per inverse with the GPU almost empty.
-template <int NW, int PW, bool GLOBAL>
+template <int NW, int PW, bool GLOBAL, int NB = ZID_NB>
 __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& a) {
     const int n = a.n, b = c.bx, tid = c.tid, warp = tid >> 5, lane = tid & 31;
     const int np = (n + 7) & ~7, lda = GLOBAL ? np : np + 4, ldr = np + 2;
@@ -258,7 +258,7 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
     cd* Out = mat_ptr(a.Ainv, b);
     cd* As = GLOBAL ? a.gwork + (long long)b * np * np : (cd*)KH_SMEM(c);      // [np][lda]
     cd* R = GLOBAL ? (cd*)KH_SMEM(c) : As + np * lda;                          // [NB][ldr]
-    zid_slot* slots = (zid_slot*)(R + ZID_NB * ldr);   // [2 parities][PW warp candidates + old row k]
+    zid_slot* slots = (zid_slot*)(R + NB * ldr);   // [2 parities][PW warp candidates + old row k]
     int* piv = (int*)(slots + 2 * (PW + 1));      // [np]
     unsigned long long* bar = (unsigned long long*)(piv + ((np + 1) & ~1));     // mbarrier of the staging copy
     if (GLOBAL) {
@@ -274,11 +274,11 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         kh_stage_rows(c, As, lda, A, a.A.ld, n, n, bar);
     }
     int bad = 0;
-    if (warp < PW) zid_panel<PW>(As, lda, np, n, 0, min(ZID_NB, np), slots, piv, bad, tid);
+    if (warp < PW) zid_panel<PW, NB>(As, lda, np, n, 0, min(NB, np), slots, piv, bad, tid);
     __syncthreads();
-    for (int k0 = 0; k0 < np; k0 += ZID_NB) {
-        const int nbk = min(ZID_NB, np - k0);     // 16 or 8
-        const int k1 = k0 + nbk, nbk1 = min(ZID_NB, np - k1);      // next panel (nbk1 <= 0: none)
+    for (int k0 = 0; k0 < np; k0 += NB) {
+        const int nbk = min(NB, np - k0);         // NB, or 8 at the end
+        const int k1 = k0 + nbk, nbk1 = min(NB, np - k1);      // next panel (nbk1 <= 0: none)
         // ---------------- interchanges of panel k0 on the other columns, pivot rows -> R (zeroed in place): thread <-> column
         {
             const int j = tid - 32 * PW;
@@ -295,7 +295,7 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         __syncthreads();
         // (a look-ahead schedule -- next panel factorised by the panel warps while the others finish this update -- was measured:
         //  no gain, the panel's dependent DFMA chain queues behind the DMMAs on the shared FP64 pipe)
-        if (nbk1 > 0 && warp < PW) zid_panel<PW>(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
+        if (nbk1 > 0 && warp < PW) zid_panel<PW, NB>(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
         __syncthreads();
     }
     // undo the row interchanges as column interchanges (reverse order): thread j follows stored column j to its final position
@@ -311,7 +311,13 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
     if (tid == 0) zinv_note(a.info, a.info_mode, b, bad);
 }
 __device__ __forceinline__ void zinv_dmma_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, 4, false>(c, a); }
-__device__ __forceinline__ void zinv_dmma8_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, 4, false>(c, a); }
+// n <= 64 with panels of 8 pivots: half the panel registers and a third less shared memory, so THREE matrices share an SM and
+// their latency-bound panels overlap (the 5x5 basis: n = 50)
+__device__ __forceinline__ void zinv_dmma8n_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<8, 2, false, 8>(c, a); }
+static inline size_t zinv_dmma8n_smem(int n) {
+    const int np = (n + 7) & ~7;
+    return ((size_t)np * (np + 4) + (size_t)8 * (np + 2)) * sizeof(cd) + 6 * sizeof(zid_slot) + (size_t)np * 4 + 32;
+}
 __device__ __forceinline__ void zinv_l2_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, 8, true>(c, a); }
 #define ZIL_NMAX 256
 static inline long long zinv_l2_work_cd(int n) { const long long np = (n + 7) & ~7; return np * np; }
@@ -520,8 +526,8 @@ static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef
     zinv_args a;
     a.n = n; a.A = A; a.Ainv = Ainv; a.info = info; a.info_mode = info_mode;
 #ifndef KH_HOST_EMU
-    if (n <= 64 && n >= 16)
-        return kh_launch<zinv_args, zinv_dmma8_body, 256, 2>(dim3(batch), 256, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
+    if (n <= 64 && n >= 16)          // panels of 8, three CTAs per SM: 5.1 -> 7.6 TFLOP/s at n = 50 against panels of 16 with two
+        return kh_launch<zinv_args, zinv_dmma8n_body, 256, 3>(dim3(batch), 256, zinv_dmma8n_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
     if (n <= ZID_NMAX && n >= 16)
         return kh_launch<zinv_args, zinv_dmma_body, 512, 1>(dim3(batch), 512, zinv_dmma_smem(n), st, a, "zinv", 8.0 * n * n * n * batch);
 #endif
