@@ -423,6 +423,108 @@ KH_DEV void zinvb_panel_body(const Cta& c, const zinvb_args& a) {
     }
 }
 
+#ifndef KH_HOST_EMU
+// Block column of 32 pivots of the blocked variant for n <= 512, built on the register-resident panel of the shared-memory kernel
+// (zid_panel: thread <-> row, 16 panel entries per row in registers, one named barrier per pivot) working directly on the L2-resident
+// matrix: ~1.2 k cycles per pivot where the shared-memory panel above (five CTA barriers and an n x nb sweep per pivot) took ~15 k at
+// n = 242.  Two half panels A, B of 16 columns; the rank-16 update of A is applied inside the kernel only where B needs it (B's
+// columns, and B's pivot rows R_B), so that the batched GEMM afterwards applies BOTH halves to the rest of the matrix in one pass
+// over it (K = 32: the update is HBM bound, n^2 32 B per pass):
+//   1 panel A   2 interchanges of A on all other columns, pivot rows -> R_A (zeroed in place)   3 B's columns += P'_A R_A
+//   4 panel B   5 interchanges of B (A's columns included)   6 rows of B's pivots -> R_B (zeroed in place, A's columns too)
+//   7 A's columns += P'_B R_B[:, A's columns]: the 32 columns are now the transformation of the whole block
+template <int PW>
+__device__ __forceinline__ void zinvb_panel32_body_t(const Cta& c, const zinvb_args& a) {
+    const int n = a.n, b = c.bx, k0 = a.k0, tid = c.tid, warp = tid >> 5;
+    const int nb = (32 < n - k0) ? 32 : n - k0, nA = nb < ZID_NB ? nb : ZID_NB, nB = nb - nA, kB = k0 + ZID_NB;
+    cd* A = mat_ptr(a.A, b);
+    const int ld = a.A.ld;
+    cd* R = a.R + (long long)b * a.r_stride;          // [32][n]
+    int* pivg = a.piv + (long long)b * a.piv_stride;
+    zid_slot* slots = (zid_slot*)KH_SMEM(c);          // [2 parities][PW warp candidates + old row k]
+    cd* T16 = (cd*)(slots + 2 * (PW + 1));            // [16][16] staging of a small operand
+    int* pivs = (int*)(T16 + ZID_NB * ZID_NB);        // [32]
+    int* piv = pivs - k0;
+    int bad = 0;
+    auto interchange = [&](int p0, int np_, int c0, int c1) {     // row swaps of the pivots p0 .. p0+np_ on the columns outside [c0, c1)
+        for (int j = tid; j < n; j += c.nthr) {
+            if (j >= c0 && j < c1) continue;
+            for (int s = 0; s < np_; ++s) {
+                const int k = p0 + s, pr = piv[k];
+                if (pr != k) { const cd x = A[(long long)k * ld + j]; A[(long long)k * ld + j] = A[(long long)pr * ld + j]; A[(long long)pr * ld + j] = x; }
+            }
+        }
+    };
+    // ---- 1, 2
+    if (warp < PW) zid_panel<PW, ZID_NB>(A, ld, n, n, k0, nA, slots, piv, bad, tid);
+    __syncthreads();
+    interchange(k0, nA, k0, k0 + nA);
+    __syncthreads();
+    for (int j = tid; j < n; j += c.nthr) {
+        if (j >= k0 && j < k0 + nA) continue;
+        for (int s = 0; s < nA; ++s) { R[(long long)s * n + j] = A[(long long)(k0 + s) * ld + j]; A[(long long)(k0 + s) * ld + j] = mk(0.0, 0.0); }
+    }
+    __syncthreads();
+    if (nB > 0) {
+        // ---- 3: B's columns += P'_A R_A[:, B]
+        for (int e = tid; e < nA * nB; e += c.nthr) { const int t = e / nB, jb = e - t * nB; T16[t * ZID_NB + jb] = R[(long long)t * n + kB + jb]; }
+        __syncthreads();
+        for (int i = tid; i < n; i += c.nthr) {
+            cd acc[ZID_NB];
+#pragma unroll
+            for (int jb = 0; jb < ZID_NB; ++jb) acc[jb] = mk(0.0, 0.0);
+            for (int t = 0; t < nA; ++t) {
+                const cd p = A[(long long)i * ld + k0 + t];
+#pragma unroll
+                for (int jb = 0; jb < ZID_NB; ++jb) cfma(acc[jb], p, T16[t * ZID_NB + jb]);
+            }
+#pragma unroll
+            for (int jb = 0; jb < ZID_NB; ++jb) if (jb < nB) { cd* q = &A[(long long)i * ld + kB + jb]; *q = *q + acc[jb]; }
+        }
+        __syncthreads();
+        // ---- 4, 5
+        if (warp < PW) zid_panel<PW, ZID_NB>(A, ld, n, n, kB, nB, slots, piv, bad, tid);
+        __syncthreads();
+        interchange(kB, nB, kB, kB + nB);
+        __syncthreads();
+        // ---- 6: R_B = the rows of B's pivots as they stand (zeroed in place).  NOT updated by A's pending rank-16 term: after step 7
+        // the 32 columns hold the Gauss-Jordan transformation of the WHOLE block, [F_A F_B] with F_A = P'_A(rows of B zeroed) +
+        // P'_B P'_A[rows of B], and  M + F_A R_A + F_B R_B(raw)  is exactly the two sequential rank-16 updates.
+        for (int j = tid; j < n; j += c.nthr) {
+            if (j >= kB && j < kB + nB) continue;
+            for (int s_ = 0; s_ < nB; ++s_) {
+                R[(long long)(ZID_NB + s_) * n + j] = A[(long long)(kB + s_) * ld + j];
+                A[(long long)(kB + s_) * ld + j] = mk(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+        // ---- 7: A's columns += P'_B R_B[:, A]
+        for (int e = tid; e < nB * nA; e += c.nthr) { const int s_ = e / nA, ja = e - s_ * nA; T16[s_ * ZID_NB + ja] = R[(long long)(ZID_NB + s_) * n + k0 + ja]; }
+        __syncthreads();
+        for (int i = tid; i < n; i += c.nthr) {
+            cd acc[ZID_NB];
+#pragma unroll
+            for (int ja = 0; ja < ZID_NB; ++ja) acc[ja] = mk(0.0, 0.0);
+            for (int s_ = 0; s_ < nB; ++s_) {
+                const cd p = A[(long long)i * ld + kB + s_];
+#pragma unroll
+                for (int ja = 0; ja < ZID_NB; ++ja) cfma(acc[ja], p, T16[s_ * ZID_NB + ja]);
+            }
+#pragma unroll
+            for (int ja = 0; ja < ZID_NB; ++ja) if (ja < nA) { cd* q = &A[(long long)i * ld + k0 + ja]; *q = *q + acc[ja]; }
+        }
+    }
+    __syncthreads();
+    if (tid < nb) pivg[k0 + tid] = pivs[tid];
+    if (a.info && tid == 0) {
+        if (a.info_mode > 0) { if (bad) KH_ATOMIC_OR(&a.info[b / a.info_mode], 2); }
+        else if (k0 == 0) a.info[b] = bad; else if (bad && a.info[b] == 0) a.info[b] = bad;
+    }
+}
+__device__ __forceinline__ void zinvb_panel32a_body(const Cta& c, const zinvb_args& a) { zinvb_panel32_body_t<8>(c, a); }      // n <= 256
+__device__ __forceinline__ void zinvb_panel32b_body(const Cta& c, const zinvb_args& a) { zinvb_panel32_body_t<16>(c, a); }     // n <= 512
+#endif
+
 // undo the row interchanges: out[:, j] = in[:, src[j]] with src = the column swaps (k <-> piv[k]) applied for k = n-1 .. 0
 KH_DEV void zinvb_unpermute_body(const Cta& c, const zinvb_args& a) {
     const int n = a.n, b = c.bx;
@@ -462,7 +564,7 @@ static inline int zinvb_nb(int n) {
     return nb;
 }
 // work space of the blocked variant, in complex elements per matrix (pivot rows + pivot indices)
-static inline long long zinv_work_cd(int n) { return (long long)zinvb_nb(n) * n + (n + 3) / 4 + 4; }
+static inline long long zinv_work_cd(int n) { const int nb = zinvb_nb(n) > 32 ? zinvb_nb(n) : 32; return (long long)nb * n + (n + 3) / 4 + 4; }
 #ifndef KH_ZINV_BLOCKED_MIN
 #define KH_ZINV_BLOCKED_MIN 101
 #endif
@@ -473,7 +575,12 @@ static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A
         zcopym_args cp{n, A, Ainv};
         if ((e = kh_launch<zcopym_args, zcopym_body>(dim3(batch), 256, 0, st, cp, "zinv", 0.0))) return e;
     }
-    const int nb = zinvb_nb(n);
+#ifndef KH_HOST_EMU
+    const bool fastpanel = n <= 512;                   // register-resident block column of 32 pivots on the L2-resident matrix
+#else
+    const bool fastpanel = false;
+#endif
+    const int nb = fastpanel ? 32 : zinvb_nb(n);
     const long long wstride = zinv_work_cd(n);
     zinvb_args a;
     a.n = n; a.nb = nb; a.A = Ainv; a.R = work; a.r_stride = wstride; a.info = info; a.lds = nb + 1; a.info_mode = info_mode;
@@ -482,6 +589,14 @@ static inline int zinv_blocked_launch(kh_stream_t st, int batch, int n, MatRef A
     for (int k0 = 0; k0 < n; k0 += nb) {
         a.k0 = k0;
         const int nbk = nb < n - k0 ? nb : n - k0;
+#ifndef KH_HOST_EMU
+        if (fastpanel) {
+            const size_t psm = (size_t)34 * sizeof(zid_slot) + (size_t)ZID_NB * ZID_NB * sizeof(cd) + 64 * sizeof(int) + 16;
+            if (n <= 256) e = kh_launch<zinvb_args, zinvb_panel32a_body, 512, 1>(dim3(batch), 512, psm, st, a, "zinv", 0.0);
+            else e = kh_launch<zinvb_args, zinvb_panel32b_body, 512, 1>(dim3(batch), 512, psm, st, a, "zinv", 0.0);
+            if (e) return e;
+        } else
+#endif
         if ((e = kh_launch<zinvb_args, zinvb_panel_body>(dim3(batch), 512, sm, st, a, "zinv", 0.0))) return e;
         MatRef Pm = Ainv; Pm.p = Ainv.p + k0;
         MatRef Rm = mref(work, wstride, n);
