@@ -528,6 +528,25 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
 }
 
 // ---------------------------------------------------------------------------- chunk layout
+// Field solves of a FEW frequencies (a field map: 17 ... 51 solves) leave most of the GPU idle in every launch of the two
+// partial-product chains (layer.py:41-59), which are independent of each other: up to this batch size the reverse chain runs on
+// a second stream beside the forward chain (own scratch, fork / join by events on the caller's stream).
+#define KH_FORK_MAXB 148
+#ifndef KH_HOST_EMU
+struct KhFork { cudaStream_t st; cudaEvent_t fork, join; };
+static KhFork* kh_fork_get() {
+    static KhFork* per_dev[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!per_dev[dev]) {
+        KhFork* f = new KhFork;
+        if (cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) { delete f; return nullptr; }
+        per_dev[dev] = f;
+    }
+    return per_dev[dev];
+}
+#endif
 struct ChunkBufs {
     cd *Kx, *Ky; double* k0;
     std::vector<cd*> layerS;        // per layer: BD table [Bc][16N] or dense sym [Bc][2][n][n] or dense full [Bc][4][n][n] (extended)
@@ -537,6 +556,7 @@ struct ChunkBufs {
     cd* dblx;                       // DBL_BLOCK_SLABS x [Bc][n][n] (doubling method only)
     LayerVec vec;
     cd* accD[2]; cd* accB[2]; cd* expA; cd* expB; cd* accR[2];
+    cd* pool2; cd* accB2[2]; cd* expA2;     // scratch of the reverse chain when it runs beside the forward chain (small batches)
     int* info;
     // extended-layer scratch (small base problems at Nb harmonics, Bc*Nb sub-solves)
     cd *eKx, *eKy; double* ek0; cd* epool; LayerVec evec; cd* eS; cd* ebd; double* ewl; cd* ekp;
@@ -572,6 +592,11 @@ static void layout_chunk(const kh_plan* p, int Bc, int flags, Bump& b, ChunkBufs
     cb.expA = b.get<cd>((size_t)Bc * 4 * n2); cb.expB = b.get<cd>((size_t)Bc * 4 * n2);
     cb.accR[0] = cb.accR[1] = nullptr;
     if (flags & KH_WANT_FIELDS) { cb.accR[0] = b.get<cd>((size_t)Bc * 4 * n2); cb.accR[1] = b.get<cd>((size_t)Bc * 4 * n2); }
+    cb.pool2 = nullptr; cb.accB2[0] = cb.accB2[1] = nullptr; cb.expA2 = nullptr;
+    if ((flags & KH_WANT_FIELDS) && Bc <= KH_FORK_MAXB) {
+        cb.pool2 = b.get<cd>((size_t)STAR_TMP_SLABS * Bc * n2); cb.expA2 = b.get<cd>((size_t)Bc * 4 * n2);
+        for (int i = 0; i < 2; ++i) cb.accB2[i] = b.get<cd>((size_t)Bc * 16 * N);
+    }
     cb.info = b.get<int>(Bc);
     cb.eKx = cb.eKy = nullptr; cb.ek0 = nullptr; cb.epool = nullptr; cb.eS = nullptr; cb.ebd = nullptr; cb.ewl = nullptr; cb.ekp = nullptr;
     if (p->has_ext) {
@@ -716,6 +741,22 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
             else { acc_full = cb.accD[pd]; pd ^= 1; }
             return e;
         };
+        bool forked = false;
+#ifndef KH_HOST_EMU
+        if (want_fields && cb.pool2) {
+            KhFork* fk = kh_fork_get();
+            if (fk && cudaEventRecord(fk->fork, st) == cudaSuccess && cudaStreamWaitEvent(fk->st, fk->fork, 0) == cudaSuccess) {
+                ChunkBufs cr = cb;                                        // the reverse chain's own scratch
+                cr.pool = cb.pool2; cr.accB[0] = cb.accB2[0]; cr.accB[1] = cb.accB2[1]; cr.expA = cb.expA2;
+                int e = reverse_chain(fk->st, p, Bc, S, cr, out, b0, info_out ? info_out : cb.info);
+                cudaEventRecord(fk->join, fk->st);                        // (joined below even after an error: nothing may outlive the call)
+                forked = true;
+                if (e) { cudaStreamWaitEvent(st, fk->join, 0); return e; }
+            }
+        }
+#endif
+        cd* final_dst = nullptr;
+        const int efw = [&]() -> int {
         if (want_fields) {
             for (int i = 0; i < Ls; ++i) {
                 const SRef& R = S[p->stack[i]];
@@ -761,14 +802,20 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         }
         if (!acc.bd && acc.blk[0].p != acc_full) acc_full = nullptr;      // acc still refers to a layer table
         if (acc.bd || !acc_full) { KH_TRY(materialise(st, Bc, N, acc, cb.accD[pd], 4 * n2, nullptr)); acc_full = cb.accD[pd]; }
-        cd* final_dst = acc_full;
+        final_dst = acc_full;
         if (out->Stot_dev) {
             copyv_args cs{4 * n2, acc_full, 4 * n2, (cd*)out->Stot_dev + (long long)b0 * 4 * n2, 4 * n2};
             KH_TRY((kh_launch<copyv_args, copyv_body>(dim3(Bc), 256, 0, st, cs)));
         }
 
+        return 0;
+        }();
         // ---- reverse chain (layer.py:49-59), only when fields are wanted
-        if (want_fields) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0, info_out ? info_out : cb.info));
+#ifndef KH_HOST_EMU
+        if (forked) { KhFork* fk = kh_fork_get(); if (!fk || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess) return fail(KH_ESTATE, "kh_solve_batch: stream join failed"); }
+#endif
+        if (efw) return efw;
+        if (want_fields && !forked) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0, info_out ? info_out : cb.info));
 
         if (flags & KH_WANT_FLUX) {
             flux_args a{Bc, N, final_dst, wl, kp, pol, p->g_dev, p->epsi, p->epse,

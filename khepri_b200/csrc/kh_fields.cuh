@@ -51,22 +51,23 @@ KH_DEV void fld_c1p_body(const Cta& c, const fld_c1p_args& a) {
 }
 
 // amplitudes in the gap right of stack position i and their free-space field vector y = R0 [c+; c-]
+// (one CTA per (solve b, stack position of the run): bx = b * run + j, which is also the batch index of the three matrix stacks)
 struct fld_amp_args {
-    int B, N;
+    int B, N, run;
     MatRef Finv, Sl21, Sr11;
     const cd* c1p; const cd* Kx; const cd* Ky;
-    cd* y12;                       // [B][2][n]
+    cd* y12;                       // [B * run][2][n]
 };
 KH_DEV void fld_amp_body(const Cta& c, const fld_amp_args& a) {
-    const int N = a.N, n = 2 * N, b = c.bx;
+    const int N = a.N, n = 2 * N, bj = c.bx, b = bj / a.run;
     cd* t0 = (cd*)c.smem; cd* cp = t0 + n; cd* cm = cp + n;
-    cta_matvec(c, mat_ptr(a.Sl21, b), a.Sl21.ld, a.c1p + (long long)b * n, t0, n, n);
+    cta_matvec(c, mat_ptr(a.Sl21, bj), a.Sl21.ld, a.c1p + (long long)b * n, t0, n, n);
     c.sync();
-    cta_matvec(c, mat_ptr(a.Finv, b), a.Finv.ld, t0, cp, n, n);
+    cta_matvec(c, mat_ptr(a.Finv, bj), a.Finv.ld, t0, cp, n, n);
     c.sync();
-    cta_matvec(c, mat_ptr(a.Sr11, b), a.Sr11.ld, cp, cm, n, n);
+    cta_matvec(c, mat_ptr(a.Sr11, bj), a.Sr11.ld, cp, cm, n, n);
     c.sync();
-    cd* y1 = a.y12 + (long long)b * 2 * n; cd* y2 = y1 + n;
+    cd* y1 = a.y12 + (long long)bj * 2 * n; cd* y2 = y1 + n;
     for (int g = c.tid; g < N; g += c.nthr) {
         m22 V0 = v0_block(a.Kx[(long long)b * N + g], a.Ky[(long long)b * N + g]);
         cd d1 = cm[g] - cp[g], d2 = cm[N + g] - cp[N + g];
@@ -76,15 +77,17 @@ KH_DEV void fld_amp_body(const Cta& c, const fld_amp_args& a) {
 }
 
 // m = R_i^-1 y :  m1 = 1/2 (W^-1 y1 - V^-1 y2),  m2 = 1/2 (W^-1 y1 + V^-1 y2)
-struct fld_modes_args { int B, n; MatRef Winv, Vinv; const cd* y12; cd* m12; long long m_stride; };
+// Winv, Vinv: [B][nL][n][n]; the layer of stack position i0 + j from the device copy of the stack
+struct fld_modes_args { int B, n, run, i0, nL; const int* stack; const cd* Winv; const cd* Vinv; const cd* y12; cd* m12; long long m_bstride; };
 KH_DEV void fld_modes_body(const Cta& c, const fld_modes_args& a) {
-    const int n = a.n, b = c.bx;
+    const int n = a.n, bj = c.bx, b = bj / a.run, i = a.i0 + (bj - b * a.run);
     cd* p = (cd*)c.smem; cd* q = p + n;
-    const cd* y1 = a.y12 + (long long)b * 2 * n;
-    cta_matvec(c, mat_ptr(a.Winv, b), a.Winv.ld, y1, p, n, n);
-    cta_matvec(c, mat_ptr(a.Vinv, b), a.Vinv.ld, y1 + n, q, n, n);
+    const cd* y1 = a.y12 + (long long)bj * 2 * n;
+    const long long wv = ((long long)b * a.nL + a.stack[i]) * n * n;
+    cta_matvec(c, a.Winv + wv, n, y1, p, n, n);
+    cta_matvec(c, a.Vinv + wv, n, y1 + n, q, n, n);
     c.sync();
-    cd* m1 = a.m12 + (long long)b * a.m_stride; cd* m2 = m1 + n;
+    cd* m1 = a.m12 + (long long)b * a.m_bstride + (long long)i * 2 * n; cd* m2 = m1 + n;
     for (int i = c.tid; i < n; i += c.nthr) { m1[i] = 0.5 * (p[i] - q[i]); m2[i] = 0.5 * (p[i] + q[i]); }
 }
 
@@ -224,24 +227,32 @@ KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) {
 
 struct FieldBufs {
     cd *Kx, *Ky; double* k0; cd* c1p; cd* Fm; cd* Finv; cd* y12; cd* m12; cd* Winv; cd* Vinv; cd* Sall; cd* Ph;
-    int* zpos; int* zlayer; double* zdist; const cd** ICp; cd* ICs; int* info;
+    int* zpos; int* zlayer; double* zdist; const cd** ICp; cd* ICs; int* info; int* stack;
+    int group;                          // stack positions (or layers) whose inverses go out as ONE batched launch
     cd* zwork; long long zwork_cd;      // work space of the blocked inverse (n beyond shared memory)
     cd* Xt; cd* Yt;                     // grid path: phase tables
 };
 static void layout_fields(const kh_plan* p, int B, int npts, int nz, Bump& b, FieldBufs& f, int nx = 0, int ny = 0) {
     const size_t N = p->N, n = p->n, n2 = n * n, nL = p->layers.size(), Ls = p->stack.size();
     f.Kx = b.get<cd>(B * N); f.Ky = b.get<cd>(B * N); f.k0 = b.get<double>(B);
-    f.c1p = b.get<cd>(B * n); f.Fm = b.get<cd>(B * n2); f.Finv = b.get<cd>(B * n2);
-    f.y12 = b.get<cd>(B * 2 * n); f.m12 = b.get<cd>(B * Ls * 2 * n);
-    f.Winv = b.get<cd>(nL * B * n2); f.Vinv = b.get<cd>(nL * B * n2);
+    // The inverses of the pipeline (W^-1, V^-1 per layer, F^-1 per stack position) are independent of each other: positions are
+    // processed in groups so that a small batch of solves (17 frequencies of a field map) still fills the GPU with one launch
+    // per group instead of one launch of B matrices per position.  Up to two waves of one CTA per SM per launch.
+    size_t group = B >= 296 ? 1 : 296 / (size_t)B;
+    if (group > (Ls > nL ? Ls : nL)) group = (Ls > nL ? Ls : nL);
+    f.group = (int)group;
+    const size_t Bz = (size_t)B * group;
+    f.c1p = b.get<cd>(B * n); f.Fm = b.get<cd>(Bz * n2); f.Finv = b.get<cd>(Bz * n2);
+    f.y12 = b.get<cd>(Bz * 2 * n); f.m12 = b.get<cd>(B * Ls * 2 * n);
+    f.Winv = b.get<cd>(nL * B * n2); f.Vinv = b.get<cd>(nL * B * n2);      // [B][nL][n][n]
     f.Sall = b.get<cd>((size_t)B * nz * 6 * N);
     if (nx > 0) { f.Ph = nullptr; f.Xt = b.get<cd>((size_t)B * N * nx); f.Yt = b.get<cd>((size_t)B * p->Q * ny); }
     else { f.Ph = b.get<cd>((size_t)B * N * npts); f.Xt = f.Yt = nullptr; }
     f.zpos = b.get<int>(nz); f.zlayer = b.get<int>(nz); f.zdist = b.get<double>(nz);
-    f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * B);
-    f.zwork_cd = (int)n >= KH_ZINV_BLOCKED_MIN ? (long long)B * zinv_work_cd((int)n) : 0;
+    f.ICp = b.get<const cd*>(nL); f.ICs = b.get<cd>(nL); f.info = b.get<int>(2 * Bz); f.stack = b.get<int>(Ls);
+    f.zwork_cd = (int)n >= KH_ZINV_BLOCKED_MIN ? (long long)Bz * zinv_work_cd((int)n) : 0;
 #ifndef KH_HOST_EMU
-    if ((int)n >= KH_ZINV_BLOCKED_MIN && (int)n <= ZIL_NMAX && (long long)B * zinv_l2_work_cd((int)n) > f.zwork_cd) f.zwork_cd = (long long)B * zinv_l2_work_cd((int)n);
+    if ((int)n >= KH_ZINV_BLOCKED_MIN && (int)n <= ZIL_NMAX && (long long)Bz * zinv_l2_work_cd((int)n) > f.zwork_cd) f.zwork_cd = (long long)Bz * zinv_l2_work_cd((int)n);
 #endif
     f.zwork = b.get<cd>((size_t)f.zwork_cd);
 }
@@ -333,26 +344,35 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
         KH_TRY((kh_launch<fld_c1p_args, fld_c1p_body>(dim3(B), 128, 0, st, a))); }
 
     cd* Wd = (cd*)solved->W_dev; cd* Vd = (cd*)solved->V_dev;
-    for (int li = 0; li < nL; ++li) {
-        if (!lay_active[li]) continue;
-        KH_TRY(zinv_launch(st, B, n, mref(Wd + (long long)li * n2, (long long)nL * n2, n), mref(f.Winv + (long long)li * B * n2, n2, n), f.info, f.zwork, f.zwork_cd));
-        KH_TRY(zinv_launch(st, B, n, mref(Vd + (long long)li * n2, (long long)nL * n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.info + B, f.zwork, f.zwork_cd));
+    KH_TRY(kh_h2d(f.stack, p->stack.data(), Ls * sizeof(int), st));
+    // W^-1, V^-1 of the layers that hold a depth: runs of consecutive active layers, at most f.group per launch; batch index
+    // b * run + j <-> (solve b, layer l0 + j) on the [B][nL][n][n] stacks
+    for (int l0 = 0; l0 < nL;) {
+        if (!lay_active[l0]) { ++l0; continue; }
+        int run = 1;
+        while (l0 + run < nL && lay_active[l0 + run] && run < f.group) ++run;
+        KH_TRY(zinv_launch(st, B * run, n, mref(Wd + (long long)l0 * n2, (long long)nL * n2, n, run, n2),
+                           mref(f.Winv + (long long)l0 * n2, (long long)nL * n2, n, run, n2), f.info, f.zwork, f.zwork_cd));
+        KH_TRY(zinv_launch(st, B * run, n, mref(Vd + (long long)l0 * n2, (long long)nL * n2, n, run, n2),
+                           mref(f.Vinv + (long long)l0 * n2, (long long)nL * n2, n, run, n2), f.info, f.zwork, f.zwork_cd));
+        l0 += run;
     }
     cd* pre = (cd*)solved->prefix_dev; cd* suf = (cd*)solved->suffix_dev;
     const long long sstride = (long long)Ls * 4 * n2;
-    for (int i = 0; i < Ls; ++i) {
-        if (!pos_active[i]) continue;
-        MatRef Sl22 = mref(pre + ((long long)i * 4 + 3) * n2, sstride, n), Sl21 = mref(pre + ((long long)i * 4 + 2) * n2, sstride, n);
-        MatRef Sr11 = mref(suf + ((long long)i * 4 + 0) * n2, sstride, n);
+    for (int i0 = 0; i0 < Ls;) {
+        if (!pos_active[i0]) { ++i0; continue; }
+        int run = 1;
+        while (i0 + run < Ls && pos_active[i0 + run] && run < f.group) ++run;
+        MatRef Sl22 = mref(pre + ((long long)i0 * 4 + 3) * n2, sstride, n, run, 4 * n2), Sl21 = mref(pre + ((long long)i0 * 4 + 2) * n2, sstride, n, run, 4 * n2);
+        MatRef Sr11 = mref(suf + ((long long)i0 * 4 + 0) * n2, sstride, n, run, 4 * n2);
         MatRef Fm = mref(f.Fm, n2, n), Fi = mref(f.Finv, n2, n);
-        KH_TRY(gemm(st, B, n, Sl22, Sr11, Fm, -1.0, nullptr, 0.0, 1.0));
-        KH_TRY(zinv_launch(st, B, n, Fm, Fi, f.info, f.zwork, f.zwork_cd));
-        {   fld_amp_args a{B, N, Fi, Sl21, Sr11, f.c1p, f.Kx, f.Ky, f.y12};
-            KH_TRY((kh_launch<fld_amp_args, fld_amp_body>(dim3(B), 256, (size_t)3 * n * sizeof(cd), st, a))); }
-        const int li = p->stack[i];
-        {   fld_modes_args a{B, n, mref(f.Winv + (long long)li * B * n2, n2, n), mref(f.Vinv + (long long)li * B * n2, n2, n), f.y12,
-                             f.m12 + (long long)i * 2 * n, (long long)Ls * 2 * n};
-            KH_TRY((kh_launch<fld_modes_args, fld_modes_body>(dim3(B), 256, (size_t)2 * n * sizeof(cd), st, a))); }
+        KH_TRY(gemm(st, B * run, n, Sl22, Sr11, Fm, -1.0, nullptr, 0.0, 1.0));
+        KH_TRY(zinv_launch(st, B * run, n, Fm, Fi, f.info, f.zwork, f.zwork_cd));
+        {   fld_amp_args a{B, N, run, Fi, Sl21, Sr11, f.c1p, f.Kx, f.Ky, f.y12};
+            KH_TRY((kh_launch<fld_amp_args, fld_amp_body>(dim3(B * run), 256, (size_t)3 * n * sizeof(cd), st, a))); }
+        {   fld_modes_args a{B, n, run, i0, nL, f.stack, f.Winv, f.Vinv, f.y12, f.m12, (long long)Ls * 2 * n};
+            KH_TRY((kh_launch<fld_modes_args, fld_modes_body>(dim3(B * run), 256, (size_t)2 * n * sizeof(cd), st, a))); }
+        i0 += run;
     }
     {   fld_z_args a{B, N, nz, f.zpos, f.zlayer, f.zdist, f.m12, (long long)Ls * 2 * n, 2LL * n,
                      Wd, Vd, (const cd*)solved->L_dev, (long long)nL * n2, nL, f.ICp, f.ICs, f.Kx, f.Ky, f.k0, f.Sall};
