@@ -45,6 +45,14 @@ KH_HD void cfma(cd& c, cd a, cd b) {
     c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
     c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
 }
+// write-once output streams (field maps): evict-first store, the data is not read again by the kernel
+KH_HD void kh_store_stream(cd* p, cd v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+#else
+    *p = v;
+#endif
+}
 // c -= a*b
 KH_HD void cfms(cd& c, cd a, cd b) {
     c.x = fma(-a.x, b.x, c.x); c.x = fma(a.y, b.y, c.x);

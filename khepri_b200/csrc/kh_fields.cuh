@@ -180,23 +180,27 @@ KH_DEV void fld_gtab_body(const Cta& c, const fld_gtab_args& a) {
 }
 #define FLD_QMAX 16
 struct fld_grid_args { int B, N, P, Q, nx, ny, maps, ysplit; const cd* Sall; const cd* Xt; const cd* Yt; cd* F; };
-KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) {
+// QT = Q at compile time (the T registers and the q loops are exact: no predicates, half the registers of the generic form, three
+// CTAs per SM); QT = 0: any Q <= FLD_QMAX.
+template <int QT>
+KH_DEV void fld_grid_body_t(const Cta& c, const fld_grid_args& a) {
+    constexpr int QN = QT > 0 ? QT : FLD_QMAX;
     const int b = c.bx, map = c.by / a.ysplit, part = c.by - map * a.ysplit;         // map = iz * 6 + component
-    const int P = a.P, Q = a.Q, N = a.N, nx = a.nx, ny = a.ny;
+    const int P = a.P, Q = QT > 0 ? QT : a.Q, N = a.N, nx = a.nx, ny = a.ny, tid = c.tid, nthr = c.nthr;
     const int y0 = (int)((long long)ny * part / a.ysplit), y1 = (int)((long long)ny * (part + 1) / a.ysplit);
     // shared: [S N][Y Q x (y1 - y0)]
     cd* Ss = (cd*)c.smem;
     cd* Ys = Ss + N;
     const int nyl = y1 - y0;
     const cd* S = a.Sall + ((long long)b * a.maps + map) * N;
-    for (int g = c.tid; g < N; g += c.nthr) Ss[g] = S[g];
-    for (int e = c.tid; e < Q * nyl; e += c.nthr) { const int q = e / nyl, i = e - q * nyl; Ys[e] = a.Yt[((long long)b * Q + q) * ny + y0 + i]; }
+    for (int g = tid; g < N; g += nthr) Ss[g] = S[g];
+    for (int e = tid; e < Q * nyl; e += nthr) { const int q = e / nyl, i = e - q * nyl; Ys[e] = a.Yt[((long long)b * Q + q) * ny + y0 + i]; }
     c.sync();
     cd* out = a.F + ((long long)b * a.maps + map) * ny * nx;
-    for (int ix = c.tid; ix < nx; ix += c.nthr) {
-        cd T[FLD_QMAX];
+    for (int ix = tid; ix < nx; ix += nthr) {
+        cd T[QN];
 #pragma unroll
-        for (int q = 0; q < FLD_QMAX; ++q) {
+        for (int q = 0; q < QN; ++q) {
             T[q] = mk(0, 0);
             if (q < Q) {
                 const cd* xr = a.Xt + ((long long)b * N + q * P) * nx + ix;
@@ -205,25 +209,31 @@ KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) {
                 T[q] = acc;
             }
         }
+        cd* o = out + (long long)y0 * nx + ix;
+        const cd* yr = Ys;
         int iy = 0;
-        for (; iy + 4 <= nyl; iy += 4) {                                   // four independent accumulation chains per thread
+        for (; iy + 4 <= nyl; iy += 4, yr += 4, o += 4LL * nx) {             // four independent accumulation chains per thread
             cd f0 = mk(0, 0), f1 = mk(0, 0), f2 = mk(0, 0), f3 = mk(0, 0);
 #pragma unroll
-            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) {
-                const cd* yq = Ys + q * nyl + iy;
+            for (int q = 0; q < QN; ++q) if (q < Q) {
+                const cd* yq = yr + q * nyl;
                 cfma(f0, T[q], yq[0]); cfma(f1, T[q], yq[1]); cfma(f2, T[q], yq[2]); cfma(f3, T[q], yq[3]);
             }
-            cd* o = out + (long long)(y0 + iy) * nx + ix;
-            o[0] = f0; o[nx] = f1; o[2LL * nx] = f2; o[3LL * nx] = f3;
+            kh_store_stream(o, f0); kh_store_stream(o + nx, f1); kh_store_stream(o + 2LL * nx, f2); kh_store_stream(o + 3LL * nx, f3);
         }
-        for (; iy < nyl; ++iy) {
+        for (; iy < nyl; ++iy, ++yr, o += nx) {
             cd f0 = mk(0, 0);
 #pragma unroll
-            for (int q = 0; q < FLD_QMAX; ++q) if (q < Q) cfma(f0, T[q], Ys[q * nyl + iy]);
-            out[(long long)(y0 + iy) * nx + ix] = f0;
+            for (int q = 0; q < QN; ++q) if (q < Q) cfma(f0, T[q], yr[q * nyl]);
+            kh_store_stream(o, f0);
         }
     }
 }
+KH_DEV void fld_grid_body(const Cta& c, const fld_grid_args& a) { fld_grid_body_t<0>(c, a); }
+KH_DEV void fld_grid5_body(const Cta& c, const fld_grid_args& a) { fld_grid_body_t<5>(c, a); }
+KH_DEV void fld_grid7_body(const Cta& c, const fld_grid_args& a) { fld_grid_body_t<7>(c, a); }
+KH_DEV void fld_grid9_body(const Cta& c, const fld_grid_args& a) { fld_grid_body_t<9>(c, a); }
+KH_DEV void fld_grid11_body(const Cta& c, const fld_grid_args& a) { fld_grid_body_t<11>(c, a); }
 
 struct FieldBufs {
     cd *Kx, *Ky; double* k0; cd* c1p; cd* Fm; cd* Finv; cd* y12; cd* m12; cd* Winv; cd* Vinv; cd* Sall; cd* Ph;
@@ -391,7 +401,15 @@ static int fields_impl(const kh_plan* plan, int B, const double* wl_dev, const v
         const size_t sm = table_bytes(ysplit);
         if (sm > (size_t)KH_SMEM_MAX) return fail(KH_EINVAL, "kh_fields_grid_batch: basis too large for the phase table in shared memory");
         const double work = 8.0 * ((double)N * nx + (double)p->Q * nx * ny) * 6.0 * nz * B;
-        return kh_launch<fld_grid_args, fld_grid_body>(dim3(B, 6 * nz * ysplit), nx >= 256 ? 256 : (nx >= 128 ? 128 : 64), sm, st, a, "fld_grid", work);
+        const dim3 gg(B, 6 * nz * ysplit);
+        const int thr = nx >= 256 ? 256 : (nx >= 128 ? 128 : 64);
+        switch (p->Q) {          // the usual odd bases with the q loops exact; anything else through the generic form
+            case 5: return kh_launch<fld_grid_args, fld_grid5_body, 256, 3>(gg, thr, sm, st, a, "fld_grid", work);
+            case 7: return kh_launch<fld_grid_args, fld_grid7_body, 256, 3>(gg, thr, sm, st, a, "fld_grid", work);
+            case 9: return kh_launch<fld_grid_args, fld_grid9_body, 256, 3>(gg, thr, sm, st, a, "fld_grid", work);
+            case 11: return kh_launch<fld_grid_args, fld_grid11_body, 256, 2>(gg, thr, sm, st, a, "fld_grid", work);
+            default: return kh_launch<fld_grid_args, fld_grid_body>(gg, thr, sm, st, a, "fld_grid", work);
+        }
     }
     {   fld_phase_args a{B, N, npts, (const cd*)kp_dev, p->g_dev, x_dev, y_dev, f.Ph};
         KH_TRY((kh_launch<fld_phase_args, fld_phase_body>(dim3(B, N), 256, 0, st, a))); }
