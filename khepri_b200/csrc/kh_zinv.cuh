@@ -219,8 +219,10 @@ __device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr
                                            int w, int nwork, int lane) {
     const int lr = lane >> 2, lk = lane & 3;
     const int nstrip = np >> 3, ncols = inside ? (c1 - c0) : nstrip - (c1 - c0), total = nstrip * ncols;
+    if (ncols <= 0) return;
+    int strip = w / ncols, tcr = w - strip * ncols;               // (one division per call; the tile index then advances incrementally)
     for (int t = w; t < total; t += nwork) {
-        const int strip = t / ncols; int tc = t - strip * ncols;
+        int tc = tcr;
         if (inside) tc += c0; else if (tc >= c0) tc += c1 - c0;
         cd* cp = As + (strip * 8 + lr) * lda + tc * 8 + 2 * lk;
         const cd* ap = As + (strip * 8 + lr) * lda + k0 + lk;
@@ -244,6 +246,8 @@ __device__ __forceinline__ void zid_update(cd* As, const cd* R, int lda, int ldr
             }
         }
         cp[0] = mk(cr0, ci0); cp[1] = mk(cr1, ci1);
+        tcr += nwork;
+        while (tcr >= ncols) { tcr -= ncols; ++strip; }
     }
 }
 // GLOBAL = false: the matrix lives in shared memory (n <= 104).  GLOBAL = true: the same single-launch algorithm with the working
@@ -293,8 +297,9 @@ __device__ __forceinline__ void zinv_dmma_body_t(const Cta& c, const zinv_args& 
         __syncthreads();
         zid_update(As, R, lda, ldr, np, k0, nbk, k0 >> 3, k1 >> 3, false, warp, NW, lane);
         __syncthreads();
-        // (a look-ahead schedule -- next panel factorised by the panel warps while the others finish this update -- was measured:
-        //  no gain, the panel's dependent DFMA chain queues behind the DMMAs on the shared FP64 pipe)
+        // (look-ahead schedules -- next panel factorised while the other warps finish this update -- were measured three times, with
+        //  the panel warps spread over all four schedulers, packed on one, and on two with the update on the rest: no gain,
+        //  profiles/r02_experiments.md)
         if (nbk1 > 0 && warp < PW) zid_panel<PW, NB>(As, lda, np, n, k1, nbk1, slots, piv, bad, tid);
         __syncthreads();
     }
