@@ -363,7 +363,9 @@ static inline size_t zgemm_smem(int T, int ST) { return (size_t)ST * (T * ZG_LDA
 // Shapes that waste less padding on 56x56 tiles (n = 50: one tile, n = 98: 2x2 tiles) use the unit-balanced kernel, the rest
 // the 64x64 strip kernel.  Measured and dropped in round 1: a strip-per-warp 56x56 pipeline, the first-generation double-buffer
 // kernels, a 104x104 one-CTA-per-matrix tile (13 warps need > 128 registers for the 13 accumulator tiles), a 3-CTA/SM 2-stage
-// variant (no gain), and a persistent grid whose cp.async pipeline runs across tile boundaries (7 % slower).
+// variant (no gain), and a persistent grid whose cp.async pipeline runs across tile boundaries (7 % slower).  Round 2: tiles staged
+// by TMA bulk copies (one per tile row) with full / empty mbarriers instead of cp.async + one CTA barrier: 30 % slower
+// (profiles/r02_experiments.md).
 static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     if (batch <= 0 || a.M <= 0 || a.N <= 0) return 0;
     const double work = 8.0 * a.M * a.N * a.K * batch;
