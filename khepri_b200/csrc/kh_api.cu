@@ -13,6 +13,8 @@
 #include "kh_peak.cuh"
 
 #include <string>
+#include <mutex>
+#include <map>
 #include <vector>
 
 static thread_local std::string g_err;
@@ -534,17 +536,21 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
 #define KH_FORK_MAXB 148
 #ifndef KH_HOST_EMU
 struct KhFork { cudaStream_t st; cudaEvent_t fork, join; };
-static KhFork* kh_fork_get() {
-    static KhFork* per_dev[64] = {nullptr};
+// one side stream + event pair per (device, caller stream): two host threads driving two streams never share events
+static KhFork* kh_fork_get(cudaStream_t caller) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, KhFork*> table;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!per_dev[dev]) {
-        KhFork* f = new KhFork;
-        if (cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) { delete f; return nullptr; }
-        per_dev[dev] = f;
-    }
-    return per_dev[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, caller);
+    auto it = table.find(key);
+    if (it != table.end()) return it->second;
+    KhFork* f = new KhFork;
+    if (cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) { delete f; return nullptr; }
+    table[key] = f;
+    return f;
 }
 #endif
 struct ChunkBufs {
@@ -744,7 +750,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         bool forked = false;
 #ifndef KH_HOST_EMU
         if (want_fields && cb.pool2) {
-            KhFork* fk = kh_fork_get();
+            KhFork* fk = kh_fork_get(st);
             if (fk && cudaEventRecord(fk->fork, st) == cudaSuccess && cudaStreamWaitEvent(fk->st, fk->fork, 0) == cudaSuccess) {
                 ChunkBufs cr = cb;                                        // the reverse chain's own scratch
                 cr.pool = cb.pool2; cr.accB[0] = cb.accB2[0]; cr.accB[1] = cb.accB2[1]; cr.expA = cb.expA2;
@@ -812,7 +818,7 @@ extern "C" int kh_solve_batch(kh_plan* plan, int B, const double* wl_dev, const 
         }();
         // ---- reverse chain (layer.py:49-59), only when fields are wanted
 #ifndef KH_HOST_EMU
-        if (forked) { KhFork* fk = kh_fork_get(); if (!fk || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess) return fail(KH_ESTATE, "kh_solve_batch: stream join failed"); }
+        if (forked) { KhFork* fk = kh_fork_get(st); if (!fk || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess) return fail(KH_ESTATE, "kh_solve_batch: stream join failed"); }
 #endif
         if (efw) return efw;
         if (want_fields && !forked) KH_TRY(reverse_chain(st, p, Bc, S, cb, out, b0, info_out ? info_out : cb.info));
