@@ -160,6 +160,41 @@ def test_fields_grid_path_matches_point_path(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_fields_batched_groups_match_single_solves(backend):
+    """The field pipeline batches its inverses over groups of stack positions / layers (up to 296 matrices per launch): a batch
+    of 40 sources over the 14-position stack splits into two runs of 7 positions, depths that skip layers leave gaps between
+    the runs.  Every solve of the batch must equal the same source solved alone (one group of all positions)."""
+    eng = engine(backend)
+    st, _, (X, Y, _) = cases.case_fields(3, slices=4, grid=(5, 4, 3))
+    cl = build_crystal(st, eng, fields=True)
+    B = 40
+    wls = 1 / np.linspace(0.49, 0.6, B)
+    cl.set_source(wavelength=float(wls[0]), te=1.0, tm=0.0)
+    cl.solve()
+    plan = cl._get_plan(True)
+    assert plan.Ls == 14
+    zp = np.asarray(cl.stack_positions)
+    z = np.array([0.5 * (zp[1] + zp[2]), 0.3 * zp[2] + 0.7 * zp[3], 0.5 * (zp[5] + zp[6]), 0.5 * (zp[11] + zp[12])])     # positions 1, 2, 5, 11
+    kp = np.zeros((B, 2), dtype=complex)
+    pol = np.tile([[1.0, 0.0]], (B, 1)).astype(complex)
+    inc = []
+    for w in wls:
+        cl.set_source(wavelength=float(w), te=1.0, tm=0.0)
+        inc.append(np.hstack(cl.get_source_as_field_vectors()))
+    inc = np.asarray(inc).reshape(B, 2, plan.n)
+    solved = eng.solve_batch(plan, wls, kp, pol, want_flux=True, want_fields=True)
+    F = eng.fields(plan, solved, wls, kp, inc, X.ravel(), Y.ravel(), z, zp).cpu().numpy()
+    zall = np.linspace(0.01, zp[-2] - 0.01, 23)                                                  # every position active: runs of 7 + 7
+    Fall = eng.fields(plan, solved, wls, kp, inc, X.ravel(), Y.ravel(), zall, zp).cpu().numpy()
+    for b in (0, 17, 39):
+        one = eng.solve_batch(plan, wls[b:b + 1], kp[b:b + 1], pol[b:b + 1], want_flux=True, want_fields=True)
+        F1 = eng.fields(plan, one, wls[b:b + 1], kp[b:b + 1], inc[b:b + 1], X.ravel(), Y.ravel(), z, zp).cpu().numpy()[0]
+        assert np.abs(F[b] - F1).max() <= 1e-11 * np.abs(F1).max()
+        F1 = eng.fields(plan, one, wls[b:b + 1], kp[b:b + 1], inc[b:b + 1], X.ravel(), Y.ravel(), zall, zp).cpu().numpy()[0]
+        assert np.abs(Fall[b] - F1).max() <= 1e-11 * np.abs(F1).max()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_bzi_beam_source_and_k_summed_fields(backend):
     """per-k source amplitudes (kh_beam_amplitudes) and the Brillouin-zone sum of the field maps, against the
     unmodified reference (examples/bzi/bzi_animation.py at test size: 1-D grating pw = (3, 1), 5 k-points)."""
