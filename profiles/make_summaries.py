@@ -67,8 +67,13 @@ for rep, out, what in ((f"r02_zgemm_{tag}.ncu-rep", "r02_zgemm56u3.txt", "zgemm5
     txt = subprocess.run([sys.executable, f"{P}/ncu_summary.py", f"{G}/{rep}"], capture_output=True, text=True).stdout
     open(f"{P}/{out}", "w").write(f"# ncu --set full --clock-control none --import-source on, one launch of {what} in: python bench.py --steps 1 --warmup 1 --no-cpu --no-extra "
                                   f"(bzi77, n=98, 4141 matrices, doubling method), round 2 capture '{tag}'; summary by profiles/ncu_summary.py\n" + txt)
+if os.path.exists(f"{G}/r02_fld_grid_{tag}.ncu-rep"):
+    txt = subprocess.run([sys.executable, f"{P}/ncu_summary.py", f"{G}/r02_fld_grid_{tag}.ncu-rep"], capture_output=True, text=True).stdout
+    open(f"{P}/r02_fld_grid.txt", "w").write(f"# ncu --set full --clock-control none --import-source on, the fld_grid launch of: python profiles/fields_bench.py 17 "
+                                              f"(C5: 9x9 harmonics, 256x256x128 grid, 17 volumes = 13.7 GB written), round 2 capture '{tag}'; summary by profiles/ncu_summary.py\n" + txt)
 # ---- bench lines, test logs
-for f in (f"r02_bench_{tag}_bzi77.json", f"r02_bench_{tag}_reference_arm.json", f"r02_bench_{tag}_bzi77_full.json", f"r02_pytest_gpu_{tag}.log", f"r02_smoke_{tag}.log", f"r02_accuracy_{tag}.jsonl", f"r02_fields_{tag}_51.jsonl"):
+for f in (f"r02_bench_{tag}_bzi77.json", f"r02_bench_{tag}_reference_arm.json", f"r02_bench_{tag}_bzi77_full.json", f"r02_pytest_gpu_{tag}.log", f"r02_smoke_{tag}.log", f"r02_accuracy_{tag}.jsonl", f"r02_fields_{tag}_51.jsonl",
+          f"r02_fields_{tag}_17.jsonl", f"r02_bench_{tag}_woodpile.json", f"r02_bench_{tag}_suh03.json"):
     if os.path.exists(f"{G}/{f}"):
         open(f"{P}/{f}", "w").write(open(f"{G}/{f}").read())
 print("ok", len(step), "launches,", f"{tot / 1000:.2f} ms serialised")
