@@ -230,6 +230,40 @@ static inline int kh_launch(dim3 grid, int block, size_t smem, kh_stream_t st, c
 }
 #define KH_ATOMIC_MAX(ptr, v) atomicMax((ptr), (v))
 #define KH_ATOMIC_OR(ptr, v) atomicOr((ptr), (v))
+// Thread-block-cluster launch (cluster_x CTAs along x share distributed shared memory; grid.x must be a multiple of it).
+template <class Args, void (*Body)(const Cta&, const Args&), int MAXT, int MINB>
+static inline int kh_launch_cluster(dim3 grid, int block, size_t smem, int cluster_x, kh_stream_t st, const Args& a, const char* name = "", double work = 0.0) {
+    if (grid.x == 0 || grid.y == 0) return 0;
+    void (*kern)(const Args) = kh_entry_lb<Args, Body, MAXT, MINB>;
+    if (smem > 48 * 1024) {
+        static size_t configured[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) configured[dev] = smem;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    g_prof.launches++;
+    cudaError_t e;
+    if (g_prof.on) {
+        KhProfRec r{name, work, kh_prof_event(), kh_prof_event()};
+        cudaEventRecord(r.e0, st);
+        e = cudaLaunchKernelEx(&cfg, kern, a);
+        cudaEventRecord(r.e1, st);
+        g_prof.recs.push_back(r);
+    } else {
+        e = cudaLaunchKernelEx(&cfg, kern, a);
+    }
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+}
 #endif
 
 // ------------------------------------------------------------------ TMA bulk copies (global -> shared, 1-D)

@@ -325,6 +325,127 @@ static inline size_t zinv_dmma8n_smem(int n) {
 }
 __device__ __forceinline__ void zinv_l2_body(const Cta& c, const zinv_args& a) { zinv_dmma_body_t<16, 8, true>(c, a); }
 #define ZIL_NMAX 256
+// ---------------------------------------------------------------------------------------------
+// Thread-block-CLUSTER variant for a HANDFUL of matrices beyond one SM's shared memory (104 < n <= 256: the
+// dependent inverses of a field-map solve, scalar solves of the 9x9 ... 11x11 bases; batch x CS <= 148, one wave).  A cluster of CS = 4 or 8 CTAs holds ONE
+// matrix in its distributed shared memory, CTA r the 16-column blocks [r bpc, (r + 1) bpc): the whole inversion runs out of shared
+// memory like zinv_dmma, where the single-CTA zinv_l2 works on an L2-resident copy.  Per block column:
+//   owner CTA : register-resident panel (zid_panel) on its own columns;
+//   cluster barrier; every CTA PULLS the finished block column P' (np x 16) and its pivot rows from the owner's shared memory
+//   (ld.shared::cluster through cooperative_groups' map_shared_rank) into a local buffer;
+//   every CTA : interchanges, pivot rows -> R, DMMA rank-16 update of its own columns (P' and C from local shared memory).
+// One cluster barrier per block column: the owner's panel columns are not touched again before the next one.
+#include <cooperative_groups.h>
+__device__ __forceinline__ void zidc_update(cd* Al, const cd* Pb, const cd* R, int ldc, int ldp, int ldr, int np, int nbk, int ntc, int s0, int s1,
+                                            int w, int nwork, int lane) {
+    // local tile columns [0, ntc) except [s0, s1) (the panel's own columns on the owner; s0 = s1 elsewhere)
+    const int lr = lane >> 2, lk = lane & 3;
+    const int nstrip = np >> 3, ncols = ntc - (s1 - s0), total = nstrip * ncols;
+    if (ncols <= 0) return;
+    int strip = w / ncols, tcr = w - strip * ncols;
+    for (int t = w; t < total; t += nwork) {
+        const int tc = tcr >= s0 ? tcr + (s1 - s0) : tcr;
+        cd* cp = Al + (strip * 8 + lr) * ldc + tc * 8 + 2 * lk;
+        const cd* ap = Pb + (strip * 8 + lr) * ldp + lk;
+        const cd* bp = R + lk * ldr + tc * 8 + lr;
+        const cd c0v = cp[0], c1v = cp[1];
+        double cr0 = c0v.x, cr1 = c1v.x, ci0 = c0v.y, ci1 = c1v.y;
+        for (int kk = 0; kk < (nbk >> 2); ++kk) {
+            const cd av = ap[kk * 4], bv = bp[kk * 4 * ldr];
+            kh_dmma(cr0, cr1, av.x, bv.x); kh_dmma(ci0, ci1, av.x, bv.y);
+            kh_dmma(cr0, cr1, -av.y, bv.y); kh_dmma(ci0, ci1, av.y, bv.x);
+        }
+        cp[0] = mk(cr0, ci0); cp[1] = mk(cr1, ci1);
+        tcr += nwork;
+        while (tcr >= ncols) { tcr -= ncols; ++strip; }
+    }
+}
+struct zidc_shape { int np, nblk, bpc, wc, ldc, ldp, ldr; size_t smem; };
+static inline __host__ __device__ zidc_shape zidc_make(int n, int CS) {
+    zidc_shape h;
+    h.np = (n + 7) & ~7; h.nblk = (h.np + ZID_NB - 1) / ZID_NB; h.bpc = (h.nblk + CS - 1) / CS; h.wc = h.bpc * ZID_NB;
+    h.ldc = h.wc + 4; h.ldr = h.wc + 2;
+    h.ldp = ZID_NB + 4;
+    auto bytes = [&](int ldp) { return (size_t)h.np * h.ldc * sizeof(cd) + (size_t)h.np * ldp * sizeof(cd) + (size_t)ZID_NB * h.ldr * sizeof(cd) +
+                                       18 * sizeof(zid_slot) + (size_t)(h.np + 2) * 4 + 64; };
+    if (bytes(h.ldp) > (size_t)227 * 1024) h.ldp = ZID_NB + 2;       // (2-way conflicts on the P' fragments instead of none)
+    h.smem = bytes(h.ldp);
+    return h;
+}
+template <int CS>
+__device__ __forceinline__ void zinv_cluster_body_t(const Cta& c, const zinv_args& a) {
+    namespace cg = cooperative_groups;
+    constexpr int NW = 16, PW = 8, NB = ZID_NB;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int n = a.n, b = c.bx / CS, tid = c.tid, warp = tid >> 5, lane = tid & 31;
+    const zidc_shape h = zidc_make(n, CS);
+    const int np = h.np, ldc = h.ldc, ldp = h.ldp, ldr = h.ldr, wc = h.wc;
+    const int c0 = rank * wc, c1 = min(np, c0 + wc), ncl = max(0, c1 - c0);        // this CTA's global columns [c0, c1)
+    const cd* A = mat_ptr(a.A, b);
+    cd* Out = mat_ptr(a.Ainv, b);
+    cd* Al = (cd*)KH_SMEM(c);                       // [np][ldc]   own columns
+    cd* Pb = Al + np * ldc;                         // [np][ldp]   block column P' of the current step
+    cd* R = Pb + np * ldp;                          // [NB][ldr]   pivot rows, own columns
+    zid_slot* slots = (zid_slot*)(R + NB * ldr);
+    int* piv = (int*)(slots + 2 * (PW + 1));        // [np] (every CTA collects all pivots)
+    unsigned long long* bar = (unsigned long long*)(piv + ((np + 2) & ~1));
+    if (rank == 0 && tid == 0 && a.info && a.info_mode == 0) a.info[b] = 0;
+    {   // own columns: rows of the matrix by TMA bulk copies, identity padding by the threads
+        const int ncv = min(c1, n) - c0;                                       // columns that exist in the matrix
+        for (int e = tid; e < np * ncl; e += 32 * NW) {
+            const int i = e / ncl, j = e - i * ncl;
+            if (i >= n || c0 + j >= n) Al[i * ldc + j] = mk(i == c0 + j ? 1.0 : 0.0, 0.0);
+        }
+        if (ncv > 0) kh_stage_rows(c, Al, ldc, A + c0, a.A.ld, n, ncv, bar);
+        else __syncthreads();
+    }
+    int bad = 0;
+    for (int kb = 0; kb < h.nblk; ++kb) {
+        const int k0 = kb * NB, nbk = min(NB, np - k0), owner = kb / h.bpc;
+        if (rank == owner) {
+            if (warp < PW) zid_panel<PW, NB>(Al - c0, ldc, np, n, k0, nbk, slots, piv, bad, tid);
+        }
+        cl.sync();                                  // the owner's block column is final; every CTA is past the previous update
+        {
+            const cd* src = cl.map_shared_rank(Al, owner) + (k0 - owner * wc);
+            const int* psrc = cl.map_shared_rank(piv, owner);
+            for (int e = tid; e < np * nbk; e += 32 * NW) { const int i = e / nbk, j = e - i * nbk; Pb[i * ldp + j] = src[i * ldc + j]; }
+            if (rank != owner && tid < nbk) piv[k0 + tid] = psrc[k0 + tid];
+        }
+        __syncthreads();
+        const int p0 = rank == owner ? k0 - c0 : 0, p1 = rank == owner ? p0 + nbk : 0;      // local columns of the panel (owner only)
+        if (tid < ncl && (tid < p0 || tid >= p1)) {     // interchanges on the own columns, pivot rows -> R (zeroed in place): thread <-> column
+            const int j = tid;
+            for (int s = 0; s < nbk; ++s) {
+                const int k = k0 + s, pr = piv[k];
+                if (pr != k) { const cd x = Al[k * ldc + j]; Al[k * ldc + j] = Al[pr * ldc + j]; Al[pr * ldc + j] = x; }
+            }
+            for (int s = 0; s < nbk; ++s) { R[s * ldr + j] = Al[(k0 + s) * ldc + j]; Al[(k0 + s) * ldc + j] = mk(0.0, 0.0); }
+        }
+        __syncthreads();
+        zidc_update(Al, Pb, R, ldc, ldp, ldr, np, nbk, ncl >> 3, p0 >> 3, p1 >> 3, warp, NW, lane);
+        __syncthreads();
+    }
+    cl.sync();                                      // (nobody leaves while a peer may still read its shared memory)
+    // undo the row interchanges as column interchanges: stored global column c0 + j goes to column dest
+    int* dest = (int*)R;
+    if (tid < ncl) {
+        int pos = c0 + tid;
+        for (int k = np - 1; k >= 0; --k) { const int pr = piv[k]; pos = (pos == k) ? pr : ((pos == pr) ? k : pos); }
+        dest[tid] = pos;
+    }
+    __syncthreads();
+    const int ncv = min(c1, n) - c0;
+    for (int i = warp; i < n; i += NW)
+        for (int j = lane; j < ncv; j += 32) Out[(long long)i * a.Ainv.ld + dest[j]] = Al[i * ldc + j];
+    if (tid == 0 && bad && a.info) {
+        if (a.info_mode > 0) KH_ATOMIC_OR(&a.info[b / a.info_mode], 2);
+        else KH_ATOMIC_MAX(&a.info[b], bad);
+    }
+}
+__device__ __forceinline__ void zinv_cluster4_body(const Cta& c, const zinv_args& a) { zinv_cluster_body_t<4>(c, a); }
+__device__ __forceinline__ void zinv_cluster8_body(const Cta& c, const zinv_args& a) { zinv_cluster_body_t<8>(c, a); }
 static inline long long zinv_l2_work_cd(int n) { const long long np = (n + 7) & ~7; return np * np; }
 static inline size_t zinv_l2_smem(int n) {
     const int np = (n + 7) & ~7;
@@ -632,6 +753,20 @@ static inline size_t zinv_smem_bytes(int n, int ld_s, int use_smem) {
 static inline int zinv_launch(kh_stream_t st, int batch, int n, MatRef A, MatRef Ainv, int* info, cd* work = nullptr, long long work_cd = 0, int info_mode = 0) {
     if (batch <= 0 || n <= 0) return 0;
 #ifndef KH_HOST_EMU
+    {   // a handful of mid-size matrices: one thread-block cluster per matrix, the matrix in distributed shared memory
+        const char* e = getenv("KH_ZINV_CLUSTER_MAXCTAS");   // (test / tuning switch; 0 disables)
+        const int maxctas = e ? atoi(e) : 148;             // one wave of clusters; beyond it zinv_l2 (one CTA per matrix) is as fast
+        if (n > ZID_NMAX && n <= ZIL_NMAX) {
+            const int CS = zidc_make(n, 4).smem <= (size_t)KH_SMEM_MAX ? 4 : 8;
+            const zidc_shape h = zidc_make(n, CS);
+            if (h.smem <= (size_t)KH_SMEM_MAX && (long long)batch * CS <= maxctas) {
+                zinv_args g;
+                g.n = n; g.A = A; g.Ainv = Ainv; g.info = info; g.info_mode = info_mode; g.use_smem = 0; g.ld_s = 0;
+                if (CS == 4) return kh_launch_cluster<zinv_args, zinv_cluster4_body, 512, 1>(dim3(batch * 4), 512, h.smem, 4, st, g, "zinv", 8.0 * n * n * n * batch);
+                return kh_launch_cluster<zinv_args, zinv_cluster8_body, 512, 1>(dim3(batch * 8), 512, h.smem, 8, st, g, "zinv", 8.0 * n * n * n * batch);
+            }
+        }
+    }
     {   // small batches of mid-size matrices: ONE launch, working copy in L2 (see zinv_dmma_body_t<.., true>)
         const char* e = getenv("KH_ZINV_L2_MAXBATCH");       // (test / tuning switch; default: two waves of one CTA per SM)
         const int l2max = e ? atoi(e) : 296;

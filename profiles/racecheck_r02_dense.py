@@ -21,6 +21,6 @@ cl = wk.build_crystal(st, eng, method="doubling")
 R, T = cl.solve_batch([s["wavelength"] for s in srcs[:2]], te=1.0, tm=0.0)
 print("suh03", R, T)
 rng = np.random.default_rng(0)
-for n in (50, 98, 130):
+for n in (50, 98, 130, 242, 300):              # 130 / 242: cluster of 4 / 8 CTAs; 300: blocked, 32-pivot block columns
     A = rng.standard_normal((1, n, n)) + 1j * rng.standard_normal((1, n, n))
     print("zinv", n, float(np.abs(eng.zinv(A).cpu().numpy() @ A - np.eye(n)).max()))

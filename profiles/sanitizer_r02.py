@@ -26,7 +26,7 @@ cl = wk.build_crystal(st, eng)
 R, T, S = cl.solve_batch([s["wavelength"] for s in srcs[:3]], te=1.0, tm=0.0, return_S=True)
 # inverses: smem resident (TMA staged), single-launch L2 variant, blocked
 rng = np.random.default_rng(0)
-for n in (18, 50, 98, 130, 300):
+for n in (18, 50, 98, 130, 242, 300):          # 130 / 242: one thread-block cluster of 4 / 8 CTAs per matrix
     A = rng.standard_normal((2, n, n)) + 1j * rng.standard_normal((2, n, n))
     Ai = eng.zinv(A).cpu().numpy()
     print("zinv", n, float(np.abs(Ai @ A - np.eye(n)).max()))

@@ -274,12 +274,15 @@ def test_energy_conservation_and_batch_invariance(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("n", [101, 119, 150, 242, 450])
-@pytest.mark.parametrize("variant", ["auto", "blocked"])
+@pytest.mark.parametrize("variant", ["auto", "l2", "blocked"])
 def test_zinv_blocked(backend, n, variant, monkeypatch):
-    """Inverse of matrices beyond shared memory: the blocked multi-launch variant (Gauss-Jordan panels + DMMA GEMM updates) and,
-    for small batches up to n = 256, the single-launch variant with the working copy in L2 ("auto" picks it for this batch)."""
-    if backend != "cuda" and (n > 150 or variant == "blocked"):
+    """Inverse of matrices beyond one SM's shared memory: the blocked multi-launch variant (Gauss-Jordan panels + DMMA GEMM
+    updates) and, for small batches up to n = 256, the two single-launch variants: one thread-block cluster per matrix with the
+    matrix in distributed shared memory ("auto" picks it for this batch) and one CTA per matrix with the working copy in L2."""
+    if backend != "cuda" and (n > 150 or variant != "auto"):
         pytest.skip("host emulation: small sizes only, one variant")
+    if variant in ("l2", "blocked"):
+        monkeypatch.setenv("KH_ZINV_CLUSTER_MAXCTAS", "0")
     if variant == "blocked":
         monkeypatch.setenv("KH_ZINV_L2_MAXBATCH", "0")
     eng = engine(backend)
