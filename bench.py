@@ -242,17 +242,19 @@ def extras(eng, dev, fp64_peak, quick, rates_only=False):
         res = eng.solve_batch(plan, w, k, p, want_flux=True, method=cl.method)         # warm-up (allocations, smem opt-in)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fb0 = eng.eig_fallbacks
         e0.record()
         for _ in range(reps):
             res = eng.solve_batch(plan, w, k, p, want_flux=True, method=cl.method)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        fallbacks = (eng.eig_fallbacks - fb0) // reps          # sources re-solved with the eigen method (conditioning guard), inside the time
         rt = res["RT"].cpu().numpy()
         n = 2 * st["pw"][0] * st["pw"][1]
         v = len(wl) / (ms * 1e-3)
         out.append({"config": name, "harmonics": list(st["pw"]), "n": n, "solves": int(len(wl)), "ms": ms, "solves_per_s": v,
-                    "nominal_tflops": nominal_flops_per_solve(st) * v / 1e12, "finite": bool(np.isfinite(rt).all()),
+                    "nominal_tflops": nominal_flops_per_solve(st) * v / 1e12, "finite": bool(np.isfinite(rt).all()), "eig_fallbacks": int(fallbacks),
                     "max_abs_R_plus_T_minus_1": float(np.nanmax(np.abs(rt.sum(1) - 1)))})
 
     freqs = np.linspace(0.49, 0.6, 151)
@@ -414,7 +416,9 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.kh_launch_count()
+    fb_start = eng.eig_fallbacks
     ms_total = timed(step_resident, args.warmup, args.steps)
+    fb_timed = eng.eig_fallbacks - fb_start
     launches = lib.kh_launch_count() - launches0
     # ---- e2e: the public API with host buffers (H2D of the sources, D2H of R and T, every step)
     step_e2e(0)
@@ -535,7 +539,8 @@ def run_gpu(args):
                            "method": method + (" (slice power series + self star products; eigensolver only when eigenspaces are retained)" if method == "doubling" else ""),
                            "parallelism": f"dp{world} (independent (freq,k) solves sharded, NCCL all_gather of R,T only)",
                            "l2": "per-step working set (workspace of several GB) exceeds the 126 MB L2, no explicit flush",
-                           "results_finite": finite, "results_info_max": info_max, "results_max_abs_R_plus_T_minus_1": energy},
+                           "results_finite": finite, "results_info_max": info_max, "results_max_abs_R_plus_T_minus_1": energy,
+                           "eig_fallbacks_in_timed_steps": int(fb_timed)},
                 "clocks": sampler.summary(),
                 "e2e": {"value": solves / (ms_e2e * 1e-3), "unit": "solves/s",
                         "h2d_bytes_per_step": int((B_total if full else B) * (8 + 32 + 32)) // (world if full else 1),

@@ -56,7 +56,8 @@ typedef struct {
     void* W_dev;                   /* [B][n_layers][n][n] layer eigenvectors, E part (Layer.W), per layer-table index */
     void* V_dev;                   /* [B][n_layers][n][n] layer eigenvectors, H part (Layer.V)                        */
     void* L_dev;                   /* [B][n_layers][n]    layer eigenvalues lambda (Layer.L)                          */
-    int* info_dev;                 /* [B] 0 = ok; bit0 eigensolver did not converge, bit1 singular pivot, bit2 doubling bound exceeded */
+    int* info_dev;                 /* [B] 0 = ok; bit0 eigensolver did not converge, bit1 singular pivot, bit2 doubling bound exceeded,
+                                      bit3 doubling method: a self star product was ill conditioned (re-solve with KH_METHOD_EIG) */
 } kh_outputs;
 
 int kh_abi_version(void);

@@ -258,6 +258,8 @@ class Crystal:
             raise np.linalg.LinAlgError("Singular matrix")
         if bad & 4:
             raise np.linalg.LinAlgError("doubling method: spectral bound exceeded (use method='eig')")
+        if bad & 8:          # (only with method='doubling' forced: 'auto' has re-solved such sources with the eigen method)
+            raise np.linalg.LinAlgError("doubling method: ill-conditioned self star product at a sub-slab resonance (use method='auto' or 'eig')")
         if bad & 1:
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 

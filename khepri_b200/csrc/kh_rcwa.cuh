@@ -542,6 +542,27 @@ KH_DEV void dbl_check_body(const Cta& c, const dbl_check_args& a) {
     if (c.tid == 0 && !(th <= a.theta_lim)) KH_ATOMIC_OR(&a.info[b], 4);
 }
 
+// Conditioning guard of a self star product: kappa_1(D) = ||D||_1 ||D^-1||_1 of D = I - S11^2.  At a resonance of the sub-slab the
+// doubling method passes through (a guided mode of a slab of depth d / 2^k between vacuum gaps) D is nearly singular and the
+// intermediate S-matrix loses digits that the eigen-decomposition does not: above the limit info bit 3 is raised and the host
+// re-solves that source with the eigen method (Engine.solve_batch, method "auto").
+struct dbl_cond_args { int B, n; const cd* D; const cd* Di; double limit; int* info; };
+KH_DEV void dbl_cond_body(const Cta& c, const dbl_cond_args& a) {
+    const int n = a.n, b = c.bx;
+    const cd* D = a.D + (long long)b * n * n;
+    const cd* Di = a.Di + (long long)b * n * n;
+    double* scratch = (double*)c.smem;
+    double m1 = 0.0, m2 = 0.0;
+    for (int j = c.tid; j < n; j += c.nthr) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < n; ++i) { s1 += cabsd(D[(long long)i * n + j]); s2 += cabsd(Di[(long long)i * n + j]); }
+        m1 = fmax(m1, s1); m2 = fmax(m2, s2);
+    }
+    m1 = cta_max(c, m1, scratch);
+    m2 = cta_max(c, m2, scratch);
+    if (c.tid == 0 && !(m1 * m2 <= a.limit)) KH_ATOMIC_OR(&a.info[b], 8);
+}
+
 // ------------------------------------------------------------------ two columns of a product (flux columns of the star chain)
 // Cout[:, c] = A B[:, c] (+ Cin[:, c]) for c in {c0, c1}: matrix-vector work, bound by reading A once (n^2 16 B per solve).
 // One CTA per solve; the two B columns are staged in shared memory, warp <-> row, lanes stride over k, shuffle reduction.

@@ -49,6 +49,16 @@ class Plan:
         self.gmax = float(np.sqrt((g_host ** 2).sum(axis=0)).max())
         self.eps_bound = max([float(L.get("eps_bound", 0.0)) for L in layers] + [0.0])
         self.has_patterned = any(int(L["kind"]) == _lib.LAYER_PIXMAP for L in layers)
+        # deepest patterned slab the flux-only solve sees: runs of one repeated layer are merged into one layer of m x depth (plan_view)
+        self.max_patterned_depth, run, prev = 0.0, 0.0, None
+        for li in self.stack:
+            L = layers[li]
+            if int(L["kind"]) != _lib.LAYER_PIXMAP:
+                run, prev = 0.0, None
+                continue
+            run = run + float(L.get("depth", 0.0)) if li == prev else float(L.get("depth", 0.0))
+            prev = li
+            self.max_patterned_depth = max(self.max_patterned_depth, run)
         self._method_state = None
         descs = (LayerDesc * len(layers))()
         for i, L in enumerate(layers):
@@ -97,6 +107,7 @@ class Engine:
             raise KhepriError("khepri_b200 only runs on CUDA devices; there is no CPU fallback.")
         self.lib = _lib.bind(lib_path)
         self._ws = None
+        self.eig_fallbacks = 0          # sources that method "auto" solved again with the eigen method (ill-conditioned doubling)
         self.workspace_cap_bytes = workspace_cap_bytes
         self.launch_count = 0
         self.doubling_theta = 10.0      # largest |lambda k0 d| of one slice of the doubling method (see _select_method)
@@ -266,8 +277,9 @@ class Engine:
         method: "auto" | "eig" | "doubling" (see _select_method).  bounds = (min wavelength, max |kp|) of the batch, optional:
         with DEVICE inputs it saves the reduction + host read the doubling method otherwise needs to size its series.
         """
+        used = None
         if (wl.numel() if isinstance(wl, torch.Tensor) else np.size(wl)) > 0:
-            self._select_method(plan, wl, kp, want_fields, method, bounds)
+            used = self._select_method(plan, wl, kp, want_fields, method, bounds)
         wl_d = self.to_dev(np.asarray(wl, dtype=np.float64).reshape(-1) if not isinstance(wl, torch.Tensor) else wl.reshape(-1), _f64)
         B = wl_d.numel()
         kp_d = self.to_dev(np.asarray(kp, dtype=np.complex128).reshape(B, 2) if not isinstance(kp, torch.Tensor) else kp.reshape(B, 2), _c128)
@@ -317,6 +329,18 @@ class Engine:
         ws_bytes = min(ws.numel(), need) if chunk else ws.numel()
         check(lib, lib.kh_solve_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(pol_d), C.byref(out), _ptr(ws), ws_bytes, self.stream()),
               "kh_solve_batch")
+        # "auto": sources whose doubling passed through an ill-conditioned self star product (info bit 3: a resonance of a
+        # sub-slab, include/khepri_b200.h) are solved again with the eigen method.  Only layers deep enough to need a self star
+        # product can raise the bit, so the usual thin-layer batches pay no host read here.
+        if used == "doubling" and method in (None, "auto") and plan._method_state[1] * plan.max_patterned_depth > 2.0 * plan._method_state[2]:
+            flagged = (res["info"] & 8) != 0
+            if bool(flagged.any().item()):
+                idx = flagged.nonzero().flatten()
+                sub = self.solve_batch(plan, wl_d[idx], kp_d[idx], pol_d[idx] if pol_d is not None else None, want_S=want_S, want_flux=want_flux,
+                                       want_orders=want_orders, want_fields=want_fields, chunk=chunk, method="eig")
+                for k, v in sub.items():
+                    res[k][idx] = v
+                self.eig_fallbacks += int(idx.numel())
         return res
 
     def star(self, SA, SB):

@@ -39,7 +39,9 @@ def gold(name):
     return np.load(os.path.join(GOLD, name + ".npz"))
 
 
-METHODS = ["eig", "doubling"]       # both ways a patterned layer gets its S-matrix (Engine._select_method)
+# both ways a patterned layer gets its S-matrix (Engine._select_method): the eigen-decomposition, and "auto" = the doubling method
+# with its conditioning guard (sources flagged by the device are solved again with the eigen method)
+METHODS = ["eig", "auto"]
 
 
 def build_crystal(st, eng, fields=False, method="auto"):
