@@ -16,7 +16,7 @@ from oracle import rcwa_oracle as orc
 from tests.cases import _st
 from tests.util import build_crystal, engine
 
-BASES = [(3, 3), (5, 3), (3, 5), (7, 1), (1, 5), (5, 5), (7, 5), (7, 7), (9, 3)]
+BASES = [(3, 3), (5, 3), (3, 5), (7, 1), (1, 5), (5, 5), (7, 5), (7, 7), (9, 3), (9, 7), (9, 9)]      # n = 18 ... 162
 TOL = 1e-9
 
 
@@ -27,7 +27,7 @@ def test_fuzz_random_structures_against_the_oracle():
     log = open(os.environ["KH_FUZZ_LOG"], "w") if os.environ.get("KH_FUZZ_LOG") else None
     eng = engine("cuda")
     rng = np.random.default_rng(seed)
-    worst = {"rt_eig": 0.0, "rt_auto": 0.0, "S_methods": 0.0, "fields": 0.0}
+    worst = {"rt_eig": 0.0, "rt_auto": 0.0, "rt_flux_eig": 0.0, "rt_flux_auto": 0.0, "S_methods": 0.0, "fields": 0.0}
     t0 = time.time()
     fb0 = eng.eig_fallbacks
     failures = []
@@ -56,6 +56,12 @@ def test_fuzz_random_structures_against_the_oracle():
             R, T, S[method] = cl.solve_batch([s["wavelength"] for s in srcs], te=[s["te"] for s in srcs], tm=[s["tm"] for s in srcs],
                                              theta=[s["theta"] for s in srcs], phi=[s["phi"] for s in srcs], return_S=True)
             rec["rt_" + method] = float(np.abs(np.stack([R, T], 1) - ref).max() / max(1.0, np.abs(ref).max()))
+            # the flux-only path (no Stot: two flux columns carried along the chain, last products associated from the right),
+            # with the per-order fluxes: same R, T, and the orders sum to them
+            (R2, Ro), (T2, To) = cl.solve_batch([s["wavelength"] for s in srcs], te=[s["te"] for s in srcs], tm=[s["tm"] for s in srcs],
+                                                theta=[s["theta"] for s in srcs], phi=[s["phi"] for s in srcs], only_total=False)
+            rec["rt_flux_" + method] = float(max(np.abs(np.stack([R2, T2], 1) - ref).max(), np.abs(Ro.sum(1) - R2).max(), np.abs(To.sum(1) - T2).max())
+                                             / max(1.0, np.abs(ref).max()))
         rec["S_methods"] = float(np.abs(S["auto"] - S["eig"]).max() / max(1.0, np.abs(S["eig"]).max()))
         # Noise floor of the full S-matrix: near a resonance of the whole stack Stot is ill conditioned whatever computes it
         # (its evanescent blocks; R and T stay at 1e-12) -- measured as the difference between the oracle's two restatements
@@ -102,7 +108,7 @@ def test_fuzz_random_structures_against_the_oracle():
             rec["fields"] = float(max(np.abs(E - Eo).max() / np.abs(Eo).max(), np.abs(H - Ho).max() / np.abs(Ho).max()))
         for k in worst:
             worst[k] = max(worst[k], rec.get(k, 0.0))
-        ok = rec["rt_eig"] <= TOL and rec["rt_auto"] <= TOL and rec["S_methods"] <= max(TOL, 10 * rec["S_floor"]) and \
+        ok = rec["rt_eig"] <= TOL and rec["rt_auto"] <= TOL and rec["rt_flux_eig"] <= TOL and rec["rt_flux_auto"] <= TOL and rec["S_methods"] <= max(TOL, 10 * rec["S_floor"]) and \
             rec.get("fields", 0.0) <= max(TOL, 10 * rec.get("fields_floor", 0.0))
         if not ok:
             failures.append(rec)
