@@ -122,3 +122,61 @@ def test_fuzz_random_structures_against_the_oracle():
                               "seconds": round(time.time() - t0, 1)}) + "\n")
         log.close()
     assert not failures, failures[:5]
+
+
+@pytest.mark.gpu
+def test_fuzz_special_cases_against_the_oracle():
+    """The corners the generator above does not reach: metallic (negative real part) and strongly lossy pixmaps, grazing incidence,
+    zero-depth and very thin layers, BZI-like stacks (many uniform layers, a thick high-index substrate) with sources given by
+    their in-plane wavevector, complex polarisation amplitudes."""
+    ntrial = int(os.environ.get("KH_FUZZ_TRIALS", "18"))
+    eng = engine("cuda")
+    rng = np.random.default_rng(int(os.environ.get("KH_FUZZ_SEED", "2026")) + 1)
+    log = open(os.environ["KH_FUZZ_LOG"] + ".special", "w") if os.environ.get("KH_FUZZ_LOG") else None
+    failures, worst = [], 0.0
+    for trial in range(ntrial):
+        pw = [(3, 3), (5, 5), (7, 3), (5, 1), (7, 7)][trial % 5]
+        res = (int(rng.integers(24, 72)), int(rng.integers(24, 72)))
+        kind = trial % 4
+        if kind == 0:                                  # metal grating
+            pm = np.where(rng.random(res) > 0.6, complex(-rng.uniform(2, 12), -rng.uniform(0.1, 2)), 1.0 + 0j)
+        elif kind == 1:                                # strongly lossy dielectric
+            pm = rng.uniform(1, 9, size=res) * (1 - 0.4j)
+        else:
+            pm = np.where(rng.random(res) > 0.5, float(rng.uniform(2, 13)), 1.0)
+        dA = float(rng.choice([0.0, 1e-4, 0.05, 0.4, 1.3]))
+        layers = {"A": ("pixmap", pm, dA), "G": ("pixmap", pm.T.copy() if res[0] == res[1] else pm[:, ::-1].copy(), float(rng.uniform(0.1, 0.5))),
+                  "S1": ("uniform", 1.0, 0.99), "S2": ("uniform", float(rng.uniform(2, 5)), float(rng.uniform(3, 17)))}
+        stack = [["S1"] * int(rng.integers(1, 6)) + ["G", "S2"], ["A", "G"], ["S2", "A", "S1", "G"], ["G", "A", "A", "S2", "S1"]][trial % 4]
+        st = _st(pw, layers, stack, epsi=1.0 if trial % 2 else float(rng.uniform(1, 2.5)), epse=float(rng.uniform(1, 4)))
+        B = 4
+        wl = rng.uniform(0.8, 2.6, size=B)
+        te = rng.uniform(0, 1, size=B) + 1j * rng.uniform(-0.5, 0.5, size=B)
+        tm = rng.uniform(0.1, 1, size=B) + 1j * rng.uniform(-0.5, 0.5, size=B)
+        if trial % 3 == 0:                             # sources by in-plane wavevector (BZ sampling), inside the light cone of the incidence medium
+            kmax = np.sqrt(st["epsi"]) * 2 * np.pi / wl
+            ang = rng.uniform(0, 2 * np.pi, size=B)
+            kr = kmax * rng.uniform(0, 0.97, size=B)
+            kps = np.stack([kr * np.cos(ang), kr * np.sin(ang)], 1)
+            ref = np.array([orc.solve_rt(st, float(wl[i]), te[i], tm[i], kp=(float(kps[i, 0]), float(kps[i, 1]))) for i in range(B)])
+            kw = dict(kps=kps)
+        else:
+            theta = np.where(rng.random(B) > 0.5, rng.uniform(80, 89.5, size=B), rng.uniform(0, 60, size=B))      # half of them grazing
+            phi = rng.uniform(0, 360, size=B)
+            ref = np.array([orc.solve_rt(st, float(wl[i]), te[i], tm[i], float(theta[i]), float(phi[i])) for i in range(B)])
+            kw = dict(theta=theta, phi=phi)
+        rec = {"trial": trial, "pw": list(pw), "kind": ["metal", "lossy", "binary", "binary"][kind], "stack": "".join(stack), "depth_A": dA}
+        for method in ("eig", "auto"):
+            cl = build_crystal(st, eng, method=method)
+            R, T = cl.solve_batch(wl, te=te, tm=tm, **kw)
+            rec["rt_" + method] = float(np.abs(np.stack([R, T], 1) - ref).max() / max(1.0, np.abs(ref).max()))
+            worst = max(worst, rec["rt_" + method])
+        if not (rec["rt_eig"] <= TOL and rec["rt_auto"] <= TOL):
+            failures.append(rec)
+        if log:
+            log.write(json.dumps(rec) + "\n")
+            log.flush()
+    if log:
+        log.write(json.dumps({"summary": True, "trials": ntrial, "worst_relative_error_RT": worst, "failures": len(failures)}) + "\n")
+        log.close()
+    assert not failures, failures[:5]
