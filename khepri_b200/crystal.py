@@ -186,7 +186,7 @@ class Crystal:
             return {"kind": _lib.LAYER_UNIFORM, "eps": layer.epsilon, "depth": layer.depth, "retain": retain}
         if f == Formulation.FFT or f == Formulation.ANALYTICAL:
             Cm, ICm = layer.convmat_device(eng)
-            return {"kind": _lib.LAYER_PIXMAP, "depth": layer.depth, "C": Cm, "IC": ICm, "retain": retain, "eps_bound": layer.eps_bound()}
+            return {"kind": _lib.LAYER_PIXMAP, "depth": layer.depth, "C": Cm, "IC": ICm, "retain": retain, "eps_bound": layer.eps_bound(), "eps_min_real": layer.eps_min_real()}
         if f == Formulation.HALF_SPACE_INC:
             return {"kind": _lib.LAYER_HALF_INC, "eps": layer.epsilon, "retain": retain}
         if f == Formulation.HALF_SPACE_TRN:

@@ -542,25 +542,30 @@ KH_DEV void dbl_check_body(const Cta& c, const dbl_check_args& a) {
     if (c.tid == 0 && !(th <= a.theta_lim)) KH_ATOMIC_OR(&a.info[b], 4);
 }
 
-// Conditioning guard of a self star product: kappa_1(D) = ||D||_1 ||D^-1||_1 of D = I - S11^2.  At a resonance of the sub-slab the
-// doubling method passes through (a guided mode of a slab of depth d / 2^k between vacuum gaps) D is nearly singular and the
-// intermediate S-matrix loses digits that the eigen-decomposition does not: above the limit info bit 3 is raised and the host
-// re-solves that source with the eigen method (Engine.solve_batch, method "auto").
-struct dbl_cond_args { int B, n; const cd* D; const cd* Di; double limit; int* info; };
+// Conditioning guard of a self star product  Y = D^-1 S12,  D = I - S11^2.  At a resonance of the sub-slab the doubling method
+// passes through (a guided mode of a slab of depth d / 2^k between vacuum gaps) D is nearly singular and the doubled S-matrix
+// loses digits that the eigen-decomposition does not.  The relative error of the computed Y is bounded by
+//     eps * kappa_1(D) * c,    c = ||D^-1||_1 ||S12||_1 / ||Y||_1   (the cancellation in the product with the explicit inverse),
+// measured in two passes (after the inverse: kappa_1(D) ||D^-1||_1 -> scratch; after the product: times ||S12||_1 / ||Y||_1).
+// Above the limit info bit 3 is raised and the host re-solves that source with the eigen method (Engine.solve_batch, "auto").
+struct dbl_cond_args { int B, n, mode; MatRef X, Z; double* scratch; double limit; int* info; };
 KH_DEV void dbl_cond_body(const Cta& c, const dbl_cond_args& a) {
     const int n = a.n, b = c.bx;
-    const cd* D = a.D + (long long)b * n * n;
-    const cd* Di = a.Di + (long long)b * n * n;
-    double* scratch = (double*)c.smem;
+    const cd* X = mat_ptr(a.X, b);
+    const cd* Z = mat_ptr(a.Z, b);
+    double* red = (double*)c.smem;
     double m1 = 0.0, m2 = 0.0;
     for (int j = c.tid; j < n; j += c.nthr) {
         double s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < n; ++i) { s1 += cabsd(D[(long long)i * n + j]); s2 += cabsd(Di[(long long)i * n + j]); }
+        for (int i = 0; i < n; ++i) { s1 += cabsd(X[(long long)i * a.X.ld + j]); s2 += cabsd(Z[(long long)i * a.Z.ld + j]); }
         m1 = fmax(m1, s1); m2 = fmax(m2, s2);
     }
-    m1 = cta_max(c, m1, scratch);
-    m2 = cta_max(c, m2, scratch);
-    if (c.tid == 0 && !(m1 * m2 <= a.limit)) KH_ATOMIC_OR(&a.info[b], 8);
+    m1 = cta_max(c, m1, red);
+    m2 = cta_max(c, m2, red);
+    if (c.tid == 0) {
+        if (a.mode == 0) a.scratch[b] = m1 * m2 * m2;                  // X = D, Z = D^-1
+        else if (!(a.scratch[b] * m1 / m2 <= a.limit)) KH_ATOMIC_OR(&a.info[b], 8);      // X = S12, Z = Y
+    }
 }
 
 // ------------------------------------------------------------------ two columns of a product (flux columns of the star chain)

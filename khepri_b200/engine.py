@@ -49,6 +49,8 @@ class Plan:
         self.gmax = float(np.sqrt((g_host ** 2).sum(axis=0)).max())
         self.eps_bound = max([float(L.get("eps_bound", 0.0)) for L in layers] + [0.0])
         self.has_patterned = any(int(L["kind"]) == _lib.LAYER_PIXMAP for L in layers)
+        # the spectral bound of the doubling method holds for dielectrics; layers without the information count as unsafe
+        self.spectrum_bounded = all(float(L.get("eps_min_real", -1.0)) >= 0.5 for L in layers if int(L["kind"]) == _lib.LAYER_PIXMAP)
         # deepest patterned slab the flux-only solve sees: runs of one repeated layer are merged into one layer of m x depth (plan_view)
         self.max_patterned_depth, run, prev = 0.0, 0.0, None
         for li in self.stack:
@@ -329,11 +331,13 @@ class Engine:
         ws_bytes = min(ws.numel(), need) if chunk else ws.numel()
         check(lib, lib.kh_solve_batch(plan.handle, B, _ptr(wl_d), _ptr(kp_d), _ptr(pol_d), C.byref(out), _ptr(ws), ws_bytes, self.stream()),
               "kh_solve_batch")
-        # "auto": sources whose doubling passed through an ill-conditioned self star product (info bit 3: a resonance of a
-        # sub-slab, include/khepri_b200.h) are solved again with the eigen method.  Only layers deep enough to need a self star
-        # product can raise the bit, so the usual thin-layer batches pay no host read here.
-        if used == "doubling" and method in (None, "auto") and plan._method_state[1] * plan.max_patterned_depth > 2.0 * plan._method_state[2]:
-            flagged = (res["info"] & 8) != 0
+        # "auto": sources the doubling method reports as unsafe -- a self star product through a sub-slab resonance (info bit 3) or a
+        # spectrum beyond the host's bound (bit 2: metallic gratings, whose inverse convolution matrix is not bounded by max |eps|) --
+        # are solved again with the eigen method.  Costs one host read of the status words, which batches that can raise neither bit
+        # (no layer deep enough for a self star product, dielectrics only) skip.
+        if used == "doubling" and method in (None, "auto") and \
+                (not plan.spectrum_bounded or plan._method_state[1] * plan.max_patterned_depth > 2.0 * plan._method_state[2]):
+            flagged = (res["info"] & 12) != 0
             if bool(flagged.any().item()):
                 idx = flagged.nonzero().flatten()
                 sub = self.solve_batch(plan, wl_d[idx], kp_d[idx], pol_d[idx] if pol_d is not None else None, want_S=want_S, want_flux=want_flux,

@@ -71,6 +71,15 @@ class Layer:
             return float(max(vals))
         return float(abs(complex(self.epsilon)))
 
+    def eps_min_real(self):
+        """min Re(epsilon) of a patterned layer.  While it stays well above zero the convolution matrix has its field of values in
+        the right half plane and max |epsilon| bounds the spectrum of Omega^2; a metallic inclusion (Re epsilon < 0) does not."""
+        if self.formulation == Formulation.FFT:
+            return float(np.min(np.real(self.epsilon)))
+        if self.formulation == Formulation.ANALYTICAL:
+            return float(min([complex(self.eps_host).real] + [complex(isl["epsilon"]).real for isl in self.epsilon]))
+        return float(complex(self.epsilon).real)
+
     @classmethod
     def pixmap_or_uniform(cls, expansion, pixmap, depth):
         eps0 = pixmap.flatten()[0]
