@@ -25,6 +25,9 @@ struct zgemm_args {
 };
 
 #define ZG_BK 16
+#ifndef KH_ZG_GROUP
+#define KH_ZG_GROUP 3           /* units whose fragments are in flight at once in the unit-balanced kernel */
+#endif
 #define ZG_LDA 20
 #define ZG_EMU_TILE 64
 
@@ -217,11 +220,20 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
 #endif
 }
 #ifndef KH_HOST_EMU
-// CNT (8-row strip, 8-column tile) units of one warp over a full K chunk; runtime smem offsets, B/A fragments in groups of 4
+// CNT (8-row strip, 8-column tile) units of one warp over a full K chunk.  The fragment addresses are 32-bit shared-memory byte
+// addresses kept in registers (stage base + per-unit offset, the k-step as an immediate): the generic-pointer form recomputed
+// (strip * 8 + lr) * LDA + ... and the shared window base for every load (2-3 dependent IMADs in front of each LDS).  Fragments of
+// G units are in flight at once (G = 2: 8 DMMAs = 128+ cycles of tensor work cover the LDS latency, and the registers that four
+// units' fragments took now hold the addresses).
+__device__ __forceinline__ cd kh_lds_cd(unsigned addr, int imm) {
+    cd v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + (unsigned)imm));
+    return v;
+}
 template <int CNT, int MAXU, int LDB>
-__device__ __forceinline__ void zgemm_mma_units(double (&cr)[MAXU][2], double (&ci)[MAXU][2], const cd* sa, const cd* sb,
-                                                const int (&aoff)[MAXU], const int (&boff)[MAXU], int ks) {
-    constexpr int G = CNT > 4 ? (CNT + 1) / 2 : CNT;
+__device__ __forceinline__ void zgemm_mma_units(double (&cr)[MAXU][2], double (&ci)[MAXU][2], unsigned sbase,
+                                                const unsigned (&aoff)[MAXU], const unsigned (&boff)[MAXU], int ks) {
+    constexpr int G = KH_ZG_GROUP < CNT ? KH_ZG_GROUP : CNT;
 #pragma unroll
     for (int kk = 0; kk < ZG_BK / 4; ++kk) {
         if (kk < ks) {
@@ -229,7 +241,7 @@ __device__ __forceinline__ void zgemm_mma_units(double (&cr)[MAXU][2], double (&
             for (int g0 = 0; g0 < CNT; g0 += G) {
                 cd av[G], bv[G];
 #pragma unroll
-                for (int t = 0; t < G; ++t) if (g0 + t < CNT) { av[t] = sa[aoff[g0 + t] + kk * 4]; bv[t] = sb[boff[g0 + t] + kk * 4 * LDB]; }
+                for (int t = 0; t < G; ++t) if (g0 + t < CNT) { av[t] = kh_lds_cd(sbase + aoff[g0 + t], kk * 4 * 16); bv[t] = kh_lds_cd(sbase + boff[g0 + t], kk * 4 * LDB * 16); }
 #pragma unroll
                 for (int t = 0; t < G; ++t) if (g0 + t < CNT) { kh_dmma(cr[g0 + t][0], cr[g0 + t][1], av[t].x, bv[t].x); kh_dmma(ci[g0 + t][0], ci[g0 + t][1], av[t].x, bv[t].y); }
 #pragma unroll
@@ -263,13 +275,14 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
     const int nk = (a.K + ZG_BK - 1) / ZG_BK;
     const int nt = min(NT, (a.N - n0 + 7) >> 3), ns = min(NW, (a.M - m0 + 7) >> 3);
     const int U = ns * nt, cnt = U / NC + (warp < U % NC ? 1 : 0), ustart = warp * (U / NC) + min(warp, U % NC);
-    int aoff[MAXU], boff[MAXU];
+    unsigned aoff[MAXU], boff[MAXU];                   // byte offsets of the unit's fragments inside a stage
 #pragma unroll
     for (int j = 0; j < MAXU; ++j) {
         const int u = ustart + (j < cnt ? j : 0), strip = u / nt, tl = u - strip * nt;
-        aoff[j] = (strip * 8 + lr) * ZG_LDA + lk;
-        boff[j] = BM * ZG_LDA + lk * LDB + tl * 8 + lr;
+        aoff[j] = (unsigned)(((strip * 8 + lr) * ZG_LDA + lk) * (int)sizeof(cd));
+        boff[j] = (unsigned)((BM * ZG_LDA + lk * LDB + tl * 8 + lr) * (int)sizeof(cd));
     }
+    const unsigned sm_u32 = (unsigned)__cvta_generic_to_shared(sm);
     const bool stager = warp < NW;
     const int am = a.transA ? tid % BM : tid >> 4, ak = a.transA ? tid / BM : tid & 15;
     const int bk = tid / BN, bn = tid - bk * BN;
@@ -315,18 +328,18 @@ KH_DEV void zgemm_body_u(const Cta& c, const zgemm_args& a) {
         __syncthreads();
         if (kc + ST - 1 < nk && stager) stage(nbuf, kc + ST - 1);
         kh_cp_async_commit();
-        const cd* sb = sm + buf * STAGE;
+        const unsigned sb = sm_u32 + (unsigned)(buf * STAGE * (int)sizeof(cd));
         const int ks = min(ZG_BK / 4, (a.K - kc * ZG_BK + 3) >> 2);
-        if (cnt == MAXU) zgemm_mma_units<MAXU, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
-        else if (cnt == MAXU - 1) zgemm_mma_units<MAXU - 1, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
-        else if (cnt == MAXU - 2) zgemm_mma_units<MAXU - 2, MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
-        else if (cnt == MAXU - 3) zgemm_mma_units<(MAXU > 3 ? MAXU - 3 : 1), MAXU, LDB>(cr, ci, sb, sb, aoff, boff, ks);
+        if (cnt == MAXU) zgemm_mma_units<MAXU, MAXU, LDB>(cr, ci, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 1) zgemm_mma_units<MAXU - 1, MAXU, LDB>(cr, ci, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 2) zgemm_mma_units<MAXU - 2, MAXU, LDB>(cr, ci, sb, aoff, boff, ks);
+        else if (cnt == MAXU - 3) zgemm_mma_units<(MAXU > 3 ? MAXU - 3 : 1), MAXU, LDB>(cr, ci, sb, aoff, boff, ks);
         else if (cnt > 0) {
             for (int kk = 0; kk < ks; ++kk) {
 #pragma unroll
                 for (int j = 0; j < MAXU; ++j) {
                     if (j < cnt) {
-                        const cd av = sb[aoff[j] + kk * 4], bv = sb[boff[j] + kk * 4 * LDB];
+                        const cd av = kh_lds_cd(sb + aoff[j] + (unsigned)(kk * 4 * (int)sizeof(cd)), 0), bv = kh_lds_cd(sb + boff[j] + (unsigned)(kk * 4 * LDB * (int)sizeof(cd)), 0);
                         kh_dmma(cr[j][0], cr[j][1], av.x, bv.x); kh_dmma(ci[j][0], ci[j][1], av.x, bv.y);
                         kh_dmma(cr[j][0], cr[j][1], -av.y, bv.y); kh_dmma(ci[j][0], ci[j][1], av.y, bv.x);
                     }
