@@ -180,3 +180,49 @@ def test_fuzz_special_cases_against_the_oracle():
         log.write(json.dumps({"summary": True, "trials": ntrial, "worst_relative_error_RT": worst, "failures": len(failures)}) + "\n")
         log.close()
     assert not failures, failures[:5]
+
+
+@pytest.mark.gpu
+def test_fuzz_twisted_bilayers_against_the_oracle():
+    """Extended (twisted-bilayer) stacks, extension.py:66-112: random twist angles, pixmaps, depths, spacer permittivities and
+    frequencies on the (3,3)+(3,3) and (3,1)+(3,1) moire bases, R and T against the oracle's solve_twisted."""
+    from khepri_b200 import Crystal, Expansion, Layer
+    ntrial = max(4, int(os.environ.get("KH_FUZZ_TRIALS", "18")) // 3)
+    eng = engine("cuda")
+    rng = np.random.default_rng(int(os.environ.get("KH_FUZZ_SEED", "2026")) + 2)
+    worst, failures = 0.0, []
+    for trial in range(ntrial):
+        pw = [(3, 3), (3, 1), (3, 3)][trial % 3]
+        ta = float(np.deg2rad(rng.uniform(2.0, 44.0)))
+        res = int(rng.integers(32, 80))
+        pm = np.where(rng.random((res, res)) > 0.55, float(rng.uniform(2, 9)), 1.0) if trial % 2 else rng.uniform(1, 5, size=(res, res))
+        d = [float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.05, 0.6)), float(rng.uniform(0.05, 0.5))]
+        eps_i = float(rng.uniform(1, 2.5))
+        freqs = rng.uniform(0.55, 0.9, size=3)
+        e1, e2 = Expansion(pw), Expansion(pw)
+        e1.rotate(ta / 2)
+        e2.rotate(-ta / 2)
+        cl = Crystal.from_expansion(e1 + e2, engine=eng)
+        cl.add_layer("upper", Layer.pixmap(e1, pm, d[0]), extended=True)
+        cl.add_layer("lower", Layer.pixmap(e2, pm.T.copy(), d[2]), extended=True)
+        cl.add_layer("inter", Layer.uniform(e1, eps_i, d[1]), extended=True)
+        cl.set_device(["upper", "inter", "lower"], [False] * 3)
+        R, T = cl.solve_batch(1 / freqs, te=1, tm=0)
+        g0 = orc.g_vectors(pw, np.eye(2))
+        ref = np.empty((len(freqs), 2))
+        for i, f in enumerate(freqs):
+            desc = {"pw": pw, "g1": orc.rotation(ta / 2) @ g0, "g2": orc.rotation(-ta / 2) @ g0, "epsi": 1, "epse": 1,
+                    "stack": ["upper", "inter", "lower"],
+                    "layers": {"upper": (("pixmap", pm, d[0]), 1), "lower": (("pixmap", pm.T.copy(), d[2]), 2), "inter": (("uniform", eps_i, d[1]), 1)}}
+            sol = orc.solve_twisted(desc, 1 / f, (0j, 0j))
+            stm = {"pw": (pw[0] ** 2, pw[1] ** 2), "epsi": 1, "epse": 1}
+            sol["layers"]["Sref"]["W"] = sol["layers"]["Strans"]["W"] = np.identity(sol["Stot"].shape[-1])
+            ref[i] = orc.flux_end(stm, sol, 1.0, 0.0)
+        err = float(np.abs(np.stack([R, T], 1) - ref).max())
+        worst = max(worst, err)
+        if not err <= TOL:
+            failures.append({"trial": trial, "pw": list(pw), "twist_deg": float(np.rad2deg(ta)), "err": err})
+    if os.environ.get("KH_FUZZ_LOG"):
+        with open(os.environ["KH_FUZZ_LOG"] + ".twisted", "w") as f:
+            f.write(json.dumps({"summary": True, "trials": ntrial, "worst_abs_error_RT": worst, "failures": failures}) + "\n")
+    assert not failures, failures[:5]
