@@ -226,3 +226,41 @@ def test_fuzz_twisted_bilayers_against_the_oracle():
         with open(os.environ["KH_FUZZ_LOG"] + ".twisted", "w") as f:
             f.write(json.dumps({"summary": True, "trials": ntrial, "worst_abs_error_RT": worst, "failures": failures}) + "\n")
     assert not failures, failures[:5]
+
+
+@pytest.mark.gpu
+def test_fuzz_analytical_layers_against_the_oracle():
+    """Layers from closed-form island transforms (Crystal.add_layer_analytical, layer.py:121-129,161-174): random rectangles and
+    discs (positions, sizes, permittivities, host medium) on square and rectangular bases, R and T against the oracle."""
+    from tests.cases import disc_island, rect_island
+    ntrial = max(4, int(os.environ.get("KH_FUZZ_TRIALS", "18")) // 3)
+    eng = engine("cuda")
+    rng = np.random.default_rng(int(os.environ.get("KH_FUZZ_SEED", "2026")) + 3)
+    worst, failures = 0.0, []
+    lat = np.eye(2)
+    for trial in range(ntrial):
+        pw = [(5, 5), (3, 5), (7, 3), (7, 7)][trial % 4]
+        islands = []
+        for _ in range(int(rng.integers(1, 4))):
+            c = (float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.3, 0.3)))
+            eps = complex(rng.uniform(1.5, 12), -rng.uniform(0, 0.3) * (trial % 2))
+            islands.append(rect_island(c, (float(rng.uniform(0.1, 0.4)), float(rng.uniform(0.1, 0.4))), eps) if rng.random() > 0.5
+                           else disc_island(c, float(rng.uniform(0.08, 0.2)), eps))
+        host = float(rng.uniform(1, 2.5))
+        layers = {"1": ("analytical", islands, float(rng.uniform(0.1, 1.2)), host, lat), "U": ("uniform", float(rng.uniform(1, 4)), float(rng.uniform(0.1, 0.8)))}
+        st = _st(pw, layers, [["1", "U"], ["U", "1", "1"], ["1"]][trial % 3], epsi=1.0, epse=float(rng.uniform(1, 2.5)))
+        srcs = [dict(wavelength=float(rng.uniform(0.9, 2.4)), te=float(rng.uniform(0, 1)), tm=float(rng.uniform(0.1, 1)),
+                     theta=float(rng.uniform(0, 60)), phi=float(rng.uniform(0, 360))) for _ in range(3)]
+        ref = np.array([orc.solve_rt(st, s["wavelength"], s["te"], s["tm"], s["theta"], s["phi"]) for s in srcs])
+        for method in ("eig", "auto"):
+            cl = build_crystal(st, eng, method=method)
+            R, T = cl.solve_batch([s["wavelength"] for s in srcs], te=[s["te"] for s in srcs], tm=[s["tm"] for s in srcs],
+                                  theta=[s["theta"] for s in srcs], phi=[s["phi"] for s in srcs])
+            err = float(np.abs(np.stack([R, T], 1) - ref).max())
+            worst = max(worst, err)
+            if not err <= TOL:
+                failures.append({"trial": trial, "pw": list(pw), "method": method, "err": err})
+    if os.environ.get("KH_FUZZ_LOG"):
+        with open(os.environ["KH_FUZZ_LOG"] + ".analytical", "w") as f:
+            f.write(json.dumps({"summary": True, "trials": ntrial, "worst_abs_error_RT": worst, "failures": failures}) + "\n")
+    assert not failures, failures[:5]
