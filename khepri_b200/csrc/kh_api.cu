@@ -521,10 +521,10 @@ static int solve_patterned_dbl(kh_stream_t st, int Bc, int N, const cd* C, const
         KH_TRY(zinv_launch(st, Bc, n, M(t0), M(t1), info_acc, S(14), 3 * slab, 1));                            // D^-1
         double* gscr = (double*)S(14);                                        // (the inverse's work space is free again)
         {   dbl_cond_args a{Bc, n, 0, M(t0), M(t1), gscr, cond_limit, info_acc};                               // guard, pass 1: kappa_1(D) ||D^-1||_1
-            KH_TRY((kh_launch<dbl_cond_args, dbl_cond_body>(dim3(Bc), 128, 256 * sizeof(double), st, a, "dbl_eo"))); }
+            KH_TRY((kh_launch<dbl_cond_args, dbl_cond_body>(dim3(Bc), 256, 256 * sizeof(double), st, a, "dbl_eo"))); }
         KH_TRY(gemm(st, Bc, n, M(t1), s12, M(t0)));                                                         // Y
         {   dbl_cond_args a{Bc, n, 1, s12, M(t0), gscr, cond_limit, info_acc};                                 // guard, pass 2 -> info bit 3
-            KH_TRY((kh_launch<dbl_cond_args, dbl_cond_body>(dim3(Bc), 128, 256 * sizeof(double), st, a, "dbl_eo"))); }
+            KH_TRY((kh_launch<dbl_cond_args, dbl_cond_body>(dim3(Bc), 256, 256 * sizeof(double), st, a, "dbl_eo"))); }
         if (!last) {
             MatRef Ap = s12; Ap.inner = 2; Ap.si = (long long)(s11.p - s12.p);                              // (S12, S11)
             zgemm_args g = zgemm_make(n, n, n, Ap, both(t0), pair(p0, p0 + 1));                             // (S12', Z)

@@ -545,21 +545,38 @@ KH_DEV void dbl_check_body(const Cta& c, const dbl_check_args& a) {
 // Conditioning guard of a self star product  Y = D^-1 S12,  D = I - S11^2.  At a resonance of the sub-slab the doubling method
 // passes through (a guided mode of a slab of depth d / 2^k between vacuum gaps) D is nearly singular and the doubled S-matrix
 // loses digits that the eigen-decomposition does not.  The relative error of the computed Y is bounded by
-//     eps * kappa_1(D) * c,    c = ||D^-1||_1 ||S12||_1 / ||Y||_1   (the cancellation in the product with the explicit inverse),
-// measured in two passes (after the inverse: kappa_1(D) ||D^-1||_1 -> scratch; after the product: times ||S12||_1 / ||Y||_1).
+//     eps * kappa(D) * c,    c = ||D^-1|| ||S12|| / ||Y||   (the cancellation in the product with the explicit inverse),
+// measured in 1-norms in two passes (after the inverse: kappa(D) ||D^-1|| -> scratch; after the product: times ||S12|| / ||Y||).
 // Above the limit info bit 3 is raised and the host re-solves that source with the eigen method (Engine.solve_batch, "auto").
 struct dbl_cond_args { int B, n, mode; MatRef X, Z; double* scratch; double limit; int* info; };
-KH_DEV void dbl_cond_body(const Cta& c, const dbl_cond_args& a) {
+KH_DEV void dbl_cond_body(const Cta& c, const dbl_cond_args& a) {        // (1-norms: column sums; lane <-> column, a warp per group of 32 columns)
     const int n = a.n, b = c.bx;
     const cd* X = mat_ptr(a.X, b);
     const cd* Z = mat_ptr(a.Z, b);
     double* red = (double*)c.smem;
     double m1 = 0.0, m2 = 0.0;
-    for (int j = c.tid; j < n; j += c.nthr) {
+#ifdef KH_HOST_EMU
+    for (int j = 0; j < n; ++j) {
         double s1 = 0.0, s2 = 0.0;
         for (int i = 0; i < n; ++i) { s1 += cabsd(X[(long long)i * a.X.ld + j]); s2 += cabsd(Z[(long long)i * a.Z.ld + j]); }
         m1 = fmax(m1, s1); m2 = fmax(m2, s2);
     }
+#else
+    const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nthr >> 5;
+    for (int j0 = warp * 32; j0 < n; j0 += nw * 32) {
+        const int j = j0 + lane;
+        if (j < n) {
+            double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+            int i = 0;
+            for (; i + 4 <= n; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { s1[u] += cabsd(X[(long long)(i + u) * a.X.ld + j]); s2[u] += cabsd(Z[(long long)(i + u) * a.Z.ld + j]); }
+            }
+            for (; i < n; ++i) { s1[0] += cabsd(X[(long long)i * a.X.ld + j]); s2[0] += cabsd(Z[(long long)i * a.Z.ld + j]); }
+            m1 = fmax(m1, (s1[0] + s1[1]) + (s1[2] + s1[3])); m2 = fmax(m2, (s2[0] + s2[1]) + (s2[2] + s2[3]));
+        }
+    }
+#endif
     m1 = cta_max(c, m1, red);
     m2 = cta_max(c, m2, red);
     if (c.tid == 0) {

@@ -227,7 +227,9 @@ KH_DEV void zgemm_body_p(const Cta& c, const zgemm_args& a) {
 // units' fragments took now hold the addresses).
 __device__ __forceinline__ cd kh_lds_cd(unsigned addr, int imm) {
     cd v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + (unsigned)imm));
+    // volatile: keeps the load behind the chunk's barrier in program order (a plain asm without a memory clobber may be moved
+    // across __syncthreads by the compiler; ptxas still schedules it freely among the DMMAs)
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + (unsigned)imm));
     return v;
 }
 template <int CNT, int MAXU, int LDB>
@@ -385,7 +387,9 @@ static inline int zgemm_launch(kh_stream_t st, int batch, const zgemm_args& a) {
     // profiler name: products with a handful of columns (the flux columns of the last star product) are matrix-vector work,
     // bound by reading A from HBM, and are reported apart from the tensor-bound GEMMs
     const char* name = a.N <= 8 ? "zgemv" : "zgemm";
-    const bool t56 = zgemm_padded(a.M, a.N, 56) < zgemm_padded(a.M, a.N, 64);
+    // (56x56 only where it saves at least 5 % of the padded work: at equal padding the 64x64 strip kernel is the faster one,
+    //  n = 450: 465 -> 491 solves/s)
+    const bool t56 = zgemm_padded(a.M, a.N, 56) * 100 < zgemm_padded(a.M, a.N, 64) * 95;
     const unsigned g56 = (unsigned)batch * ((a.M + 55) / 56) * ((a.N + 55) / 56), g64 = (unsigned)batch * ((a.M + 63) / 64) * ((a.N + 63) / 64);
     if (t56) return kh_launch<zgemm_args, zgemm56u3_body, 256, 2>(dim3(g56), 256, zgemm_smem(56, 3), st, a, name, work);
     return kh_launch<zgemm_args, zgemm64p3_body, 256, 2>(dim3(g64), 256, zgemm_smem(64, 3), st, a, name, work);
