@@ -106,6 +106,16 @@ static int cols2(kh_stream_t st, int Bc, int n, int fc, MatRef Amat, MatRef Bsrc
     zgemv2_args a{n, fc, fc + n / 2, Amat, Bsrc, Cin ? *Cin : mref(nullptr, 0, 0), Cout};
     return kh_launch<zgemv2_args, zgemv2_body>(dim3(Bc), 256, (size_t)2 * n * sizeof(cd), st, a, "zgemv", 16.0 * n * n * Bc);
 }
+// One step of iterative refinement of  X = F^-1 R  computed with the explicit inverse:  X += F^-1 (R - F X).  The product with the
+// explicit inverse is accurate to eps kappa(F) ||F^-1|| ||R|| / ||X||: where a layer's S-matrix has evanescent entries of tens
+// (deep high-contrast layers) that cancellation costs digits in the evanescent blocks of the result which a backward-stable solve
+// (what the reference's numpy.linalg.solve is) keeps; the refined product has the solve's accuracy.  Two GEMMs; used on the full
+// (Stot / field) products only -- the flux columns of the flux-only chain are not affected (tests/test_fuzz_parity.py).
+static int refine_solve(kh_stream_t st, int Bc, int n, MatRef F, MatRef Fi, MatRef R, MatRef X, MatRef T) {
+    int e;
+    if ((e = gemm(st, Bc, n, F, X, T, -1.0, &R, 1.0))) return e;          // T = R - F X
+    return gemm(st, Bc, n, Fi, T, X, 1.0, &X, 1.0);                       // X += F^-1 T
+}
 static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& B, cd* out, cd* tmp, int* info, int fc = -1, bool last = false, int imode = 0) {
     const long long n2 = (long long)n * n, slab = (long long)Bc * n2;
     MatRef F = mref(tmp, n2, n), Fi = mref(tmp + slab, n2, n), X = mref(tmp + 2 * slab, n2, n), Y = mref(tmp + 3 * slab, n2, n);
@@ -122,11 +132,13 @@ static int dense_star(kh_stream_t st, int Bc, int n, const SRef& A, const SRef& 
         if (last) return 0;
     } else {
         if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                // X = F^-1 A21
+        if ((e = refine_solve(st, Bc, n, F, Fi, A.blk[2], X, Vt))) return e;
         if ((e = gemm(st, Bc, n, B.blk[2], X, O.blk[2]))) return e;                          // S21 = B21 X
         if ((e = gemm(st, Bc, n, B.blk[0], X, U))) return e;                                 // U = B11 X
         if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;     // S11 = A11 + A12 U
     }
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                    // Y = F^-1 A22
+    if (fc < 0 && (e = refine_solve(st, Bc, n, F, Fi, A.blk[3], Y, Vt))) return e;
     if ((e = gemm(st, Bc, n, Y, B.blk[1], Z))) return e;                                     // Z = Y B12
     if ((e = gemm(st, Bc, n, B.blk[2], Z, O.blk[3], 1.0, &B.blk[3], 1.0))) return e;         // S22 = B22 + B21 Z
     if ((e = gemm(st, Bc, n, B.blk[0], Z, Vt, 1.0, &B.blk[1], 1.0))) return e;               // Vt = B12 + B11 Z
@@ -186,6 +198,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
         if ((e = cols2(st, Bc, n, fc, Fi, A.blk[2], X))) return e;                                 // X = F^-1 A21  (flux columns)
     } else {
         if ((e = gemm(st, Bc, n, Fi, A.blk[2], X))) return e;                                      // X = F^-1 A21
+        if ((e = refine_solve(st, Bc, n, F, Fi, A.blk[2], X, Vt))) return e;
     }
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, X, O.blk[2], 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e;      // S21 = B21 X
     if ((e = bdmul(st, Bc, N, 0, Bd, 0, X, U, 1.0, nullptr, 0.0, 0.0, nullptr, 0, fc))) return e;             // U = B11 X
@@ -196,6 +209,7 @@ static int star_dense_bd(kh_stream_t st, int Bc, int N, const SRef& A, const cd*
         if ((e = gemm(st, Bc, n, A.blk[1], U, O.blk[0], 1.0, &A.blk[0], 1.0))) return e;           // S11 = A11 + A12 U
     }
     if ((e = gemm(st, Bc, n, Fi, A.blk[3], Y))) return e;                                          // Y = F^-1 A22
+    if (fc < 0 && (e = refine_solve(st, Bc, n, F, Fi, A.blk[3], Y, Vt))) return e;
     if ((e = bdmul(st, Bc, N, 1, Bd, 1, Y, Z))) return e;                                          // Z = Y B12
     if ((e = bdmul(st, Bc, N, 0, Bd, 2, Z, O.blk[3], 1.0, nullptr, 0.0, 0.0, Bd, 3))) return e;    // S22 = B22 + B21 Z
     if ((e = bdmul(st, Bc, N, 0, Bd, 0, Z, Vt, 1.0, nullptr, 0.0, 0.0, Bd, 1))) return e;          // Vt = B12 + B11 Z
