@@ -27,7 +27,7 @@ def test_fuzz_random_structures_against_the_oracle():
     log = open(os.environ["KH_FUZZ_LOG"], "w") if os.environ.get("KH_FUZZ_LOG") else None
     eng = engine("cuda")
     rng = np.random.default_rng(seed)
-    worst = {"rt_eig": 0.0, "rt_auto": 0.0, "rt_flux_eig": 0.0, "rt_flux_auto": 0.0, "S_methods": 0.0, "fields": 0.0}
+    worst = {"rt_eig": 0.0, "rt_auto": 0.0, "rt_flux_eig": 0.0, "rt_flux_auto": 0.0, "S_methods": 0.0, "S_oracle": 0.0, "fields": 0.0}
     t0 = time.time()
     fb0 = eng.eig_fallbacks
     failures = []
@@ -66,8 +66,8 @@ def test_fuzz_random_structures_against_the_oracle():
         # Noise floor of the full S-matrix: near a resonance of the whole stack Stot is ill conditioned whatever computes it
         # (its evanescent blocks; R and T stay at 1e-12) -- measured as the difference between the oracle's two restatements
         # of the reference (eigen-decomposition / expm + doublings) on the same sources.
-        floor = 0.0
-        for s_ in srcs:
+        floor, s_orc = 0.0, 0.0
+        for i_, s_ in enumerate(srcs):
             kp_ = tuple(orc.kplanar(st["epsi"], s_["wavelength"], s_["theta"], s_["phi"]))
             Se = np.asarray(orc.solve_structure(st, s_["wavelength"], kp_, want_reverse=False)["Stot"])
             orc.PATTERNED_BY_DOUBLING = 4
@@ -76,7 +76,10 @@ def test_fuzz_random_structures_against_the_oracle():
             finally:
                 orc.PATTERNED_BY_DOUBLING = None
             floor = max(floor, float(np.abs(Sd - Se).max() / max(1.0, np.abs(Se).max())))
+            s_orc = max(s_orc, float(np.abs(S["eig"][i_] - Se).max() / max(1.0, np.abs(Se).max())),
+                        float(np.abs(S["auto"][i_] - Se).max() / max(1.0, np.abs(Se).max())))
         rec["S_floor"] = floor
+        rec["S_oracle"] = s_orc           # both methods' Stot against the oracle's (the star-product chain is common to both methods)
         if trial % 3 == 2:
             # Field maps on the stack cut into slices of depth <= 0.35, the way field maps are computed in practice:
             # inside a deep layer the reference's own reconstruction loses digits (growing exponentials clipped at 1e14,
@@ -108,7 +111,7 @@ def test_fuzz_random_structures_against_the_oracle():
             rec["fields"] = float(max(np.abs(E - Eo).max() / np.abs(Eo).max(), np.abs(H - Ho).max() / np.abs(Ho).max()))
         for k in worst:
             worst[k] = max(worst[k], rec.get(k, 0.0))
-        ok = rec["rt_eig"] <= TOL and rec["rt_auto"] <= TOL and rec["rt_flux_eig"] <= TOL and rec["rt_flux_auto"] <= TOL and rec["S_methods"] <= max(TOL, 10 * rec["S_floor"]) and \
+        ok = rec["rt_eig"] <= TOL and rec["rt_auto"] <= TOL and rec["rt_flux_eig"] <= TOL and rec["rt_flux_auto"] <= TOL and rec["S_methods"] <= max(TOL, 10 * rec["S_floor"]) and rec["S_oracle"] <= max(TOL, 10 * rec["S_floor"]) and \
             rec.get("fields", 0.0) <= max(TOL, 10 * rec.get("fields_floor", 0.0))
         if not ok:
             failures.append(rec)
